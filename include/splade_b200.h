@@ -1,0 +1,156 @@
+/*
+ * splade_b200.h — C-ABI of libsplade_b200.so: the B200-native (sm_100a) SPLADE-max head + SPLADELossV33
+ * hot path of opensearch-neural-pre-train.
+ *
+ * The reference has no FFI: its "operator interface" for this path is two Python nn.Modules
+ * (src/model/splade_modern.py:19-114, src/model/losses.py:14-301).  Every entry point below replaces one
+ * slice of those modules' forward/backward and is what a ctypes / cffi / pybind stub on the reference
+ * side binds.  Conventions for all calls:
+ *
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *   - row-major, innermost dimension contiguous; "bf16" is passed as const void* (raw 16-bit words);
+ *   - the caller (PyTorch) owns every buffer, including workspaces sized by splade_workspace_bytes();
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation inside;
+ *   - return value 0 = success, otherwise an error code; the message is splade_last_error()
+ *     (thread-local).  Nothing throws or aborts across this boundary;
+ *   - unsupported device (not sm_100) or shape is an ERROR, never a fallback.
+ */
+#ifndef SPLADE_B200_H_
+#define SPLADE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPLADE_B200_ABI_VERSION 1
+
+/* error codes */
+#define SPLADE_OK 0
+#define SPLADE_ERR_INVALID_ARG 1
+#define SPLADE_ERR_UNSUPPORTED_SHAPE 2
+#define SPLADE_ERR_UNSUPPORTED_DEVICE 3
+#define SPLADE_ERR_WORKSPACE 4
+#define SPLADE_ERR_CUDA 5
+#define SPLADE_ERR_DRIVER 6
+
+/* op ids for splade_workspace_bytes */
+#define SPLADE_OP_HEAD_FWD 0      /* (B,S,H,V)            head forward, token_weights not requested   */
+#define SPLADE_OP_HEAD_FWD_TOKW 1 /* (B,S,H,V)            head forward with token_weights             */
+#define SPLADE_OP_HEAD_BWD 2      /* (B,S,H,V)            head backward                               */
+#define SPLADE_OP_FLOPS_NNZ 3     /* (B=N rows, V)        FLOPS regulariser + nonzero count           */
+#define SPLADE_OP_SCORES 4        /* (B=Bq, k=N docs, V)  q.d score matrix                            */
+
+int splade_abi_version(void);
+const char* splade_last_error(void);
+size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k);
+
+/*
+ * Fused vocabulary projection + log1p(relu) + padding mask + max-pool over the sequence (+ argmax).
+ * Replaces src/model/splade_modern.py:69-86 (decoder Linear of transformers' ModernBertForMaskedLM,
+ * modeling_modernbert.py:562, included).  Numerics = the reference under torch.autocast(bf16):
+ * fp32 accumulate, + bias, one RNE rounding to bf16, relu, max with ties to the lowest position.
+ *
+ *   hidden [B,S,H] bf16   output of model.head (dense->GELU->LayerNorm), cast to bf16
+ *   W      [V,H]   bf16   decoder.weight (tied to the token embeddings)
+ *   bias   [V]     fp32   decoder.bias (pass it pre-rounded to bf16 to mirror autocast)
+ *   mask   [B,S]   int32  attention mask, nonzero = real token
+ *   rep    [B,V]   fp32   sparse_repr                       (out)
+ *   argmax [B,V]   int32  position of the max, 0 if rep==0  (out; what autograd keeps in the reference)
+ *   tokw   [B,S]   fp32   token_weights, or NULL to skip    (out)
+ * H must be a multiple of 64; S <= 65535.
+ */
+int splade_head_fwd(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S, int H,
+                    int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
+                    void* stream);
+
+/*
+ * Gather-driven sparse backward of splade_head_fwd (replaces autograd of splade_modern.py:69-83, invoked at
+ * src/train/cli/train_v33_ddp.py:364).  dlogit[b,argmax[b,v],v] = g_rep[b,v] * exp(-rep[b,v]) for rep>0.
+ *   d_hidden [B,S,H] fp32, dW [V,H] fp32, dbias [V] fp32 are fully overwritten (dense, DDP-ready).
+ */
+int splade_head_bwd(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden, const void* W,
+                    int B, int S, int H, int V, float* d_hidden, float* dW, float* dbias, void* workspace,
+                    size_t ws_bytes, void* stream);
+
+/*
+ * FLOPS regulariser (src/model/losses.py:57-73) and nonzero monitoring (losses.py:272-273) in one pass.
+ *   rep [N,V] fp32 -> colmean [V] (kept for backward), out2[0] = sum_j colmean_j^2, out2[1] = mean_i #(rep_i > 0)
+ */
+int splade_flops_nnz(const float* rep, int N, int V, float* colmean, float* out2, void* workspace, size_t ws_bytes,
+                     void* stream);
+
+/*
+ * raw[i,j] = sum_v q[i,v] * docs[j,v]  (torch.mm(anchor, positive.t()), losses.py:155,243).
+ * round_bf16 != 0 mirrors autocast: operands are rounded to bf16 first (fp32 accumulate); the output
+ * rounding is applied by splade_v33_scalars.  Deterministic split-K (fixed-order reduction).
+ */
+int splade_scores(const float* q, int Bq, const float* docs, int N, int V, int round_bf16, float* raw,
+                  void* workspace, size_t ws_bytes, void* stream);
+
+/* out[i,j] = sum_v q[i,v] * docs[i,j,v], fp32 (hard-negative scores losses.py:161-169, margins :115-130). */
+int splade_rowdot(const float* q, const float* docs, int Bq, int k, int V, float* out, void* stream);
+
+/* Scalar stage of SPLADELossV33.forward (losses.py:136-181, 209-269): InfoNCE cross-entropy, optional KL-KD and
+ * MarginMSE on the tiny score matrices, total loss, and the gradients w.r.t. the raw dot products. */
+typedef struct splade_v33_scalar_args {
+  /* sizes */
+  int32_t Bq;           /* local queries                                                    */
+  int32_t N;            /* in-batch documents (Bq, or world*Bq with gathered negatives)      */
+  int32_t k;            /* hard negatives per query (>=1)                                   */
+  int32_t label_offset; /* positive of query i is document label_offset + i                 */
+  int32_t round_bf16;   /* mirror autocast: raw_inbatch -> bf16 -> /T -> bf16               */
+  int32_t has_kd;       /* teacher_scores present and lambda_kd > 0 (requires N == Bq)      */
+  int32_t has_mmse;     /* teacher pos/neg scores present and lambda_margin_mse > 0         */
+  int32_t reserved;
+  /* hyper-parameters (already scheduled on the host, losses.py:75-90) */
+  float temperature, kd_temperature;
+  float lambda_q, lambda_d, lambda_neg, lambda_kd, lambda_mmse;
+  float reserved_f;
+  /* inputs */
+  const float* raw_inbatch; /* [Bq,N]  from splade_scores                                  */
+  const float* raw_hard;    /* [Bq,k]  from splade_rowdot                                  */
+  const float* raw_pos;     /* [Bq]    fp32 q_i.p_i (MarginMSE only) or NULL               */
+  const float* teacher_kd;  /* [Bq,Bq] or NULL                                             */
+  const float* teacher_pos; /* [Bq]    or NULL                                             */
+  const float* teacher_neg; /* [Bq,k]  or NULL                                             */
+  const float* flops3;      /* [6]: {flops_q,nnz_q, flops_d,nnz_d, flops_neg,nnz_neg}      */
+  /* outputs */
+  float* scalars;   /* [16]: 0 loss, 1 infonce, 2 flops_q, 3 flops_d, 4 flops_neg, 5 kd, 6 margin_mse,
+                             7 nonzero_q, 8 nonzero_d                                       */
+  float* g_inbatch; /* [Bq,N] d loss / d raw_inbatch                                       */
+  float* g_hard;    /* [Bq,k] d loss / d raw_hard                                          */
+} splade_v33_scalar_args;
+
+int splade_v33_scalars(const splade_v33_scalar_args* args, void* stream);
+
+/*
+ * Backward of the scoring + FLOPS terms onto the sparse representations (autograd of losses.py:155-181,
+ * 72-73).  With gl = *g_loss:
+ *   dq[i,:]     = gl * ( sum_j g_inbatch[i,j] docs[j,:] + sum_k g_hard[i,k] negs[i,k,:] + cq * colmean_q )
+ *   ddocs[j,:]  = gl * ( sum_i g_inbatch[i,j] q[i,:] + [label_offset <= j < label_offset+Bq] cd * colmean_d )
+ *   dnegs[i,k,:]= gl * ( g_hard[i,k] q[i,:] + cn * colmean_n )
+ * cq = 2*lambda_q/Bq, cd = 2*lambda_d/Bq, cn = 2*lambda_neg/(Bq*k).
+ */
+int splade_loss_bwd(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,
+                    int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
+                    const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
+                    const float* g_loss, float* dq, float* ddocs, float* dnegs, void* stream);
+
+/*
+ * Top-k pruning with the production emit semantics (benchmark/encoders.py:320-343): keep weight > 0, drop
+ * block-listed term ids (special tokens and tokens starting with '[' or '<'), order by weight descending
+ * with ties by ascending term id, keep the first k.
+ *   rep [B,V] fp32, blocklist [V] uint8 (nonzero = drop) or NULL, k <= 1024
+ *   ids [B,k] int32 (-1 padded), vals [B,k] fp32 (0 padded), counts [B] int32
+ */
+int splade_topk(const float* rep, int B, int V, const uint8_t* blocklist, int k, int32_t* ids, float* vals,
+                int32_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SPLADE_B200_H_ */

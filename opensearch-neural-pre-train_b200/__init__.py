@@ -1,0 +1,19 @@
+"""splade_b200 — B200-native (sm_100a) SPLADE-max head + SPLADELossV33 hot path.
+
+Drop-in for ``SPLADEModernBERT`` / ``SPLADELossV33`` of opensearch-neural-pre-train
+(src/model/splade_modern.py, src/model/losses.py).  The arithmetic lives in ``libsplade_b200.so``
+(hand-written tcgen05/TMEM/TMA CUDA, C-ABI in ``include/splade_b200.h``); this package is the host-side
+mirror of the reference's Python interface.  There is no CPU fallback.
+"""
+from ._lib import ABI_VERSION, LIB_PATH, load_library  # noqa: F401
+from .distributed import all_gather_documents, shard_range  # noqa: F401
+from .encoder import SPLADEModernBERT  # noqa: F401
+from .ops import (flops_nnz, head_backward, head_forward, rowdot, scores, splade_head, topk)  # noqa: F401
+from .sparse_emit import SparseEmitter, build_blocklist, bulk_encode  # noqa: F401
+from .v33_loss import SPLADELossV33  # noqa: F401
+
+__all__ = [
+    "SPLADEModernBERT", "SPLADELossV33", "SparseEmitter", "build_blocklist", "bulk_encode",
+    "splade_head", "head_forward", "head_backward", "flops_nnz", "scores", "rowdot", "topk",
+    "all_gather_documents", "shard_range", "load_library", "LIB_PATH", "ABI_VERSION",
+]

@@ -1,0 +1,94 @@
+"""ctypes binding of ``libsplade_b200.so`` (C-ABI declared in ``include/splade_b200.h``).
+
+The library is built in-tree by ``csrc/build.sh`` (see ``__graft_entry__.build``).  There is NO fallback:
+if the shared object is missing or a call returns a non-zero code, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p)
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libsplade_b200.so")
+ABI_VERSION = 1
+
+# op ids for splade_workspace_bytes (include/splade_b200.h)
+OP_HEAD_FWD = 0
+OP_HEAD_FWD_TOKW = 1
+OP_HEAD_BWD = 2
+OP_FLOPS_NNZ = 3
+OP_SCORES = 4
+
+
+class V33ScalarArgs(Structure):
+    """Mirror of ``splade_v33_scalar_args`` (include/splade_b200.h)."""
+
+    _fields_ = [
+        ("Bq", c_int32), ("N", c_int32), ("k", c_int32), ("label_offset", c_int32),
+        ("round_bf16", c_int32), ("has_kd", c_int32), ("has_mmse", c_int32), ("reserved", c_int32),
+        ("temperature", c_float), ("kd_temperature", c_float),
+        ("lambda_q", c_float), ("lambda_d", c_float), ("lambda_neg", c_float),
+        ("lambda_kd", c_float), ("lambda_mmse", c_float), ("reserved_f", c_float),
+        ("raw_inbatch", c_void_p), ("raw_hard", c_void_p), ("raw_pos", c_void_p),
+        ("teacher_kd", c_void_p), ("teacher_pos", c_void_p), ("teacher_neg", c_void_p),
+        ("flops3", c_void_p),
+        ("scalars", c_void_p), ("g_inbatch", c_void_p), ("g_hard", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/splade_b200.h declares
+EXPORTS = {
+    "splade_abi_version": (c_int, []),
+    "splade_last_error": (c_char_p, []),
+    "splade_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "splade_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "splade_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "splade_flops_nnz": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "splade_scores": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                              c_void_p]),
+    "splade_rowdot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "splade_v33_scalars": (c_int, [POINTER(V33ScalarArgs), c_void_p]),
+    "splade_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "splade_topk": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library() -> ctypes.CDLL:
+    """Load (once) and type the shared library.  Raises if it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"splade_b200: native library not found at {LIB_PATH}. Build it with "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` (or csrc/build.sh). "
+                f"There is no CPU / eager fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in EXPORTS.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = restype
+            fn.argtypes = argtypes
+        got = lib.splade_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"splade_b200: ABI version mismatch (library {got}, python {ABI_VERSION})")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().splade_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

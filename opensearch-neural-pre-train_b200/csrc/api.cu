@@ -1,0 +1,174 @@
+// C-ABI of libsplade_b200.so (declared in include/splade_b200.h) + error / device plumbing.
+//
+// Contract: plain pointers and sizes, every call returns 0 or an error code and never
+// throws or aborts; the message is available through splade_last_error() (thread-local, because DDP runs
+// backward on a different host thread than forward); all work is enqueued on the caller's stream; the
+// library owns no device memory.
+#include "../../include/splade_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace splade {
+
+namespace {
+thread_local char g_last_error[512] = "";
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return kOk;
+  return set_error(kErrCuda, "CUDA error %s (%s) at: %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
+}
+
+int require_sm100(const char* who) {
+  int dev = 0;
+  SPLADE_CUDA_OK(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  SPLADE_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  SPLADE_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10)
+    return set_error(kErrUnsupportedDevice,
+                     "%s: device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", who, dev,
+                     major, minor);
+  return kOk;
+}
+
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  return n;
+}
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+}  // namespace
+
+// bf16 tensor, innermost dimension contiguous, 128-byte swizzle, out-of-bounds elements read as zero.
+int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(kErrDriver, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                        const_cast<void*>(gptr), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(kErrDriver, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", static_cast<int>(r),
+                     rank);
+  return kOk;
+}
+
+}  // namespace splade
+
+using namespace splade;
+
+extern "C" {
+
+int splade_abi_version(void) { return SPLADE_B200_ABI_VERSION; }
+
+const char* splade_last_error(void) { return g_last_error; }
+
+size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k) {
+  (void)H;
+  switch (op) {
+    case SPLADE_OP_HEAD_FWD:
+      return head_fwd_workspace_bytes(B, S, V, /*want_tokw=*/false);
+    case SPLADE_OP_HEAD_FWD_TOKW:
+      return head_fwd_workspace_bytes(B, S, V, /*want_tokw=*/true);
+    case SPLADE_OP_HEAD_BWD:
+      return head_bwd_workspace_bytes(B, S, V);
+    case SPLADE_OP_FLOPS_NNZ:
+      return flops_workspace_bytes(B, V);
+    case SPLADE_OP_SCORES:
+      return scores_workspace_bytes(B, k, V);
+    default:
+      return 0;
+  }
+}
+
+int splade_head_fwd(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S, int H,
+                    int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
+                    void* stream) {
+  return head_fwd_launch(hidden, W, bias, mask, B, S, H, V, rep, argmax, tokw, workspace, ws_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int splade_head_bwd(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden, const void* W,
+                    int B, int S, int H, int V, float* d_hidden, float* dW, float* dbias, void* workspace,
+                    size_t ws_bytes, void* stream) {
+  return head_bwd_launch(g_rep, rep, argmax, hidden, W, B, S, H, V, d_hidden, dW, dbias, workspace, ws_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int splade_flops_nnz(const float* rep, int N, int V, float* colmean, float* out2, void* workspace, size_t ws_bytes,
+                     void* stream) {
+  return flops_nnz_launch(rep, N, V, colmean, out2, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int splade_scores(const float* q, int Bq, const float* docs, int N, int V, int round_bf16, float* raw,
+                  void* workspace, size_t ws_bytes, void* stream) {
+  return scores_launch(q, Bq, docs, N, V, round_bf16, raw, workspace, ws_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int splade_rowdot(const float* q, const float* docs, int Bq, int k, int V, float* out, void* stream) {
+  return rowdot_launch(q, docs, Bq, k, V, out, static_cast<cudaStream_t>(stream));
+}
+
+int splade_v33_scalars(const splade_v33_scalar_args* args, void* stream) {
+  return v33_scalars_launch(args, static_cast<cudaStream_t>(stream));
+}
+
+int splade_loss_bwd(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,
+                    int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
+                    const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
+                    const float* g_loss, float* dq, float* ddocs, float* dnegs, void* stream) {
+  return loss_bwd_launch(q, docs, negs, Bq, N, k, V, label_offset, g_inbatch, g_hard, colmean_q, colmean_d,
+                         colmean_n, cq, cd, cn, g_loss, dq, ddocs, dnegs, static_cast<cudaStream_t>(stream));
+}
+
+int splade_topk(const float* rep, int B, int V, const uint8_t* blocklist, int k, int32_t* ids, float* vals,
+                int32_t* counts, void* stream) {
+  return topk_launch(rep, B, V, blocklist, k, ids, vals, counts, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+# Builds libsplade_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v"
+mkdir -p build
+pids=()
+for f in api head_fwd head_bwd loss topk; do
+  ( $NVCC $FLAGS -c $f.cu -o build/$f.o > build/$f.log 2>&1 || { cat build/$f.log; exit 1; } ) &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait $p; done
+$NVCC -shared -o ../libsplade_b200.so build/api.o build/head_fwd.o build/head_bwd.o build/loss.o build/topk.o
+echo "built $(cd .. && pwd)/libsplade_b200.so"

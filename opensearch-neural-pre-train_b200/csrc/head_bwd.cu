@@ -1,0 +1,302 @@
+// Gather-driven sparse backward of the fused SPLADE-max head (sm_100a).
+//
+// The reference back-propagates through dense [B,S,V] tensors (autograd of src/model/splade_modern.py:69-83
+// run from src/train/cli/train_v33_ddp.py:364): value_selecting_reduction_backward scatters g to the argmax
+// position, the element-wise chain multiplies by mask / (1+x) / relu', and two dense GEMMs produce dX and dW.
+// Because max-pooling routes the whole gradient of (doc b, term v) to ONE sequence position, dlogits has
+// exactly one non-zero per (b,v):
+//     coef[b,v] = g_rep[b,v] * d/dx log1p(x) = g_rep[b,v] * exp(-rep[b,v])      (rep > 0, else 0)
+// so
+//     dbias[v]      = sum_b coef[b,v]
+//     dW[v,:]       = sum_b coef[b,v] * hidden[b, argmax[b,v], :]                 (gather of B rows per term)
+//     dHidden[b,s,:]= sum_{v : argmax[b,v]=s} coef[b,v] * W[v,:]                  (gather after bucketing by s)
+// Both gathers read 16-bit rows that live in the 126 MB L2 (hidden 25 MB, W 77 MB at the headline shape);
+// the kernels are L2-gather-bound, not tensor-core work.
+//
+// Kernels: (1) bucket_by_position: per document counting sort of the active terms by argmax position;
+//          (2) dhidden_kernel: one warp per (b,s) row sums coef * W[v,:] over its bucket;
+//          (3) dw_kernel: one warp per vocabulary row sums coef * hidden[b,argmax,:] over the batch.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace splade {
+namespace {
+
+constexpr int kBucketThreads = 1024;
+
+__device__ __forceinline__ float coef_of(float g, float rep) { return rep > 0.f ? g * expf(-rep) : 0.f; }
+
+size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+// ---------------------------------------------------------------------------------------------
+// (1) per-document counting sort of active (b,v) by position.  One CTA per document.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBucketThreads)
+bucket_by_position_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep,
+                          const int32_t* __restrict__ argmax, int S, int V, int32_t* __restrict__ row_ptr,
+                          int32_t* __restrict__ sorted_v, float* __restrict__ sorted_c) {
+  extern __shared__ int32_t sm[];
+  int32_t* cnt = sm;          // [S] counts, then exclusive offsets
+  int32_t* cur = sm + S;      // [S] scatter cursors
+  __shared__ int32_t warp_tot[32];
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const size_t base = static_cast<size_t>(b) * V;
+
+  for (int s = tid; s < S; s += kBucketThreads) cnt[s] = 0;
+  __syncthreads();
+  for (int v = tid; v < V; v += kBucketThreads) {
+    const float c = coef_of(g_rep[base + v], rep[base + v]);
+    if (c != 0.f) atomicAdd(&cnt[argmax[base + v]], 1);
+  }
+  __syncthreads();
+
+  // block-wide exclusive scan over S entries: contiguous chunk per thread
+  const int per = (S + kBucketThreads - 1) / kBucketThreads;
+  const int lo = min(S, tid * per), hi = min(S, lo + per);
+  int tsum = 0;
+  for (int s = lo; s < hi; ++s) tsum += cnt[s];
+  int incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += n;
+  }
+  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = warp_tot[tid];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, wi, o);
+      if (tid >= o) wi += n;
+    }
+    warp_tot[tid] = wi - w;  // exclusive
+  }
+  __syncthreads();
+  int run = warp_tot[tid >> 5] + incl - tsum;
+  int32_t* rp = row_ptr + static_cast<size_t>(b) * (S + 1);
+  for (int s = lo; s < hi; ++s) {
+    const int c = cnt[s];
+    cur[s] = run;
+    rp[s] = run;
+    run += c;
+  }
+  if (tid == kBucketThreads - 1) rp[S] = run;  // last thread's running total = number of active terms
+  __syncthreads();
+
+  for (int v = tid; v < V; v += kBucketThreads) {
+    const float c = coef_of(g_rep[base + v], rep[base + v]);
+    if (c != 0.f) {
+      const int slot = atomicAdd(&cur[argmax[base + v]], 1);
+      sorted_v[base + slot] = v;
+      sorted_c[base + slot] = c;
+    }
+  }
+}
+
+// acc[8] += c * (8 bf16 packed in a uint4)
+__device__ __forceinline__ void fma_bf16x8(float (&acc)[8], float c, const uint4& u) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc[2 * i] = fmaf(c, __uint_as_float(w[i] << 16), acc[2 * i]);
+    acc[2 * i + 1] = fmaf(c, __uint_as_float(w[i] & 0xFFFF0000u), acc[2 * i + 1]);
+  }
+}
+
+__device__ __forceinline__ void store_row8(float* dst, const float (&acc)[8], float scale) {
+  float4 a = make_float4(acc[0] * scale, acc[1] * scale, acc[2] * scale, acc[3] * scale);
+  float4 b = make_float4(acc[4] * scale, acc[5] * scale, acc[6] * scale, acc[7] * scale);
+  reinterpret_cast<float4*>(dst)[0] = a;
+  reinterpret_cast<float4*>(dst)[1] = b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2) dHidden: one warp per (b,s) row.  kChunks = ceil(H / 256); lane l owns h = i*256 + l*8 .. +8.
+// ---------------------------------------------------------------------------------------------
+template <int kChunks>
+__global__ void __launch_bounds__(256)
+dhidden_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ sorted_v,
+               const float* __restrict__ sorted_c, const uint16_t* __restrict__ W, int B, int S, int H, int V,
+               float* __restrict__ d_hidden) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= static_cast<long long>(B) * S) return;
+  const int b = static_cast<int>(row / S);
+  const int s = static_cast<int>(row - static_cast<long long>(b) * S);
+  const int32_t* rp = row_ptr + static_cast<size_t>(b) * (S + 1);
+  const int beg = rp[s], end = rp[s + 1];
+  const size_t lbase = static_cast<size_t>(b) * V;
+
+  float acc[kChunks][8];
+#pragma unroll
+  for (int i = 0; i < kChunks; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int n = min(32, end - e0);
+    int my_v = 0;
+    float my_c = 0.f;
+    if (lane < n) {
+      my_v = sorted_v[lbase + e0 + lane];
+      my_c = sorted_c[lbase + e0 + lane];
+    }
+#pragma unroll 4
+    for (int l = 0; l < n; ++l) {
+      const int v = __shfl_sync(0xffffffffu, my_v, l);
+      const float c = __shfl_sync(0xffffffffu, my_c, l);
+      const uint16_t* wrow = W + static_cast<size_t>(v) * H;
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) {
+        const int h = i * 256 + lane * 8;
+        if (h < H) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(wrow + h));
+          fma_bf16x8(acc[i], c, u);
+        }
+      }
+    }
+  }
+  float* out = d_hidden + static_cast<size_t>(row) * H;
+#pragma unroll
+  for (int i = 0; i < kChunks; ++i) {
+    const int h = i * 256 + lane * 8;
+    if (h < H) store_row8(out + h, acc[i], 1.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (3) dW + dbias: one warp per vocabulary row.
+// ---------------------------------------------------------------------------------------------
+template <int kChunks>
+__global__ void __launch_bounds__(256)
+dw_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep, const int32_t* __restrict__ argmax,
+          const uint16_t* __restrict__ hidden, int B, int S, int H, int V, float* __restrict__ dW,
+          float* __restrict__ dbias) {
+  const int lane = threadIdx.x & 31;
+  const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (v >= V) return;
+
+  float acc[kChunks][8];
+#pragma unroll
+  for (int i = 0; i < kChunks; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+  float bsum = 0.f;
+
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int n = min(32, B - b0);
+    float my_c = 0.f;
+    int my_s = 0;
+    if (lane < n) {
+      const size_t o = static_cast<size_t>(b0 + lane) * V + v;
+      my_c = coef_of(g_rep[o], rep[o]);
+      my_s = argmax[o];
+    }
+    bsum += my_c;
+#pragma unroll 4
+    for (int l = 0; l < n; ++l) {
+      const float c = __shfl_sync(0xffffffffu, my_c, l);
+      const int s = __shfl_sync(0xffffffffu, my_s, l);
+      if (c == 0.f) continue;  // warp-uniform
+      const uint16_t* hrow = hidden + (static_cast<size_t>(b0 + l) * S + s) * H;
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) {
+        const int h = i * 256 + lane * 8;
+        if (h < H) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(hrow + h));
+          fma_bf16x8(acc[i], c, u);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+  if (lane == 0) dbias[v] = bsum;
+  float* out = dW + static_cast<size_t>(v) * H;
+#pragma unroll
+  for (int i = 0; i < kChunks; ++i) {
+    const int h = i * 256 + lane * 8;
+    if (h < H) store_row8(out + h, acc[i], 1.f);
+  }
+}
+
+}  // namespace
+
+size_t head_bwd_workspace_bytes(int B, int S, int V) {
+  return align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t)) +
+         2 * align256(static_cast<size_t>(B) * V * sizeof(int32_t));
+}
+
+int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden,
+                    const void* W, int B, int S, int H, int V, float* d_hidden, float* dW, float* dbias,
+                    void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  if (!g_rep || !rep || !argmax || !hidden || !W || !d_hidden || !dW || !dbias)
+    return set_error(kErrInvalidArg, "splade_head_bwd: null pointer argument");
+  if (B < 0 || S < 1 || V < 1 || H < 1)
+    return set_error(kErrInvalidArg, "splade_head_bwd: bad sizes B=%d S=%d H=%d V=%d", B, S, H, V);
+  if (H % 8 != 0 || H > 1024)
+    return set_error(kErrUnsupportedShape, "splade_head_bwd: hidden size %d must be a multiple of 8 and <= 1024",
+                     H);
+  const size_t bucket_smem = static_cast<size_t>(2) * S * sizeof(int32_t);
+  if (bucket_smem > 200 * 1024)
+    return set_error(kErrUnsupportedShape, "splade_head_bwd: sequence length %d too long for the bucket pass", S);
+  int rc = require_sm100("splade_head_bwd");
+  if (rc != kOk) return rc;
+  const size_t need = head_bwd_workspace_bytes(B, S, V);
+  if (!workspace || ws_bytes < need)
+    return set_error(kErrWorkspace, "splade_head_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+
+  if (B == 0) {
+    SPLADE_CUDA_OK(cudaMemsetAsync(dW, 0, static_cast<size_t>(V) * H * sizeof(float), stream));
+    SPLADE_CUDA_OK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * sizeof(float), stream));
+    return kOk;
+  }
+
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int32_t* row_ptr = reinterpret_cast<int32_t*>(ws);
+  ws += align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t));
+  int32_t* sorted_v = reinterpret_cast<int32_t*>(ws);
+  ws += align256(static_cast<size_t>(B) * V * sizeof(int32_t));
+  float* sorted_c = reinterpret_cast<float*>(ws);
+
+  if (bucket_smem > 48 * 1024) {
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(bucket_by_position_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(bucket_smem)));
+  }
+  bucket_by_position_kernel<<<B, kBucketThreads, bucket_smem, stream>>>(g_rep, rep, argmax, S, V, row_ptr,
+                                                                      sorted_v, sorted_c);
+  SPLADE_CUDA_OK(cudaGetLastError());
+
+  const uint16_t* Wb = static_cast<const uint16_t*>(W);
+  const uint16_t* Hb = static_cast<const uint16_t*>(hidden);
+  const long long rows = static_cast<long long>(B) * S;
+  const unsigned grid_h = static_cast<unsigned>((rows + 7) / 8);
+  const unsigned grid_w = static_cast<unsigned>((V + 7) / 8);
+  const int chunks = (H + 255) / 256;
+  switch (chunks) {
+    case 1:
+      dhidden_kernel<1><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
+      dw_kernel<1><<<grid_w, 256, 0, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
+      break;
+    case 2:
+      dhidden_kernel<2><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
+      dw_kernel<2><<<grid_w, 256, 0, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
+      break;
+    case 3:
+      dhidden_kernel<3><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
+      dw_kernel<3><<<grid_w, 256, 0, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
+      break;
+    default:
+      dhidden_kernel<4><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
+      dw_kernel<4><<<grid_w, 256, 0, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
+      break;
+  }
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace splade

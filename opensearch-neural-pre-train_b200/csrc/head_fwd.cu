@@ -1,0 +1,428 @@
+// Fused SPLADE-max head forward for sm_100a.
+//
+// Replaces, in one kernel, the reference chain
+//   logits = decoder(hidden)                       (transformers modeling_modernbert.py:562, K1)
+//   w = log1p(relu(logits))                        (src/model/splade_modern.py:76, K2/K3)
+//   w = w * attention_mask[..., None]              (src/model/splade_modern.py:79-80, K4)
+//   sparse_repr, argmax = w.max(dim=1)             (src/model/splade_modern.py:83, K5)
+//   token_weights = w.max(dim=-1).values           (src/model/splade_modern.py:86, K6)
+// without ever writing the [B,S,V] logits to HBM.
+//
+// Orientation: the GEMM is computed TRANSPOSED, D[v, t] = sum_h W[v,h] * hidden[t,h]:
+//   * UMMA M (= 128 TMEM lanes)  <- vocabulary rows of decoder.weight  (A operand, K-major, TMA 2D)
+//   * UMMA N (<= 256 TMEM cols)  <- tokens of whole documents          (B operand, K-major, TMA 3D box
+//                                                                       (64 h, s_box tokens, b_box docs))
+// so every epilogue thread owns ONE vocabulary entry and walks the sequence positions of a document
+// left-to-right in registers: max-pool over the sequence and its first-occurrence argmax need no
+// cross-thread traffic and no atomics (for S <= 256).  The per-position max over the vocabulary
+// (token_weights) is one REDUX per column plus one 32-lane RED per 32 positions.
+//
+// Numerics follow the reference's autocast(bf16) path exactly: fp32 accumulate, + bias in fp32, ONE
+// RNE rounding to bf16, relu, compare on the rounded value with ties to the lowest position, padded
+// positions contribute 0, argmax 0 when the pooled value is 0; log1p is applied once per (doc, term)
+// after the max (log1p∘relu is monotone).
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over (vocab tile, token tile) items):
+//   warp 0 lane 0 : TMA producer         (4-stage ring of {A 16 KB, B <=32 KB}, 128B swizzle)
+//   warp 1 lane 0 : tcgen05.mma issuer   (128 x N x 16 per instruction, fp32 accumulators in TMEM)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue             (TMEM lanes 32*(warp%4) .. +31), double-buffered accumulators
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+
+namespace splade {
+namespace {
+
+constexpr int BLOCK_V = 128;  // UMMA M
+constexpr int BLOCK_T = 256;  // max UMMA N
+constexpr int BLOCK_K = 64;   // one 128-byte swizzle row of bf16
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_V * BLOCK_K * 2;
+constexpr int B_BYTES = BLOCK_T * BLOCK_K * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;  // two 128 x 256 fp32 accumulators
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+
+struct HeadFwdParams {
+  const float* bias;
+  const int32_t* mask;  // [B,S], nonzero = real token
+  float* rep;           // [B,V]
+  int32_t* argmax;      // [B,V]
+  uint32_t* packed;     // [B,V] (bf16 bits << 16 | 0xFFFF - pos), only when a doc spans several tiles
+  uint32_t* tokw_bits;  // [B,S] bf16 bits of the per-position max logit, or nullptr
+  int B, S, H, V;
+  int s_box, b_box;     // tokens per doc / docs per token tile (TMA box of hidden)
+  int n_tt, n_vt;       // token tiles, vocab tiles
+  int chunks_per_doc;   // 1 when S <= 256
+  int umma_n;
+  uint32_t stage_tx_bytes;
+};
+
+struct TileCoord {
+  int vt, b0, nb, s0, ns;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const HeadFwdParams& p, int item) {
+  TileCoord t;
+  t.vt = item / p.n_tt;
+  const int tt = item - t.vt * p.n_tt;
+  if (p.chunks_per_doc == 1) {
+    t.b0 = tt * p.b_box;
+    t.nb = min(p.b_box, p.B - t.b0);
+    t.s0 = 0;
+    t.ns = p.S;
+  } else {
+    t.b0 = tt / p.chunks_per_doc;
+    t.nb = 1;
+    t.s0 = (tt - t.b0 * p.chunks_per_doc) * BLOCK_T;
+    t.ns = min(BLOCK_T, p.S - t.s0);
+  }
+  return t;
+}
+
+// One 32-column window of one document, for one vocabulary entry per thread.
+// Returns max over the window of key_j = (bf16(acc_j + bias) << 16) | (31 - j) as a signed int:
+// negative logits (sign bit set) lose against 0, positive bf16 bit patterns order like the floats,
+// and equal values keep the smallest j.
+template <bool kAllValid, bool kTokW>
+__device__ __forceinline__ int window_max(const uint32_t (&r)[32], float bias_v, uint32_t vw, uint32_t lane,
+                                          int& tok_mine) {
+  int wkey = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float x0 = __uint_as_float(r[j]) + bias_v;
+    const float x1 = __uint_as_float(r[j + 1]) + bias_v;
+    const uint32_t pk = cvt_bf16x2(x1, x0);
+    int k0 = static_cast<int>((pk << 16) | static_cast<uint32_t>(31 - j));
+    int k1 = static_cast<int>((pk & 0xFFFF0000u) | static_cast<uint32_t>(30 - j));
+    if (!kAllValid) {
+      k0 = ((vw >> j) & 1u) ? k0 : 0;
+      k1 = ((vw >> (j + 1)) & 1u) ? k1 : 0;
+    }
+    wkey = max(wkey, max(k0, k1));
+    if (kTokW) {
+      const int t0 = warp_max_s32(k0);
+      const int t1 = warp_max_s32(k1);
+      tok_mine = (lane == static_cast<uint32_t>(j)) ? t0 : tok_mine;
+      tok_mine = (lane == static_cast<uint32_t>(j + 1)) ? t1 : tok_mine;
+    }
+  }
+  return wkey;
+}
+
+template <bool kTokW>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
+                const HeadFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_h);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_items = p.n_vt * p.n_tt;
+  const int num_kb = p.H / BLOCK_K;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const TileCoord t = tile_coord(p, item);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* a_dst = smem + stage * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
+          tma_load_2d(a_dst, &tmap_w, &full_bar[stage], kb * BLOCK_K, t.vt * BLOCK_V);
+          tma_load_3d(b_dst, &tmap_h, &full_bar[stage], kb * BLOCK_K, t.s0, t.b0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(BLOCK_V, static_cast<uint32_t>(p.umma_n));
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_T;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
+            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const uint32_t q = warp & 3u;  // TMEM lane quarter this warp may read
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const TileCoord t = tile_coord(p, item);
+
+      // Column validity bitmap of this tile (256 bits); lane w keeps word w.
+      uint32_t my_word = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int col = w * 32 + static_cast<int>(lane);
+        const int d = col / p.s_box;
+        const int s = col - d * p.s_box;
+        bool ok = false;
+        if (d < t.nb && s < t.ns) ok = __ldg(&p.mask[static_cast<size_t>(t.b0 + d) * p.S + t.s0 + s]) != 0;
+        const uint32_t word = __ballot_sync(0xffffffffu, ok);
+        my_word = (lane == static_cast<uint32_t>(w)) ? word : my_word;
+      }
+
+      const int v = t.vt * BLOCK_V + static_cast<int>(q * 32u + lane);
+      const float bias_v = (v < p.V) ? __ldg(&p.bias[v]) : 0.f;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_lane = tmem_base + ((q * 32u) << 16) + acc * BLOCK_T;
+
+      for (int d = 0; d < t.nb; ++d) {
+        const int b = t.b0 + d;
+        const int col_base = d * p.s_box;
+        int best_val = 0, best_pos = 0;
+        const int nwin = (t.ns + 31) >> 5;
+        for (int c = 0; c < nwin; ++c) {
+          const int w0 = min(col_base + 32 * c, BLOCK_T - 32);
+          const int jlo = max(0, col_base - w0);
+          const int jhi = min(32, col_base + t.ns - w0);
+          uint32_t range = (jhi >= 32) ? 0xffffffffu : ((1u << jhi) - 1u);
+          range &= 0xffffffffu << jlo;
+          const uint32_t lo = __shfl_sync(0xffffffffu, my_word, w0 >> 5);
+          const uint32_t hi = __shfl_sync(0xffffffffu, my_word, min(7, (w0 >> 5) + 1));
+          const uint32_t vw = __funnelshift_r(lo, hi, w0 & 31) & range;
+          if (vw == 0u) continue;  // warp-uniform: fully padded window
+
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(w0), r);
+          tmem_ld_wait();
+
+          int tok_mine = 0;
+          int wkey;
+          if (vw == 0xffffffffu) {
+            wkey = window_max<true, kTokW>(r, bias_v, vw, lane, tok_mine);
+          } else {
+            wkey = window_max<false, kTokW>(r, bias_v, vw, lane, tok_mine);
+          }
+          const int pos0 = t.s0 + (w0 - col_base);  // sequence position of window column 0
+          const int wval = wkey >> 16;
+          if (wval > best_val) {  // strict: earlier windows win ties (first occurrence)
+            best_val = wval;
+            best_pos = pos0 + 31 - (wkey & 31);
+          }
+          if (kTokW) {
+            const int tv = tok_mine >> 16;
+            if (tv > 0 && ((vw >> lane) & 1u)) {
+              atomicMax(&p.tokw_bits[static_cast<size_t>(b) * p.S + pos0 + static_cast<int>(lane)],
+                        static_cast<uint32_t>(tv));
+            }
+          }
+        }
+        if (v < p.V) {
+          const size_t o = static_cast<size_t>(b) * p.V + v;
+          if (p.chunks_per_doc == 1) {
+            p.rep[o] = log1pf(bf16_bits_to_float(static_cast<uint32_t>(best_val)));
+            p.argmax[o] = best_pos;
+          } else {
+            atomicMax(&p.packed[o], (static_cast<uint32_t>(best_val) << 16) |
+                                        (0xFFFFu - static_cast<uint32_t>(best_pos)));
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// packed (bf16 bits << 16 | 0xFFFF - pos) -> fp32 log1p weight + int32 argmax (documents longer than one tile)
+__global__ void finalize_packed_kernel(const uint32_t* __restrict__ packed, float* __restrict__ rep,
+                                       int32_t* __restrict__ argmax, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = packed[i];
+  rep[i] = log1pf(bf16_bits_to_float(k >> 16));
+  argmax[i] = static_cast<int32_t>(0xFFFFu - (k & 0xFFFFu));
+}
+
+// token_weights[b,s] = log1p(max_v relu(bf16 logit)) ; 0 for padded positions (buffer was zero-initialised)
+__global__ void finalize_tokw_kernel(const uint32_t* __restrict__ bits, float* __restrict__ tokw, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tokw[i] = log1pf(bf16_bits_to_float(bits[i]));
+}
+
+size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+}  // namespace
+
+void head_fwd_plan(int B, int S, int* s_box, int* b_box, int* chunks_per_doc, int* n_tt, int* umma_n) {
+  if (S <= BLOCK_T) {
+    *s_box = S;
+    *b_box = std::max(1, std::min(BLOCK_T / S, B));
+    *chunks_per_doc = 1;
+    *n_tt = (B + *b_box - 1) / *b_box;
+  } else {
+    *s_box = BLOCK_T;
+    *b_box = 1;
+    *chunks_per_doc = (S + BLOCK_T - 1) / BLOCK_T;
+    *n_tt = B * *chunks_per_doc;
+  }
+  const int cols = *s_box * *b_box;
+  *umma_n = std::max(16, (cols + 15) / 16 * 16);
+}
+
+size_t head_fwd_workspace_bytes(int B, int S, int V, bool want_tokw) {
+  size_t bytes = 0;
+  if (S > BLOCK_T) bytes += align256(static_cast<size_t>(B) * V * sizeof(uint32_t));
+  if (want_tokw) bytes += align256(static_cast<size_t>(B) * S * sizeof(uint32_t));
+  return bytes;
+}
+
+int head_fwd_launch(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S,
+                    int H, int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
+                    cudaStream_t stream) {
+  if (B == 0) return kOk;
+  if (!hidden || !W || !bias || !mask || !rep || !argmax)
+    return set_error(kErrInvalidArg, "splade_head_fwd: null pointer argument");
+  if (B < 0 || S < 1 || V < 1 || H < 1)
+    return set_error(kErrInvalidArg, "splade_head_fwd: bad sizes B=%d S=%d H=%d V=%d", B, S, H, V);
+  if (H % BLOCK_K != 0)
+    return set_error(kErrUnsupportedShape, "splade_head_fwd: hidden size %d is not a multiple of %d", H, BLOCK_K);
+  if (S > 65535)
+    return set_error(kErrUnsupportedShape, "splade_head_fwd: sequence length %d exceeds 65535", S);
+  if ((reinterpret_cast<uintptr_t>(hidden) | reinterpret_cast<uintptr_t>(W)) & 15u)
+    return set_error(kErrInvalidArg, "splade_head_fwd: hidden and W must be 16-byte aligned");
+  int rc = require_sm100("splade_head_fwd");
+  if (rc != kOk) return rc;
+
+  HeadFwdParams p{};
+  p.bias = bias;
+  p.mask = mask;
+  p.rep = rep;
+  p.argmax = argmax;
+  p.B = B;
+  p.S = S;
+  p.H = H;
+  p.V = V;
+  head_fwd_plan(B, S, &p.s_box, &p.b_box, &p.chunks_per_doc, &p.n_tt, &p.umma_n);
+  p.n_vt = (V + BLOCK_V - 1) / BLOCK_V;
+  p.stage_tx_bytes = static_cast<uint32_t>(A_BYTES + p.s_box * p.b_box * BLOCK_K * 2);
+
+  const size_t need = head_fwd_workspace_bytes(B, S, V, tokw != nullptr);
+  if (need > 0 && (!workspace || ws_bytes < need))
+    return set_error(kErrWorkspace, "splade_head_fwd: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  if (p.chunks_per_doc > 1) {
+    p.packed = reinterpret_cast<uint32_t*>(ws);
+    const size_t n = static_cast<size_t>(B) * V * sizeof(uint32_t);
+    SPLADE_CUDA_OK(cudaMemsetAsync(p.packed, 0, n, stream));
+    ws += align256(n);
+  }
+  if (tokw) {
+    p.tokw_bits = reinterpret_cast<uint32_t*>(ws);
+    SPLADE_CUDA_OK(cudaMemsetAsync(p.tokw_bits, 0, static_cast<size_t>(B) * S * sizeof(uint32_t), stream));
+  }
+
+  CUtensorMap tmap_w, tmap_h;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(H), static_cast<uint64_t>(V)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(H) * 2};
+    const uint32_t box[2] = {BLOCK_K, BLOCK_V};
+    rc = encode_tmap_bf16(&tmap_w, W, 2, dims, strides, box);
+    if (rc != kOk) return rc;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(H), static_cast<uint64_t>(S), static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(H) * 2, static_cast<uint64_t>(S) * H * 2};
+    const uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.s_box), static_cast<uint32_t>(p.b_box)};
+    rc = encode_tmap_bf16(&tmap_h, hidden, 3, dims, strides, box);
+    if (rc != kOk) return rc;
+  }
+
+  const int total_items = p.n_vt * p.n_tt;
+  const int grid = std::min(sm_count(), total_items);
+  auto kernel = tokw ? head_fwd_kernel<true> : head_fwd_kernel<false>;
+  SPLADE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmap_w, tmap_h, p);
+  SPLADE_CUDA_OK(cudaGetLastError());
+
+  if (p.chunks_per_doc > 1) {
+    const size_t n = static_cast<size_t>(B) * V;
+    finalize_packed_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p.packed, rep, argmax, n);
+    SPLADE_CUDA_OK(cudaGetLastError());
+  }
+  if (tokw) {
+    const size_t n = static_cast<size_t>(B) * S;
+    finalize_tokw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p.tokw_bits, tokw, n);
+    SPLADE_CUDA_OK(cudaGetLastError());
+  }
+  return kOk;
+}
+
+}  // namespace splade

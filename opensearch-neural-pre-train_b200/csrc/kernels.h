@@ -1,0 +1,50 @@
+// Internal launcher declarations (host side). The public C-ABI is include/splade_b200.h.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+struct splade_v33_scalar_args;
+
+namespace splade {
+
+// api.cu
+int require_sm100(const char* who);
+int sm_count();
+int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box);
+
+// head_fwd.cu
+void head_fwd_plan(int B, int S, int* s_box, int* b_box, int* chunks_per_doc, int* n_tt, int* umma_n);
+size_t head_fwd_workspace_bytes(int B, int S, int V, bool want_tokw);
+int head_fwd_launch(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S,
+                    int H, int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
+                    cudaStream_t stream);
+
+// head_bwd.cu
+size_t head_bwd_workspace_bytes(int B, int S, int V);
+int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden,
+                    const void* W, int B, int S, int H, int V, float* d_hidden, float* dW, float* dbias,
+                    void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+// loss.cu
+size_t flops_workspace_bytes(int N, int V);
+int flops_nnz_launch(const float* rep, int N, int V, float* colmean, float* out2, void* workspace,
+                     size_t ws_bytes, cudaStream_t stream);
+size_t scores_workspace_bytes(int Bq, int N, int V);
+int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int round_bf16, float* raw,
+                  void* workspace, size_t ws_bytes, cudaStream_t stream);
+int rowdot_launch(const float* q, const float* docs, int Bq, int k, int V, float* out, cudaStream_t stream);
+int v33_scalars_launch(const struct splade_v33_scalar_args* args, cudaStream_t stream);
+int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,
+                    int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
+                    const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
+                    const float* g_loss, float* dq, float* ddocs, float* dnegs, cudaStream_t stream);
+
+// topk.cu
+int topk_launch(const float* rep, int B, int V, const uint8_t* blocklist, int k, int32_t* ids, float* vals,
+                int32_t* counts, cudaStream_t stream);
+
+}  // namespace splade

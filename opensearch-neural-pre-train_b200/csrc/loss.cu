@@ -1,0 +1,553 @@
+// SPLADELossV33 on the pooled sparse vectors (sm_100a): FLOPS regulariser + nonzero monitoring, q.d score
+// matrix, per-row hard-negative dots, the scalar stage (InfoNCE / KL-KD / MarginMSE / total) and the
+// backward onto the sparse representations.  Reference: src/model/losses.py:57-73 (FLOPS), :136-181 (InfoNCE),
+// :92-134 (MarginMSE), :239-253 (KL-KD), :271-295 (monitoring, loss_dict).
+//
+// All of these are HBM/L2-bandwidth or launch bound ([N,V] fp32 streams, V = 50 000): they are written as
+// coalesced, vectorised CUDA-core kernels with warp-shuffle reductions; every cross-CTA reduction goes
+// through a fixed-order second stage so results are run-to-run deterministic.
+#include "../../include/splade_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+
+namespace splade {
+namespace {
+
+size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FLOPS + nnz:  colmean[j] = mean_i rep[i,j];  flops = sum_j colmean_j^2;  nnz = (#rep>0) / N
+// ---------------------------------------------------------------------------------------------
+constexpr int kFlopsThreads = 256;
+
+__global__ void __launch_bounds__(kFlopsThreads)
+flops_cols_kernel(const float* __restrict__ rep, int N, int V, float* __restrict__ colmean,
+                  float2* __restrict__ partials) {
+  const int j = blockIdx.x * kFlopsThreads + threadIdx.x;
+  float sum = 0.f, cnt = 0.f;
+  if (j < V) {
+    const float* p = rep + j;
+    int i = 0;
+    for (; i + 4 <= N; i += 4) {
+      const float a = p[static_cast<size_t>(i) * V];
+      const float b = p[static_cast<size_t>(i + 1) * V];
+      const float c = p[static_cast<size_t>(i + 2) * V];
+      const float d = p[static_cast<size_t>(i + 3) * V];
+      sum += a;
+      sum += b;
+      sum += c;
+      sum += d;
+      cnt += (a > 0.f) + (b > 0.f) + (c > 0.f) + (d > 0.f);
+    }
+    for (; i < N; ++i) {
+      const float a = p[static_cast<size_t>(i) * V];
+      sum += a;
+      cnt += (a > 0.f);
+    }
+  }
+  const float mean = (N > 0) ? sum / static_cast<float>(N) : 0.f;
+  if (j < V) colmean[j] = mean;
+  float sq = warp_sum(mean * mean);
+  float ct = warp_sum(cnt);
+  __shared__ float s_sq[kFlopsThreads / 32], s_ct[kFlopsThreads / 32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    s_sq[w] = sq;
+    s_ct[w] = ct;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < kFlopsThreads / 32; ++i) {
+      a += s_sq[i];
+      b += s_ct[i];
+    }
+    partials[blockIdx.x] = make_float2(a, b);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+flops_final_kernel(const float2* __restrict__ partials, int nblocks, int N, float* __restrict__ out2) {
+  __shared__ float s_a[256], s_b[256];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += 256) {
+    a += partials[i].x;
+    b += partials[i].y;
+  }
+  s_a[threadIdx.x] = a;
+  s_b[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_a[threadIdx.x] += s_a[threadIdx.x + o];
+      s_b[threadIdx.x] += s_b[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out2[0] = s_a[0];
+    out2[1] = (N > 0) ? s_b[0] / static_cast<float>(N) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw[i,j] = sum_v q[i,v] docs[j,v]   (split over v, fixed-order reduction)
+// ---------------------------------------------------------------------------------------------
+constexpr int TI = 64, TJ = 64, TK = 32, TP = 65;
+
+__global__ void __launch_bounds__(256)
+scores_partial_kernel(const float* __restrict__ q, int Bq, const float* __restrict__ docs, int N, int V,
+                      int round_bf16, int chunk, float* __restrict__ out /* [ksplit][Bq][N] */) {
+  __shared__ float As[TK][TP];
+  __shared__ float Bs[TK][TP];
+  const int j0 = blockIdx.x * TJ, i0 = blockIdx.y * TI;
+  const int v_beg = blockIdx.z * chunk;
+  const int v_end = min(V, v_beg + chunk);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  const int lrow = threadIdx.x >> 3;       // 0..31
+  const int lk = (threadIdx.x & 7) * 4;    // 0,4,..,28
+  for (int v0 = v_beg; v0 < v_end; v0 += TK) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = lrow + 32 * half;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int v = v0 + lk + e;
+        float a = 0.f, b = 0.f;
+        if (v < v_end) {
+          if (i0 + r < Bq) a = q[static_cast<size_t>(i0 + r) * V + v];
+          if (j0 + r < N) b = docs[static_cast<size_t>(j0 + r) * V + v];
+          if (round_bf16) {
+            a = bf16_round(a);
+            b = bf16_round(b);
+          }
+        }
+        As[lk + e][r] = a;
+        Bs[lk + e][r] = b;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < TK; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[kk][ty * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[kk][tx * 4 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+  float* o = out + static_cast<size_t>(blockIdx.z) * Bq * N;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = i0 + ty * 4 + a;
+    if (i >= Bq) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = j0 + tx * 4 + b;
+      if (j < N) o[static_cast<size_t>(i) * N + j] = acc[a][b];
+    }
+  }
+}
+
+__global__ void scores_reduce_kernel(const float* __restrict__ partial, int ksplit, size_t n,
+                                     float* __restrict__ raw) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < ksplit; ++k) s += partial[static_cast<size_t>(k) * n + i];
+  raw[i] = s;
+}
+
+void scores_plan(int Bq, int N, int V, int* ksplit, int* chunk) {
+  const int tiles = ((Bq + TI - 1) / TI) * ((N + TJ - 1) / TJ);
+  int ks = std::max(1, (2 * sm_count()) / std::max(1, tiles));
+  const int kblocks = (V + TK - 1) / TK;
+  ks = std::min(ks, kblocks);
+  const int per = (kblocks + ks - 1) / ks;
+  *chunk = per * TK;
+  *ksplit = (kblocks + per - 1) / per;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[i,j] = sum_v q[i,v] * docs[i,j,v]    one CTA per (i,j)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const float* __restrict__ q, const float* __restrict__ docs, int k, int V,
+              float* __restrict__ out) {
+  const int i = blockIdx.x / k;
+  const float* a = q + static_cast<size_t>(i) * V;
+  const float* b = docs + static_cast<size_t>(blockIdx.x) * V;
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) s = fmaf(a[v], b[v], s);
+  s = warp_sum(s);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    out[blockIdx.x] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scalar stage: one CTA, one warp per query row (rows w, w+8, ... in order => deterministic sums).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) v33_scalars_kernel(const splade_v33_scalar_args a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Bq = a.Bq, N = a.N, k = a.k;
+  const float invB = 1.f / static_cast<float>(Bq);
+  float acc_nce = 0.f, acc_kd = 0.f, acc_mm = 0.f;
+
+  for (int i = warp; i < Bq; i += 8) {
+    const float* rin = a.raw_inbatch + static_cast<size_t>(i) * N;
+    const float* rh = a.raw_hard + static_cast<size_t>(i) * k;
+    float* gin = a.g_inbatch + static_cast<size_t>(i) * N;
+    float* gh = a.g_hard + static_cast<size_t>(i) * k;
+    const int label = a.label_offset + i;
+
+    // ---- InfoNCE: CE over [in-batch | hard] scores (losses.py:155-181)
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) {
+      float s = rin[j];
+      s = a.round_bf16 ? bf16_round(bf16_round(s) / a.temperature) : s / a.temperature;
+      m = fmaxf(m, s);
+    }
+    for (int j = lane; j < k; j += 32) m = fmaxf(m, rh[j] / a.temperature);
+    m = warp_max(m);
+    float se = 0.f, s_lab = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      float s = rin[j];
+      s = a.round_bf16 ? bf16_round(bf16_round(s) / a.temperature) : s / a.temperature;
+      se += expf(s - m);
+      if (j == label) s_lab = s;
+    }
+    for (int j = lane; j < k; j += 32) se += expf(rh[j] / a.temperature - m);
+    se = warp_sum(se);
+    s_lab = warp_sum(s_lab);
+    const float lse = m + logf(se);
+    acc_nce += lse - s_lab;
+    const float gscale = invB / a.temperature;
+    for (int j = lane; j < N; j += 32) {
+      float s = rin[j];
+      s = a.round_bf16 ? bf16_round(bf16_round(s) / a.temperature) : s / a.temperature;
+      gin[j] = (expf(s - lse) - (j == label ? 1.f : 0.f)) * gscale;
+    }
+    for (int j = lane; j < k; j += 32) gh[j] = expf(rh[j] / a.temperature - lse) * gscale;
+    __syncwarp();
+
+    // ---- optional KL-KD on the in-batch matrix (losses.py:239-253); requires N == Bq
+    if (a.has_kd) {
+      const float* tr = a.teacher_kd + static_cast<size_t>(i) * N;
+      float ms = -INFINITY, mt = -INFINITY;
+      for (int j = lane; j < N; j += 32) {
+        float s = rin[j];
+        s = a.round_bf16 ? bf16_round(bf16_round(s) / a.kd_temperature) : s / a.kd_temperature;
+        ms = fmaxf(ms, s);
+        mt = fmaxf(mt, tr[j] / a.kd_temperature);
+      }
+      ms = warp_max(ms);
+      mt = warp_max(mt);
+      float ss = 0.f, st = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        float s = rin[j];
+        s = a.round_bf16 ? bf16_round(bf16_round(s) / a.kd_temperature) : s / a.kd_temperature;
+        ss += expf(s - ms);
+        st += expf(tr[j] / a.kd_temperature - mt);
+      }
+      ss = warp_sum(ss);
+      st = warp_sum(st);
+      const float lss = ms + logf(ss), lst = mt + logf(st);
+      float kl = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        float s = rin[j];
+        s = a.round_bf16 ? bf16_round(bf16_round(s) / a.kd_temperature) : s / a.kd_temperature;
+        const float logp = s - lss;
+        const float logt = tr[j] / a.kd_temperature - lst;
+        const float t = expf(logt);
+        if (t > 0.f) kl += t * (logt - logp);
+        gin[j] += a.lambda_kd * (expf(logp) - t) * invB / a.kd_temperature;
+      }
+      acc_kd += warp_sum(kl);
+      __syncwarp();
+    }
+
+    // ---- optional MarginMSE (losses.py:92-134): raw (un-tempered) fp32 dots
+    if (a.has_mmse) {
+      const float sp = a.raw_pos[i];
+      const float tp = a.teacher_pos[i];
+      const float c = 2.f * invB / static_cast<float>(k);
+      float sq = 0.f, gpos = 0.f;
+      for (int j = lane; j < k; j += 32) {
+        const float diff = (sp - rh[j]) - (tp - a.teacher_neg[static_cast<size_t>(i) * k + j]);
+        sq += diff * diff;
+        gpos += c * diff;
+        gh[j] += a.lambda_mmse * (-c * diff);
+      }
+      acc_mm += warp_sum(sq);
+      gpos = warp_sum(gpos);
+      if (lane == 0) gin[label] += a.lambda_mmse * gpos;
+      __syncwarp();
+    }
+  }
+
+  __shared__ float s_part[3][8];
+  if (lane == 0) {
+    s_part[0][warp] = acc_nce;
+    s_part[1][warp] = acc_kd;
+    s_part[2][warp] = acc_mm;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float nce = 0.f, kd = 0.f, mm = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      nce += s_part[0][w];
+      kd += s_part[1][w];
+      mm += s_part[2][w];
+    }
+    nce *= invB;
+    kd *= invB;                                    // kl_div(reduction="batchmean")
+    mm *= invB / static_cast<float>(k);            // mse_loss mean over [Bq,k]
+    const float fq = a.flops3[0], fd = a.flops3[2], fn = a.flops3[4];
+    float loss = nce + a.lambda_q * fq + a.lambda_d * fd + a.lambda_neg * fn;
+    if (a.has_kd) loss += a.lambda_kd * kd;
+    if (a.has_mmse) loss += a.lambda_mmse * mm;
+    a.scalars[0] = loss;
+    a.scalars[1] = nce;
+    a.scalars[2] = fq;
+    a.scalars[3] = fd;
+    a.scalars[4] = fn;
+    a.scalars[5] = a.has_kd ? kd : 0.f;
+    a.scalars[6] = a.has_mmse ? mm : 0.f;
+    a.scalars[7] = a.flops3[1];
+    a.scalars[8] = a.flops3[3];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward onto q / docs / negs.  One thread per vocabulary column, 128 columns per CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int BT = 32;  // tile edge over queries / documents
+
+__global__ void __launch_bounds__(128)
+loss_bwd_kernel(const float* __restrict__ q, const float* __restrict__ docs, const float* __restrict__ negs,
+                int Bq, int N, int k, int V, int label_offset, const float* __restrict__ g_in,
+                const float* __restrict__ g_hard, const float* __restrict__ cm_q, const float* __restrict__ cm_d,
+                const float* __restrict__ cm_n, float cq, float cd, float cn, const float* __restrict__ g_loss,
+                float* __restrict__ dq, float* __restrict__ ddocs, float* __restrict__ dnegs) {
+  __shared__ __align__(16) float Gs[BT][BT];
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  const bool live = col < V;
+  const float gl = *g_loss;
+  const float fq = live ? cq * cm_q[col] : 0.f;
+  const float fd = live ? cd * cm_d[col] : 0.f;
+  const float fn = live ? cn * cm_n[col] : 0.f;
+
+  // ---- dq (and dnegs)
+  for (int i0 = 0; i0 < Bq; i0 += BT) {
+    float acc[BT];
+#pragma unroll
+    for (int ii = 0; ii < BT; ++ii) acc[ii] = 0.f;
+    for (int j0 = 0; j0 < N; j0 += BT) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < BT * BT; e += 128) {
+        const int ii = e / BT, jj = e % BT;
+        Gs[ii][jj] = (i0 + ii < Bq && j0 + jj < N) ? g_in[static_cast<size_t>(i0 + ii) * N + j0 + jj] : 0.f;
+      }
+      __syncthreads();
+      float d[BT];
+#pragma unroll
+      for (int jj = 0; jj < BT; ++jj)
+        d[jj] = (live && j0 + jj < N) ? docs[static_cast<size_t>(j0 + jj) * V + col] : 0.f;
+#pragma unroll
+      for (int ii = 0; ii < BT; ++ii) {
+#pragma unroll
+        for (int jj = 0; jj < BT; jj += 4) {
+          const float4 g = *reinterpret_cast<const float4*>(&Gs[ii][jj]);
+          acc[ii] = fmaf(g.x, d[jj], acc[ii]);
+          acc[ii] = fmaf(g.y, d[jj + 1], acc[ii]);
+          acc[ii] = fmaf(g.z, d[jj + 2], acc[ii]);
+          acc[ii] = fmaf(g.w, d[jj + 3], acc[ii]);
+        }
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int ii = 0; ii < BT; ++ii) {
+        const int i = i0 + ii;
+        if (i < Bq) {
+          const float qv = q[static_cast<size_t>(i) * V + col];
+          float extra = 0.f;
+          for (int kk = 0; kk < k; ++kk) {
+            const float gh = __ldg(&g_hard[static_cast<size_t>(i) * k + kk]);
+            const size_t o = (static_cast<size_t>(i) * k + kk) * V + col;
+            extra = fmaf(gh, negs[o], extra);
+            dnegs[o] = gl * (gh * qv + fn);
+          }
+          dq[static_cast<size_t>(i) * V + col] = gl * (acc[ii] + extra + fq);
+        }
+      }
+    }
+  }
+
+  // ---- ddocs
+  for (int j0 = 0; j0 < N; j0 += BT) {
+    float acc[BT];
+#pragma unroll
+    for (int jj = 0; jj < BT; ++jj) acc[jj] = 0.f;
+    for (int i0 = 0; i0 < Bq; i0 += BT) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < BT * BT; e += 128) {
+        const int ii = e / BT, jj = e % BT;
+        Gs[ii][jj] = (i0 + ii < Bq && j0 + jj < N) ? g_in[static_cast<size_t>(i0 + ii) * N + j0 + jj] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ii = 0; ii < BT; ++ii) {
+        const float qv = (live && i0 + ii < Bq) ? q[static_cast<size_t>(i0 + ii) * V + col] : 0.f;
+#pragma unroll
+        for (int jj = 0; jj < BT; jj += 4) {
+          const float4 g = *reinterpret_cast<const float4*>(&Gs[ii][jj]);
+          acc[jj] = fmaf(g.x, qv, acc[jj]);
+          acc[jj + 1] = fmaf(g.y, qv, acc[jj + 1]);
+          acc[jj + 2] = fmaf(g.z, qv, acc[jj + 2]);
+          acc[jj + 3] = fmaf(g.w, qv, acc[jj + 3]);
+        }
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int jj = 0; jj < BT; ++jj) {
+        const int j = j0 + jj;
+        if (j < N) {
+          const bool local = (j >= label_offset) && (j < label_offset + Bq);
+          ddocs[static_cast<size_t>(j) * V + col] = gl * (acc[jj] + (local ? fd : 0.f));
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+size_t flops_workspace_bytes(int N, int V) {
+  (void)N;
+  return align256(static_cast<size_t>((V + kFlopsThreads - 1) / kFlopsThreads) * sizeof(float2));
+}
+
+int flops_nnz_launch(const float* rep, int N, int V, float* colmean, float* out2, void* workspace,
+                     size_t ws_bytes, cudaStream_t stream) {
+  if (!rep || !colmean || !out2) return set_error(kErrInvalidArg, "splade_flops_nnz: null pointer argument");
+  if (N < 1 || V < 1) return set_error(kErrInvalidArg, "splade_flops_nnz: bad sizes N=%d V=%d", N, V);
+  const size_t need = flops_workspace_bytes(N, V);
+  if (!workspace || ws_bytes < need)
+    return set_error(kErrWorkspace, "splade_flops_nnz: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+  const int nblocks = (V + kFlopsThreads - 1) / kFlopsThreads;
+  float2* partials = static_cast<float2*>(workspace);
+  flops_cols_kernel<<<nblocks, kFlopsThreads, 0, stream>>>(rep, N, V, colmean, partials);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  flops_final_kernel<<<1, 256, 0, stream>>>(partials, nblocks, N, out2);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+size_t scores_workspace_bytes(int Bq, int N, int V) {
+  if (Bq < 1 || N < 1 || V < 1) return 0;
+  int ksplit, chunk;
+  scores_plan(Bq, N, V, &ksplit, &chunk);
+  return align256(static_cast<size_t>(ksplit) * Bq * N * sizeof(float));
+}
+
+int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int round_bf16, float* raw,
+                  void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  if (!q || !docs || !raw) return set_error(kErrInvalidArg, "splade_scores: null pointer argument");
+  if (Bq < 1 || N < 1 || V < 1) return set_error(kErrInvalidArg, "splade_scores: bad sizes Bq=%d N=%d V=%d", Bq, N, V);
+  int ksplit, chunk;
+  scores_plan(Bq, N, V, &ksplit, &chunk);
+  const size_t need = align256(static_cast<size_t>(ksplit) * Bq * N * sizeof(float));
+  if (!workspace || ws_bytes < need)
+    return set_error(kErrWorkspace, "splade_scores: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+  float* partial = static_cast<float*>(workspace);
+  dim3 grid((N + TJ - 1) / TJ, (Bq + TI - 1) / TI, ksplit);
+  scores_partial_kernel<<<grid, 256, 0, stream>>>(q, Bq, docs, N, V, round_bf16, chunk, partial);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  const size_t n = static_cast<size_t>(Bq) * N;
+  scores_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(partial, ksplit, n, raw);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+int rowdot_launch(const float* q, const float* docs, int Bq, int k, int V, float* out, cudaStream_t stream) {
+  if (!q || !docs || !out) return set_error(kErrInvalidArg, "splade_rowdot: null pointer argument");
+  if (Bq < 1 || k < 1 || V < 1) return set_error(kErrInvalidArg, "splade_rowdot: bad sizes Bq=%d k=%d V=%d", Bq, k, V);
+  rowdot_kernel<<<Bq * k, 256, 0, stream>>>(q, docs, k, V, out);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+int v33_scalars_launch(const splade_v33_scalar_args* a, cudaStream_t stream) {
+  if (!a) return set_error(kErrInvalidArg, "splade_v33_scalars: null args");
+  if (a->Bq < 1 || a->N < 1 || a->k < 1)
+    return set_error(kErrInvalidArg, "splade_v33_scalars: bad sizes Bq=%d N=%d k=%d", a->Bq, a->N, a->k);
+  if (!a->raw_inbatch || !a->raw_hard || !a->flops3 || !a->scalars || !a->g_inbatch || !a->g_hard)
+    return set_error(kErrInvalidArg, "splade_v33_scalars: null pointer argument");
+  if (a->label_offset < 0 || a->label_offset + a->Bq > a->N)
+    return set_error(kErrInvalidArg, "splade_v33_scalars: labels [%d,%d) outside the %d in-batch documents",
+                     a->label_offset, a->label_offset + a->Bq, a->N);
+  if (a->has_kd && (!a->teacher_kd || a->N != a->Bq))
+    return set_error(kErrInvalidArg, "splade_v33_scalars: KL-KD needs teacher_scores [Bq,Bq] and N == Bq");
+  if (a->has_mmse && (!a->raw_pos || !a->teacher_pos || !a->teacher_neg))
+    return set_error(kErrInvalidArg, "splade_v33_scalars: MarginMSE needs raw_pos, teacher_pos and teacher_neg");
+  if (!(a->temperature > 0.f) || (a->has_kd && !(a->kd_temperature > 0.f)))
+    return set_error(kErrInvalidArg, "splade_v33_scalars: temperatures must be positive");
+  v33_scalars_kernel<<<1, 256, 0, stream>>>(*a);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,
+                    int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
+                    const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
+                    const float* g_loss, float* dq, float* ddocs, float* dnegs, cudaStream_t stream) {
+  if (!q || !docs || !negs || !g_inbatch || !g_hard || !colmean_q || !colmean_d || !colmean_n || !g_loss || !dq ||
+      !ddocs || !dnegs)
+    return set_error(kErrInvalidArg, "splade_loss_bwd: null pointer argument");
+  if (Bq < 1 || N < 1 || k < 1 || V < 1)
+    return set_error(kErrInvalidArg, "splade_loss_bwd: bad sizes Bq=%d N=%d k=%d V=%d", Bq, N, k, V);
+  loss_bwd_kernel<<<(V + 127) / 128, 128, 0, stream>>>(q, docs, negs, Bq, N, k, V, label_offset, g_inbatch,
+                                                       g_hard, colmean_q, colmean_d, colmean_n, cq, cd, cn,
+                                                       g_loss, dq, ddocs, dnegs);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace splade

@@ -1,0 +1,300 @@
+"""Torch-tensor wrappers and autograd Functions over the C-ABI (``include/splade_b200.h``).
+
+PyTorch is plumbing here: it allocates every buffer (inputs, outputs, workspaces), supplies the current CUDA
+stream and records the autograd graph.  All arithmetic happens in ``libsplade_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, load_library
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"splade_b200: `{name}` is on {t.device}; this path runs only on an sm_100 CUDA device "
+            f"(no CPU fallback)."
+        )
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ws(nbytes: int, device) -> Tuple[Optional[torch.Tensor], int]:
+    if nbytes <= 0:
+        return None, 0
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return buf, buf.data_ptr()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# raw ops
+# ------------------------------------------------------------------------------------------------
+def head_forward(hidden: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, mask: torch.Tensor,
+                 want_token_weights: bool = True):
+    """hidden [B,S,H] bf16, weight [V,H] bf16, bias [V] fp32, mask [B,S] int32 ->
+    (rep [B,V] fp32, argmax [B,V] int32, token_weights [B,S] fp32 | None)."""
+    lib = load_library()
+    for n, t in (("hidden", hidden), ("weight", weight), ("bias", bias), ("mask", mask)):
+        _require_cuda(t, n)
+    assert hidden.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
+    assert bias.dtype == torch.float32 and mask.dtype == torch.int32
+    assert hidden.is_contiguous() and weight.is_contiguous() and bias.is_contiguous() and mask.is_contiguous()
+    B, S, H = hidden.shape
+    V = weight.shape[0]
+    assert weight.shape[1] == H and bias.shape[0] == V and tuple(mask.shape) == (B, S)
+    dev = hidden.device
+    with torch.cuda.device(dev):
+        rep = torch.empty((B, V), dtype=torch.float32, device=dev)
+        argmax = torch.empty((B, V), dtype=torch.int32, device=dev)
+        tokw = torch.empty((B, S), dtype=torch.float32, device=dev) if want_token_weights else None
+        op = _lib.OP_HEAD_FWD_TOKW if want_token_weights else _lib.OP_HEAD_FWD
+        nbytes = lib.splade_workspace_bytes(op, B, S, H, V, 0)
+        ws, ws_ptr = _ws(nbytes, dev)
+        check(lib.splade_head_fwd(hidden.data_ptr(), weight.data_ptr(), bias.data_ptr(), mask.data_ptr(),
+                                  B, S, H, V, rep.data_ptr(), argmax.data_ptr(), _ptr(tokw), ws_ptr, nbytes,
+                                  _stream(hidden)), "splade_head_fwd")
+    return rep, argmax, tokw
+
+
+def head_backward(g_rep: torch.Tensor, rep: torch.Tensor, argmax: torch.Tensor, hidden: torch.Tensor,
+                  weight: torch.Tensor):
+    """-> (d_hidden [B,S,H] fp32, dW [V,H] fp32, dbias [V] fp32)"""
+    lib = load_library()
+    B, S, H = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    g_rep = _f32c(g_rep)
+    with torch.cuda.device(dev):
+        d_hidden = torch.empty((B, S, H), dtype=torch.float32, device=dev)
+        dW = torch.empty((V, H), dtype=torch.float32, device=dev)
+        dbias = torch.empty((V,), dtype=torch.float32, device=dev)
+        nbytes = lib.splade_workspace_bytes(_lib.OP_HEAD_BWD, B, S, H, V, 0)
+        ws, ws_ptr = _ws(nbytes, dev)
+        check(lib.splade_head_bwd(g_rep.data_ptr(), rep.data_ptr(), argmax.data_ptr(), hidden.data_ptr(),
+                                  weight.data_ptr(), B, S, H, V, d_hidden.data_ptr(), dW.data_ptr(),
+                                  dbias.data_ptr(), ws_ptr, nbytes, _stream(hidden)), "splade_head_bwd")
+    return d_hidden, dW, dbias
+
+
+def flops_nnz(rep: torch.Tensor, out2: Optional[torch.Tensor] = None):
+    """rep [N,V] fp32 -> (colmean [V], out2 [2] = {sum_j mean_j^2, mean_i nnz_i})"""
+    lib = load_library()
+    _require_cuda(rep, "rep")
+    rep = _f32c(rep)
+    N, V = rep.shape
+    dev = rep.device
+    with torch.cuda.device(dev):
+        colmean = torch.empty((V,), dtype=torch.float32, device=dev)
+        if out2 is None:
+            out2 = torch.empty((2,), dtype=torch.float32, device=dev)
+        nbytes = lib.splade_workspace_bytes(_lib.OP_FLOPS_NNZ, N, 0, 0, V, 0)
+        ws, ws_ptr = _ws(nbytes, dev)
+        check(lib.splade_flops_nnz(rep.data_ptr(), N, V, colmean.data_ptr(), out2.data_ptr(), ws_ptr, nbytes,
+                                   _stream(rep)), "splade_flops_nnz")
+    return colmean, out2
+
+
+def scores(q: torch.Tensor, docs: torch.Tensor, round_bf16: bool) -> torch.Tensor:
+    """raw[i,j] = <q_i, docs_j>  ([Bq,V] x [N,V] -> [Bq,N] fp32)"""
+    lib = load_library()
+    _require_cuda(q, "q")
+    q, docs = _f32c(q), _f32c(docs)
+    Bq, V = q.shape
+    N = docs.shape[0]
+    dev = q.device
+    with torch.cuda.device(dev):
+        raw = torch.empty((Bq, N), dtype=torch.float32, device=dev)
+        nbytes = lib.splade_workspace_bytes(_lib.OP_SCORES, Bq, 0, 0, V, N)
+        ws, ws_ptr = _ws(nbytes, dev)
+        check(lib.splade_scores(q.data_ptr(), Bq, docs.data_ptr(), N, V, int(round_bf16), raw.data_ptr(), ws_ptr,
+                                nbytes, _stream(q)), "splade_scores")
+    return raw
+
+
+def rowdot(q: torch.Tensor, docs: torch.Tensor) -> torch.Tensor:
+    """out[i,j] = <q_i, docs_{i,j}>  ([Bq,V] x [Bq,k,V] -> [Bq,k] fp32)"""
+    lib = load_library()
+    _require_cuda(q, "q")
+    q, docs = _f32c(q), _f32c(docs)
+    Bq, V = q.shape
+    k = docs.shape[1]
+    with torch.cuda.device(q.device):
+        out = torch.empty((Bq, k), dtype=torch.float32, device=q.device)
+        check(lib.splade_rowdot(q.data_ptr(), docs.data_ptr(), Bq, k, V, out.data_ptr(), _stream(q)),
+              "splade_rowdot")
+    return out
+
+
+def topk(rep: torch.Tensor, k: int, blocklist: Optional[torch.Tensor] = None):
+    """rep [B,V] fp32 -> (ids [B,k] int32 (-1 pad), vals [B,k] fp32, counts [B] int32); order = (weight desc,
+    id asc); keeps weight > 0 and ids not in the blocklist (uint8 [V], nonzero = drop)."""
+    lib = load_library()
+    _require_cuda(rep, "rep")
+    rep = _f32c(rep)
+    B, V = rep.shape
+    dev = rep.device
+    if blocklist is not None:
+        assert blocklist.dtype == torch.uint8 and blocklist.numel() == V and blocklist.device == dev
+        blocklist = blocklist.contiguous()
+    with torch.cuda.device(dev):
+        ids = torch.empty((B, k), dtype=torch.int32, device=dev)
+        vals = torch.empty((B, k), dtype=torch.float32, device=dev)
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        check(lib.splade_topk(rep.data_ptr(), B, V, _ptr(blocklist), k, ids.data_ptr(), vals.data_ptr(),
+                              counts.data_ptr(), _stream(rep)), "splade_topk")
+    return ids, vals, counts
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: fused head
+# ------------------------------------------------------------------------------------------------
+_WEIGHT_CACHE = {}
+
+
+def cached_bf16(weight: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of a parameter, reused until the parameter is modified in place (optimizer step).
+    Mirrors autocast's own weight-cast cache; saves two 77 MB casts per micro-step."""
+    if weight.dtype == torch.bfloat16 and weight.is_contiguous():
+        return weight.detach()
+    key = (weight.data_ptr(), weight.device)
+    hit = _WEIGHT_CACHE.get(key)
+    if hit is not None and hit[0] == weight._version and hit[1].shape == weight.shape:
+        return hit[1]
+    w = weight.detach().to(torch.bfloat16).contiguous()
+    _WEIGHT_CACHE.clear()  # one live entry is enough (the tied decoder/embedding matrix)
+    _WEIGHT_CACHE[key] = (weight._version, w)
+    return w
+
+
+class SpladeHeadFunction(torch.autograd.Function):
+    """sparse_repr, token_weights = SPLADE-max head(hidden, decoder.weight, decoder.bias, attention_mask).
+
+    Replaces src/model/splade_modern.py:73-86 + the decoder Linear.  Backward is the gather-driven sparse
+    backward (splade_head_bwd)."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, bias, attention_mask, want_token_weights: bool, round_bias: bool):
+        _require_cuda(hidden, "hidden")
+        h16 = hidden.detach().to(torch.bfloat16).contiguous()
+        w16 = cached_bf16(weight)
+        if bias is None:
+            b32 = torch.zeros(weight.shape[0], dtype=torch.float32, device=hidden.device)
+        else:
+            b32 = bias.detach()
+            if round_bias:  # autocast hands F.linear a bf16 bias
+                b32 = b32.to(torch.bfloat16)
+            b32 = b32.to(torch.float32).contiguous()
+        m32 = attention_mask.detach().to(torch.int32).contiguous()
+        rep, argmax, tokw = head_forward(h16, w16, b32, m32, want_token_weights)
+        ctx.save_for_backward(rep, argmax, h16, w16)
+        ctx.in_dtypes = (hidden.dtype, weight.dtype, None if bias is None else bias.dtype)
+        if tokw is None:
+            tokw = torch.zeros((0,), dtype=torch.float32, device=hidden.device)
+        ctx.mark_non_differentiable(tokw)
+        return rep, tokw
+
+    @staticmethod
+    def backward(ctx, g_rep, _g_tokw):
+        rep, argmax, h16, w16 = ctx.saved_tensors
+        d_hidden, dW, dbias = head_backward(g_rep, rep, argmax, h16, w16)
+        hd, wd, bd = ctx.in_dtypes
+        return (d_hidden.to(hd), dW.to(wd), None if bd is None else dbias.to(bd), None, None, None)
+
+
+def splade_head(hidden, weight, bias, attention_mask, want_token_weights: bool = True,
+                round_bias: Optional[bool] = None):
+    if round_bias is None:
+        round_bias = torch.is_autocast_enabled("cuda") if hidden.is_cuda else False
+    rep, tokw = SpladeHeadFunction.apply(hidden, weight, bias, attention_mask, want_token_weights, round_bias)
+    return rep, (tokw if want_token_weights else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: SPLADELossV33 on the pooled vectors
+# ------------------------------------------------------------------------------------------------
+class V33LossFunction(torch.autograd.Function):
+    """total loss + packed scalars from (anchor [Bq,V], docs [N,V], negatives [Bq,k,V]).
+
+    Forward = src/model/losses.py:209-269; ``scalars`` (non-differentiable, one D2H copy on the caller's side)
+    holds {loss, infonce, flops_q, flops_d, flops_neg, kd, margin_mse, nonzero_q, nonzero_d}."""
+
+    @staticmethod
+    def forward(ctx, anchor, docs, negatives, teacher_kd, teacher_pos, teacher_neg, cfg: dict):
+        lib = load_library()
+        _require_cuda(anchor, "anchor_repr")
+        dev = anchor.device
+        q = _f32c(anchor)
+        d = _f32c(docs)
+        n = _f32c(negatives)
+        Bq, V = q.shape
+        N = d.shape[0]
+        k = n.shape[1]
+        off = int(cfg["label_offset"])
+        round_bf16 = bool(cfg["round_bf16"])
+        has_kd = teacher_kd is not None and cfg["lambda_kd"] > 0
+        has_mmse = teacher_pos is not None and teacher_neg is not None and cfg["lambda_mmse"] > 0
+        with torch.cuda.device(dev):
+            flops3 = torch.empty((6,), dtype=torch.float32, device=dev)
+            d_local = d[off:off + Bq]
+            cm_q, _ = flops_nnz(q, flops3[0:2])
+            cm_d, _ = flops_nnz(d_local, flops3[2:4])
+            cm_n, _ = flops_nnz(n.view(Bq * k, V), flops3[4:6])
+            raw_in = scores(q, d, round_bf16)
+            raw_hard = rowdot(q, n)
+            raw_pos = rowdot(q, d_local.unsqueeze(1)).view(Bq) if has_mmse else None
+            scalars = torch.zeros((16,), dtype=torch.float32, device=dev)
+            g_in = torch.empty((Bq, N), dtype=torch.float32, device=dev)
+            g_hard = torch.empty((Bq, k), dtype=torch.float32, device=dev)
+            t_kd = _f32c(teacher_kd) if has_kd else None
+            t_pos = _f32c(teacher_pos).view(Bq) if has_mmse else None
+            t_neg = _f32c(teacher_neg).view(Bq, k) if has_mmse else None
+            args = _lib.V33ScalarArgs(
+                Bq=Bq, N=N, k=k, label_offset=off, round_bf16=int(round_bf16), has_kd=int(has_kd),
+                has_mmse=int(has_mmse), reserved=0,
+                temperature=cfg["temperature"], kd_temperature=cfg["kd_temperature"],
+                lambda_q=cfg["lambda_q"], lambda_d=cfg["lambda_d"], lambda_neg=cfg["lambda_neg"],
+                lambda_kd=cfg["lambda_kd"], lambda_mmse=cfg["lambda_mmse"], reserved_f=0.0,
+                raw_inbatch=raw_in.data_ptr(), raw_hard=raw_hard.data_ptr(), raw_pos=_ptr(raw_pos),
+                teacher_kd=_ptr(t_kd), teacher_pos=_ptr(t_pos), teacher_neg=_ptr(t_neg),
+                flops3=flops3.data_ptr(), scalars=scalars.data_ptr(), g_inbatch=g_in.data_ptr(),
+                g_hard=g_hard.data_ptr())
+            check(lib.splade_v33_scalars(ctypes.byref(args), _stream(q)), "splade_v33_scalars")
+        ctx.save_for_backward(q, d, n, g_in, g_hard, cm_q, cm_d, cm_n)
+        ctx.meta = (Bq, N, k, V, off, cfg["lambda_q"], cfg["lambda_d"], cfg["lambda_neg"],
+                    anchor.dtype, docs.dtype, negatives.dtype, tuple(negatives.shape))
+        loss = scalars[0].clone()
+        ctx.mark_non_differentiable(scalars)
+        return loss, scalars
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_scalars):
+        lib = load_library()
+        q, d, n, g_in, g_hard, cm_q, cm_d, cm_n = ctx.saved_tensors
+        Bq, N, k, V, off, lq, ld, ln, qd, dd, nd, nshape = ctx.meta
+        dev = q.device
+        gl = _f32c(g_loss).reshape(1)
+        with torch.cuda.device(dev):
+            dq = torch.empty_like(q)
+            ddocs = torch.empty_like(d)
+            dnegs = torch.empty_like(n)
+            check(lib.splade_loss_bwd(q.data_ptr(), d.data_ptr(), n.data_ptr(), Bq, N, k, V, off,
+                                      g_in.data_ptr(), g_hard.data_ptr(), cm_q.data_ptr(), cm_d.data_ptr(),
+                                      cm_n.data_ptr(), 2.0 * lq / Bq, 2.0 * ld / Bq, 2.0 * ln / (Bq * k),
+                                      gl.data_ptr(), dq.data_ptr(), ddocs.data_ptr(), dnegs.data_ptr(),
+                                      _stream(q)), "splade_loss_bwd")
+        return dq.to(qd), ddocs.to(dd), dnegs.view(nshape).to(nd), None, None, None, None

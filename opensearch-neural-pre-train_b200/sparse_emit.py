@@ -1,0 +1,112 @@
+"""Top-k pruning + sparse emit with the reference's production semantics, and sharded bulk encoding.
+
+Reference: ``NeuralSparseEncoderV33._encode_batch`` (benchmark/encoders.py:309-345) keeps ``weight > 0``, drops
+the special token ids (``:277-287``) and tokens whose string starts with ``[`` or ``<`` (``:332``), and — when
+``top_k`` is given and more survive — keeps the ``top_k`` largest by a stable descending sort, i.e. ties go
+to the lower term id.  The reference does that per row on the host (``.cpu()`` + python loops); here the
+selection is one CUDA kernel over the whole batch (``splade_topk``) and only ``[B,k]`` ids/weights cross
+PCIe.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+from .distributed import shard_range, world_info
+from .ops import topk
+
+
+def build_blocklist(tokenizer, model_vocab_size: int, device=None) -> torch.Tensor:
+    """uint8 [V] with 1 for every term id the reference never emits (benchmark/encoders.py:277-287, :332):
+    cls/sep/pad/unk/bos/eos ids, tokens starting with '[' or '<', empty tokens, and ids beyond the tokenizer's
+    vocabulary (the model has V=50 000 rows, the tokenizer 49 999 entries)."""
+    block = torch.zeros(model_vocab_size, dtype=torch.uint8)
+    special = {tokenizer.cls_token_id, tokenizer.sep_token_id, tokenizer.pad_token_id, tokenizer.unk_token_id,
+               tokenizer.bos_token_id, tokenizer.eos_token_id}
+    for tid in special:
+        if tid is not None and 0 <= tid < model_vocab_size:
+            block[tid] = 1
+    n_tok = min(tokenizer.vocab_size, model_vocab_size)
+    tokens = tokenizer.convert_ids_to_tokens(list(range(n_tok)))
+    for i, tok in enumerate(tokens):
+        if not tok or tok.startswith(("[", "<")):
+            block[i] = 1
+    block[n_tok:] = 1
+    return block if device is None else block.to(device)
+
+
+class SparseEmitter:
+    """GPU top-k + host-side dict / bulk-line emit.
+
+    ``token_lookup`` maps term id -> token string (``tokenizer.convert_ids_to_tokens``); without it the emit
+    uses the decimal id as key (the ``sparse_vector`` format of scripts/neural_sparse_search_aws.py:753).
+    """
+
+    def __init__(self, blocklist: Optional[torch.Tensor] = None, token_lookup: Optional[Sequence[str]] = None):
+        self.blocklist = blocklist
+        self.token_lookup = token_lookup
+
+    @classmethod
+    def from_tokenizer(cls, tokenizer, model_vocab_size: int, device=None) -> "SparseEmitter":
+        lookup = tokenizer.convert_ids_to_tokens(list(range(min(tokenizer.vocab_size, model_vocab_size))))
+        return cls(build_blocklist(tokenizer, model_vocab_size, device), lookup)
+
+    def select(self, sparse_repr: torch.Tensor, top_k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """[B,V] fp32 (CUDA) -> ids [B,k] int32 (-1 padded), weights [B,k] fp32, counts [B] int32."""
+        block = self.blocklist
+        if block is not None and block.device != sparse_repr.device:
+            block = self.blocklist = block.to(sparse_repr.device)
+        return topk(sparse_repr, top_k, block)
+
+    def to_dicts(self, ids: torch.Tensor, vals: torch.Tensor, counts: torch.Tensor,
+                 round_decimals: Optional[int] = None) -> List[Dict[str, float]]:
+        """One device->host copy of the compact buffers, then ``{token: weight}`` per row."""
+        ids_h, vals_h, counts_h = ids.cpu().tolist(), vals.cpu().tolist(), counts.cpu().tolist()
+        out = []
+        for row_ids, row_vals, n in zip(ids_h, vals_h, counts_h):
+            d = {}
+            for tid, w in zip(row_ids[:n], row_vals[:n]):
+                key = self.token_lookup[tid] if self.token_lookup is not None else str(tid)
+                d[key] = round(w, round_decimals) if round_decimals is not None else w
+            out.append(d)
+        return out
+
+    def encode_batch(self, sparse_repr: torch.Tensor, top_k: int) -> List[Dict[str, float]]:
+        return self.to_dicts(*self.select(sparse_repr, top_k))
+
+
+@torch.no_grad()
+def bulk_encode(model, input_ids: torch.Tensor, attention_mask: torch.Tensor, top_k: int,
+                emitter: Optional[SparseEmitter] = None, batch_size: int = 64, group=None,
+                autocast_dtype: Optional[torch.dtype] = torch.bfloat16):
+    """Encode this rank's contiguous shard of a corpus (BASELINE config 5) and return compact top-k buffers.
+
+    ``input_ids`` / ``attention_mask`` are the FULL corpus tensors [N,S] (host or device); rank r encodes rows
+    ``shard_range(N, r, W)``.  No collective on the data path; callers concatenate the per-rank results in rank
+    order.  Returns (ids [n,k] int32, weights [n,k] fp32, counts [n] int32, (lo, hi)).
+    """
+    rank, world = world_info(group)
+    lo, hi = shard_range(input_ids.shape[0], rank, world)
+    emitter = emitter or SparseEmitter()
+    device = next(model.parameters()).device
+    out_ids, out_vals, out_counts = [], [], []
+    for b0 in range(lo, hi, batch_size):
+        b1 = min(hi, b0 + batch_size)
+        ids_b = input_ids[b0:b1].to(device, non_blocking=True)
+        mask_b = attention_mask[b0:b1].to(device, non_blocking=True)
+        if autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=autocast_dtype):
+                rep = model.encode(ids_b, mask_b)
+        else:
+            rep = model.encode(ids_b, mask_b)
+        i, v, c = emitter.select(rep, top_k)
+        out_ids.append(i)
+        out_vals.append(v)
+        out_counts.append(c)
+    if not out_ids:
+        dev = device
+        return (torch.empty((0, top_k), dtype=torch.int32, device=dev),
+                torch.empty((0, top_k), dtype=torch.float32, device=dev),
+                torch.empty((0,), dtype=torch.int32, device=dev), (lo, hi))
+    return torch.cat(out_ids), torch.cat(out_vals), torch.cat(out_counts), (lo, hi)

@@ -1,0 +1,68 @@
+"""CPU: the C-ABI shared library is present, loads, and exports every symbol include/splade_b200.h declares.
+No compute calls (no GPU here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "splade_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(splade_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = _declared_symbols()
+    for s in ("splade_head_fwd", "splade_head_bwd", "splade_flops_nnz", "splade_scores", "splade_rowdot",
+              "splade_v33_scalars", "splade_loss_bwd", "splade_topk", "splade_workspace_bytes",
+              "splade_last_error", "splade_abi_version"):
+        assert s in syms
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import splade_b200
+    from splade_b200 import _lib
+    assert os.path.exists(splade_b200.LIB_PATH), "run __graft_entry__.build() first"
+    lib = splade_b200.load_library()
+    declared = _declared_symbols()
+    assert set(declared) == set(_lib.EXPORTS), "python binding and header disagree"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.splade_abi_version() == splade_b200.ABI_VERSION
+    # pure host helper: workspace sizing needs no device
+    assert lib.splade_workspace_bytes(_lib.OP_HEAD_FWD, 64, 256, 768, 50000, 0) == 0
+    assert lib.splade_workspace_bytes(_lib.OP_HEAD_FWD_TOKW, 64, 256, 768, 50000, 0) >= 64 * 256 * 4
+    assert lib.splade_workspace_bytes(_lib.OP_HEAD_FWD, 2, 300, 64, 260, 0) >= 2 * 260 * 4
+    assert lib.splade_workspace_bytes(_lib.OP_HEAD_BWD, 64, 256, 768, 50000, 0) >= 2 * 64 * 50000 * 4
+
+
+def test_struct_layout_matches_header():
+    import ctypes
+    from splade_b200._lib import V33ScalarArgs
+    # 8 int32 + 8 float + 10 pointers, no padding on LP64
+    assert ctypes.sizeof(V33ScalarArgs) == 8 * 4 + 8 * 4 + 10 * 8
+
+
+def test_product_refuses_cpu_tensors():
+    import torch
+    import splade_b200
+    h = torch.zeros(1, 4, 64, dtype=torch.bfloat16)
+    w = torch.zeros(8, 64, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        splade_b200.head_forward(h, w, torch.zeros(8), torch.ones(1, 4, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        splade_b200.topk(torch.rand(2, 16), 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        splade_b200.SPLADELossV33()(torch.rand(2, 8), torch.rand(2, 8), torch.rand(2, 8))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "opensearch-neural-pre-train_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
