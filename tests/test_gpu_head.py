@@ -6,7 +6,7 @@ import torch
 
 from oracle import splade_oracle as O
 from oracle import torch_reference as TR
-from tests.gpu_util import assert_argmax_parity, make_head_inputs, run_head
+from tests.gpu_util import assert_argmax_parity, assert_weights_parity, make_head_inputs, run_head
 
 pytestmark = pytest.mark.gpu
 
@@ -20,12 +20,9 @@ def _check_forward(hidden, W, bias, mask, want_tokw=True, what=""):
     flips = assert_argmax_parity(arg.cpu().numpy(), ref_arg, near, what)
     # weights: identical bf16 logit -> log1p agrees to an fp32 ulp; near-tie flips may move by one bf16 ulp
     got = rep.cpu().numpy()
-    np.testing.assert_allclose(got[~near], ref_rep[~near], rtol=2e-6, atol=1e-7, err_msg=what)
-    np.testing.assert_allclose(got, ref_rep, rtol=1e-2, atol=1e-2, err_msg=what)  # north_star tolerance
+    assert_weights_parity(got, ref_rep, what)
     if want_tokw:
-        np.testing.assert_allclose(tokw.cpu().numpy(), ref_tokw, rtol=1e-2, atol=1e-6, err_msg=what)
-        frac_exact = np.mean(np.isclose(tokw.cpu().numpy(), ref_tokw, rtol=2e-6, atol=1e-7))
-        assert frac_exact > 0.999, (what, frac_exact)
+        assert_weights_parity(tokw.cpu().numpy(), ref_tokw, what + " token_weights", max_flip_frac=1e-3)
     else:
         assert tokw is None
     return flips
@@ -38,8 +35,8 @@ def test_golden_forward_backward(cuda_device, golden, name):
     rep, arg, tokw = run_head(t["hidden"], t["W"], t["bias"], t["mask"])
     near = O.near_tie_mask(g["hidden"], g["W"], g["bias"], g["mask"], mode="bf16")
     assert_argmax_parity(arg.cpu().numpy(), g["argmax"], near, name)
-    np.testing.assert_allclose(rep.cpu().numpy()[~near], g["sparse_repr"][~near], rtol=2e-6, atol=1e-7)
-    np.testing.assert_allclose(tokw.cpu().numpy(), g["token_weights"], rtol=1e-2, atol=1e-6)
+    assert_weights_parity(rep.cpu().numpy(), g["sparse_repr"], name)
+    assert_weights_parity(tokw.cpu().numpy(), g["token_weights"], name + " token_weights", max_flip_frac=1e-3)
 
     import splade_b200
     # feed the REFERENCE's rep/argmax so that the backward check is independent of near-tie flips
@@ -91,11 +88,10 @@ def test_headline_shape_vs_torch_autocast(cuda_device):
     del x
     near = (top2[:, 0] - top2[:, 1]) <= top2[:, 0].abs().clamp_min(2.0 ** -126) * 2.0 ** -7
     flips = assert_argmax_parity(arg.cpu().numpy(), ref_arg.cpu().numpy(), near.cpu().numpy(), "C2 vs autocast")
-    ok = ~near
-    torch.testing.assert_close(rep[ok], ref_rep[ok], rtol=2e-6, atol=1e-7)
-    torch.testing.assert_close(rep, ref_rep, rtol=1e-2, atol=1e-2)
-    torch.testing.assert_close(tokw, ref_tokw, rtol=1e-2, atol=1e-6)
-    print(f"C2 argmax flips at near-ties: {flips} of {B * V}; near-tie cells: {int(near.sum())}")
+    wflips = assert_weights_parity(rep.cpu().numpy(), ref_rep.cpu().numpy(), "C2 vs autocast")
+    assert_weights_parity(tokw.cpu().numpy(), ref_tokw.cpu().numpy(), "C2 token_weights", max_flip_frac=1e-3)
+    print(f"C2 vs cuBLAS+ATen autocast chain: argmax flips {flips} of {B * V} (all at near-ties, "
+          f"{int(near.sum())} near-tie cells); weights off by one bf16 ulp: {wflips}")
 
 
 def test_size_independent_properties(cuda_device):
