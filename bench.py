@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the SPLADE-max head hot path (BASELINE.json metric: SPLADE encode docs/sec at L=256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: BASELINE config 2, the fused
+vocabulary projection + log1p(relu) + mask + max-pool of 64 documents x 256 tokens (hidden 768 -> 50 000
+terms, 1.258 TFLOP).  With N GPUs every rank encodes its own 64-document shard (documents are independent:
+no data-path collective, weak scaling); `value` is the whole-job docs/s = N*64*K / max-over-ranks time.
+
+  value     device-resident: hidden states already in HBM when the timed region starts
+  e2e       the same metric through the public API with HOST buffers: every step copies its hidden states
+            and mask from pinned host memory, runs the fused head, and copies the [64, 50 000] fp32 sparse
+            vectors back to pinned host memory (copies overlapped with compute on separate streams)
+  roofline  the tcgen05 head kernel against the measured cuBLAS bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference
+            the reference's CPU torch path (oracle/torch_reference.py, fp32, all host threads) on a bounded
+            sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_DOCS, SEQ, HIDDEN, VOCAB = 64, 256, 768, 50000
+WORKLOAD = "C2: SPLADE-max head encode, A.X-Encoder-base head shape (hidden 768 -> vocab 50000), batch 64 x L=256"
+FLOP_PER_STEP = 2.0 * B_DOCS * SEQ * HIDDEN * VOCAB          # 76.8 MFLOP per token
+N_ROTATE = 3                                                 # distinct input sets (see config.l2)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"burst": float(p["bf16_tflops"]), "sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the run through NVML (same counters as the nvidia-smi clocks line of the recipe)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x0000000000000004: "sw_power_cap",
+        0x0000000000000008: "hw_slowdown",
+        0x0000000000000020: "sw_thermal_slowdown",
+        0x0000000000000040: "hw_thermal_slowdown",
+        0x0000000000000080: "hw_power_brake_slowdown",
+    }
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.samples = []  # (t, sm_mhz, reasons_mask)
+        self.period = period_s
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = None
+            try:  # CUDA ordinal -> NVML handle through the UUID (robust to CUDA_VISIBLE_DEVICES remapping)
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.nv, self.h, self.err = None, None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), float(mhz), int(mask)))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+
+    def summary(self, t0: float, t1: float):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        win = [s for s in self.samples if t0 <= s[0] <= t1]
+        note = "sampled inside the timed regions"
+        if len(win) < 3:
+            win = self.samples
+            note = "timed regions shorter than the sampling period: all samples of the loaded run"
+        mhz = sorted(s[1] for s in win)
+        mask = 0
+        for s in win:
+            mask |= s[2]
+        reasons = [name for bit, name in self.REASONS.items() if mask & bit]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(win), "note": note}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU torch path on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(docs_per_step: int, seed: int = 0):
+    import torch
+
+    from oracle import torch_reference as TR
+    g = torch.Generator().manual_seed(seed)
+    hidden = torch.randn(docs_per_step, SEQ, HIDDEN, generator=g)
+    W = torch.randn(VOCAB, HIDDEN, generator=g) * 0.0176
+    bias = torch.randn(VOCAB, generator=g) * 0.02
+    mask = torch.ones(docs_per_step, SEQ, dtype=torch.int64)
+
+    def step():
+        with torch.no_grad():
+            return TR.head_chain(hidden, W, bias, mask)[0]
+
+    return step
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def time_cpu_reference(docs_per_step: int, steps: int, warmup: int):
+    import torch
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    step = cpu_reference_step_factory(docs_per_step)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return docs_per_step * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    """`--impl reference`: rank 0 times the reference's own CPU implementation of the path."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # size the per-step sample so that the whole run stays within ~2 minutes
+    probe_docs = 4
+    rate, t_step, cores = time_cpu_reference(probe_docs, steps=1, warmup=1)
+    budget_s = 120.0
+    per_step_budget = budget_s / max(1, args.steps + args.warmup)
+    docs = int(max(1, min(B_DOCS, per_step_budget * rate)))
+    value, t_step, cores = time_cpu_reference(docs, args.steps, args.warmup)
+    sample = f"{docs} docs x L={SEQ} per step (of the 64-doc batch), fp32 torch CPU head chain, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "splade_head_encode_docs_per_sec", "value": value, "unit": "docs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "docs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import splade_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic inputs: hidden ~ N(0,1), W ~ N(0, 0.0176^2), bias ~ N(0, 0.02), full lengths
+    g = torch.Generator(device="cpu").manual_seed(42 + rank)
+    sets = []
+    for i in range(N_ROTATE):
+        hidden = torch.randn(B_DOCS, SEQ, HIDDEN, generator=g).to(torch.bfloat16).to(dev)
+        W = (torch.randn(VOCAB, HIDDEN, generator=g) * 0.0176).to(torch.bfloat16).to(dev)
+        bias = (torch.randn(VOCAB, generator=g) * 0.02).to(torch.bfloat16).float().to(dev)
+        mask = torch.ones(B_DOCS, SEQ, dtype=torch.int32, device=dev)
+        sets.append((hidden, W, bias, mask))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- (1) device-resident throughput + per-launch kernel time
+    def step(i):
+        h, w, b, m = sets[i % N_ROTATE]
+        return splade_b200.head_forward(h, w, b, m, want_token_weights=False)
+
+    for i in range(Wm):
+        step(i)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    t_load0 = time.perf_counter()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(K):
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    end.record()
+    barrier()
+    t_load1 = time.perf_counter()
+    total_ms = max_over_ranks(start.elapsed_time(end))
+    kernel_ms = sum(a.elapsed_time(b) for a, b in ev) / K
+    value = world * B_DOCS * K / (total_ms * 1e-3)
+
+    # ---- (2) end to end with host buffers: H2D(hidden, mask) -> fused head -> D2H(sparse_repr), 3 streams
+    n_e2e = K
+    host_in = [torch.randn(B_DOCS, SEQ, HIDDEN, generator=g).to(torch.bfloat16).pin_memory() for _ in range(2)]
+    host_mask = torch.ones(B_DOCS, SEQ, dtype=torch.int32).pin_memory()
+    host_out = [torch.empty(B_DOCS, VOCAB, dtype=torch.float32).pin_memory() for _ in range(2)]
+    dev_in = [torch.empty(B_DOCS, SEQ, HIDDEN, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    dev_mask = [torch.empty(B_DOCS, SEQ, dtype=torch.int32, device=dev) for _ in range(2)]
+    s_h2d, s_cmp, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    w16, b32 = sets[0][1], sets[0][2]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_cmp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    reps = [None, None]
+
+    def e2e_loop(n):
+        for i in range(n):
+            j = i & 1
+            with torch.cuda.stream(s_h2d):
+                s_h2d.wait_event(ev_cmp[j])            # slot's previous compute has consumed dev_in[j]
+                dev_in[j].copy_(host_in[j], non_blocking=True)
+                dev_mask[j].copy_(host_mask, non_blocking=True)
+                ev_in[j].record(s_h2d)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[j])
+                s_cmp.wait_event(ev_out[j])            # slot's previous result has left the device
+                reps[j] = splade_b200.head_forward(dev_in[j], w16, b32, dev_mask[j], want_token_weights=False)[0]
+                ev_cmp[j].record(s_cmp)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_cmp[j])
+                host_out[j].copy_(reps[j], non_blocking=True)
+                ev_out[j].record(s_d2h)
+
+    e2e_loop(Wm)
+    barrier()
+    t_load2 = time.perf_counter()
+    t0 = time.perf_counter()
+    e2e_loop(n_e2e)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    t_load3 = time.perf_counter()
+    e2e_value = world * B_DOCS * n_e2e / e2e_s
+    h2d_bytes = host_in[0].numel() * 2 + host_mask.numel() * 4
+    d2h_bytes = host_out[0].numel() * 4
+    checksum = float(host_out[(n_e2e - 1) & 1][0, :8].sum())  # touch the result on the host
+
+    sampler.stop()
+    clocks = sampler.summary(t_load0, t_load3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- (3) roofline + cpu baseline (rank 0, N=1 leg of the contract)
+    peaks = load_peaks()
+    timed_s = total_ms * 1e-3
+    peak_kind = "burst" if timed_s < 2.0 else "sustained"
+    achieved = FLOP_PER_STEP / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "head_fwd_traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks[peak_kind], "unit": "TFLOP/s",
+                "frac": achieved / peaks[peak_kind], "traffic": traffic, "kernel": "head_fwd_kernel<false>",
+                "kernel_ms": kernel_ms, "peak_kind": f"{peak_kind}, {peaks['source']}",
+                "algorithmic_flop_per_launch": FLOP_PER_STEP}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        docs = 8
+        v, t_step, cores = time_cpu_reference(docs, steps=3, warmup=1)
+        if t_step * 4 < 3.0:  # fast host: use a larger sample to reach ~10-30 s of CPU work
+            docs = min(B_DOCS, int(docs * 3.0 / max(t_step, 1e-3)))
+            v, t_step, cores = time_cpu_reference(docs, steps=3, warmup=1)
+        cpu = {"value": v, "unit": "docs/s", "cores": cores, "kind": "port",
+               "sample": f"{docs} docs x L={SEQ} per pass, 3 timed passes after 1 warm-up, fp32 torch CPU head chain "
+                         f"(oracle/torch_reference.py)"}
+
+    line = {
+        "metric": "splade_head_encode_docs_per_sec", "value": value, "unit": "docs/s", "n_gpus": world,
+        "steps": K, "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "docs_per_gpu_per_step": B_DOCS, "seq_len": SEQ, "hidden": HIDDEN,
+                   "vocab": VOCAB, "sharding": f"documents sharded over {world} rank(s), no data-path collective",
+                   "l2": f"inputs larger than L2: rotating {N_ROTATE} distinct (hidden, W, bias) sets, "
+                         f"{N_ROTATE} x 102 MB > 126 MB"},
+        "tokens_per_s": value * SEQ,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "steps": n_e2e,
+                "api": "splade_b200.head_forward (C-ABI splade_head_fwd) on pinned host buffers, "
+                       "H2D / compute / D2H on 3 streams, 2 slots", "checksum": checksum},
+        "gpu_launches": K,  # one head_fwd_kernel launch per step in the device-resident region (e2e: +K)
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
