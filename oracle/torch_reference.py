@@ -48,3 +48,20 @@ def v33_loss(anchor, positive, negative, lam_q, lam_d, lam_neg, temperature=1.0)
     labels = torch.arange(anchor.shape[0], device=anchor.device)
     infonce = F.cross_entropy(torch.cat([in_batch, hard], dim=1), labels)
     return infonce + lam_q * flops_reg(anchor) + lam_d * flops_reg(positive) + lam_neg * flops_reg(neg_flat)
+
+
+class ReferenceSpladeModule(torch.nn.Module):
+    """The reference model's statement (src/model/splade_modern.py:31-88) around a given HF MLM model: used by
+    the GPU parity tests as the same-device oracle for the drop-in encoder (the reference package itself does
+    not exist on the GPU box)."""
+
+    def __init__(self, hf_mlm_model):
+        super().__init__()
+        self.model = hf_mlm_model
+        self.config = hf_mlm_model.config
+        self.relu = torch.nn.ReLU()
+
+    def forward(self, input_ids, attention_mask, token_type_ids=None):
+        logits = self.model(input_ids=input_ids, attention_mask=attention_mask).logits
+        scores = torch.log1p(self.relu(logits)) * attention_mask.unsqueeze(-1).float()
+        return scores.max(dim=1).values, scores.max(dim=-1).values

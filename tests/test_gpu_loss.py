@@ -147,3 +147,18 @@ def test_loss_dict_is_one_sync_and_ema(cuda_device):
         want = 0.9 * want + 0.1 * nq
     assert fn.get_avg_nonzero()[0] == pytest.approx(want, rel=1e-6)
     assert d["nonzero_q"] == pytest.approx(nq)
+
+
+def test_inbatch_scores_bit_exact_at_training_shape(cuda_device):
+    """torch.mm under autocast (bf16 in, fp32 accumulate, bf16 out) vs splade_scores with round_bf16 at
+    [64, 50 000] x [50 000, 64]: identical bf16 bit patterns (up to rounding-boundary cases)."""
+    import splade_b200
+    q = _reps(64, 50000, 5, 0.05, cuda_device)
+    p = _reps(64, 50000, 6, 0.08, cuda_device)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ref = torch.mm(q, p.t())
+    ours = splade_b200.scores(q, p, True).to(torch.bfloat16)
+    assert ref.dtype == torch.bfloat16
+    assert int((ours != ref).sum()) <= 2
+    exact = q.double() @ p.double().t()
+    torch.testing.assert_close(splade_b200.scores(q, p, False).double(), exact, rtol=1e-5, atol=1e-4)
