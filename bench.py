@@ -187,6 +187,122 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------------
+# secondary metric: training-step tokens/s of the hot path (BASELINE config 4)
+# ------------------------------------------------------------------------------------------------------
+def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False):
+    """One C4 micro-step of the HOT PATH per rank: fused head forward for query (64x64), positive (64x256)
+    and k negatives (64k x 256) hidden states, SPLADELossV33 (InfoNCE + FLOPS, optional cross-GPU negatives),
+    backward through the loss and the sparse head backward, then the gradient all-reduce DDP would do for the
+    tensors this path owns (tied decoder/embedding matrix 153.6 MB fp32 + bias).  The ModernBERT trunk is not
+    part of the path (it stays the reference's) and is not timed here."""
+    import torch
+    import torch.distributed as dist
+
+    import splade_b200
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    Bq = B_DOCS
+    hq = torch.randn(Bq, 64, HIDDEN, generator=g).to(dev).requires_grad_(True)
+    hp = torch.randn(Bq, SEQ, HIDDEN, generator=g).to(dev).requires_grad_(True)
+    hn = torch.randn(Bq * k_neg, SEQ, HIDDEN, generator=g).to(dev).requires_grad_(True)
+    W = (torch.randn(VOCAB, HIDDEN, generator=g) * 0.0176).to(dev).requires_grad_(True)       # fp32 master copy
+    bias = (torch.randn(VOCAB, generator=g) * 0.02 - 1.0).to(dev).requires_grad_(True)        # sparse-ish regime
+    ones = lambda n, s: torch.ones(n, s, dtype=torch.int64, device=dev)  # noqa: E731
+    mq, mp, mn = ones(Bq, 64), ones(Bq, SEQ), ones(Bq * k_neg, SEQ)
+    loss_fn = splade_b200.SPLADELossV33(gather_negatives=gather)
+
+    def step(i):
+        for t in (hq, hp, hn, W, bias):
+            t.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            a, _ = splade_b200.splade_head(hq, W, bias, mq)
+            p, _ = splade_b200.splade_head(hp, W, bias, mp)
+            n, _ = splade_b200.splade_head(hn, W, bias, mn)
+            if k_neg > 1:
+                n = n.view(Bq, k_neg, -1)
+            loss, d = loss_fn(a, p, n, global_step=1000 + i)
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(W.grad, op=dist.ReduceOp.AVG)
+            dist.all_reduce(bias.grad, op=dist.ReduceOp.AVG)
+        with torch.no_grad():  # stand-in for the optimizer: bumps the version so the bf16 weight copy is re-cast
+            W.add_(W.grad, alpha=-1e-6)
+        return d
+
+    for i in range(warmup):
+        d = step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        d = step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    tokens = world * Bq * (64 + SEQ + SEQ * k_neg) * steps
+    head_flop = 2.0 * HIDDEN * VOCAB * Bq * (64 + SEQ + SEQ * k_neg)
+    return {"tokens_per_s": tokens / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
+            "workload": f"C4 hot path per GPU: head fwd+bwd for q 64x64 / pos 64x256 / neg {64 * k_neg}x256 + "
+                        f"SPLADELossV33 fwd+bwd (k={k_neg}, gather_negatives={gather}) + all-reduce of the tied "
+                        f"decoder matrix and bias grads; trunk excluded",
+            "head_fwd_tflop_per_step_per_gpu": head_flop / 1e12, "nonzero_d": d["nonzero_d"],
+            "scaling": "weak"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# context: full encode (unchanged ModernBERT trunk + head), ours vs the reference statement on the same GPU
+# ------------------------------------------------------------------------------------------------------
+def run_full_encode_leg(dev, steps=5, warmup=2):
+    """SPLADEModernBERT.encode on a random-init A.X-Encoder-base-shaped model (22 layers, hidden 768, vocab
+    50 000; config restated from huggingface/v33/config.json), batch 64 x L=256, under autocast(bf16): the
+    drop-in encoder vs the reference's statement (HF logits -> relu -> log1p -> mask -> max) on the same
+    device.  The trunk is identical on both sides; this shows what the fused head buys end to end."""
+    import tempfile
+
+    import torch
+    from transformers import AutoModelForMaskedLM, ModernBertConfig
+
+    import splade_b200
+    from oracle import torch_reference as TR
+    cfg = ModernBertConfig(vocab_size=VOCAB, hidden_size=HIDDEN, intermediate_size=1152, num_hidden_layers=22,
+                           num_attention_heads=12, pad_token_id=VOCAB - 1, bos_token_id=0, eos_token_id=1,
+                           cls_token_id=0, sep_token_id=1, max_position_embeddings=16384,
+                           global_attn_every_n_layers=3, local_attention=128)
+    torch.manual_seed(0)
+    hf = AutoModelForMaskedLM.from_config(cfg)
+    with tempfile.TemporaryDirectory() as d:
+        hf.save_pretrained(d)
+        ours = splade_b200.SPLADEModernBERT(model_name=d).to(dev).eval()
+    ref = TR.ReferenceSpladeModule(ours.model).eval()
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(6, VOCAB - 1, (B_DOCS, SEQ), generator=g).to(dev)
+    mask = torch.ones(B_DOCS, SEQ, dtype=torch.int64, device=dev)
+    out = {"params": sum(p.numel() for p in ours.parameters()), "batch": B_DOCS, "seq_len": SEQ}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for name, fn in (("ours", lambda: ours.encode(ids, mask)), ("reference_chain", lambda: ref(ids, mask)[0])):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_batch": ms, "docs_per_s": B_DOCS / ms * 1e3}
+    out["speedup"] = out["reference_chain"]["ms_per_batch"] / out["ours"]["ms_per_batch"]
+    return out
+
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
@@ -299,6 +415,19 @@ def run_ours(args):
     d2h_bytes = host_out[0].numel() * 4
     checksum = float(host_out[(n_e2e - 1) & 1][0, :8].sum())  # touch the result on the host
 
+    train = None
+    if not args.no_train:
+        del sets[1:], host_in, host_out, dev_in
+        train = run_train_leg(dev, world, rank, steps=max(3, min(20, K)), warmup=3, k_neg=1,
+                              gather=(world > 1 and args.gather_negatives))
+
+    full = None
+    if world == 1 and rank == 0 and not args.no_full_model:
+        try:
+            full = run_full_encode_leg(dev)
+        except Exception as e:  # context only: never fail the bench line over it
+            full = {"error": repr(e)[:200]}
+
     sampler.stop()
     clocks = sampler.summary(t_load0, t_load3)
 
@@ -350,6 +479,8 @@ def run_ours(args):
         "gpu_launches": K,  # one head_fwd_kernel launch per step in the device-resident region (e2e: +K)
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "train": train,
+        "full_encode": full,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -363,6 +494,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step leg")
+    ap.add_argument("--no-full-model", action="store_true", help="skip the trunk+head context leg")
+    ap.add_argument("--gather-negatives", action="store_true",
+                    help="training leg: all-gather positives across ranks (north-star extension)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -43,6 +43,11 @@ int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq
                     const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
                     const float* g_loss, float* dq, float* ddocs, float* dnegs, cudaStream_t stream);
 
+// scores_tc.cu (tcgen05 path used when round_bf16 != 0)
+size_t scores_tc_workspace_bytes(int Bq, int N, int V);
+int scores_tc_launch(const float* q, int Bq, const float* docs, int N, int V, void* workspace, size_t ws_bytes,
+                     float** partial_out, int* ksplit_out, cudaStream_t stream);
+
 // topk.cu
 int topk_launch(const float* rep, int B, int V, const uint8_t* blocklist, int k, int32_t* ids, float* vals,
                 int32_t* counts, cudaStream_t stream);

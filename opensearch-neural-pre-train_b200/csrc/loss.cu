@@ -484,13 +484,27 @@ size_t scores_workspace_bytes(int Bq, int N, int V) {
   if (Bq < 1 || N < 1 || V < 1) return 0;
   int ksplit, chunk;
   scores_plan(Bq, N, V, &ksplit, &chunk);
-  return align256(static_cast<size_t>(ksplit) * Bq * N * sizeof(float));
+  const size_t cuda_core = align256(static_cast<size_t>(ksplit) * Bq * N * sizeof(float));
+  return std::max(cuda_core, scores_tc_workspace_bytes(Bq, N, V));
 }
 
 int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int round_bf16, float* raw,
                   void* workspace, size_t ws_bytes, cudaStream_t stream) {
   if (!q || !docs || !raw) return set_error(kErrInvalidArg, "splade_scores: null pointer argument");
   if (Bq < 1 || N < 1 || V < 1) return set_error(kErrInvalidArg, "splade_scores: bad sizes Bq=%d N=%d V=%d", Bq, N, V);
+  const size_t n_out = static_cast<size_t>(Bq) * N;
+  if (round_bf16) {
+    // autocast mode: bf16 operands, fp32 accumulate -> tcgen05 tensor-core path (scores_tc.cu)
+    float* tc_partial = nullptr;
+    int tc_ksplit = 0;
+    const int rc = scores_tc_launch(q, Bq, docs, N, V, workspace, ws_bytes, &tc_partial, &tc_ksplit, stream);
+    if (rc != kOk) return rc;
+    scores_reduce_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, stream>>>(tc_partial, tc_ksplit,
+                                                                                       n_out, raw);
+    SPLADE_CUDA_OK(cudaGetLastError());
+    return kOk;
+  }
+  // fp32 mode (no autocast): full-precision CUDA-core path
   int ksplit, chunk;
   scores_plan(Bq, N, V, &ksplit, &chunk);
   const size_t need = align256(static_cast<size_t>(ksplit) * Bq * N * sizeof(float));

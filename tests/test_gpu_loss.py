@@ -162,3 +162,17 @@ def test_inbatch_scores_bit_exact_at_training_shape(cuda_device):
     assert int((ours != ref).sum()) <= 2
     exact = q.double() @ p.double().t()
     torch.testing.assert_close(splade_b200.scores(q, p, False).double(), exact, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("Bq,N,V", [(5, 7, 130), (64, 64, 50000), (130, 300, 1001), (64, 512, 50000), (1, 1, 8)])
+def test_tensor_core_scores_shapes(cuda_device, Bq, N, V):
+    """round_bf16 path = tcgen05 split-K GEMM (scores_tc.cu): bf16-rounded operands, fp32 accumulation, against a
+    float64 product of the same rounded operands; covers ragged M/N tiles, V not a multiple of 8 or 64."""
+    import splade_b200
+    q = _reps(Bq, V, 31, 0.3, cuda_device)
+    d = _reps(N, V, 32, 0.3, cuda_device)
+    raw = splade_b200.scores(q, d, True)
+    want = q.to(torch.bfloat16).double() @ d.to(torch.bfloat16).double().t()
+    torch.testing.assert_close(raw.double(), want, rtol=2e-5, atol=1e-4)
+    raw2 = splade_b200.scores(q, d, True)
+    assert torch.equal(raw, raw2)          # fixed-order split-K reduction: run-to-run deterministic
