@@ -26,7 +26,8 @@
 //   warp 0 lane 0 : TMA producer         (4-stage ring of {A 16 KB, B <=32 KB}, 128B swizzle)
 //   warp 1 lane 0 : tcgen05.mma issuer   (128 x N x 16 per instruction, fp32 accumulators in TMEM)
 //   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue             (TMEM lanes 32*(warp%4) .. +31), double-buffered accumulators
+//   warps 4..7    : epilogue             (TMEM lanes 32*(warp%4) .. +31), double-buffered accumulators;
+//                   the next tile's mask word and bias are prefetched one tile ahead
 #include "common.cuh"
 #include "kernels.h"
 
@@ -50,6 +51,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alig
 struct HeadFwdParams {
   const float* bias;
   const int32_t* mask;  // [B,S], nonzero = real token
+  const uint32_t* tile_masks;  // [n_tt][8]: 256-bit column validity bitmap per token tile (prepass)
   float* rep;           // [B,V]
   int32_t* argmax;      // [B,V]
   uint32_t* packed;     // [B,V] (bf16 bits << 16 | 0xFFFF - pos), only when a doc spans several tiles
@@ -82,6 +84,20 @@ __device__ __forceinline__ TileCoord tile_coord(const HeadFwdParams& p, int item
     t.ns = min(BLOCK_T, p.S - t.s0);
   }
   return t;
+}
+
+// Prepass: the 256-bit column-validity bitmap of every token tile (bit c = column c of the tile is a real,
+// unmasked token).  One CTA of 256 threads (8 warps = 8 words) per token tile; a few microseconds, and it takes
+// eight dependent global loads + ballots per tile out of the epilogue warps' critical path.
+__global__ void __launch_bounds__(256) build_tile_masks_kernel(const HeadFwdParams p, uint32_t* __restrict__ out) {
+  TileCoord t = tile_coord(p, blockIdx.x);  // vt = 0 since blockIdx.x < n_tt
+  const int col = threadIdx.x;
+  const int d = col / p.s_box;
+  const int s = col - d * p.s_box;
+  bool ok = false;
+  if (d < t.nb && s < t.ns) ok = p.mask[static_cast<size_t>(t.b0 + d) * p.S + t.s0 + s] != 0;
+  const uint32_t word = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0) out[blockIdx.x * 8 + (threadIdx.x >> 5)] = word;
 }
 
 // One 32-column window of one document, for one vocabulary entry per thread.
@@ -210,26 +226,45 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     // ------------------------------------------------------------------ epilogue (4 warps)
     const uint32_t q = warp & 3u;  // TMEM lane quarter this warp may read
     uint32_t it = 0;
+    // Operands of the NEXT tile (its mask word and this thread's bias) are fetched one tile ahead so that their
+    // global-load latency overlaps the window processing of the current tile (one warp per SM sub-partition has
+    // nothing else to hide it with).
+    uint32_t next_word = 0;
+    float next_bias = 0.f;
+    if (static_cast<int>(blockIdx.x) < total_items) {
+      const int vt0 = static_cast<int>(blockIdx.x) / p.n_tt;
+      const int tt0 = static_cast<int>(blockIdx.x) - vt0 * p.n_tt;
+      if (lane < 8) next_word = __ldg(&p.tile_masks[tt0 * 8 + lane]);
+      const int v0 = vt0 * BLOCK_V + static_cast<int>(q * 32u + lane);
+      if (v0 < p.V) next_bias = __ldg(&p.bias[v0]);
+    }
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const TileCoord t = tile_coord(p, item);
-
-      // Column validity bitmap of this tile (256 bits); lane w keeps word w.
-      uint32_t my_word = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const int col = w * 32 + static_cast<int>(lane);
-        const int d = col / p.s_box;
-        const int s = col - d * p.s_box;
-        bool ok = false;
-        if (d < t.nb && s < t.ns) ok = __ldg(&p.mask[static_cast<size_t>(t.b0 + d) * p.S + t.s0 + s]) != 0;
-        const uint32_t word = __ballot_sync(0xffffffffu, ok);
-        my_word = (lane == static_cast<uint32_t>(w)) ? word : my_word;
-      }
-
+      const uint32_t my_word = next_word;  // lane w < 8 keeps word w of this tile's validity bitmap
+      const float bias_v = next_bias;
       const int v = t.vt * BLOCK_V + static_cast<int>(q * 32u + lane);
-      const float bias_v = (v < p.V) ? __ldg(&p.bias[v]) : 0.f;
+      {
+        const int nitem = item + static_cast<int>(gridDim.x);
+        next_word = 0;
+        next_bias = 0.f;
+        if (nitem < total_items) {
+          const int nvt = nitem / p.n_tt;
+          const int ntt = nitem - nvt * p.n_tt;
+          if (lane < 8) next_word = __ldg(&p.tile_masks[ntt * 8 + lane]);
+          const int nv = nvt * BLOCK_V + static_cast<int>(q * 32u + lane);
+          if (nv < p.V) next_bias = __ldg(&p.bias[nv]);
+        }
+      }
+      // Is every column of every document of this tile valid?  (the common case: no padding inside the tile)
+      const int cols_valid = (t.ns == p.s_box) ? t.nb * p.s_box : -1;
+      uint32_t expect = 0;
+      if (lane < 8) {
+        const int rem = cols_valid - 32 * static_cast<int>(lane);
+        expect = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+      }
+      const bool tile_full = (cols_valid >= 0) && (__ballot_sync(0xffffffffu, my_word != expect) == 0u);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
@@ -246,9 +281,12 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           const int jhi = min(32, col_base + t.ns - w0);
           uint32_t range = (jhi >= 32) ? 0xffffffffu : ((1u << jhi) - 1u);
           range &= 0xffffffffu << jlo;
-          const uint32_t lo = __shfl_sync(0xffffffffu, my_word, w0 >> 5);
-          const uint32_t hi = __shfl_sync(0xffffffffu, my_word, min(7, (w0 >> 5) + 1));
-          const uint32_t vw = __funnelshift_r(lo, hi, w0 & 31) & range;
+          uint32_t vw = range;
+          if (!tile_full) {  // warp-uniform
+            const uint32_t lo = __shfl_sync(0xffffffffu, my_word, w0 >> 5);
+            const uint32_t hi = __shfl_sync(0xffffffffu, my_word, min(7, (w0 >> 5) + 1));
+            vw &= __funnelshift_r(lo, hi, w0 & 31);
+          }
           if (vw == 0u) continue;  // warp-uniform: fully padded window
 
           uint32_t r[32];
@@ -338,7 +376,10 @@ void head_fwd_plan(int B, int S, int* s_box, int* b_box, int* chunks_per_doc, in
 }
 
 size_t head_fwd_workspace_bytes(int B, int S, int V, bool want_tokw) {
-  size_t bytes = 0;
+  if (B <= 0 || S <= 0) return 0;
+  int s_box, b_box, cpd, n_tt, umma_n;
+  head_fwd_plan(B, S, &s_box, &b_box, &cpd, &n_tt, &umma_n);
+  size_t bytes = align256(static_cast<size_t>(n_tt) * 8 * sizeof(uint32_t));
   if (S > BLOCK_T) bytes += align256(static_cast<size_t>(B) * V * sizeof(uint32_t));
   if (want_tokw) bytes += align256(static_cast<size_t>(B) * S * sizeof(uint32_t));
   return bytes;
@@ -378,6 +419,9 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
   if (need > 0 && (!workspace || ws_bytes < need))
     return set_error(kErrWorkspace, "splade_head_fwd: workspace too small (%zu < %zu bytes)", ws_bytes, need);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint32_t* tile_masks = reinterpret_cast<uint32_t*>(ws);
+  p.tile_masks = tile_masks;
+  ws += align256(static_cast<size_t>(p.n_tt) * 8 * sizeof(uint32_t));
   if (p.chunks_per_doc > 1) {
     p.packed = reinterpret_cast<uint32_t*>(ws);
     const size_t n = static_cast<size_t>(B) * V * sizeof(uint32_t);
@@ -404,6 +448,9 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
     rc = encode_tmap_bf16(&tmap_h, hidden, 3, dims, strides, box);
     if (rc != kOk) return rc;
   }
+
+  build_tile_masks_kernel<<<p.n_tt, 256, 0, stream>>>(p, tile_masks);
+  SPLADE_CUDA_OK(cudaGetLastError());
 
   const int total_items = p.n_vt * p.n_tt;
   const int grid = std::min(sm_count(), total_items);
