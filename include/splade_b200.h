@@ -122,6 +122,7 @@ typedef struct splade_v33_scalar_args {
                              7 nonzero_q, 8 nonzero_d                                       */
   float* g_inbatch; /* [Bq,N] d loss / d raw_inbatch                                       */
   float* g_hard;    /* [Bq,k] d loss / d raw_hard                                          */
+  float* row_scratch; /* [3*Bq] per-row partial sums (workspace)                           */
 } splade_v33_scalar_args;
 
 int splade_v33_scalars(const splade_v33_scalar_args* args, void* stream);

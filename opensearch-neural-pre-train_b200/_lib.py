@@ -34,7 +34,7 @@ class V33ScalarArgs(Structure):
         ("raw_inbatch", c_void_p), ("raw_hard", c_void_p), ("raw_pos", c_void_p),
         ("teacher_kd", c_void_p), ("teacher_pos", c_void_p), ("teacher_neg", c_void_p),
         ("flops3", c_void_p),
-        ("scalars", c_void_p), ("g_inbatch", c_void_p), ("g_hard", c_void_p),
+        ("scalars", c_void_p), ("g_inbatch", c_void_p), ("g_hard", c_void_p), ("row_scratch", c_void_p),
     ]
 
 

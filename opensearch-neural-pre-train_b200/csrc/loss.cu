@@ -176,13 +176,16 @@ scores_partial_kernel(const float* __restrict__ q, int Bq, const float* __restri
   }
 }
 
-__global__ void scores_reduce_kernel(const float* __restrict__ partial, int ksplit, size_t n,
-                                     float* __restrict__ raw) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+// One warp per output element: lanes stride over the k-splits, then a fixed-order shuffle tree (deterministic).
+__global__ void __launch_bounds__(256)
+scores_reduce_kernel(const float* __restrict__ partial, int ksplit, size_t n, float* __restrict__ raw) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (i >= n) return;
+  const int lane = threadIdx.x & 31;
   float s = 0.f;
-  for (int k = 0; k < ksplit; ++k) s += partial[static_cast<size_t>(k) * n + i];
-  raw[i] = s;
+  for (int k = lane; k < ksplit; k += 32) s += partial[static_cast<size_t>(k) * n + i];
+  s = warp_sum(s);
+  if (lane == 0) raw[i] = s;
 }
 
 void scores_plan(int Bq, int N, int V, int* ksplit, int* chunk) {
@@ -205,7 +208,28 @@ rowdot_kernel(const float* __restrict__ q, const float* __restrict__ docs, int k
   const float* a = q + static_cast<size_t>(i) * V;
   const float* b = docs + static_cast<size_t>(blockIdx.x) * V;
   float s = 0.f;
-  for (int v = threadIdx.x; v < V; v += 256) s = fmaf(a[v], b[v], s);
+  if ((V & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    const int n4 = V >> 2;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int v0 = threadIdx.x; v0 < n4; v0 += 4 * 256) {  // four independent 16-byte load pairs in flight
+      float4 x[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * 256;
+        x[u] = (v < n4) ? __ldg(&a4[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        y[u] = (v < n4) ? __ldg(&b4[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      s0 = fmaf(x[0].x, y[0].x, fmaf(x[0].y, y[0].y, fmaf(x[0].z, y[0].z, fmaf(x[0].w, y[0].w, s0))));
+      s1 = fmaf(x[1].x, y[1].x, fmaf(x[1].y, y[1].y, fmaf(x[1].z, y[1].z, fmaf(x[1].w, y[1].w, s1))));
+      s2 = fmaf(x[2].x, y[2].x, fmaf(x[2].y, y[2].y, fmaf(x[2].z, y[2].z, fmaf(x[2].w, y[2].w, s2))));
+      s3 = fmaf(x[3].x, y[3].x, fmaf(x[3].y, y[3].y, fmaf(x[3].z, y[3].z, fmaf(x[3].w, y[3].w, s3))));
+    }
+    s = (s0 + s1) + (s2 + s3);
+  } else {
+    for (int v = threadIdx.x; v < V; v += 256) s = fmaf(a[v], b[v], s);
+  }
   s = warp_sum(s);
   __shared__ float sm[8];
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
@@ -219,7 +243,8 @@ rowdot_kernel(const float* __restrict__ q, const float* __restrict__ docs, int k
 }
 
 // ---------------------------------------------------------------------------------------------
-// Scalar stage: one CTA, one warp per query row (rows w, w+8, ... in order => deterministic sums).
+// Scalar stage: one warp per query row (8 rows per CTA) writes that row's loss terms and gradient rows;
+// v33_finalize_kernel then adds the rows up in index order (deterministic) and forms the total.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) v33_scalars_kernel(const splade_v33_scalar_args a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -227,7 +252,8 @@ __global__ void __launch_bounds__(256) v33_scalars_kernel(const splade_v33_scala
   const float invB = 1.f / static_cast<float>(Bq);
   float acc_nce = 0.f, acc_kd = 0.f, acc_mm = 0.f;
 
-  for (int i = warp; i < Bq; i += 8) {
+  const int i = blockIdx.x * 8 + warp;
+  if (i < Bq) {
     const float* rin = a.raw_inbatch + static_cast<size_t>(i) * N;
     const float* rh = a.raw_hard + static_cast<size_t>(i) * k;
     float* gin = a.g_inbatch + static_cast<size_t>(i) * N;
@@ -319,24 +345,38 @@ __global__ void __launch_bounds__(256) v33_scalars_kernel(const splade_v33_scala
     }
   }
 
-  __shared__ float s_part[3][8];
-  if (lane == 0) {
-    s_part[0][warp] = acc_nce;
-    s_part[1][warp] = acc_kd;
-    s_part[2][warp] = acc_mm;
+  if (i < Bq && lane == 0) {
+    a.row_scratch[i] = acc_nce;
+    a.row_scratch[Bq + i] = acc_kd;
+    a.row_scratch[2 * Bq + i] = acc_mm;
   }
+}
+
+__global__ void __launch_bounds__(256) v33_finalize_kernel(const splade_v33_scalar_args a) {
+  __shared__ float s_part[3][256];
+  const int Bq = a.Bq, k = a.k;
+  float nce = 0.f, kd = 0.f, mm = 0.f;
+  for (int i = threadIdx.x; i < Bq; i += 256) {  // fixed assignment + fixed tree => deterministic
+    nce += a.row_scratch[i];
+    kd += a.row_scratch[Bq + i];
+    mm += a.row_scratch[2 * Bq + i];
+  }
+  s_part[0][threadIdx.x] = nce;
+  s_part[1][threadIdx.x] = kd;
+  s_part[2][threadIdx.x] = mm;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float nce = 0.f, kd = 0.f, mm = 0.f;
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      nce += s_part[0][w];
-      kd += s_part[1][w];
-      mm += s_part[2][w];
+      for (int c = 0; c < 3; ++c) s_part[c][threadIdx.x] += s_part[c][threadIdx.x + o];
     }
-    nce *= invB;
-    kd *= invB;                                    // kl_div(reduction="batchmean")
-    mm *= invB / static_cast<float>(k);            // mse_loss mean over [Bq,k]
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float invB = 1.f / static_cast<float>(Bq);
+    nce = s_part[0][0] * invB;
+    kd = s_part[1][0] * invB;                            // kl_div(reduction="batchmean")
+    mm = s_part[2][0] * invB / static_cast<float>(k);    // mse_loss mean over [Bq,k]
     const float fq = a.flops3[0], fd = a.flops3[2], fn = a.flops3[4];
     float loss = nce + a.lambda_q * fq + a.lambda_d * fd + a.lambda_neg * fn;
     if (a.has_kd) loss += a.lambda_kd * kd;
@@ -457,6 +497,138 @@ loss_bwd_kernel(const float* __restrict__ q, const float* __restrict__ docs, con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Vectorised backward (V % 4 == 0): each thread owns FOUR vocabulary columns (16-byte loads/stores), a CTA of
+// 128 threads 512 columns and a tile of 16 queries (dq) or 16 documents (ddocs); the 16 x 32 block of G is
+// broadcast from shared memory with one LDS.128 per 16 FMAs.
+// ---------------------------------------------------------------------------------------------
+constexpr int VT = 16;   // rows (queries or documents) per CTA
+constexpr int VK = 32;   // reduction tile
+
+__device__ __forceinline__ void fma4(float4& a, float g, const float4& x) {
+  a.x = fmaf(g, x.x, a.x);
+  a.y = fmaf(g, x.y, a.y);
+  a.z = fmaf(g, x.z, a.z);
+  a.w = fmaf(g, x.w, a.w);
+}
+
+__global__ void __launch_bounds__(128)
+loss_bwd_dq_kernel(const float* __restrict__ q, const float* __restrict__ docs, const float* __restrict__ negs,
+                   int Bq, int N, int k, int V, const float* __restrict__ g_in, const float* __restrict__ g_hard,
+                   const float* __restrict__ cm_q, const float* __restrict__ cm_n, float cq, float cn,
+                   const float* __restrict__ g_loss, float* __restrict__ dq, float* __restrict__ dnegs) {
+  __shared__ __align__(16) float Gs[VT][VK];
+  const int c4 = blockIdx.x * 128 + threadIdx.x;  // float4 column index
+  const int n4 = V >> 2;
+  const bool live = c4 < n4;
+  const int i0 = blockIdx.y * VT;
+  const float gl = *g_loss;
+  float4 acc[VT];
+#pragma unroll
+  for (int ii = 0; ii < VT; ++ii) acc[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* docs4 = reinterpret_cast<const float4*>(docs);
+  for (int j0 = 0; j0 < N; j0 += VK) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < VT * VK; e += 128) {
+      const int ii = e / VK, jj = e % VK;
+      Gs[ii][jj] = (i0 + ii < Bq && j0 + jj < N) ? g_in[static_cast<size_t>(i0 + ii) * N + j0 + jj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int jj = 0; jj < VK; jj += 4) {
+      float4 d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        d[u] = (live && j0 + jj + u < N) ? __ldg(&docs4[static_cast<size_t>(j0 + jj + u) * n4 + c4])
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ii = 0; ii < VT; ++ii) {
+        const float4 g = *reinterpret_cast<const float4*>(&Gs[ii][jj]);
+        fma4(acc[ii], g.x, d[0]);
+        fma4(acc[ii], g.y, d[1]);
+        fma4(acc[ii], g.z, d[2]);
+        fma4(acc[ii], g.w, d[3]);
+      }
+    }
+  }
+  if (!live) return;
+  const float4 mq = __ldg(reinterpret_cast<const float4*>(cm_q) + c4);
+  const float4 mn = __ldg(reinterpret_cast<const float4*>(cm_n) + c4);
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  const float4* negs4 = reinterpret_cast<const float4*>(negs);
+  float4* dq4 = reinterpret_cast<float4*>(dq);
+  float4* dnegs4 = reinterpret_cast<float4*>(dnegs);
+#pragma unroll
+  for (int ii = 0; ii < VT; ++ii) {
+    const int i = i0 + ii;
+    if (i >= Bq) break;
+    const float4 qv = __ldg(&q4[static_cast<size_t>(i) * n4 + c4]);
+    float4 a = acc[ii];
+    for (int kk = 0; kk < k; ++kk) {
+      const float gh = __ldg(&g_hard[static_cast<size_t>(i) * k + kk]);
+      const size_t o = (static_cast<size_t>(i) * k + kk) * n4 + c4;
+      const float4 nv = __ldg(&negs4[o]);
+      fma4(a, gh, nv);
+      dnegs4[o] = make_float4(gl * (gh * qv.x + cn * mn.x), gl * (gh * qv.y + cn * mn.y),
+                              gl * (gh * qv.z + cn * mn.z), gl * (gh * qv.w + cn * mn.w));
+    }
+    dq4[static_cast<size_t>(i) * n4 + c4] = make_float4(gl * (a.x + cq * mq.x), gl * (a.y + cq * mq.y),
+                                                        gl * (a.z + cq * mq.z), gl * (a.w + cq * mq.w));
+  }
+}
+
+__global__ void __launch_bounds__(128)
+loss_bwd_ddocs_kernel(const float* __restrict__ q, int Bq, int N, int V, int label_offset,
+                      const float* __restrict__ g_in, const float* __restrict__ cm_d, float cd,
+                      const float* __restrict__ g_loss, float* __restrict__ ddocs) {
+  __shared__ __align__(16) float Gt[VT][VK];  // Gt[jj][ii] = g_in[i0+ii][j0+jj]
+  const int c4 = blockIdx.x * 128 + threadIdx.x;
+  const int n4 = V >> 2;
+  const bool live = c4 < n4;
+  const int j0 = blockIdx.y * VT;
+  const float gl = *g_loss;
+  float4 acc[VT];
+#pragma unroll
+  for (int jj = 0; jj < VT; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  for (int i0 = 0; i0 < Bq; i0 += VK) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < VT * VK; e += 128) {
+      const int ii = e / VT, jj = e % VT;  // consecutive threads read consecutive j of one query row
+      Gt[jj][ii] = (i0 + ii < Bq && j0 + jj < N) ? g_in[static_cast<size_t>(i0 + ii) * N + j0 + jj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int ii = 0; ii < VK; ii += 4) {
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        x[u] = (live && i0 + ii + u < Bq) ? __ldg(&q4[static_cast<size_t>(i0 + ii + u) * n4 + c4])
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int jj = 0; jj < VT; ++jj) {
+        const float4 g = *reinterpret_cast<const float4*>(&Gt[jj][ii]);
+        fma4(acc[jj], g.x, x[0]);
+        fma4(acc[jj], g.y, x[1]);
+        fma4(acc[jj], g.z, x[2]);
+        fma4(acc[jj], g.w, x[3]);
+      }
+    }
+  }
+  if (!live) return;
+  const float4 md = __ldg(reinterpret_cast<const float4*>(cm_d) + c4);
+  float4* dd4 = reinterpret_cast<float4*>(ddocs);
+#pragma unroll
+  for (int jj = 0; jj < VT; ++jj) {
+    const int j = j0 + jj;
+    if (j >= N) break;
+    const float f = (j >= label_offset && j < label_offset + Bq) ? cd : 0.f;
+    dd4[static_cast<size_t>(j) * n4 + c4] = make_float4(gl * (acc[jj].x + f * md.x), gl * (acc[jj].y + f * md.y),
+                                                        gl * (acc[jj].z + f * md.z), gl * (acc[jj].w + f * md.w));
+  }
+}
+
 }  // namespace
 
 size_t flops_workspace_bytes(int N, int V) {
@@ -499,8 +671,8 @@ int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int r
     int tc_ksplit = 0;
     const int rc = scores_tc_launch(q, Bq, docs, N, V, workspace, ws_bytes, &tc_partial, &tc_ksplit, stream);
     if (rc != kOk) return rc;
-    scores_reduce_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, stream>>>(tc_partial, tc_ksplit,
-                                                                                       n_out, raw);
+    scores_reduce_kernel<<<static_cast<unsigned>((n_out + 7) / 8), 256, 0, stream>>>(tc_partial, tc_ksplit, n_out,
+                                                                                   raw);
     SPLADE_CUDA_OK(cudaGetLastError());
     return kOk;
   }
@@ -515,7 +687,7 @@ int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int r
   scores_partial_kernel<<<grid, 256, 0, stream>>>(q, Bq, docs, N, V, round_bf16, chunk, partial);
   SPLADE_CUDA_OK(cudaGetLastError());
   const size_t n = static_cast<size_t>(Bq) * N;
-  scores_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(partial, ksplit, n, raw);
+  scores_reduce_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(partial, ksplit, n, raw);
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }
@@ -532,7 +704,8 @@ int v33_scalars_launch(const splade_v33_scalar_args* a, cudaStream_t stream) {
   if (!a) return set_error(kErrInvalidArg, "splade_v33_scalars: null args");
   if (a->Bq < 1 || a->N < 1 || a->k < 1)
     return set_error(kErrInvalidArg, "splade_v33_scalars: bad sizes Bq=%d N=%d k=%d", a->Bq, a->N, a->k);
-  if (!a->raw_inbatch || !a->raw_hard || !a->flops3 || !a->scalars || !a->g_inbatch || !a->g_hard)
+  if (!a->raw_inbatch || !a->raw_hard || !a->flops3 || !a->scalars || !a->g_inbatch || !a->g_hard ||
+      !a->row_scratch)
     return set_error(kErrInvalidArg, "splade_v33_scalars: null pointer argument");
   if (a->label_offset < 0 || a->label_offset + a->Bq > a->N)
     return set_error(kErrInvalidArg, "splade_v33_scalars: labels [%d,%d) outside the %d in-batch documents",
@@ -543,7 +716,8 @@ int v33_scalars_launch(const splade_v33_scalar_args* a, cudaStream_t stream) {
     return set_error(kErrInvalidArg, "splade_v33_scalars: MarginMSE needs raw_pos, teacher_pos and teacher_neg");
   if (!(a->temperature > 0.f) || (a->has_kd && !(a->kd_temperature > 0.f)))
     return set_error(kErrInvalidArg, "splade_v33_scalars: temperatures must be positive");
-  v33_scalars_kernel<<<1, 256, 0, stream>>>(*a);
+  v33_scalars_kernel<<<(a->Bq + 7) / 8, 256, 0, stream>>>(*a);
+  v33_finalize_kernel<<<1, 256, 0, stream>>>(*a);
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }
@@ -557,9 +731,21 @@ int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq
     return set_error(kErrInvalidArg, "splade_loss_bwd: null pointer argument");
   if (Bq < 1 || N < 1 || k < 1 || V < 1)
     return set_error(kErrInvalidArg, "splade_loss_bwd: bad sizes Bq=%d N=%d k=%d V=%d", Bq, N, k, V);
-  loss_bwd_kernel<<<(V + 127) / 128, 128, 0, stream>>>(q, docs, negs, Bq, N, k, V, label_offset, g_inbatch,
-                                                       g_hard, colmean_q, colmean_d, colmean_n, cq, cd, cn,
-                                                       g_loss, dq, ddocs, dnegs);
+  auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+  const bool vec_ok = (V % 4 == 0) && aligned16(q) && aligned16(docs) && aligned16(negs) && aligned16(dq) &&
+                      aligned16(ddocs) && aligned16(dnegs) && aligned16(colmean_q) && aligned16(colmean_d) &&
+                      aligned16(colmean_n);
+  if (vec_ok) {
+    const unsigned cx = static_cast<unsigned>((V / 4 + 127) / 128);
+    loss_bwd_dq_kernel<<<dim3(cx, (Bq + VT - 1) / VT), 128, 0, stream>>>(
+        q, docs, negs, Bq, N, k, V, g_inbatch, g_hard, colmean_q, colmean_n, cq, cn, g_loss, dq, dnegs);
+    loss_bwd_ddocs_kernel<<<dim3(cx, (N + VT - 1) / VT), 128, 0, stream>>>(q, Bq, N, V, label_offset, g_inbatch,
+                                                                         colmean_d, cd, g_loss, ddocs);
+  } else {
+    loss_bwd_kernel<<<(V + 127) / 128, 128, 0, stream>>>(q, docs, negs, Bq, N, k, V, label_offset, g_inbatch,
+                                                         g_hard, colmean_q, colmean_d, colmean_n, cq, cd, cn,
+                                                         g_loss, dq, ddocs, dnegs);
+  }
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }

@@ -30,15 +30,28 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 constexpr int TMEM_COLS = 256;
 
-__global__ void pack_bf16_kernel(const float* __restrict__ src, int rows, int V, int Vp,
-                                 __nv_bfloat16* __restrict__ dst) {
-  const size_t n = static_cast<size_t>(rows) * Vp;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t r = i / Vp;
-    const int v = static_cast<int>(i - r * Vp);
-    dst[i] = __float2bfloat16_rn(v < V ? src[r * V + v] : 0.f);
+// fp32 [rows, V] -> bf16 [rows, Vp] (Vp = V rounded up to 8, zero padded); grid (column chunks, rows).
+__global__ void __launch_bounds__(256)
+pack_bf16_kernel(const float* __restrict__ src, int V, int Vp, __nv_bfloat16* __restrict__ dst) {
+  const float* s = src + static_cast<size_t>(blockIdx.y) * V;
+  __nv_bfloat16* d = dst + static_cast<size_t>(blockIdx.y) * Vp;
+  const int v0 = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (v0 >= Vp) return;
+  float x[8];
+  if (v0 + 8 <= V && (reinterpret_cast<uintptr_t>(s + v0) & 15u) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(s + v0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(s + v0 + 4));
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = (v0 + e < V) ? s[v0 + e] : 0.f;
   }
+  uint4 o;
+  o.x = cvt_bf16x2(x[1], x[0]);
+  o.y = cvt_bf16x2(x[3], x[2]);
+  o.z = cvt_bf16x2(x[5], x[4]);
+  o.w = cvt_bf16x2(x[7], x[6]);
+  *reinterpret_cast<uint4*>(d + v0) = o;  // Vp % 8 == 0 and the workspace is 256-byte aligned
 }
 
 struct ScoresTcParams {
@@ -195,9 +208,9 @@ int scores_tc_launch(const float* q, int Bq, const float* docs, int N, int V, vo
   ws += align256(static_cast<size_t>(N) * Vp * 2);
   float* partial = reinterpret_cast<float*>(ws);
 
-  const int pack_grid = 4 * sm_count();
-  pack_bf16_kernel<<<pack_grid, 256, 0, stream>>>(q, Bq, V, Vp, q16);
-  pack_bf16_kernel<<<pack_grid, 256, 0, stream>>>(docs, N, V, Vp, d16);
+  const unsigned chunks = static_cast<unsigned>((Vp / 8 + 255) / 256);
+  pack_bf16_kernel<<<dim3(chunks, Bq), 256, 0, stream>>>(q, V, Vp, q16);
+  pack_bf16_kernel<<<dim3(chunks, N), 256, 0, stream>>>(docs, V, Vp, d16);
   SPLADE_CUDA_OK(cudaGetLastError());
 
   CUtensorMap tmap_q, tmap_d;

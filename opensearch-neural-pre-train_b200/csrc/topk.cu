@@ -2,20 +2,23 @@
 // (benchmark/encoders.py:320-343): keep weight > 0, drop block-listed ids, stable sort by weight descending
 // (=> ties by ascending term id, because the reference builds its dict in ascending id order), first k.
 // The reference does this per row on the host (.cpu(), python loops, sorted()); here one CTA handles one row:
-//   1. 3-pass MSB radix select (11/11/10 bits) on the fp32 bit patterns (positive floats order like uints)
-//      finds the k-th largest weight T;
-//   2. a coalesced, id-ordered compaction takes every weight > T plus the lowest-id ties == T;
+//   0. the row is read from HBM ONCE: filtered fp32 bit patterns ("keys", 0 = not a candidate) are staged in
+//      shared memory (200 KB for V = 50 000, one CTA of 1024 threads per SM); rows that do not fit fall back to
+//      re-reading the keys from global memory / L2 in every pass;
+//   1. 3-pass MSB radix select (11/11/10 bits) on the keys (positive floats order like uints) finds the k-th
+//      largest weight T; histogram updates are warp-aggregated (match.any) because pooled SPLADE weights take
+//      only ~200 distinct values per row;
+//   2. an id-ordered warp-ballot compaction takes every weight > T plus the lowest-id ties == T;
 //   3. a bitonic sort of the <= k survivors on (weight desc, id asc).
-// HBM/L2-bound: the row (V * 4 B) is streamed 5 times out of L2.
+// HBM-bound: algorithmic bytes = B * V * 4.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace splade {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kMaxK = 1024;
+constexpr int kSmemBudget = 227 * 1024;
 
 __device__ __forceinline__ uint32_t cand_key(const float* __restrict__ row, const uint8_t* __restrict__ block,
                                              int v) {
@@ -25,77 +28,162 @@ __device__ __forceinline__ uint32_t cand_key(const float* __restrict__ row, cons
   return __float_as_uint(x);  // > 0 for every candidate
 }
 
-__global__ void __launch_bounds__(kThreads)
-topk_kernel(const float* __restrict__ rep, int V, const uint8_t* __restrict__ block, int k, int kpad,
-            int32_t* __restrict__ ids, float* __restrict__ vals, int32_t* __restrict__ counts) {
-  extern __shared__ unsigned long long s_keys[];  // [kpad] (weight bits << 32 | ~id), sorted descending
-  __shared__ uint32_t hist[2048];
-  __shared__ uint32_t s_prefix, s_need, s_total;
-  __shared__ uint32_t w_gt[kWarps], w_eq[kWarps];
-
+// 3-pass MSB radix select (11/11/10 bits) over n keys delivered by key_fn (0 = not a candidate; keys below
+// `floor_key` are ignored).  Finds the key T of rank `k_rank` from the top.  Returns true when there are at most
+// k_rank candidates (then everything is kept); otherwise *T_out = T and *need_out = how many keys == T belong
+// to the top k_rank.  Block-uniform result; all threads of the CTA must call it.
+template <int kThreads, class KeyFn>
+__device__ __forceinline__ bool radix_select(KeyFn key_fn, int n, uint32_t k_rank, uint32_t floor_key,
+                                             uint32_t* hist, uint32_t* w_scratch, uint32_t* s_misc,
+                                             uint32_t* T_out, uint32_t* need_out) {
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kBinsPerThread = 2048 / kThreads;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* row = rep + static_cast<size_t>(blockIdx.x) * V;
-
-  // ---- 1. radix select the k-th largest candidate key
   uint32_t prefix = 0, prefix_mask = 0;
-  uint32_t need = static_cast<uint32_t>(k);  // rank (1-based, from the top) still to locate inside `prefix`
-  bool take_all = false;
+  uint32_t need = k_rank;  // rank (1-based, from the top) still to locate inside `prefix`
   const int shifts[3] = {21, 10, 0};
   const int bits[3] = {11, 11, 10};
   for (int pass = 0; pass < 3; ++pass) {
     for (int i = tid; i < 2048; i += kThreads) hist[i] = 0;
     __syncthreads();
     const uint32_t dmask = (1u << bits[pass]) - 1u;
-    for (int v = tid; v < V; v += kThreads) {
-      const uint32_t key = cand_key(row, block, v);
-      if (key != 0u && (key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shifts[pass]) & dmask], 1u);
+    for (int v0 = warp * 32; v0 < n; v0 += kThreads) {
+      const int v = v0 + lane;
+      const uint32_t key = (v < n) ? key_fn(v) : 0u;
+      const bool active = key != 0u && key >= floor_key && (key & prefix_mask) == prefix;
+      const uint32_t am = __ballot_sync(0xffffffffu, active);
+      if (active) {  // warp-aggregated histogram update: one shared-memory atomic per distinct digit
+        const uint32_t digit = (key >> shifts[pass]) & dmask;
+        const uint32_t peers = __match_any_sync(am, digit);
+        if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], static_cast<uint32_t>(__popc(peers)));
+      }
     }
     __syncthreads();
     {
-      // Parallel suffix scan over the 2048 bins: thread t owns bins [8t, 8t+8).  The wanted digit d* is the
-      // largest d with (number of keys whose digit >= d) >= need.
-      uint32_t local[8], tsum = 0;
+      // Parallel suffix scan over the 2048 bins: thread t owns kBinsPerThread consecutive bins.  The wanted
+      // digit d* is the largest d with (number of keys whose digit >= d) >= need.
+      uint32_t local[kBinsPerThread], tsum = 0;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        local[e] = hist[tid * 8 + e];
+      for (int e = 0; e < kBinsPerThread; ++e) {
+        local[e] = hist[tid * kBinsPerThread + e];
         tsum += local[e];
       }
       uint32_t incl = tsum;  // inclusive suffix sum across lanes (towards higher lanes)
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_down_sync(0xffffffffu, incl, o);
-        if (lane + o < 32) incl += n;
+        const uint32_t nn = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += nn;
       }
-      if (lane == 0) w_gt[warp] = incl;  // warp totals (w_gt reused as scratch before the compaction)
+      if (lane == 0) w_scratch[warp] = incl;
       __syncthreads();
       uint32_t above = 0, total = 0;
       for (int w = 0; w < kWarps; ++w) {
-        if (w > warp) above += w_gt[w];
-        total += w_gt[w];
+        const uint32_t t = w_scratch[w];
+        if (w > warp) above += t;
+        total += t;
       }
       uint32_t running = above + incl - tsum;  // keys with digit above this thread's bins
-      if (tid == 0) s_total = total;
+      if (tid == 0) s_misc[2] = total;
 #pragma unroll
-      for (int e = 7; e >= 0; --e) {
+      for (int e = kBinsPerThread - 1; e >= 0; --e) {
         if (running < need && running + local[e] >= need) {
-          s_prefix = static_cast<uint32_t>(tid * 8 + e);
-          s_need = need - running;
+          s_misc[0] = static_cast<uint32_t>(tid * kBinsPerThread + e);
+          s_misc[1] = need - running;
         }
         running += local[e];
       }
     }
     __syncthreads();
-    if (pass == 0 && s_total <= static_cast<uint32_t>(k)) {
-      take_all = true;  // fewer candidates than k: keep them all (block-uniform)
-      break;
-    }
-    prefix |= s_prefix << shifts[pass];
+    const uint32_t total = s_misc[2], digit = s_misc[0], new_need = s_misc[1];
+    __syncthreads();  // s_misc / w_scratch may be rewritten by the next pass
+    if (pass == 0 && total <= k_rank) return true;  // fewer candidates than k_rank: keep them all
+    prefix |= digit << shifts[pass];
     prefix_mask |= dmask << shifts[pass];
-    need = s_need;
-    __syncthreads();
+    need = new_need;
   }
-  // Now: take_all, or `prefix` = T (the k-th largest key) and `need` = how many keys == T to keep.
-  const uint32_t T = take_all ? 0u : prefix;
+  *T_out = prefix;
+  *need_out = need;
+  return false;
+}
+
+// kStaged: keys live in shared memory; otherwise they are recomputed from global memory on every access.
+template <int kThreads, bool kStaged>
+__global__ void __launch_bounds__(kThreads)
+topk_kernel(const float* __restrict__ rep, int V, const uint8_t* __restrict__ block, int k, int kpad,
+            int32_t* __restrict__ ids, float* __restrict__ vals, int32_t* __restrict__ counts) {
+  constexpr int kWarps = kThreads / 32;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_dyn);     // [kpad] sorted descending
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_dyn + static_cast<size_t>(kpad) * 8);  // [2048]
+  uint32_t* w_gt = hist + 2048;        // [kWarps]
+  uint32_t* w_eq = w_gt + kWarps;      // [kWarps]
+  uint32_t* s_misc = w_eq + kWarps;    // [4]: digit, need, total
+  uint32_t* tmax = s_misc + 4;         // [kThreads] per-thread maxima
+  uint32_t* staged = tmax + kThreads;  // [V] when kStaged
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = rep + static_cast<size_t>(blockIdx.x) * V;
+
+  // ---- 0. read the row once; remember each thread's largest key.  16-byte loads, four in flight per thread:
+  //          a single CTA has to pull its 200 KB row out of HBM with enough memory-level parallelism.
+  uint32_t my_max = 0;
+  const bool vec_ok = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+  if (vec_ok) {
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int n4 = V >> 2;
+    for (int i0 = tid; i0 < n4; i0 += 4 * kThreads) {
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kThreads;
+        x[u] = (i < n4) ? __ldg(&row4[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kThreads;
+        if (i < n4) {
+          const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+          uint32_t ks[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int v = 4 * i + e;
+            uint32_t key = (xs[e] > 0.f) ? __float_as_uint(xs[e]) : 0u;
+            if (key != 0u && block != nullptr && block[v] != 0) key = 0u;
+            ks[e] = key;
+            my_max = max(my_max, key);
+          }
+          if (kStaged) *reinterpret_cast<uint4*>(&staged[4 * i]) = make_uint4(ks[0], ks[1], ks[2], ks[3]);
+        }
+      }
+    }
+  } else {
+    for (int v = tid; v < V; v += kThreads) {
+      const uint32_t key = cand_key(row, block, v);
+      if (kStaged) staged[v] = key;
+      my_max = max(my_max, key);
+    }
+  }
+  tmax[tid] = my_max;
+  __syncthreads();
+  auto key_at = [&](int v) -> uint32_t { return kStaged ? staged[v] : cand_key(row, block, v); };
+
+  // ---- 1a. lower bound: the k largest per-thread maxima are k distinct elements of the row, so the k-th
+  //          largest key of the row is >= their k-th largest.  Everything below that bound (all but ~2k
+  //          elements of a dense row) is skipped by the histogram passes, whose cost is the number of
+  //          shared-memory atomics.
+  uint32_t floor_key = 0, T = 0, need = 0;
+  if (k <= kThreads) {
+    uint32_t dummy = 0;
+    const bool few = radix_select<kThreads>([&](int i) -> uint32_t { return tmax[i]; }, kThreads,
+                                            static_cast<uint32_t>(k), 0u, hist, w_gt, s_misc, &floor_key, &dummy);
+    if (few) floor_key = 0;
+  }
+  // ---- 1b. exact k-th largest key of the row
+  const bool take_all = radix_select<kThreads>(key_at, V, static_cast<uint32_t>(k), floor_key, hist, w_gt, s_misc,
+                                               &T, &need);
+  // "keep every candidate": with a lower bound in force the candidates are the keys >= floor_key
+  if (take_all) T = floor_key ? floor_key - 1u : 0u;
+  // Now: take_all, or T = the k-th largest key and `need` = how many keys == T to keep.
 
   // ---- 2. id-ordered compaction: warp w owns the contiguous id range [w*seg, (w+1)*seg)
   const int seg = ((V + kWarps - 1) / kWarps + 31) / 32 * 32;
@@ -103,10 +191,11 @@ topk_kernel(const float* __restrict__ rep, int V, const uint8_t* __restrict__ bl
   uint32_t n_gt = 0, n_eq = 0;
   for (int v0 = vbeg; v0 < vend; v0 += 32) {
     const int v = v0 + lane;
-    const uint32_t key = (v < vend) ? cand_key(row, block, v) : 0u;
+    const uint32_t key = (v < vend) ? key_at(v) : 0u;
     n_gt += __popc(__ballot_sync(0xffffffffu, key > T));
     n_eq += __popc(__ballot_sync(0xffffffffu, !take_all && key == T && key != 0u));
   }
+  __syncthreads();  // every thread is done reading w_gt as scan scratch
   if (lane == 0) {
     w_gt[warp] = n_gt;
     w_eq[warp] = n_eq;
@@ -127,7 +216,7 @@ topk_kernel(const float* __restrict__ rep, int V, const uint8_t* __restrict__ bl
   __syncthreads();
   for (int v0 = vbeg; v0 < vend; v0 += 32) {
     const int v = v0 + lane;
-    const uint32_t key = (v < vend) ? cand_key(row, block, v) : 0u;
+    const uint32_t key = (v < vend) ? key_at(v) : 0u;
     const bool gt = key > T;
     const bool eq = !take_all && key == T && key != 0u;
     const uint32_t m_gt = __ballot_sync(0xffffffffu, gt);
@@ -190,8 +279,17 @@ int topk_launch(const float* rep, int B, int V, const uint8_t* blocklist, int k,
   if (k < 1 || k > kMaxK) return set_error(kErrUnsupportedShape, "splade_topk: k=%d outside [1,%d]", k, kMaxK);
   int kpad = 2;
   while (kpad < k) kpad <<= 1;
-  topk_kernel<<<B, kThreads, static_cast<size_t>(kpad) * sizeof(unsigned long long), stream>>>(
-      rep, V, blocklist, k, kpad, ids, vals, counts);
+  const size_t fixed_1024 = static_cast<size_t>(kpad) * 8 + 2048 * 4 + (2 * 32 + 4 + 1024) * 4;
+  const size_t fixed_256 = static_cast<size_t>(kpad) * 8 + 2048 * 4 + (2 * 8 + 4 + 256) * 4;
+  const size_t staged_bytes = fixed_1024 + static_cast<size_t>(V) * 4;
+  if (staged_bytes <= static_cast<size_t>(kSmemBudget)) {
+    auto kernel = topk_kernel<1024, true>;
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(staged_bytes)));
+    kernel<<<B, 1024, staged_bytes, stream>>>(rep, V, blocklist, k, kpad, ids, vals, counts);
+  } else {
+    topk_kernel<256, false><<<B, 256, fixed_256, stream>>>(rep, V, blocklist, k, kpad, ids, vals, counts);
+  }
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }

@@ -260,6 +260,7 @@ class V33LossFunction(torch.autograd.Function):
             scalars = torch.zeros((16,), dtype=torch.float32, device=dev)
             g_in = torch.empty((Bq, N), dtype=torch.float32, device=dev)
             g_hard = torch.empty((Bq, k), dtype=torch.float32, device=dev)
+            row_scratch = torch.empty((3 * Bq,), dtype=torch.float32, device=dev)
             t_kd = _f32c(teacher_kd) if has_kd else None
             t_pos = _f32c(teacher_pos).view(Bq) if has_mmse else None
             t_neg = _f32c(teacher_neg).view(Bq, k) if has_mmse else None
@@ -272,7 +273,7 @@ class V33LossFunction(torch.autograd.Function):
                 raw_inbatch=raw_in.data_ptr(), raw_hard=raw_hard.data_ptr(), raw_pos=_ptr(raw_pos),
                 teacher_kd=_ptr(t_kd), teacher_pos=_ptr(t_pos), teacher_neg=_ptr(t_neg),
                 flops3=flops3.data_ptr(), scalars=scalars.data_ptr(), g_inbatch=g_in.data_ptr(),
-                g_hard=g_hard.data_ptr())
+                g_hard=g_hard.data_ptr(), row_scratch=row_scratch.data_ptr())
             check(lib.splade_v33_scalars(ctypes.byref(args), _stream(q)), "splade_v33_scalars")
         ctx.save_for_backward(q, d, n, g_in, g_hard, cm_q, cm_d, cm_n)
         ctx.meta = (Bq, N, k, V, off, cfg["lambda_q"], cfg["lambda_d"], cfg["lambda_neg"],

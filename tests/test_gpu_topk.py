@@ -77,3 +77,14 @@ def test_query_encode_shape_properties(cuda_device):
     assert bool(((rep > kth).sum(1) < k).all())                                          # nothing larger left out
     rows = [0, 17, 511]
     _compare(ids[rows], vals[rows], counts[rows], O.topk_emit(rep[rows].cpu().numpy(), k, None), k)
+
+
+def test_rows_larger_than_shared_memory_use_the_streaming_path(cuda_device):
+    """V = 250 002 (the older XLM-R vocabulary size) does not fit one SM's shared memory: same results through the
+    multi-pass global-memory variant."""
+    import splade_b200
+    g = torch.Generator().manual_seed(5)
+    B, V, k = 3, 250002, 100
+    rep = (torch.rand(B, V, generator=g) * 32).floor() / 32 * (torch.rand(B, V, generator=g) < 0.01)
+    ids, vals, counts = splade_b200.topk(rep.to(cuda_device), k, None)
+    _compare(ids, vals, counts, O.topk_emit(rep.numpy(), k, None), k)

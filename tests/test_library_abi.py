@@ -42,8 +42,8 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     import ctypes
     from splade_b200._lib import V33ScalarArgs
-    # 8 int32 + 8 float + 10 pointers, no padding on LP64
-    assert ctypes.sizeof(V33ScalarArgs) == 8 * 4 + 8 * 4 + 10 * 8
+    # 8 int32 + 8 float + 11 pointers, no padding on LP64
+    assert ctypes.sizeof(V33ScalarArgs) == 8 * 4 + 8 * 4 + 11 * 8
 
 
 def test_product_refuses_cpu_tensors():
