@@ -317,6 +317,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    numa_bound = splade_b200.distributed.bind_to_device_numa_node(local_rank) if world > 1 else False
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, max(args.warmup, 3)
@@ -475,7 +476,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "steps": n_e2e,
                 "api": "splade_b200.head_forward (C-ABI splade_head_fwd) on pinned host buffers, "
-                       "H2D / compute / D2H on 3 streams, 2 slots", "checksum": checksum},
+                       "H2D / compute / D2H on 3 streams, 2 slots", "checksum": checksum,
+                "numa_bound": numa_bound},
         "gpu_launches": K,  # one head_fwd_kernel launch per step in the device-resident region (e2e: +K)
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -19,6 +19,9 @@ namespace {
 
 constexpr int kMaxK = 1024;
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int32_t kNeedsFallback = -1;  // marker in counts[]: the fast kernel hands this row to the exact kernel
+constexpr int kListCap = 4096;           // fast path: candidates >= lower bound
+constexpr int kSortCap = 2048;           // fast path: survivors (> T plus all ties == T)
 
 __device__ __forceinline__ uint32_t cand_key(const float* __restrict__ row, const uint8_t* __restrict__ block,
                                              int v) {
@@ -110,7 +113,7 @@ __device__ __forceinline__ bool radix_select(KeyFn key_fn, int n, uint32_t k_ran
 template <int kThreads, bool kStaged>
 __global__ void __launch_bounds__(kThreads)
 topk_kernel(const float* __restrict__ rep, int V, const uint8_t* __restrict__ block, int k, int kpad,
-            int32_t* __restrict__ ids, float* __restrict__ vals, int32_t* __restrict__ counts) {
+            int32_t* __restrict__ ids, float* __restrict__ vals, int32_t* __restrict__ counts, int only_flagged) {
   constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_dyn);     // [kpad] sorted descending
@@ -123,6 +126,7 @@ topk_kernel(const float* __restrict__ rep, int V, const uint8_t* __restrict__ bl
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* row = rep + static_cast<size_t>(blockIdx.x) * V;
+  if (only_flagged && counts[blockIdx.x] != kNeedsFallback) return;  // block-uniform
 
   // ---- 0. read the row once; remember each thread's largest key.  16-byte loads, four in flight per thread:
   //          a single CTA has to pull its 200 KB row out of HBM with enough memory-level parallelism.
@@ -269,6 +273,187 @@ topk_kernel(const float* __restrict__ rep, int V, const uint8_t* __restrict__ bl
   if (tid == 0) counts[blockIdx.x] = static_cast<int32_t>(n_out);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path (the common case).  Two coalesced sweeps over the row instead of keeping it on chip:
+//   A. per-thread maxima -> lower bound L on the k-th largest key (see topk_kernel, step 1a);
+//   B. second sweep (L2-hot): every candidate >= L is appended to a small shared-memory list (warp-aggregated
+//      slot allocation).  A dense random-init row leaves ~2k of 50 000 elements, a trained one ~60;
+//   C. radix select on the LIST finds the exact k-th largest key T; everything > T and all ties == T move to
+//      the sort buffer;
+//   D. bitonic sort on (weight desc, id asc); the first k entries are the result.
+// Rows whose candidate list or tie set overflows the buffers (pathological ties, e.g. a constant row) are
+// flagged in counts[] and redone by the exact multi-pass kernel.
+// ---------------------------------------------------------------------------------------------
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads)
+topk_fast_kernel(const float* __restrict__ rep, int V, const uint8_t* __restrict__ block, int k,
+                 int32_t* __restrict__ ids, float* __restrict__ vals, int32_t* __restrict__ counts) {
+  constexpr int kWarps = kThreads / 32;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(smem_dyn);  // [kListCap]
+  unsigned long long* sortbuf = list + kListCap;                               // [kSortCap]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(sortbuf + kSortCap);            // [2048]
+  uint32_t* tmax = hist + 2048;                                                // [kThreads]
+  uint32_t* w_scratch = tmax + kThreads;                                       // [kWarps]
+  uint32_t* s_misc = w_scratch + kWarps;                                       // [4]
+  uint32_t* s_cnt = s_misc + 4;                                                // [2]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = rep + static_cast<size_t>(blockIdx.x) * V;
+  const bool vec_ok = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  const int n4 = V >> 2;
+  if (tid < 2) s_cnt[tid] = 0;
+
+  // ---- A. thread maxima over unblocked candidates
+  uint32_t my_max = 0;
+  auto consider = [&](float x, int v) {
+    const uint32_t key = (x > 0.f) ? __float_as_uint(x) : 0u;
+    if (key > my_max && !(block != nullptr && block[v] != 0)) my_max = key;
+  };
+  if (vec_ok) {
+    for (int i0 = tid; i0 < n4; i0 += 4 * kThreads) {
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kThreads;
+        x[u] = (i < n4) ? __ldg(&row4[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = 4 * (i0 + u * kThreads);
+        consider(x[u].x, v);
+        consider(x[u].y, v + 1);
+        consider(x[u].z, v + 2);
+        consider(x[u].w, v + 3);
+      }
+    }
+  } else {
+    for (int v = tid; v < V; v += kThreads) consider(row[v], v);
+  }
+  tmax[tid] = my_max;
+  __syncthreads();
+  uint32_t floor_key = 0, dummy = 0;
+  if (radix_select<kThreads>([&](int i) -> uint32_t { return tmax[i]; }, kThreads, static_cast<uint32_t>(k), 0u,
+                             hist, w_scratch, s_misc, &floor_key, &dummy))
+    floor_key = 0;
+  const uint32_t lo_key = max(floor_key, 1u);
+
+  // ---- B. collect every candidate >= lower bound (unordered)
+  auto append = [&](bool pred, uint32_t key, int v) {  // warp-collective
+    const uint32_t m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0u) return;
+    uint32_t base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(&s_cnt[0], static_cast<uint32_t>(__popc(m)));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (pred) {
+      const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+      if (slot < static_cast<uint32_t>(kListCap))
+        list[slot] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(~static_cast<uint32_t>(v));
+    }
+  };
+  auto test = [&](float x, int v, bool in) -> bool {
+    if (!in || !(x > 0.f) || __float_as_uint(x) < lo_key) return false;
+    return !(block != nullptr && block[v] != 0);
+  };
+  if (vec_ok) {
+    for (int b0 = warp * 32; b0 < n4; b0 += 2 * kThreads) {  // warp-uniform trip count
+      float4 x[2];
+      bool in[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = b0 + u * kThreads + lane;
+        in[u] = i < n4;
+        x[u] = in[u] ? __ldg(&row4[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int v = 4 * (b0 + u * kThreads + lane);
+        append(test(x[u].x, v, in[u]), __float_as_uint(x[u].x), v);
+        append(test(x[u].y, v + 1, in[u]), __float_as_uint(x[u].y), v + 1);
+        append(test(x[u].z, v + 2, in[u]), __float_as_uint(x[u].z), v + 2);
+        append(test(x[u].w, v + 3, in[u]), __float_as_uint(x[u].w), v + 3);
+      }
+    }
+  } else {
+    for (int b0 = warp * 32; b0 < V; b0 += kThreads) {
+      const int v = b0 + lane;
+      const bool in = v < V;
+      const float x = in ? row[v] : 0.f;
+      append(test(x, v, in), __float_as_uint(x), v);
+    }
+  }
+  __syncthreads();
+  const uint32_t n_list = s_cnt[0];
+  if (n_list > static_cast<uint32_t>(kListCap)) {  // block-uniform
+    if (tid == 0) counts[blockIdx.x] = kNeedsFallback;
+    return;
+  }
+
+  // ---- C. exact k-th largest inside the list; move survivors to the sort buffer
+  uint32_t T = 0, need = 0;
+  const bool take_all = radix_select<kThreads>([&](int i) -> uint32_t { return static_cast<uint32_t>(list[i] >> 32); },
+                                               static_cast<int>(n_list), static_cast<uint32_t>(k), 0u, hist,
+                                               w_scratch, s_misc, &T, &need);
+  if (take_all) T = 0;  // every list entry survives (there are at most k of them)
+  for (int b0 = warp * 32; b0 < static_cast<int>(n_list); b0 += kThreads) {
+    const int i = b0 + lane;
+    const unsigned long long e = (i < static_cast<int>(n_list)) ? list[i] : 0ull;
+    const bool pred = (i < static_cast<int>(n_list)) && static_cast<uint32_t>(e >> 32) >= max(T, 1u);
+    const uint32_t m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0u) continue;
+    uint32_t base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(&s_cnt[1], static_cast<uint32_t>(__popc(m)));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (pred) {
+      const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+      if (slot < static_cast<uint32_t>(kSortCap)) sortbuf[slot] = e;
+    }
+  }
+  __syncthreads();
+  const uint32_t n_sort = s_cnt[1];
+  if (n_sort > static_cast<uint32_t>(kSortCap)) {  // too many ties at the k-th value
+    if (tid == 0) counts[blockIdx.x] = kNeedsFallback;
+    return;
+  }
+  int npad = 2;
+  while (npad < static_cast<int>(n_sort)) npad <<= 1;
+  for (int i = static_cast<int>(n_sort) + tid; i < npad; i += kThreads) sortbuf[i] = 0ull;
+  __syncthreads();
+
+  // ---- D. bitonic sort, descending, on (weight bits, ~id)
+  for (int size = 2; size <= npad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < npad / 2; i += kThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = sortbuf[lo], b = sortbuf[hi];
+        if ((a < b) == desc) {
+          sortbuf[lo] = b;
+          sortbuf[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t n_out = min(static_cast<uint32_t>(k), n_sort);
+  int32_t* oid = ids + static_cast<size_t>(blockIdx.x) * k;
+  float* oval = vals + static_cast<size_t>(blockIdx.x) * k;
+  for (int i = tid; i < k; i += kThreads) {
+    if (static_cast<uint32_t>(i) < n_out) {
+      const unsigned long long p = sortbuf[i];
+      oid[i] = static_cast<int32_t>(~static_cast<uint32_t>(p & 0xffffffffull));
+      oval[i] = __uint_as_float(static_cast<uint32_t>(p >> 32));
+    } else {
+      oid[i] = -1;
+      oval[i] = 0.f;
+    }
+  }
+  if (tid == 0) counts[blockIdx.x] = static_cast<int32_t>(n_out);
+}
+
 }  // namespace
 
 int topk_launch(const float* rep, int B, int V, const uint8_t* blocklist, int k, int32_t* ids, float* vals,
@@ -279,6 +464,13 @@ int topk_launch(const float* rep, int B, int V, const uint8_t* blocklist, int k,
   if (k < 1 || k > kMaxK) return set_error(kErrUnsupportedShape, "splade_topk: k=%d outside [1,%d]", k, kMaxK);
   int kpad = 2;
   while (kpad < k) kpad <<= 1;
+  // 1. fast path for every row; 2. the exact kernel re-does only the rows the fast path flagged (it exits at once
+  //    for all others), so there is no host round trip and no data-dependent launch.
+  const size_t fast_smem = static_cast<size_t>(kListCap + kSortCap) * 8 + (2048 + 1024 + 32 + 4 + 2) * 4;
+  SPLADE_CUDA_OK(cudaFuncSetAttribute(topk_fast_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(fast_smem)));
+  topk_fast_kernel<1024><<<B, 1024, fast_smem, stream>>>(rep, V, blocklist, k, ids, vals, counts);
+  SPLADE_CUDA_OK(cudaGetLastError());
   const size_t fixed_1024 = static_cast<size_t>(kpad) * 8 + 2048 * 4 + (2 * 32 + 4 + 1024) * 4;
   const size_t fixed_256 = static_cast<size_t>(kpad) * 8 + 2048 * 4 + (2 * 8 + 4 + 256) * 4;
   const size_t staged_bytes = fixed_1024 + static_cast<size_t>(V) * 4;
@@ -286,9 +478,9 @@ int topk_launch(const float* rep, int B, int V, const uint8_t* blocklist, int k,
     auto kernel = topk_kernel<1024, true>;
     SPLADE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(staged_bytes)));
-    kernel<<<B, 1024, staged_bytes, stream>>>(rep, V, blocklist, k, kpad, ids, vals, counts);
+    kernel<<<B, 1024, staged_bytes, stream>>>(rep, V, blocklist, k, kpad, ids, vals, counts, 1);
   } else {
-    topk_kernel<256, false><<<B, 256, fixed_256, stream>>>(rep, V, blocklist, k, kpad, ids, vals, counts);
+    topk_kernel<256, false><<<B, 256, fixed_256, stream>>>(rep, V, blocklist, k, kpad, ids, vals, counts, 1);
   }
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;

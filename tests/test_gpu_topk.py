@@ -88,3 +88,22 @@ def test_rows_larger_than_shared_memory_use_the_streaming_path(cuda_device):
     rep = (torch.rand(B, V, generator=g) * 32).floor() / 32 * (torch.rand(B, V, generator=g) < 0.01)
     ids, vals, counts = splade_b200.topk(rep.to(cuda_device), k, None)
     _compare(ids, vals, counts, O.topk_emit(rep.numpy(), k, None), k)
+
+
+def test_pathological_rows_take_the_exact_fallback(cuda_device):
+    """Constant rows / huge tie sets overflow the fast path's candidate list and must be re-done by the exact
+    kernel with identical semantics (lowest ids win the ties)."""
+    import splade_b200
+    V, k = 50000, 64
+    rep = torch.zeros(5, V)
+    rep[0] = 0.5                                   # every entry ties
+    rep[1, ::2] = 0.25                             # 25 000 ties
+    rep[2] = torch.rand(V, generator=torch.Generator().manual_seed(1))   # ordinary dense row in between
+    rep[3, 100:5000] = 1.0                         # more ties at the k-th value than the sort buffer holds
+    rep[3, :10] = 2.0
+    rep[4, 7] = 3.0                                # almost empty row
+    block = torch.zeros(V, dtype=torch.uint8)
+    block[0] = 1
+    ids, vals, counts = splade_b200.topk(rep.to(cuda_device), k, block.to(cuda_device))
+    _compare(ids, vals, counts, O.topk_emit(rep.numpy(), k, block.numpy()), k)
+    assert ids[0].tolist() == list(range(1, 65)) and ids[3, :9].tolist() == list(range(1, 10))
