@@ -13,7 +13,8 @@
 // Both gathers read 16-bit rows that live in the 126 MB L2 (hidden 25 MB, W 77 MB at the headline shape);
 // the kernels are L2-gather-bound, not tensor-core work.
 //
-// Kernels: (1) bucket_by_position: per document counting sort of the active terms by argmax position;
+// Kernels: (1) bucket_count / bucket_scan / bucket_scatter: per-document counting sort of the active terms by
+//              argmax position, spread over (document, vocabulary chunk) CTAs;
 //          (2) dhidden_kernel: one warp per (b,s) row sums coef * W[v,:] over its bucket;
 //          (3) dw_kernel: one warp per vocabulary row sums coef * hidden[b,argmax,:] over the batch.
 #include "common.cuh"
@@ -29,34 +30,56 @@ __device__ __forceinline__ float coef_of(float g, float rep) { return rep > 0.f 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 // ---------------------------------------------------------------------------------------------
-// (1) per-document counting sort of active (b,v) by position.  One CTA per document.
+// (1) per-document counting sort of active (b,v) by position, spread over (document, vocabulary chunk) CTAs:
+//     count (shared-memory histogram per chunk, warp-aggregated, merged with global atomics) ->
+//     per-document exclusive scan -> scatter (warp-aggregated cursor allocation).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBucketThreads)
-bucket_by_position_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep,
-                          const int32_t* __restrict__ argmax, int S, int V, int32_t* __restrict__ row_ptr,
-                          int32_t* __restrict__ sorted_v, float* __restrict__ sorted_c) {
-  extern __shared__ int32_t sm[];
-  int32_t* cnt = sm;          // [S] counts, then exclusive offsets
-  int32_t* cur = sm + S;      // [S] scatter cursors
-  __shared__ int32_t warp_tot[32];
+constexpr int kChunk = 4096;  // vocabulary entries per CTA in the count / scatter passes
 
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x;
+__global__ void __launch_bounds__(256)
+bucket_count_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep,
+                    const int32_t* __restrict__ argmax, int S, int V, int32_t* __restrict__ counts /*[B,S+1]*/) {
+  extern __shared__ int32_t sm[];  // [S]
+  const int b = blockIdx.y;
+  const int v0 = blockIdx.x * kChunk, v1 = min(V, v0 + kChunk);
   const size_t base = static_cast<size_t>(b) * V;
-
-  for (int s = tid; s < S; s += kBucketThreads) cnt[s] = 0;
+  const int lane = threadIdx.x & 31;
+  for (int s = threadIdx.x; s < S; s += 256) sm[s] = 0;
   __syncthreads();
-  for (int v = tid; v < V; v += kBucketThreads) {
-    const float c = coef_of(g_rep[base + v], rep[base + v]);
-    if (c != 0.f) atomicAdd(&cnt[argmax[base + v]], 1);
+  for (int vb = v0 + (threadIdx.x & ~31); vb < v1; vb += 256) {  // warp-uniform trip count
+    const int v = vb + lane;
+    bool act = false;
+    int pos = 0;
+    if (v < v1) {
+      act = coef_of(g_rep[base + v], rep[base + v]) != 0.f;
+      pos = argmax[base + v];
+    }
+    const uint32_t am = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      const uint32_t peers = __match_any_sync(am, pos);
+      if (lane == __ffs(peers) - 1) atomicAdd(&sm[pos], __popc(peers));
+    }
   }
   __syncthreads();
+  int32_t* c = counts + static_cast<size_t>(b) * (S + 1);
+  for (int s = threadIdx.x; s < S; s += 256) {
+    const int n = sm[s];
+    if (n) atomicAdd(&c[s], n);
+  }
+}
 
-  // block-wide exclusive scan over S entries: contiguous chunk per thread
+// counts [B,S+1] -> row_ptr (exclusive scan, in place) and cursor copy.  One CTA per document.
+__global__ void __launch_bounds__(kBucketThreads)
+bucket_scan_kernel(int S, int32_t* __restrict__ row_ptr, int32_t* __restrict__ cursor) {
+  __shared__ int32_t warp_tot[32];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  int32_t* rp = row_ptr + static_cast<size_t>(b) * (S + 1);
+  int32_t* cur = cursor + static_cast<size_t>(b) * (S + 1);
   const int per = (S + kBucketThreads - 1) / kBucketThreads;
   const int lo = min(S, tid * per), hi = min(S, lo + per);
   int tsum = 0;
-  for (int s = lo; s < hi; ++s) tsum += cnt[s];
+  for (int s = lo; s < hi; ++s) tsum += rp[s];
   int incl = tsum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -66,7 +89,7 @@ bucket_by_position_kernel(const float* __restrict__ g_rep, const float* __restri
   if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
   __syncthreads();
   if (tid < 32) {
-    int w = warp_tot[tid];
+    const int w = warp_tot[tid];
     int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -77,20 +100,41 @@ bucket_by_position_kernel(const float* __restrict__ g_rep, const float* __restri
   }
   __syncthreads();
   int run = warp_tot[tid >> 5] + incl - tsum;
-  int32_t* rp = row_ptr + static_cast<size_t>(b) * (S + 1);
   for (int s = lo; s < hi; ++s) {
-    const int c = cnt[s];
-    cur[s] = run;
+    const int c = rp[s];
     rp[s] = run;
+    cur[s] = run;
     run += c;
   }
-  if (tid == kBucketThreads - 1) rp[S] = run;  // last thread's running total = number of active terms
-  __syncthreads();
+  if (tid == kBucketThreads - 1) rp[S] = run;  // total number of active terms of this document
+}
 
-  for (int v = tid; v < V; v += kBucketThreads) {
-    const float c = coef_of(g_rep[base + v], rep[base + v]);
-    if (c != 0.f) {
-      const int slot = atomicAdd(&cur[argmax[base + v]], 1);
+__global__ void __launch_bounds__(256)
+bucket_scatter_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep,
+                      const int32_t* __restrict__ argmax, int S, int V, int32_t* __restrict__ cursor,
+                      int32_t* __restrict__ sorted_v, float* __restrict__ sorted_c) {
+  const int b = blockIdx.y;
+  const int v0 = blockIdx.x * kChunk, v1 = min(V, v0 + kChunk);
+  const size_t base = static_cast<size_t>(b) * V;
+  const int lane = threadIdx.x & 31;
+  int32_t* cur = cursor + static_cast<size_t>(b) * (S + 1);
+  for (int vb = v0 + (threadIdx.x & ~31); vb < v1; vb += 256) {
+    const int v = vb + lane;
+    float c = 0.f;
+    int pos = 0;
+    if (v < v1) {
+      c = coef_of(g_rep[base + v], rep[base + v]);
+      pos = argmax[base + v];
+    }
+    const bool act = c != 0.f;
+    const uint32_t am = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      const uint32_t peers = __match_any_sync(am, pos);
+      const int leader = __ffs(peers) - 1;
+      int slot0 = 0;
+      if (lane == leader) slot0 = atomicAdd(&cur[pos], __popc(peers));
+      slot0 = __shfl_sync(peers, slot0, leader);
+      const int slot = slot0 + __popc(peers & ((1u << lane) - 1u));
       sorted_v[base + slot] = v;
       sorted_c[base + slot] = c;
     }
@@ -169,40 +213,52 @@ dhidden_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// (3) dW + dbias: one warp per vocabulary row.
+// (3) dW + dbias.  A CTA owns 32 consecutive vocabulary rows: it first stages coef[b][32] and argmax[b][32]
+//     for the whole batch in shared memory with fully coalesced 128-byte reads (the three [B,V] arrays are read
+//     exactly once), then each of its 8 warps produces 4 rows, skipping inactive (b,v) pairs.
 // ---------------------------------------------------------------------------------------------
 template <int kChunks>
 __global__ void __launch_bounds__(256)
 dw_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep, const int32_t* __restrict__ argmax,
           const uint16_t* __restrict__ hidden, int B, int S, int H, int V, float* __restrict__ dW,
           float* __restrict__ dbias) {
-  const int lane = threadIdx.x & 31;
-  const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (v >= V) return;
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  float* s_c = reinterpret_cast<float*>(dw_smem);                  // [B][32]
+  int32_t* s_p = reinterpret_cast<int32_t*>(s_c + static_cast<size_t>(B) * 32);  // [B][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v0 = blockIdx.x * 32;
 
-  float acc[kChunks][8];
-#pragma unroll
-  for (int i = 0; i < kChunks; ++i)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
-  float bsum = 0.f;
-
-  for (int b0 = 0; b0 < B; b0 += 32) {
-    const int n = min(32, B - b0);
-    float my_c = 0.f;
-    int my_s = 0;
-    if (lane < n) {
-      const size_t o = static_cast<size_t>(b0 + lane) * V + v;
-      my_c = coef_of(g_rep[o], rep[o]);
-      my_s = argmax[o];
+  for (int idx = threadIdx.x; idx < B * 32; idx += 256) {
+    const int b = idx >> 5, j = idx & 31;
+    const int v = v0 + j;
+    float c = 0.f;
+    int pos = 0;
+    if (v < V) {
+      const size_t o = static_cast<size_t>(b) * V + v;
+      c = coef_of(g_rep[o], rep[o]);
+      pos = argmax[o];
     }
-    bsum += my_c;
+    s_c[idx] = c;
+    s_p[idx] = pos;
+  }
+  __syncthreads();
+
+  for (int r = 0; r < 4; ++r) {
+    const int j = warp * 4 + r;
+    const int v = v0 + j;
+    if (v >= V) break;  // warp-uniform
+    float acc[kChunks][8];
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+    float bsum = 0.f;
 #pragma unroll 4
-    for (int l = 0; l < n; ++l) {
-      const float c = __shfl_sync(0xffffffffu, my_c, l);
-      const int s = __shfl_sync(0xffffffffu, my_s, l);
-      if (c == 0.f) continue;  // warp-uniform
-      const uint16_t* hrow = hidden + (static_cast<size_t>(b0 + l) * S + s) * H;
+    for (int b = 0; b < B; ++b) {
+      const float c = s_c[b * 32 + j];  // broadcast
+      if (c == 0.f) continue;           // warp-uniform
+      bsum += c;
+      const uint16_t* hrow = hidden + (static_cast<size_t>(b) * S + s_p[b * 32 + j]) * H;
 #pragma unroll
       for (int i = 0; i < kChunks; ++i) {
         const int h = i * 256 + lane * 8;
@@ -212,22 +268,20 @@ dw_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep, const 
         }
       }
     }
-  }
+    if (lane == 0) dbias[v] = bsum;
+    float* out = dW + static_cast<size_t>(v) * H;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-  if (lane == 0) dbias[v] = bsum;
-  float* out = dW + static_cast<size_t>(v) * H;
-#pragma unroll
-  for (int i = 0; i < kChunks; ++i) {
-    const int h = i * 256 + lane * 8;
-    if (h < H) store_row8(out + h, acc[i], 1.f);
+    for (int i = 0; i < kChunks; ++i) {
+      const int h = i * 256 + lane * 8;
+      if (h < H) store_row8(out + h, acc[i], 1.f);
+    }
   }
 }
 
 }  // namespace
 
 size_t head_bwd_workspace_bytes(int B, int S, int V) {
-  return align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t)) +
+  return 2 * align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t)) +
          2 * align256(static_cast<size_t>(B) * V * sizeof(int32_t));
 }
 
@@ -241,9 +295,11 @@ int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax,
   if (H % 8 != 0 || H > 1024)
     return set_error(kErrUnsupportedShape, "splade_head_bwd: hidden size %d must be a multiple of 8 and <= 1024",
                      H);
-  const size_t bucket_smem = static_cast<size_t>(2) * S * sizeof(int32_t);
+  const size_t bucket_smem = static_cast<size_t>(S) * sizeof(int32_t);
   if (bucket_smem > 200 * 1024)
     return set_error(kErrUnsupportedShape, "splade_head_bwd: sequence length %d too long for the bucket pass", S);
+  if (static_cast<size_t>(B) * 32 * 8 > 200 * 1024)
+    return set_error(kErrUnsupportedShape, "splade_head_bwd: batch %d too large for the dW staging buffer (<= 800)", B);
   int rc = require_sm100("splade_head_bwd");
   if (rc != kOk) return rc;
   const size_t need = head_bwd_workspace_bytes(B, S, V);
@@ -259,40 +315,54 @@ int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax,
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int32_t* row_ptr = reinterpret_cast<int32_t*>(ws);
   ws += align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t));
+  int32_t* cursor = reinterpret_cast<int32_t*>(ws);
+  ws += align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t));
   int32_t* sorted_v = reinterpret_cast<int32_t*>(ws);
   ws += align256(static_cast<size_t>(B) * V * sizeof(int32_t));
   float* sorted_c = reinterpret_cast<float*>(ws);
 
+  SPLADE_CUDA_OK(cudaMemsetAsync(row_ptr, 0, static_cast<size_t>(B) * (S + 1) * sizeof(int32_t), stream));
   if (bucket_smem > 48 * 1024) {
-    SPLADE_CUDA_OK(cudaFuncSetAttribute(bucket_by_position_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(bucket_smem)));
   }
-  bucket_by_position_kernel<<<B, kBucketThreads, bucket_smem, stream>>>(g_rep, rep, argmax, S, V, row_ptr,
-                                                                      sorted_v, sorted_c);
+  const dim3 vchunks((V + kChunk - 1) / kChunk, B);
+  bucket_count_kernel<<<vchunks, 256, bucket_smem, stream>>>(g_rep, rep, argmax, S, V, row_ptr);
+  bucket_scan_kernel<<<B, kBucketThreads, 0, stream>>>(S, row_ptr, cursor);
+  bucket_scatter_kernel<<<vchunks, 256, 0, stream>>>(g_rep, rep, argmax, S, V, cursor, sorted_v, sorted_c);
   SPLADE_CUDA_OK(cudaGetLastError());
 
   const uint16_t* Wb = static_cast<const uint16_t*>(W);
   const uint16_t* Hb = static_cast<const uint16_t*>(hidden);
   const long long rows = static_cast<long long>(B) * S;
   const unsigned grid_h = static_cast<unsigned>((rows + 7) / 8);
-  const unsigned grid_w = static_cast<unsigned>((V + 7) / 8);
+  const unsigned grid_w = static_cast<unsigned>((V + 31) / 32);
+  const size_t dw_smem_bytes = static_cast<size_t>(B) * 32 * 8;
   const int chunks = (H + 255) / 256;
   switch (chunks) {
     case 1:
       dhidden_kernel<1><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
-      dw_kernel<1><<<grid_w, 256, 0, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
+      SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(dw_smem_bytes)));
+      dw_kernel<1><<<grid_w, 256, dw_smem_bytes, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
       break;
     case 2:
       dhidden_kernel<2><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
-      dw_kernel<2><<<grid_w, 256, 0, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
+      SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(dw_smem_bytes)));
+      dw_kernel<2><<<grid_w, 256, dw_smem_bytes, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
       break;
     case 3:
       dhidden_kernel<3><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
-      dw_kernel<3><<<grid_w, 256, 0, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
+      SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(dw_smem_bytes)));
+      dw_kernel<3><<<grid_w, 256, dw_smem_bytes, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
       break;
     default:
       dhidden_kernel<4><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
-      dw_kernel<4><<<grid_w, 256, 0, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
+      SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(dw_smem_bytes)));
+      dw_kernel<4><<<grid_w, 256, dw_smem_bytes, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
       break;
   }
   SPLADE_CUDA_OK(cudaGetLastError());
