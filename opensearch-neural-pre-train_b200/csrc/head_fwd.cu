@@ -32,6 +32,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace splade {
 namespace {
@@ -62,16 +63,22 @@ struct HeadFwdParams {
   int chunks_per_doc;   // 1 when S <= 256
   int umma_n;
   uint32_t stage_tx_bytes;
+  // CTA-pair kernel only: how the token rows of a tile are split between the two CTAs
+  int pair_split_docs;   // 1: each CTA takes b_box/2 documents; 0: each CTA takes half of one document's rows
+  int pair_half_rows;    // token rows per CTA (= umma_n / 2)
 };
 
 struct TileCoord {
   int vt, b0, nb, s0, ns;
 };
 
-__device__ __forceinline__ TileCoord tile_coord(const HeadFwdParams& p, int item) {
+// item -> (vocab tile, token tile).  vt_mul / vt_add map the item's vocabulary index to this CTA's 128-row tile:
+// (1, 0) for the single-CTA kernel, (2, cluster rank) for the CTA-pair kernel (256 rows per item).
+__device__ __forceinline__ TileCoord tile_coord(const HeadFwdParams& p, int item, int vt_mul = 1, int vt_add = 0) {
   TileCoord t;
-  t.vt = item / p.n_tt;
-  const int tt = item - t.vt * p.n_tt;
+  const int vi = item / p.n_tt;
+  t.vt = vi * vt_mul + vt_add;
+  const int tt = item - vi * p.n_tt;
   if (p.chunks_per_doc == 1) {
     t.b0 = tt * p.b_box;
     t.nb = min(p.b_box, p.B - t.b0);
@@ -128,6 +135,128 @@ __device__ __forceinline__ int window_max(const uint32_t (&r)[32], float bias_v,
     }
   }
   return wkey;
+}
+
+// Everything the epilogue warps need to know about the kernel they run in.
+struct EpilogueCtx {
+  uint32_t tmem_base;
+  uint64_t* tfull_bar;    // [2] accumulator-ready barriers of THIS CTA
+  uint32_t tempty_addr;   // shared::cluster address of tempty_bar[0] of the CTA that issues the MMAs
+  int item0, item_step, n_items;
+  int vt_mul, vt_add;
+};
+
+// Epilogue of one CTA: drains 128 TMEM lanes (vocabulary rows) x up to 256 columns (tokens) per item.
+// Called by the four epilogue warps (warp % 4 = TMEM lane quarter).
+template <bool kTokW>
+__device__ __forceinline__ void epilogue_loop(const HeadFwdParams& p, const EpilogueCtx& c, uint32_t warp,
+                                              uint32_t lane) {
+  const uint32_t q = warp & 3u;  // TMEM lane quarter this warp may read
+  uint32_t it = 0;
+  // Operands of the NEXT tile (its mask word and this thread's bias) are fetched one tile ahead so that their
+  // global-load latency overlaps the window processing of the current tile (one warp per SM sub-partition has
+  // nothing else to hide it with).
+  uint32_t next_word = 0;
+  float next_bias = 0.f;
+  if (c.item0 < c.n_items) {
+    const int vi0 = c.item0 / p.n_tt;
+    const int vt0 = vi0 * c.vt_mul + c.vt_add;
+    const int tt0 = c.item0 - vi0 * p.n_tt;
+    if (lane < 8) next_word = __ldg(&p.tile_masks[tt0 * 8 + lane]);
+    const int v0 = vt0 * BLOCK_V + static_cast<int>(q * 32u + lane);
+    if (v0 < p.V) next_bias = __ldg(&p.bias[v0]);
+  }
+  for (int item = c.item0; item < c.n_items; item += c.item_step, ++it) {
+    const uint32_t acc = it & 1u;
+    const uint32_t acc_phase = (it >> 1) & 1u;
+    const TileCoord t = tile_coord(p, item, c.vt_mul, c.vt_add);
+    const uint32_t my_word = next_word;  // lane w < 8 keeps word w of this tile's validity bitmap
+    const float bias_v = next_bias;
+    const int v = t.vt * BLOCK_V + static_cast<int>(q * 32u + lane);
+    {
+      const int nitem = item + c.item_step;
+      next_word = 0;
+      next_bias = 0.f;
+      if (nitem < c.n_items) {
+        const int nvi = nitem / p.n_tt;
+        const int nvt = nvi * c.vt_mul + c.vt_add;
+        const int ntt = nitem - nvi * p.n_tt;
+        if (lane < 8) next_word = __ldg(&p.tile_masks[ntt * 8 + lane]);
+        const int nv = nvt * BLOCK_V + static_cast<int>(q * 32u + lane);
+        if (nv < p.V) next_bias = __ldg(&p.bias[nv]);
+      }
+    }
+    // Is every column of every document of this tile valid?  (the common case: no padding inside the tile)
+    const int cols_valid = (t.ns == p.s_box) ? t.nb * p.s_box : -1;
+    uint32_t expect = 0;
+    if (lane < 8) {
+      const int rem = cols_valid - 32 * static_cast<int>(lane);
+      expect = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+    }
+    const bool tile_full = (cols_valid >= 0) && (__ballot_sync(0xffffffffu, my_word != expect) == 0u);
+
+    mbar_wait(&c.tfull_bar[acc], acc_phase);
+    tcgen05_fence_after();
+    const uint32_t t_lane = c.tmem_base + ((q * 32u) << 16) + acc * BLOCK_T;
+
+    for (int d = 0; d < t.nb; ++d) {
+      const int b = t.b0 + d;
+      const int col_base = d * p.s_box;
+      int best_val = 0, best_pos = 0;
+      const int nwin = (t.ns + 31) >> 5;
+      for (int cw = 0; cw < nwin; ++cw) {
+        const int w0 = min(col_base + 32 * cw, BLOCK_T - 32);
+        const int jlo = max(0, col_base - w0);
+        const int jhi = min(32, col_base + t.ns - w0);
+        uint32_t range = (jhi >= 32) ? 0xffffffffu : ((1u << jhi) - 1u);
+        range &= 0xffffffffu << jlo;
+        uint32_t vw = range;
+        if (!tile_full) {  // warp-uniform
+          const uint32_t lo = __shfl_sync(0xffffffffu, my_word, w0 >> 5);
+          const uint32_t hi = __shfl_sync(0xffffffffu, my_word, min(7, (w0 >> 5) + 1));
+          vw &= __funnelshift_r(lo, hi, w0 & 31);
+        }
+        if (vw == 0u) continue;  // warp-uniform: fully padded window
+
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(w0), r);
+        tmem_ld_wait();
+
+        int tok_mine = 0;
+        int wkey;
+        if (vw == 0xffffffffu) {
+          wkey = window_max<true, kTokW>(r, bias_v, vw, lane, tok_mine);
+        } else {
+          wkey = window_max<false, kTokW>(r, bias_v, vw, lane, tok_mine);
+        }
+        const int pos0 = t.s0 + (w0 - col_base);  // sequence position of window column 0
+        const int wval = wkey >> 16;
+        if (wval > best_val) {  // strict: earlier windows win ties (first occurrence)
+          best_val = wval;
+          best_pos = pos0 + 31 - (wkey & 31);
+        }
+        if (kTokW) {
+          const int tv = tok_mine >> 16;
+          if (tv > 0 && ((vw >> lane) & 1u)) {
+            atomicMax(&p.tokw_bits[static_cast<size_t>(b) * p.S + pos0 + static_cast<int>(lane)],
+                      static_cast<uint32_t>(tv));
+          }
+        }
+      }
+      if (v < p.V) {
+        const size_t o = static_cast<size_t>(b) * p.V + v;
+        if (p.chunks_per_doc == 1) {
+          p.rep[o] = log1pf(bf16_bits_to_float(static_cast<uint32_t>(best_val)));
+          p.argmax[o] = best_pos;
+        } else {
+          atomicMax(&p.packed[o], (static_cast<uint32_t>(best_val) << 16) |
+                                      (0xFFFFu - static_cast<uint32_t>(best_pos)));
+        }
+      }
+    }
+    tcgen05_fence_before();
+    mbar_arrive_cluster(c.tempty_addr + acc * 8u);
+  }
 }
 
 template <bool kTokW>
@@ -224,110 +353,16 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (4 warps)
-    const uint32_t q = warp & 3u;  // TMEM lane quarter this warp may read
-    uint32_t it = 0;
-    // Operands of the NEXT tile (its mask word and this thread's bias) are fetched one tile ahead so that their
-    // global-load latency overlaps the window processing of the current tile (one warp per SM sub-partition has
-    // nothing else to hide it with).
-    uint32_t next_word = 0;
-    float next_bias = 0.f;
-    if (static_cast<int>(blockIdx.x) < total_items) {
-      const int vt0 = static_cast<int>(blockIdx.x) / p.n_tt;
-      const int tt0 = static_cast<int>(blockIdx.x) - vt0 * p.n_tt;
-      if (lane < 8) next_word = __ldg(&p.tile_masks[tt0 * 8 + lane]);
-      const int v0 = vt0 * BLOCK_V + static_cast<int>(q * 32u + lane);
-      if (v0 < p.V) next_bias = __ldg(&p.bias[v0]);
-    }
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-      const uint32_t acc = it & 1u;
-      const uint32_t acc_phase = (it >> 1) & 1u;
-      const TileCoord t = tile_coord(p, item);
-      const uint32_t my_word = next_word;  // lane w < 8 keeps word w of this tile's validity bitmap
-      const float bias_v = next_bias;
-      const int v = t.vt * BLOCK_V + static_cast<int>(q * 32u + lane);
-      {
-        const int nitem = item + static_cast<int>(gridDim.x);
-        next_word = 0;
-        next_bias = 0.f;
-        if (nitem < total_items) {
-          const int nvt = nitem / p.n_tt;
-          const int ntt = nitem - nvt * p.n_tt;
-          if (lane < 8) next_word = __ldg(&p.tile_masks[ntt * 8 + lane]);
-          const int nv = nvt * BLOCK_V + static_cast<int>(q * 32u + lane);
-          if (nv < p.V) next_bias = __ldg(&p.bias[nv]);
-        }
-      }
-      // Is every column of every document of this tile valid?  (the common case: no padding inside the tile)
-      const int cols_valid = (t.ns == p.s_box) ? t.nb * p.s_box : -1;
-      uint32_t expect = 0;
-      if (lane < 8) {
-        const int rem = cols_valid - 32 * static_cast<int>(lane);
-        expect = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-      }
-      const bool tile_full = (cols_valid >= 0) && (__ballot_sync(0xffffffffu, my_word != expect) == 0u);
-
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t t_lane = tmem_base + ((q * 32u) << 16) + acc * BLOCK_T;
-
-      for (int d = 0; d < t.nb; ++d) {
-        const int b = t.b0 + d;
-        const int col_base = d * p.s_box;
-        int best_val = 0, best_pos = 0;
-        const int nwin = (t.ns + 31) >> 5;
-        for (int c = 0; c < nwin; ++c) {
-          const int w0 = min(col_base + 32 * c, BLOCK_T - 32);
-          const int jlo = max(0, col_base - w0);
-          const int jhi = min(32, col_base + t.ns - w0);
-          uint32_t range = (jhi >= 32) ? 0xffffffffu : ((1u << jhi) - 1u);
-          range &= 0xffffffffu << jlo;
-          uint32_t vw = range;
-          if (!tile_full) {  // warp-uniform
-            const uint32_t lo = __shfl_sync(0xffffffffu, my_word, w0 >> 5);
-            const uint32_t hi = __shfl_sync(0xffffffffu, my_word, min(7, (w0 >> 5) + 1));
-            vw &= __funnelshift_r(lo, hi, w0 & 31);
-          }
-          if (vw == 0u) continue;  // warp-uniform: fully padded window
-
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(w0), r);
-          tmem_ld_wait();
-
-          int tok_mine = 0;
-          int wkey;
-          if (vw == 0xffffffffu) {
-            wkey = window_max<true, kTokW>(r, bias_v, vw, lane, tok_mine);
-          } else {
-            wkey = window_max<false, kTokW>(r, bias_v, vw, lane, tok_mine);
-          }
-          const int pos0 = t.s0 + (w0 - col_base);  // sequence position of window column 0
-          const int wval = wkey >> 16;
-          if (wval > best_val) {  // strict: earlier windows win ties (first occurrence)
-            best_val = wval;
-            best_pos = pos0 + 31 - (wkey & 31);
-          }
-          if (kTokW) {
-            const int tv = tok_mine >> 16;
-            if (tv > 0 && ((vw >> lane) & 1u)) {
-              atomicMax(&p.tokw_bits[static_cast<size_t>(b) * p.S + pos0 + static_cast<int>(lane)],
-                        static_cast<uint32_t>(tv));
-            }
-          }
-        }
-        if (v < p.V) {
-          const size_t o = static_cast<size_t>(b) * p.V + v;
-          if (p.chunks_per_doc == 1) {
-            p.rep[o] = log1pf(bf16_bits_to_float(static_cast<uint32_t>(best_val)));
-            p.argmax[o] = best_pos;
-          } else {
-            atomicMax(&p.packed[o], (static_cast<uint32_t>(best_val) << 16) |
-                                        (0xFFFFu - static_cast<uint32_t>(best_pos)));
-          }
-        }
-      }
-      tcgen05_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
-    }
+    EpilogueCtx c;
+    c.tmem_base = tmem_base;
+    c.tfull_bar = tfull_bar;
+    c.tempty_addr = smem_u32(&tempty_bar[0]);
+    c.item0 = static_cast<int>(blockIdx.x);
+    c.item_step = static_cast<int>(gridDim.x);
+    c.n_items = total_items;
+    c.vt_mul = 1;
+    c.vt_add = 0;
+    epilogue_loop<kTokW>(p, c, warp, lane);
   }
 
   tcgen05_fence_before();
@@ -335,6 +370,146 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2).  A cluster of two CTAs (one TPC) works on a 256-row vocabulary tile
+// x one token tile: each CTA stages ITS 128 vocabulary rows (A) and HALF of the token rows (B); the leader's
+// single MMA thread issues 256 x N x 16 instructions that read both CTAs' shared memory and write both CTAs'
+// TMEM.  Per CTA and k-block that is 16 KB + 16 KB of TMA traffic instead of 16 KB + 32 KB, and the B operand is
+// read from shared memory once per pair instead of once per CTA - less L2->SM and SMEM->tensor-core traffic for
+// the same math.  Each CTA runs the same epilogue as the single-CTA kernel on its own 128 TMEM lanes.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int P_STAGES = 6;
+constexpr int P_A_BYTES = BLOCK_V * BLOCK_K * 2;         // 16 KB: this CTA's 128 vocabulary rows
+constexpr int P_B_BYTES = (BLOCK_T / 2) * BLOCK_K * 2;   // 16 KB: this CTA's half of the token rows
+constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 256 + 1024;
+
+template <bool kTokW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+head_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
+                     const HeadFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES);  // used in the leader
+  uint64_t* empty_bar = full_bar + P_STAGES;                                         // per CTA
+  uint64_t* tfull_bar = empty_bar + P_STAGES;                                        // per CTA
+  uint64_t* tempty_bar = tfull_bar + 2;                                              // used in the leader
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_h);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // the leader's arrive.expect_tx; bytes come from both CTAs' TMA loads
+      mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);     // one multicast tcgen05.commit
+      mbar_init(&tempty_bar[a], 256);  // 128 epilogue threads of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+  tcgen05_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / TMA credit
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n_vt2 = (p.n_vt + 1) / 2;
+  const int total_items = n_vt2 * p.n_tt;
+  const int num_kb = p.H / BLOCK_K;
+  const int item0 = static_cast<int>(blockIdx.x >> 1);
+  const int item_step = static_cast<int>(gridDim.x >> 1);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t full0 = map_to_cta(smem_u32(&full_bar[0]), 0);  // leader's full barriers
+      for (int item = item0; item < total_items; item += item_step) {
+        const TileCoord t = tile_coord(p, item, 2, static_cast<int>(rank));
+        // this CTA's half of the token rows: docs [b0 + rank*b_half, ..) or positions [s0 + rank*s_half, ..)
+        const int my_s = t.s0 + (p.pair_split_docs ? 0 : static_cast<int>(rank) * p.pair_half_rows);
+        const int my_b = t.b0 + (p.pair_split_docs ? static_cast<int>(rank) * (p.b_box / 2) : 0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* a_dst = smem + stage * P_STAGE_BYTES;
+          uint8_t* b_dst = a_dst + P_A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
+          const uint32_t bar = full0 + stage * 8u;
+          tma_load_2d_pair(a_dst, &tmap_w, bar, kb * BLOCK_K, t.vt * BLOCK_V);
+          tma_load_3d_pair(b_dst, &tmap_h, bar, kb * BLOCK_K, my_s, my_b);
+          if (++stage == P_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(2 * BLOCK_V, static_cast<uint32_t>(p.umma_n));
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int item = item0; item < total_items; item += item_step, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_T;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * P_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + P_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
+            umma_bf16_pair(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 0x3);  // frees this stage in BOTH CTAs
+          if (++stage == P_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_pair(&tfull_bar[acc], 0x3);  // accumulator halves ready in both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps, both CTAs)
+    EpilogueCtx c;
+    c.tmem_base = tmem_base;
+    c.tfull_bar = tfull_bar;
+    c.tempty_addr = map_to_cta(smem_u32(&tempty_bar[0]), 0);
+    c.item0 = item0;
+    c.item_step = item_step;
+    c.n_items = total_items;
+    c.vt_mul = 2;
+    c.vt_add = static_cast<int>(rank);
+    epilogue_loop<kTokW>(p, c, warp, lane);
+  }
+
+  __syncwarp();  // reconverge the single-lane role warps before the aligned cluster barrier
+  tcgen05_fence_before();
+  cluster_sync_all();  // the peer may still be reading our shared memory / arriving on our barriers
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -356,6 +531,15 @@ __global__ void finalize_tokw_kernel(const uint32_t* __restrict__ bits, float* _
 }
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+// SPLADE_B200_CTA_PAIR=1 selects the cta_group::2 kernel where the shape allows it (default: single-CTA kernel).
+bool pair_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("SPLADE_B200_CTA_PAIR");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
 
 }  // namespace
 
@@ -433,6 +617,10 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
     SPLADE_CUDA_OK(cudaMemsetAsync(p.tokw_bits, 0, static_cast<size_t>(B) * S * sizeof(uint32_t), stream));
   }
 
+  // CTA-pair (cta_group::2) path: needs the tile's token rows to split evenly between two CTAs.
+  const int cols = p.s_box * p.b_box;
+  bool use_pair = pair_enabled() && (sm_count() % 2 == 0) && (cols % 16 == 0) &&
+                  ((p.b_box % 2 == 0) || (p.b_box == 1 && p.s_box % 16 == 0));
   CUtensorMap tmap_w, tmap_h;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(H), static_cast<uint64_t>(V)};
@@ -444,7 +632,15 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(H), static_cast<uint64_t>(S), static_cast<uint64_t>(B)};
     const uint64_t strides[2] = {static_cast<uint64_t>(H) * 2, static_cast<uint64_t>(S) * H * 2};
-    const uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.s_box), static_cast<uint32_t>(p.b_box)};
+    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.s_box), static_cast<uint32_t>(p.b_box)};
+    if (use_pair) {
+      p.pair_split_docs = (p.b_box % 2 == 0) ? 1 : 0;
+      p.pair_half_rows = cols / 2;
+      if (p.pair_split_docs) box[2] = static_cast<uint32_t>(p.b_box / 2);
+      else box[1] = static_cast<uint32_t>(p.s_box / 2);
+      p.umma_n = cols;
+      p.stage_tx_bytes = static_cast<uint32_t>(2 * (P_A_BYTES + p.pair_half_rows * BLOCK_K * 2));
+    }
     rc = encode_tmap_bf16(&tmap_h, hidden, 3, dims, strides, box);
     if (rc != kOk) return rc;
   }
@@ -452,11 +648,19 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
   build_tile_masks_kernel<<<p.n_tt, 256, 0, stream>>>(p, tile_masks);
   SPLADE_CUDA_OK(cudaGetLastError());
 
-  const int total_items = p.n_vt * p.n_tt;
-  const int grid = std::min(sm_count(), total_items);
-  auto kernel = tokw ? head_fwd_kernel<true> : head_fwd_kernel<false>;
-  SPLADE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmap_w, tmap_h, p);
+  if (use_pair) {
+    const int total_pairs = ((p.n_vt + 1) / 2) * p.n_tt;
+    const int grid = 2 * std::min(sm_count() / 2, total_pairs);
+    auto kernel = tokw ? head_fwd_pair_kernel<true> : head_fwd_pair_kernel<false>;
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    kernel<<<grid, NUM_THREADS, P_SMEM_BYTES, stream>>>(tmap_w, tmap_h, p);
+  } else {
+    const int total_items = p.n_vt * p.n_tt;
+    const int grid = std::min(sm_count(), total_items);
+    auto kernel = tokw ? head_fwd_kernel<true> : head_fwd_kernel<false>;
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmap_w, tmap_h, p);
+  }
   SPLADE_CUDA_OK(cudaGetLastError());
 
   if (p.chunks_per_doc > 1) {

@@ -156,3 +156,19 @@ def test_autograd_function_matches_torch_chain(cuda_device):
         scale = float(r.abs().max())
         err = float((a - r).abs().max())
         assert err <= 1e-2 * scale + 1e-6, (name, err, scale)
+
+
+def test_cta_pair_kernel_passes_the_same_parity_suite(cuda_device):
+    """SPLADE_B200_CTA_PAIR=1 selects the cta_group::2 kernel (two CTAs of a cluster share one 256 x N tile).  The
+    switch is read once per process, so the forward parity tests are re-run in a child process."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("SPLADE_B200_CTA_PAIR") == "1":
+        pytest.skip("already running in CTA-pair mode")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPLADE_B200_CTA_PAIR="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_head.py", "-m", "gpu", "-q", "-x", "-k",
+                        "forward_vs_oracle or golden or headline or all_padding or properties"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
