@@ -42,6 +42,7 @@ extern "C" {
 #define SPLADE_OP_HEAD_BWD 2      /* (B,S,H,V)            head backward                               */
 #define SPLADE_OP_FLOPS_NNZ 3     /* (B=N rows, V)        FLOPS regulariser + nonzero count           */
 #define SPLADE_OP_SCORES 4        /* (B=Bq, k=N docs, V)  q.d score matrix                            */
+#define SPLADE_OP_V33_LOSS_FWD 5  /* (B=Bq, S=N docs, V, k) whole SPLADELossV33 forward               */
 
 int splade_abi_version(void);
 const char* splade_last_error(void);
@@ -126,6 +127,34 @@ typedef struct splade_v33_scalar_args {
 } splade_v33_scalar_args;
 
 int splade_v33_scalars(const splade_v33_scalar_args* args, void* stream);
+
+/*
+ * The whole SPLADELossV33 forward (losses.py:209-295) in ONE call: the three FLOPS/nonzero passes, the q.d score
+ * GEMM, the hard-negative (and MarginMSE positive) row dots and the scalar stage are enqueued back to back on
+ * `stream` - one host call and no intermediate allocation instead of ~10.  Same arithmetic as the fine-grained
+ * entry points above (it calls the same launchers).
+ */
+typedef struct splade_v33_fwd_args {
+  int32_t Bq, N, k, V;  /* queries, in-batch documents, hard negatives per query, vocabulary */
+  int32_t label_offset, round_bf16, has_kd, has_mmse;
+  float temperature, kd_temperature;
+  float lambda_q, lambda_d, lambda_neg, lambda_kd, lambda_mmse;
+  float reserved_f;
+  const float* q;           /* [Bq,V]   */
+  const float* docs;        /* [N,V]    positives; rows [label_offset, label_offset+Bq) are the local ones */
+  const float* negs;        /* [Bq,k,V] */
+  const float* teacher_kd;  /* [Bq,Bq] or NULL */
+  const float* teacher_pos; /* [Bq]    or NULL */
+  const float* teacher_neg; /* [Bq,k]  or NULL */
+  float* colmean;           /* [3,V] out: column means of q, local docs, negatives (kept for backward) */
+  float* scalars;           /* [16]  out, layout as in splade_v33_scalar_args */
+  float* g_inbatch;         /* [Bq,N] out */
+  float* g_hard;            /* [Bq,k] out */
+  void* workspace;          /* splade_workspace_bytes(SPLADE_OP_V33_LOSS_FWD, Bq, N, 0, V, k) */
+  size_t ws_bytes;
+} splade_v33_fwd_args;
+
+int splade_v33_loss_fwd(const splade_v33_fwd_args* args, void* stream);
 
 /*
  * Backward of the scoring + FLOPS terms onto the sparse representations (autograd of losses.py:155-181,

@@ -20,6 +20,7 @@ OP_HEAD_FWD_TOKW = 1
 OP_HEAD_BWD = 2
 OP_FLOPS_NNZ = 3
 OP_SCORES = 4
+OP_V33_LOSS_FWD = 5
 
 
 class V33ScalarArgs(Structure):
@@ -38,6 +39,22 @@ class V33ScalarArgs(Structure):
     ]
 
 
+class V33FwdArgs(Structure):
+    """Mirror of ``splade_v33_fwd_args`` (include/splade_b200.h)."""
+
+    _fields_ = [
+        ("Bq", c_int32), ("N", c_int32), ("k", c_int32), ("V", c_int32),
+        ("label_offset", c_int32), ("round_bf16", c_int32), ("has_kd", c_int32), ("has_mmse", c_int32),
+        ("temperature", c_float), ("kd_temperature", c_float),
+        ("lambda_q", c_float), ("lambda_d", c_float), ("lambda_neg", c_float),
+        ("lambda_kd", c_float), ("lambda_mmse", c_float), ("reserved_f", c_float),
+        ("q", c_void_p), ("docs", c_void_p), ("negs", c_void_p),
+        ("teacher_kd", c_void_p), ("teacher_pos", c_void_p), ("teacher_neg", c_void_p),
+        ("colmean", c_void_p), ("scalars", c_void_p), ("g_inbatch", c_void_p), ("g_hard", c_void_p),
+        ("workspace", c_void_p), ("ws_bytes", c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/splade_b200.h declares
 EXPORTS = {
     "splade_abi_version": (c_int, []),
@@ -52,6 +69,7 @@ EXPORTS = {
                               c_void_p]),
     "splade_rowdot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "splade_v33_scalars": (c_int, [POINTER(V33ScalarArgs), c_void_p]),
+    "splade_v33_loss_fwd": (c_int, [POINTER(V33FwdArgs), c_void_p]),
     "splade_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -120,6 +120,8 @@ size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k) {
       return flops_workspace_bytes(B, V);
     case SPLADE_OP_SCORES:
       return scores_workspace_bytes(B, k, V);
+    case SPLADE_OP_V33_LOSS_FWD:
+      return v33_loss_fwd_workspace_bytes(B, S, V, k);
     default:
       return 0;
   }
@@ -156,6 +158,10 @@ int splade_rowdot(const float* q, const float* docs, int Bq, int k, int V, float
 
 int splade_v33_scalars(const splade_v33_scalar_args* args, void* stream) {
   return v33_scalars_launch(args, static_cast<cudaStream_t>(stream));
+}
+
+int splade_v33_loss_fwd(const splade_v33_fwd_args* args, void* stream) {
+  return v33_loss_fwd_launch(args, static_cast<cudaStream_t>(stream));
 }
 
 int splade_loss_bwd(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,

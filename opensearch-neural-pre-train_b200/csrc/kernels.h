@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 struct splade_v33_scalar_args;
+struct splade_v33_fwd_args;
 
 namespace splade {
 
@@ -38,6 +39,8 @@ int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int r
                   void* workspace, size_t ws_bytes, cudaStream_t stream);
 int rowdot_launch(const float* q, const float* docs, int Bq, int k, int V, float* out, cudaStream_t stream);
 int v33_scalars_launch(const struct splade_v33_scalar_args* args, cudaStream_t stream);
+size_t v33_loss_fwd_workspace_bytes(int Bq, int N, int V, int k);
+int v33_loss_fwd_launch(const struct splade_v33_fwd_args* args, cudaStream_t stream);
 int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,
                     int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
                     const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,

@@ -722,6 +722,88 @@ int v33_scalars_launch(const splade_v33_scalar_args* a, cudaStream_t stream) {
   return kOk;
 }
 
+size_t v33_loss_fwd_workspace_bytes(int Bq, int N, int V, int k) {
+  if (Bq < 1 || N < 1 || V < 1 || k < 1) return 0;
+  const size_t flops_ws = std::max(flops_workspace_bytes(Bq, V), flops_workspace_bytes(Bq * k, V));
+  return align256(flops_ws) + align256(scores_workspace_bytes(Bq, N, V)) +
+         align256(static_cast<size_t>(Bq) * N * 4) + align256(static_cast<size_t>(Bq) * k * 4) +
+         align256(static_cast<size_t>(Bq) * 4) + align256(6 * 4) + align256(static_cast<size_t>(3) * Bq * 4);
+}
+
+int v33_loss_fwd_launch(const splade_v33_fwd_args* a, cudaStream_t stream) {
+  if (!a) return set_error(kErrInvalidArg, "splade_v33_loss_fwd: null args");
+  if (a->Bq < 1 || a->N < 1 || a->k < 1 || a->V < 1)
+    return set_error(kErrInvalidArg, "splade_v33_loss_fwd: bad sizes Bq=%d N=%d k=%d V=%d", a->Bq, a->N, a->k, a->V);
+  if (!a->q || !a->docs || !a->negs || !a->colmean || !a->scalars || !a->g_inbatch || !a->g_hard)
+    return set_error(kErrInvalidArg, "splade_v33_loss_fwd: null pointer argument");
+  if (a->label_offset < 0 || a->label_offset + a->Bq > a->N)
+    return set_error(kErrInvalidArg, "splade_v33_loss_fwd: labels outside the in-batch documents");
+  const int Bq = a->Bq, N = a->N, k = a->k, V = a->V;
+  const size_t need = v33_loss_fwd_workspace_bytes(Bq, N, V, k);
+  if (!a->workspace || a->ws_bytes < need)
+    return set_error(kErrWorkspace, "splade_v33_loss_fwd: workspace too small (%zu < %zu bytes)", a->ws_bytes, need);
+  uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+  const size_t flops_ws = align256(std::max(flops_workspace_bytes(Bq, V), flops_workspace_bytes(Bq * k, V)));
+  void* w_flops = ws;
+  ws += flops_ws;
+  const size_t scores_ws = align256(scores_workspace_bytes(Bq, N, V));
+  void* w_scores = ws;
+  ws += scores_ws;
+  float* raw_in = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(Bq) * N * 4);
+  float* raw_hard = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(Bq) * k * 4);
+  float* raw_pos = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(Bq) * 4);
+  float* flops3 = reinterpret_cast<float*>(ws);
+  ws += align256(6 * 4);
+  float* row_scratch = reinterpret_cast<float*>(ws);
+
+  const float* local_docs = a->docs + static_cast<size_t>(a->label_offset) * V;
+  int rc = flops_nnz_launch(a->q, Bq, V, a->colmean, flops3, w_flops, flops_ws, stream);
+  if (rc != kOk) return rc;
+  rc = flops_nnz_launch(local_docs, Bq, V, a->colmean + V, flops3 + 2, w_flops, flops_ws, stream);
+  if (rc != kOk) return rc;
+  rc = flops_nnz_launch(a->negs, Bq * k, V, a->colmean + 2 * static_cast<size_t>(V), flops3 + 4, w_flops, flops_ws,
+                        stream);
+  if (rc != kOk) return rc;
+  rc = scores_launch(a->q, Bq, a->docs, N, V, a->round_bf16, raw_in, w_scores, scores_ws, stream);
+  if (rc != kOk) return rc;
+  rc = rowdot_launch(a->q, a->negs, Bq, k, V, raw_hard, stream);
+  if (rc != kOk) return rc;
+  if (a->has_mmse) {
+    rc = rowdot_launch(a->q, local_docs, Bq, 1, V, raw_pos, stream);
+    if (rc != kOk) return rc;
+  }
+  splade_v33_scalar_args sa{};
+  sa.Bq = Bq;
+  sa.N = N;
+  sa.k = k;
+  sa.label_offset = a->label_offset;
+  sa.round_bf16 = a->round_bf16;
+  sa.has_kd = a->has_kd;
+  sa.has_mmse = a->has_mmse;
+  sa.temperature = a->temperature;
+  sa.kd_temperature = a->kd_temperature;
+  sa.lambda_q = a->lambda_q;
+  sa.lambda_d = a->lambda_d;
+  sa.lambda_neg = a->lambda_neg;
+  sa.lambda_kd = a->lambda_kd;
+  sa.lambda_mmse = a->lambda_mmse;
+  sa.raw_inbatch = raw_in;
+  sa.raw_hard = raw_hard;
+  sa.raw_pos = a->has_mmse ? raw_pos : nullptr;
+  sa.teacher_kd = a->teacher_kd;
+  sa.teacher_pos = a->teacher_pos;
+  sa.teacher_neg = a->teacher_neg;
+  sa.flops3 = flops3;
+  sa.scalars = a->scalars;
+  sa.g_inbatch = a->g_inbatch;
+  sa.g_hard = a->g_hard;
+  sa.row_scratch = row_scratch;
+  return v33_scalars_launch(&sa, stream);
+}
+
 int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,
                     int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
                     const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,

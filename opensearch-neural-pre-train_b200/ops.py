@@ -249,32 +249,27 @@ class V33LossFunction(torch.autograd.Function):
         has_kd = teacher_kd is not None and cfg["lambda_kd"] > 0
         has_mmse = teacher_pos is not None and teacher_neg is not None and cfg["lambda_mmse"] > 0
         with torch.cuda.device(dev):
-            flops3 = torch.empty((6,), dtype=torch.float32, device=dev)
-            d_local = d[off:off + Bq]
-            cm_q, _ = flops_nnz(q, flops3[0:2])
-            cm_d, _ = flops_nnz(d_local, flops3[2:4])
-            cm_n, _ = flops_nnz(n.view(Bq * k, V), flops3[4:6])
-            raw_in = scores(q, d, round_bf16)
-            raw_hard = rowdot(q, n)
-            raw_pos = rowdot(q, d_local.unsqueeze(1)).view(Bq) if has_mmse else None
-            scalars = torch.zeros((16,), dtype=torch.float32, device=dev)
+            colmean = torch.empty((3, V), dtype=torch.float32, device=dev)
+            scalars = torch.empty((16,), dtype=torch.float32, device=dev)
             g_in = torch.empty((Bq, N), dtype=torch.float32, device=dev)
             g_hard = torch.empty((Bq, k), dtype=torch.float32, device=dev)
-            row_scratch = torch.empty((3 * Bq,), dtype=torch.float32, device=dev)
             t_kd = _f32c(teacher_kd) if has_kd else None
             t_pos = _f32c(teacher_pos).view(Bq) if has_mmse else None
             t_neg = _f32c(teacher_neg).view(Bq, k) if has_mmse else None
-            args = _lib.V33ScalarArgs(
-                Bq=Bq, N=N, k=k, label_offset=off, round_bf16=int(round_bf16), has_kd=int(has_kd),
-                has_mmse=int(has_mmse), reserved=0,
+            nbytes = lib.splade_workspace_bytes(_lib.OP_V33_LOSS_FWD, Bq, N, 0, V, k)
+            ws, ws_ptr = _ws(nbytes, dev)
+            args = _lib.V33FwdArgs(
+                Bq=Bq, N=N, k=k, V=V, label_offset=off, round_bf16=int(round_bf16), has_kd=int(has_kd),
+                has_mmse=int(has_mmse),
                 temperature=cfg["temperature"], kd_temperature=cfg["kd_temperature"],
                 lambda_q=cfg["lambda_q"], lambda_d=cfg["lambda_d"], lambda_neg=cfg["lambda_neg"],
                 lambda_kd=cfg["lambda_kd"], lambda_mmse=cfg["lambda_mmse"], reserved_f=0.0,
-                raw_inbatch=raw_in.data_ptr(), raw_hard=raw_hard.data_ptr(), raw_pos=_ptr(raw_pos),
+                q=q.data_ptr(), docs=d.data_ptr(), negs=n.data_ptr(),
                 teacher_kd=_ptr(t_kd), teacher_pos=_ptr(t_pos), teacher_neg=_ptr(t_neg),
-                flops3=flops3.data_ptr(), scalars=scalars.data_ptr(), g_inbatch=g_in.data_ptr(),
-                g_hard=g_hard.data_ptr(), row_scratch=row_scratch.data_ptr())
-            check(lib.splade_v33_scalars(ctypes.byref(args), _stream(q)), "splade_v33_scalars")
+                colmean=colmean.data_ptr(), scalars=scalars.data_ptr(), g_inbatch=g_in.data_ptr(),
+                g_hard=g_hard.data_ptr(), workspace=ws_ptr, ws_bytes=nbytes)
+            check(lib.splade_v33_loss_fwd(ctypes.byref(args), _stream(q)), "splade_v33_loss_fwd")
+            cm_q, cm_d, cm_n = colmean[0], colmean[1], colmean[2]
         ctx.save_for_backward(q, d, n, g_in, g_hard, cm_q, cm_d, cm_n)
         ctx.meta = (Bq, N, k, V, off, cfg["lambda_q"], cfg["lambda_d"], cfg["lambda_neg"],
                     anchor.dtype, docs.dtype, negatives.dtype, tuple(negatives.shape))

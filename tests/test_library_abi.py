@@ -17,7 +17,7 @@ def _declared_symbols():
 def test_header_declares_expected_entry_points():
     syms = _declared_symbols()
     for s in ("splade_head_fwd", "splade_head_bwd", "splade_flops_nnz", "splade_scores", "splade_rowdot",
-              "splade_v33_scalars", "splade_loss_bwd", "splade_topk", "splade_workspace_bytes",
+              "splade_v33_scalars", "splade_v33_loss_fwd", "splade_loss_bwd", "splade_topk", "splade_workspace_bytes",
               "splade_last_error", "splade_abi_version"):
         assert s in syms
 
@@ -33,7 +33,8 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert lib.splade_abi_version() == splade_b200.ABI_VERSION
     # pure host helper: workspace sizing needs no device
-    assert lib.splade_workspace_bytes(_lib.OP_HEAD_FWD, 64, 256, 768, 50000, 0) == 0
+    assert lib.splade_workspace_bytes(_lib.OP_HEAD_FWD, 64, 256, 768, 50000, 0) >= 64 * 8 * 4   # tile validity bitmaps
+    assert lib.splade_workspace_bytes(_lib.OP_V33_LOSS_FWD, 64, 64, 0, 50000, 1) > 64 * 64 * 4
     assert lib.splade_workspace_bytes(_lib.OP_HEAD_FWD_TOKW, 64, 256, 768, 50000, 0) >= 64 * 256 * 4
     assert lib.splade_workspace_bytes(_lib.OP_HEAD_FWD, 2, 300, 64, 260, 0) >= 2 * 260 * 4
     assert lib.splade_workspace_bytes(_lib.OP_HEAD_BWD, 64, 256, 768, 50000, 0) >= 2 * 64 * 50000 * 4
@@ -41,9 +42,11 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     import ctypes
-    from splade_b200._lib import V33ScalarArgs
+    from splade_b200._lib import V33FwdArgs, V33ScalarArgs
     # 8 int32 + 8 float + 11 pointers, no padding on LP64
     assert ctypes.sizeof(V33ScalarArgs) == 8 * 4 + 8 * 4 + 11 * 8
+    # 8 int32 + 8 float + 11 pointers + size_t
+    assert ctypes.sizeof(V33FwdArgs) == 8 * 4 + 8 * 4 + 11 * 8 + 8
 
 
 def test_product_refuses_cpu_tensors():
