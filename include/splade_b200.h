@@ -68,6 +68,20 @@ int splade_head_fwd(const void* hidden, const void* W, const float* bias, const 
                     void* stream);
 
 /*
+ * Host-buffer form of splade_head_fwd for callers whose activations live in host memory (and for the end-to-end
+ * benchmark): enqueues  H2D(hidden_host, mask_host) -> splade_head_fwd -> D2H(rep, argmax)  on `stream` and
+ * returns without synchronising.  W and bias are model weights and stay resident on the device.  The caller owns
+ * the device staging buffers (hidden_dev [B,S,H] bf16, mask_dev [B,S] int32, rep_dev [B,V] fp32, argmax_dev [B,V]
+ * int32, workspace) and must keep the host buffers alive (ideally pinned) until the stream has drained.
+ * rep_host / argmax_host may be NULL to skip that copy.  Use two slots on two streams to overlap the copies of
+ * one batch with the compute of the other.
+ */
+int splade_head_fwd_host(const void* hidden_host, const int32_t* mask_host, const void* W, const float* bias, int B,
+                         int S, int H, int V, void* hidden_dev, int32_t* mask_dev, float* rep_dev,
+                         int32_t* argmax_dev, float* rep_host, int32_t* argmax_host, void* workspace,
+                         size_t ws_bytes, void* stream);
+
+/*
  * Gather-driven sparse backward of splade_head_fwd (replaces autograd of splade_modern.py:69-83, invoked at
  * src/train/cli/train_v33_ddp.py:364).  dlogit[b,argmax[b,v],v] = g_rep[b,v] * exp(-rep[b,v]) for rep>0.
  *   d_hidden [B,S,H] fp32, dW [V,H] fp32, dbias [V] fp32 are fully overwritten (dense, DDP-ready).

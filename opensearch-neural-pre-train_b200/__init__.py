@@ -8,12 +8,13 @@ mirror of the reference's Python interface.  There is no CPU fallback.
 from ._lib import ABI_VERSION, LIB_PATH, load_library  # noqa: F401
 from .distributed import all_gather_documents, shard_range  # noqa: F401
 from .encoder import SPLADEModernBERT  # noqa: F401
-from .ops import (flops_nnz, head_backward, head_forward, rowdot, scores, splade_head, topk)  # noqa: F401
+from .ops import (HostEncodeSlot, flops_nnz, head_backward, head_forward, head_forward_host, rowdot, scores,  # noqa: F401
+                  splade_head, topk)
 from .sparse_emit import SparseEmitter, build_blocklist, bulk_encode  # noqa: F401
 from .v33_loss import SPLADELossV33  # noqa: F401
 
 __all__ = [
     "SPLADEModernBERT", "SPLADELossV33", "SparseEmitter", "build_blocklist", "bulk_encode",
-    "splade_head", "head_forward", "head_backward", "flops_nnz", "scores", "rowdot", "topk",
+    "splade_head", "head_forward", "head_forward_host", "HostEncodeSlot", "head_backward", "flops_nnz", "scores", "rowdot", "topk",
     "all_gather_documents", "shard_range", "load_library", "LIB_PATH", "ABI_VERSION",
 ]

@@ -134,6 +134,28 @@ int splade_head_fwd(const void* hidden, const void* W, const float* bias, const 
                          static_cast<cudaStream_t>(stream));
 }
 
+int splade_head_fwd_host(const void* hidden_host, const int32_t* mask_host, const void* W, const float* bias, int B,
+                         int S, int H, int V, void* hidden_dev, int32_t* mask_dev, float* rep_dev,
+                         int32_t* argmax_dev, float* rep_host, int32_t* argmax_host, void* workspace,
+                         size_t ws_bytes, void* stream) {
+  if (!hidden_host || !mask_host || !hidden_dev || !mask_dev || !rep_dev || !argmax_dev)
+    return set_error(kErrInvalidArg, "splade_head_fwd_host: null pointer argument");
+  if (B < 0 || S < 1 || H < 1 || V < 1)
+    return set_error(kErrInvalidArg, "splade_head_fwd_host: bad sizes B=%d S=%d H=%d V=%d", B, S, H, V);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t tokens = static_cast<size_t>(B) * S;
+  SPLADE_CUDA_OK(cudaMemcpyAsync(hidden_dev, hidden_host, tokens * H * 2, cudaMemcpyHostToDevice, st));
+  SPLADE_CUDA_OK(cudaMemcpyAsync(mask_dev, mask_host, tokens * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const int rc = head_fwd_launch(hidden_dev, W, bias, mask_dev, B, S, H, V, rep_dev, argmax_dev, nullptr, workspace,
+                                 ws_bytes, st);
+  if (rc != kOk) return rc;
+  const size_t out = static_cast<size_t>(B) * V;
+  if (rep_host) SPLADE_CUDA_OK(cudaMemcpyAsync(rep_host, rep_dev, out * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (argmax_host)
+    SPLADE_CUDA_OK(cudaMemcpyAsync(argmax_host, argmax_dev, out * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return kOk;
+}
+
 int splade_head_bwd(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden, const void* W,
                     int B, int S, int H, int V, float* d_hidden, float* dW, float* dbias, void* workspace,
                     size_t ws_bytes, void* stream) {

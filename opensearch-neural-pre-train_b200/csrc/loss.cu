@@ -43,16 +43,15 @@ flops_cols_kernel(const float* __restrict__ rep, int N, int V, float* __restrict
   if (j < V) {
     const float* p = rep + j;
     int i = 0;
-    for (; i + 4 <= N; i += 4) {
-      const float a = p[static_cast<size_t>(i) * V];
-      const float b = p[static_cast<size_t>(i + 1) * V];
-      const float c = p[static_cast<size_t>(i + 2) * V];
-      const float d = p[static_cast<size_t>(i + 3) * V];
-      sum += a;
-      sum += b;
-      sum += c;
-      sum += d;
-      cnt += (a > 0.f) + (b > 0.f) + (c > 0.f) + (d > 0.f);
+    for (; i + 16 <= N; i += 16) {  // 16 independent loads in flight per thread (latency-bound otherwise)
+      float x[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) x[u] = p[static_cast<size_t>(i + u) * V];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        sum += x[u];
+        cnt += (x[u] > 0.f);
+      }
     }
     for (; i < N; ++i) {
       const float a = p[static_cast<size_t>(i) * V];
@@ -201,7 +200,9 @@ void scores_plan(int Bq, int N, int V, int* ksplit, int* chunk) {
 // ---------------------------------------------------------------------------------------------
 // out[i,j] = sum_v q[i,v] * docs[i,j,v]    one CTA per (i,j)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kRowdotThreads = 1024;
+
+__global__ void __launch_bounds__(kRowdotThreads)
 rowdot_kernel(const float* __restrict__ q, const float* __restrict__ docs, int k, int V,
               float* __restrict__ out) {
   const int i = blockIdx.x / k;
@@ -213,11 +214,11 @@ rowdot_kernel(const float* __restrict__ q, const float* __restrict__ docs, int k
     const float4* b4 = reinterpret_cast<const float4*>(b);
     const int n4 = V >> 2;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    for (int v0 = threadIdx.x; v0 < n4; v0 += 4 * 256) {  // four independent 16-byte load pairs in flight
+    for (int v0 = threadIdx.x; v0 < n4; v0 += 4 * kRowdotThreads) {  // four independent 16-byte load pairs in flight
       float4 x[4], y[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int v = v0 + u * 256;
+        const int v = v0 + u * kRowdotThreads;
         x[u] = (v < n4) ? __ldg(&a4[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
         y[u] = (v < n4) ? __ldg(&b4[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -228,16 +229,16 @@ rowdot_kernel(const float* __restrict__ q, const float* __restrict__ docs, int k
     }
     s = (s0 + s1) + (s2 + s3);
   } else {
-    for (int v = threadIdx.x; v < V; v += 256) s = fmaf(a[v], b[v], s);
+    for (int v = threadIdx.x; v < V; v += kRowdotThreads) s = fmaf(a[v], b[v], s);
   }
   s = warp_sum(s);
-  __shared__ float sm[8];
+  __shared__ float sm[kRowdotThreads / 32];
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += sm[w];
+    for (int w = 0; w < kRowdotThreads / 32; ++w) t += sm[w];
     out[blockIdx.x] = t;
   }
 }
@@ -695,7 +696,7 @@ int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int r
 int rowdot_launch(const float* q, const float* docs, int Bq, int k, int V, float* out, cudaStream_t stream) {
   if (!q || !docs || !out) return set_error(kErrInvalidArg, "splade_rowdot: null pointer argument");
   if (Bq < 1 || k < 1 || V < 1) return set_error(kErrInvalidArg, "splade_rowdot: bad sizes Bq=%d k=%d V=%d", Bq, k, V);
-  rowdot_kernel<<<Bq * k, 256, 0, stream>>>(q, docs, k, V, out);
+  rowdot_kernel<<<Bq * k, kRowdotThreads, 0, stream>>>(q, docs, k, V, out);
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }

@@ -71,6 +71,40 @@ def head_forward(hidden: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
     return rep, argmax, tokw
 
 
+class HostEncodeSlot:
+    """Device staging buffers for one in-flight host-buffer encode (``splade_head_fwd_host``)."""
+
+    def __init__(self, B: int, S: int, H: int, V: int, device):
+        lib = load_library()
+        self.shape = (B, S, H, V)
+        self.hidden = torch.empty((B, S, H), dtype=torch.bfloat16, device=device)
+        self.mask = torch.empty((B, S), dtype=torch.int32, device=device)
+        self.rep = torch.empty((B, V), dtype=torch.float32, device=device)
+        self.argmax = torch.empty((B, V), dtype=torch.int32, device=device)
+        self.ws_bytes = lib.splade_workspace_bytes(_lib.OP_HEAD_FWD, B, S, H, V, 0)
+        self.ws = torch.empty(max(self.ws_bytes, 1), dtype=torch.uint8, device=device)
+
+
+def head_forward_host(hidden_host: torch.Tensor, mask_host: torch.Tensor, weight: torch.Tensor,
+                      bias: torch.Tensor, slot: HostEncodeSlot, rep_host: torch.Tensor,
+                      argmax_host: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None):
+    """Host buffers in, host buffers out (pinned CPU tensors): H2D -> fused head -> D2H enqueued on `stream`
+    through ONE C-ABI call; returns immediately (synchronise the stream before reading ``rep_host``)."""
+    lib = load_library()
+    assert not hidden_host.is_cuda and hidden_host.dtype == torch.bfloat16 and hidden_host.is_contiguous()
+    assert not mask_host.is_cuda and mask_host.dtype == torch.int32 and not rep_host.is_cuda
+    _require_cuda(weight, "weight")
+    B, S, H, V = slot.shape
+    assert tuple(hidden_host.shape) == (B, S, H) and tuple(rep_host.shape) == (B, V)
+    st = stream if stream is not None else torch.cuda.current_stream(weight.device)
+    with torch.cuda.device(weight.device):
+        check(lib.splade_head_fwd_host(hidden_host.data_ptr(), mask_host.data_ptr(), weight.data_ptr(),
+                                       bias.data_ptr(), B, S, H, V, slot.hidden.data_ptr(), slot.mask.data_ptr(),
+                                       slot.rep.data_ptr(), slot.argmax.data_ptr(), rep_host.data_ptr(),
+                                       _ptr(argmax_host), slot.ws.data_ptr(), slot.ws_bytes, st.cuda_stream),
+              "splade_head_fwd_host")
+
+
 def head_backward(g_rep: torch.Tensor, rep: torch.Tensor, argmax: torch.Tensor, hidden: torch.Tensor,
                   weight: torch.Tensor):
     """-> (d_hidden [B,S,H] fp32, dW [V,H] fp32, dbias [V] fp32)"""

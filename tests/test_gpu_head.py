@@ -172,3 +172,23 @@ def test_cta_pair_kernel_passes_the_same_parity_suite(cuda_device):
                         "forward_vs_oracle or golden or headline or all_padding or properties"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_host_buffer_entry_point(cuda_device):
+    """splade_head_fwd_host: pinned host hidden/mask in, pinned host sparse_repr/argmax out, one C-ABI call on a
+    side stream; same results as the device-resident call."""
+    import splade_b200
+    B, S, H, V = 6, 40, 128, 3000
+    hidden, W, bias, mask = make_head_inputs(B, S, H, V, seed=21, device=cuda_device)
+    h16, w16 = hidden.to(torch.bfloat16).contiguous(), W.to(torch.bfloat16).contiguous()
+    rep, arg, _ = splade_b200.head_forward(h16, w16, bias, mask, False)
+    slot = splade_b200.HostEncodeSlot(B, S, H, V, cuda_device)
+    h_host = h16.cpu().pin_memory()
+    m_host = mask.cpu().pin_memory()
+    rep_host = torch.empty(B, V, dtype=torch.float32).pin_memory()
+    arg_host = torch.empty(B, V, dtype=torch.int32).pin_memory()
+    st = torch.cuda.Stream(cuda_device)
+    st.wait_stream(torch.cuda.current_stream(cuda_device))
+    splade_b200.head_forward_host(h_host, m_host, w16, bias, slot, rep_host, arg_host, st)
+    st.synchronize()
+    assert torch.equal(rep_host, rep.cpu()) and torch.equal(arg_host, arg.cpu())

@@ -16,7 +16,7 @@ def _declared_symbols():
 
 def test_header_declares_expected_entry_points():
     syms = _declared_symbols()
-    for s in ("splade_head_fwd", "splade_head_bwd", "splade_flops_nnz", "splade_scores", "splade_rowdot",
+    for s in ("splade_head_fwd", "splade_head_fwd_host", "splade_head_bwd", "splade_flops_nnz", "splade_scores", "splade_rowdot",
               "splade_v33_scalars", "splade_v33_loss_fwd", "splade_loss_bwd", "splade_topk", "splade_workspace_bytes",
               "splade_last_error", "splade_abi_version"):
         assert s in syms
