@@ -193,6 +193,20 @@ int splade_loss_bwd(const float* q, const float* docs, const float* negs, int Bq
 int splade_topk(const float* rep, int B, int V, const uint8_t* blocklist, int k, int32_t* ids, float* vals,
                 int32_t* counts, void* stream);
 
+/*
+ * HOST-side emit (no device work): serialise compact top-k buffers (host copies of splade_topk's outputs) into
+ * one JSON object per document, the value of the `sparse_embedding` field the reference indexes
+ * (benchmark/encoders.py:320-343 -> benchmark/indexer.py:112-138).
+ *   token_bytes/token_offsets [n_tokens+1]: concatenated UTF-8 token strings -> {"token": w} (rank_features);
+ *   NULL -> {"<term id>": w} (sparse_vector, scripts/neural_sparse_search_aws.py:745-770);
+ *   round_decimals >= 0 -> fixed decimals (the AWS script uses 4), < 0 -> shortest fp32 round-trip (%.9g).
+ *   out [out_cap] receives the objects back to back; out_offsets [B+1] their byte ranges; *bytes_needed the total
+ *   (call once with out_cap = 0 to size the buffer: returns SPLADE_ERR_WORKSPACE and the size).
+ */
+int splade_emit_json(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B, int k,
+                     const char* token_bytes, const int64_t* token_offsets, int n_tokens, int round_decimals,
+                     char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,59 @@ class SparseEmitter:
     def encode_batch(self, sparse_repr: torch.Tensor, top_k: int) -> List[Dict[str, float]]:
         return self.to_dicts(*self.select(sparse_repr, top_k))
 
+    def _token_table(self):
+        """Concatenated UTF-8 token bytes + offsets for the C emitter (built once)."""
+        if self.token_lookup is None:
+            return None
+        if getattr(self, "_table", None) is None:
+            import numpy as np
+            enc = [(t or "").encode("utf-8") for t in self.token_lookup]
+            offsets = np.zeros(len(enc) + 1, dtype=np.int64)
+            np.cumsum([len(e) for e in enc], out=offsets[1:])
+            self._table = (b"".join(enc), offsets)
+        return self._table
+
+    def to_json(self, ids: torch.Tensor, vals: torch.Tensor, counts: torch.Tensor,
+                round_decimals: Optional[int] = None) -> List[bytes]:
+        """One JSON object (bytes) per document — ``{"token": weight, ...}`` or, without a token table,
+        ``{"<id>": weight, ...}`` — produced by the C emitter ``splade_emit_json`` from ONE device->host copy of
+        the compact buffers (no python object per term)."""
+        import ctypes
+
+        import numpy as np
+
+        from ._lib import check, load_library
+        lib = load_library()
+        ids_h = np.ascontiguousarray(ids.cpu().numpy(), dtype=np.int32)
+        vals_h = np.ascontiguousarray(vals.cpu().numpy(), dtype=np.float32)
+        counts_h = np.ascontiguousarray(counts.cpu().numpy(), dtype=np.int32)
+        B, k = ids_h.shape
+        table = self._token_table()
+        tok_ptr = off_ptr = None
+        n_tok = 0
+        if table is not None:
+            tok_buf = ctypes.create_string_buffer(table[0], len(table[0]) + 1)
+            tok_ptr, off_ptr, n_tok = ctypes.addressof(tok_buf), table[1].ctypes.data, len(table[1]) - 1
+        offsets = np.zeros(B + 1, dtype=np.int64)
+        need = ctypes.c_size_t(0)
+        dec = -1 if round_decimals is None else int(round_decimals)
+        cap = B * (2 + k * 40)  # first guess; grown once if tokens are long
+        for _ in range(2):
+            out = ctypes.create_string_buffer(max(cap, 1))
+            rc = lib.splade_emit_json(ids_h.ctypes.data, vals_h.ctypes.data, counts_h.ctypes.data, B, k, tok_ptr,
+                                      off_ptr, n_tok, dec, ctypes.addressof(out), cap, offsets.ctypes.data,
+                                      ctypes.byref(need))
+            if rc == 0:
+                break
+            if need.value > cap:
+                cap = need.value
+                continue
+            check(rc, "splade_emit_json")
+        else:
+            check(rc, "splade_emit_json")
+        raw = out.raw
+        return [raw[offsets[b]:offsets[b + 1]] for b in range(B)]
+
 
 @torch.no_grad()
 def bulk_encode(model, input_ids: torch.Tensor, attention_mask: torch.Tensor, top_k: int,

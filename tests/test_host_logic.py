@@ -87,3 +87,35 @@ def test_blocklist_from_tokenizer_contract():
 
     block = splade_b200.build_blocklist(Tok(), 10)
     assert block.tolist() == [1, 1, 1, 1, 1, 1, 0, 0, 1, 1]
+
+
+def test_c_emitter_json_matches_python_dicts():
+    """splade_emit_json is host code: it runs in the CPU suite.  Its output must parse to exactly the dicts
+    SparseEmitter.to_dicts builds (rank_features form), to {"<id>": w} without a token table (sparse_vector form),
+    and to round(w, 4) when asked for the AWS script's 4 decimals."""
+    import json
+
+    import splade_b200
+    tokens = ["plain", 'quo"te', "back\\slash", "한국어", "tab\there", "nl\nx", "ctl\x01", "", "last"]
+    ids = torch.tensor([[3, 1, 0, 8], [4, 5, 6, 2], [0, -1, -1, -1], [-1, -1, -1, -1]], dtype=torch.int32)
+    vals = torch.tensor([[1.4142135, 0.7049465, 0.33333334, 1e-7], [0.5, 0.25, 0.125, 3.0],
+                         [0.1, 0, 0, 0], [0, 0, 0, 0]], dtype=torch.float32)
+    counts = torch.tensor([4, 4, 1, 0], dtype=torch.int32)
+    em = splade_b200.SparseEmitter(None, tokens)
+    objs = em.to_json(ids, vals, counts)
+    dicts = em.to_dicts(ids, vals, counts)
+    parsed = [json.loads(o.decode("utf-8")) for o in objs]
+    assert [list(d_.keys()) for d_ in parsed] == [list(d_.keys()) for d_ in dicts]
+    import numpy as np
+    for g_, w_ in zip(parsed, dicts):   # "%.9g" round-trips every fp32 weight exactly
+        assert all(np.float32(g_[k_]) == np.float32(w_[k_]) for k_ in g_)
+    assert objs[3] == b"{}" and list(json.loads(objs[0]).keys()) == ["한국어", 'quo"te', "plain", "last"]
+    # sparse_vector form: decimal term ids as keys, 4 decimals
+    em_ids = splade_b200.SparseEmitter(None, None)
+    objs4 = em_ids.to_json(ids, vals, counts, round_decimals=4)
+    want = em_ids.to_dicts(ids, vals, counts, round_decimals=4)
+    got = [json.loads(o) for o in objs4]
+    for g, w in zip(got, want):
+        assert list(g.keys()) == list(w.keys())
+        assert all(abs(g[k_] - w[k_]) <= 1e-4 for k_ in g)
+    assert objs4[0].startswith(b'{"3": 1.4142, "1": 0.7049')
