@@ -13,12 +13,14 @@
 // Both gathers read 16-bit rows that live in the 126 MB L2 (hidden 25 MB, W 77 MB at the headline shape);
 // the kernels are L2-gather-bound, not tensor-core work.
 //
-// Kernels: (1) bucket_count / bucket_scan / bucket_scatter: per-document counting sort of the active terms by
-//              argmax position, spread over (document, vocabulary chunk) CTAs;
+// Kernels: (1) bucket_count / bucket_scan / bucket_scatter: deterministic per-document counting sort of the active
+//              terms by argmax position, one warp per (document, 1024-term chunk);
 //          (2) dhidden_kernel: one warp per (b,s) row sums coef * W[v,:] over its bucket;
 //          (3) dw_kernel: one warp per vocabulary row sums coef * hidden[b,argmax,:] over the batch.
 #include "common.cuh"
 #include "kernels.h"
+
+#include <algorithm>
 
 namespace splade {
 namespace {
@@ -30,56 +32,78 @@ __device__ __forceinline__ float coef_of(float g, float rep) { return rep > 0.f 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 // ---------------------------------------------------------------------------------------------
-// (1) per-document counting sort of active (b,v) by position, spread over (document, vocabulary chunk) CTAs:
-//     count (shared-memory histogram per chunk, warp-aggregated, merged with global atomics) ->
-//     per-document exclusive scan -> scatter (warp-aggregated cursor allocation).
+// (1) DETERMINISTIC per-document counting sort of the active (b,v) pairs by position.
+//     The vocabulary of every document is cut into chunks of kChunk terms; ONE WARP walks a chunk in term order:
+//       count   : per-(doc, chunk, position) counts            (warp-private shared-memory counters)
+//       scan    : row_ptr[b][s] and, per chunk, the first slot of each position (prefix over chunks)
+//       scatter : the same walk again; slot = chunk base + running count + rank among the lanes of the same
+//                 position (lanes are in term order)  => every bucket lists its terms in ascending term id,
+//                 so dHidden sums in a fixed order: run-to-run bit-identical.
 // ---------------------------------------------------------------------------------------------
-constexpr int kChunk = 4096;  // vocabulary entries per CTA in the count / scatter passes
+constexpr int kChunk = 1024;  // vocabulary entries per warp
 
 __global__ void __launch_bounds__(256)
 bucket_count_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep,
-                    const int32_t* __restrict__ argmax, int S, int V, int32_t* __restrict__ counts /*[B,S+1]*/) {
-  extern __shared__ int32_t sm[];  // [S]
-  const int b = blockIdx.y;
-  const int v0 = blockIdx.x * kChunk, v1 = min(V, v0 + kChunk);
+                    const int32_t* __restrict__ argmax, int B, int S, int V, int n_chunks, int warps_per_cta,
+                    int32_t* __restrict__ chunk_counts /*[B][n_chunks][S]*/) {
+  extern __shared__ int32_t sm[];  // [warps_per_cta][S]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= warps_per_cta) return;
+  const long long job = static_cast<long long>(blockIdx.x) * warps_per_cta + warp;  // (b, chunk)
+  if (job >= static_cast<long long>(B) * n_chunks) return;
+  const int b = static_cast<int>(job / n_chunks), ch = static_cast<int>(job % n_chunks);
+  int32_t* cnt = sm + static_cast<size_t>(warp) * S;
+  for (int s = lane; s < S; s += 32) cnt[s] = 0;
+  __syncwarp();
+  const int v0 = ch * kChunk, v1 = min(V, v0 + kChunk);
   const size_t base = static_cast<size_t>(b) * V;
-  const int lane = threadIdx.x & 31;
-  for (int s = threadIdx.x; s < S; s += 256) sm[s] = 0;
-  __syncthreads();
-  for (int vb = v0 + (threadIdx.x & ~31); vb < v1; vb += 256) {  // warp-uniform trip count
-    const int v = vb + lane;
-    bool act = false;
-    int pos = 0;
-    if (v < v1) {
-      act = coef_of(g_rep[base + v], rep[base + v]) != 0.f;
-      pos = argmax[base + v];
+  for (int vb = v0; vb < v1; vb += 128) {  // four 32-term steps per trip: their loads are issued together
+    float gg[4], rr[4];
+    int pp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = vb + 32 * u + lane;
+      gg[u] = rr[u] = 0.f;
+      pp[u] = 0;
+      if (v < v1) {
+        gg[u] = g_rep[base + v];
+        rr[u] = rep[base + v];
+        pp[u] = argmax[base + v];
+      }
     }
-    const uint32_t am = __ballot_sync(0xffffffffu, act);
-    if (act) {
-      const uint32_t peers = __match_any_sync(am, pos);
-      if (lane == __ffs(peers) - 1) atomicAdd(&sm[pos], __popc(peers));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool act = coef_of(gg[u], rr[u]) != 0.f;
+      const uint32_t am = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const uint32_t peers = __match_any_sync(am, pp[u]);
+        if (lane == __ffs(peers) - 1) cnt[pp[u]] += __popc(peers);  // one lane per distinct position: no race
+      }
+      __syncwarp();
     }
   }
-  __syncthreads();
-  int32_t* c = counts + static_cast<size_t>(b) * (S + 1);
-  for (int s = threadIdx.x; s < S; s += 256) {
-    const int n = sm[s];
-    if (n) atomicAdd(&c[s], n);
-  }
+  int32_t* out = chunk_counts + (static_cast<size_t>(b) * n_chunks + ch) * S;
+  for (int s = lane; s < S; s += 32) out[s] = cnt[s];
 }
 
-// counts [B,S+1] -> row_ptr (exclusive scan, in place) and cursor copy.  One CTA per document.
+// chunk_counts -> row_ptr [B][S+1] (exclusive scan over positions of the per-position totals) and, in place,
+// chunk_counts[b][ch][s] := row_ptr[b][s] + sum_{ch' < ch} counts[b][ch'][s].  One CTA per document.
 __global__ void __launch_bounds__(kBucketThreads)
-bucket_scan_kernel(int S, int32_t* __restrict__ row_ptr, int32_t* __restrict__ cursor) {
+bucket_scan_kernel(int S, int n_chunks, int32_t* __restrict__ chunk_counts, int32_t* __restrict__ row_ptr) {
   __shared__ int32_t warp_tot[32];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
+  int32_t* cc = chunk_counts + static_cast<size_t>(b) * n_chunks * S;
   int32_t* rp = row_ptr + static_cast<size_t>(b) * (S + 1);
-  int32_t* cur = cursor + static_cast<size_t>(b) * (S + 1);
   const int per = (S + kBucketThreads - 1) / kBucketThreads;
   const int lo = min(S, tid * per), hi = min(S, lo + per);
   int tsum = 0;
-  for (int s = lo; s < hi; ++s) tsum += rp[s];
+  for (int s = lo; s < hi; ++s) {
+    int tot = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) tot += cc[static_cast<size_t>(ch) * S + s];
+    rp[s] = tot;  // per-position total, turned into the exclusive offset below
+    tsum += tot;
+  }
   int incl = tsum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -101,42 +125,70 @@ bucket_scan_kernel(int S, int32_t* __restrict__ row_ptr, int32_t* __restrict__ c
   __syncthreads();
   int run = warp_tot[tid >> 5] + incl - tsum;
   for (int s = lo; s < hi; ++s) {
-    const int c = rp[s];
+    const int tot = rp[s];
     rp[s] = run;
-    cur[s] = run;
-    run += c;
+    int acc = run;
+    for (int ch = 0; ch < n_chunks; ++ch) {  // first slot of position s for each chunk
+      const size_t i = static_cast<size_t>(ch) * S + s;
+      const int c = cc[i];
+      cc[i] = acc;
+      acc += c;
+    }
+    run += tot;
   }
   if (tid == kBucketThreads - 1) rp[S] = run;  // total number of active terms of this document
 }
 
 __global__ void __launch_bounds__(256)
 bucket_scatter_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep,
-                      const int32_t* __restrict__ argmax, int S, int V, int32_t* __restrict__ cursor,
-                      int32_t* __restrict__ sorted_v, float* __restrict__ sorted_c) {
-  const int b = blockIdx.y;
-  const int v0 = blockIdx.x * kChunk, v1 = min(V, v0 + kChunk);
+                      const int32_t* __restrict__ argmax, int B, int S, int V, int n_chunks, int warps_per_cta,
+                      const int32_t* __restrict__ chunk_base, int32_t* __restrict__ sorted_v,
+                      float* __restrict__ sorted_c) {
+  extern __shared__ int32_t sm[];  // [warps_per_cta][S] running slot per position
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= warps_per_cta) return;
+  const long long job = static_cast<long long>(blockIdx.x) * warps_per_cta + warp;
+  if (job >= static_cast<long long>(B) * n_chunks) return;
+  const int b = static_cast<int>(job / n_chunks), ch = static_cast<int>(job % n_chunks);
+  int32_t* cur = sm + static_cast<size_t>(warp) * S;
+  const int32_t* cb = chunk_base + (static_cast<size_t>(b) * n_chunks + ch) * S;
+  for (int s = lane; s < S; s += 32) cur[s] = cb[s];
+  __syncwarp();
+  const int v0 = ch * kChunk, v1 = min(V, v0 + kChunk);
   const size_t base = static_cast<size_t>(b) * V;
-  const int lane = threadIdx.x & 31;
-  int32_t* cur = cursor + static_cast<size_t>(b) * (S + 1);
-  for (int vb = v0 + (threadIdx.x & ~31); vb < v1; vb += 256) {
-    const int v = vb + lane;
-    float c = 0.f;
-    int pos = 0;
-    if (v < v1) {
-      c = coef_of(g_rep[base + v], rep[base + v]);
-      pos = argmax[base + v];
+  for (int vb = v0; vb < v1; vb += 128) {
+    float cc4[4];
+    int pp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = vb + 32 * u + lane;
+      cc4[u] = 0.f;
+      pp[u] = 0;
+      if (v < v1) {
+        cc4[u] = coef_of(g_rep[base + v], rep[base + v]);
+        pp[u] = argmax[base + v];
+      }
     }
-    const bool act = c != 0.f;
-    const uint32_t am = __ballot_sync(0xffffffffu, act);
-    if (act) {
-      const uint32_t peers = __match_any_sync(am, pos);
-      const int leader = __ffs(peers) - 1;
-      int slot0 = 0;
-      if (lane == leader) slot0 = atomicAdd(&cur[pos], __popc(peers));
-      slot0 = __shfl_sync(peers, slot0, leader);
-      const int slot = slot0 + __popc(peers & ((1u << lane) - 1u));
-      sorted_v[base + slot] = v;
-      sorted_c[base + slot] = c;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = vb + 32 * u + lane;
+      const float c = cc4[u];
+      const int pos = pp[u];
+      const bool act = c != 0.f;
+      const uint32_t am = __ballot_sync(0xffffffffu, act);
+      uint32_t peers = 0;
+      int slot = 0;
+      if (act) {
+        peers = __match_any_sync(am, pos);
+        slot = cur[pos] + __popc(peers & ((1u << lane) - 1u));  // lanes are in term order
+      }
+      __syncwarp();
+      if (act) {
+        if (lane == __ffs(peers) - 1) cur[pos] += __popc(peers);
+        sorted_v[base + slot] = v;
+        sorted_c[base + slot] = c;
+      }
+      __syncwarp();
     }
   }
 }
@@ -281,7 +333,9 @@ dw_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep, const 
 }  // namespace
 
 size_t head_bwd_workspace_bytes(int B, int S, int V) {
-  return 2 * align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t)) +
+  const size_t n_chunks = (static_cast<size_t>(V) + kChunk - 1) / kChunk;
+  return align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t)) +
+         align256(static_cast<size_t>(B) * n_chunks * S * sizeof(int32_t)) +
          2 * align256(static_cast<size_t>(B) * V * sizeof(int32_t));
 }
 
@@ -315,21 +369,29 @@ int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax,
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int32_t* row_ptr = reinterpret_cast<int32_t*>(ws);
   ws += align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t));
-  int32_t* cursor = reinterpret_cast<int32_t*>(ws);
-  ws += align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t));
+  const int n_chunks = (V + kChunk - 1) / kChunk;
+  int32_t* chunk_tab = reinterpret_cast<int32_t*>(ws);
+  ws += align256(static_cast<size_t>(B) * n_chunks * S * sizeof(int32_t));
   int32_t* sorted_v = reinterpret_cast<int32_t*>(ws);
   ws += align256(static_cast<size_t>(B) * V * sizeof(int32_t));
   float* sorted_c = reinterpret_cast<float*>(ws);
 
-  SPLADE_CUDA_OK(cudaMemsetAsync(row_ptr, 0, static_cast<size_t>(B) * (S + 1) * sizeof(int32_t), stream));
-  if (bucket_smem > 48 * 1024) {
+  // warp-private position counters live in shared memory: as many warps per CTA as fit
+  const int warps_per_cta = static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / bucket_smem)));
+  const size_t smem_cs = bucket_smem * warps_per_cta;
+  if (smem_cs > 48 * 1024) {
     SPLADE_CUDA_OK(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(bucket_smem)));
+                                        static_cast<int>(smem_cs)));
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem_cs)));
   }
-  const dim3 vchunks((V + kChunk - 1) / kChunk, B);
-  bucket_count_kernel<<<vchunks, 256, bucket_smem, stream>>>(g_rep, rep, argmax, S, V, row_ptr);
-  bucket_scan_kernel<<<B, kBucketThreads, 0, stream>>>(S, row_ptr, cursor);
-  bucket_scatter_kernel<<<vchunks, 256, 0, stream>>>(g_rep, rep, argmax, S, V, cursor, sorted_v, sorted_c);
+  const long long jobs = static_cast<long long>(B) * n_chunks;
+  const unsigned grid_cs = static_cast<unsigned>((jobs + warps_per_cta - 1) / warps_per_cta);
+  bucket_count_kernel<<<grid_cs, 256, smem_cs, stream>>>(g_rep, rep, argmax, B, S, V, n_chunks, warps_per_cta,
+                                                        chunk_tab);
+  bucket_scan_kernel<<<B, kBucketThreads, 0, stream>>>(S, n_chunks, chunk_tab, row_ptr);
+  bucket_scatter_kernel<<<grid_cs, 256, smem_cs, stream>>>(g_rep, rep, argmax, B, S, V, n_chunks, warps_per_cta,
+                                                          chunk_tab, sorted_v, sorted_c);
   SPLADE_CUDA_OK(cudaGetLastError());
 
   const uint16_t* Wb = static_cast<const uint16_t*>(W);

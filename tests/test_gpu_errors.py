@@ -54,10 +54,10 @@ def test_forward_paths_are_deterministic(cuda_device):
         loss.backward()
         outs.append((loss.detach(), q.grad, p.grad, n.grad))
     assert all(torch.equal(x, y) for x, y in zip(*outs))
-    # dW / dbias of the head backward sum over the batch in a fixed order
+    # the head backward is bit-reproducible too: dW / dbias sum over the batch in a fixed order,
     g = torch.randn_like(rep)
     h16, w16 = hidden.to(torch.bfloat16).contiguous(), W.to(torch.bfloat16).contiguous()
     b1 = splade_b200.head_backward(g, rep, a[1], h16, w16)
     b2 = splade_b200.head_backward(g, rep, a[1], h16, w16)
     assert torch.equal(b1[1], b2[1]) and torch.equal(b1[2], b2[2])
-    torch.testing.assert_close(b1[0], b2[0], rtol=1e-5, atol=1e-6)   # dHidden: bucket order is an atomic cursor
+    assert torch.equal(b1[0], b2[0])   # dHidden: buckets list their terms in ascending term id (ordered counting sort)
