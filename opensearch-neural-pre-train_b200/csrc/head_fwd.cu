@@ -53,6 +53,8 @@ struct HeadFwdParams {
   const float* bias;
   const int32_t* mask;  // [B,S], nonzero = real token
   const uint32_t* tile_masks;  // [n_tt][8]: 256-bit column validity bitmap per token tile (prepass)
+  const int32_t* tile_n16;     // [n_tt]: columns up to the last valid one, rounded up to 16 (UMMA N of the tile)
+  int trim_rows;               // 1: one document per tile -> the producer also loads only ceil64(n16) token rows
   float* rep;           // [B,V]
   int32_t* argmax;      // [B,V]
   uint32_t* packed;     // [B,V] (bf16 bits << 16 | 0xFFFF - pos), only when a doc spans several tiles
@@ -96,7 +98,11 @@ __device__ __forceinline__ TileCoord tile_coord(const HeadFwdParams& p, int item
 // Prepass: the 256-bit column-validity bitmap of every token tile (bit c = column c of the tile is a real,
 // unmasked token).  One CTA of 256 threads (8 warps = 8 words) per token tile; a few microseconds, and it takes
 // eight dependent global loads + ballots per tile out of the epilogue warps' critical path.
-__global__ void __launch_bounds__(256) build_tile_masks_kernel(const HeadFwdParams p, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+build_tile_masks_kernel(const HeadFwdParams p, uint32_t* __restrict__ out, int32_t* __restrict__ n16_out) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = -1;
+  __syncthreads();
   TileCoord t = tile_coord(p, blockIdx.x);  // vt = 0 since blockIdx.x < n_tt
   const int col = threadIdx.x;
   const int d = col / p.s_box;
@@ -104,7 +110,14 @@ __global__ void __launch_bounds__(256) build_tile_masks_kernel(const HeadFwdPara
   bool ok = false;
   if (d < t.nb && s < t.ns) ok = p.mask[static_cast<size_t>(t.b0 + d) * p.S + t.s0 + s] != 0;
   const uint32_t word = __ballot_sync(0xffffffffu, ok);
-  if ((threadIdx.x & 31) == 0) out[blockIdx.x * 8 + (threadIdx.x >> 5)] = word;
+  if ((threadIdx.x & 31) == 0) {
+    out[blockIdx.x * 8 + (threadIdx.x >> 5)] = word;
+    if (word) atomicMax(&s_last, static_cast<int>(threadIdx.x) + 31 - __clz(word));
+  }
+  __syncthreads();
+  // Padding is a suffix in practice (right-padded batches): everything after the last valid column of the tile
+  // needs no MMA work at all.  N must be a multiple of 16 and at least 16.
+  if (threadIdx.x == 0) n16_out[blockIdx.x] = min(p.umma_n, max(16, (s_last + 1 + 15) / 16 * 16));
 }
 
 // One 32-column window of one document, for one vocabulary entry per thread.
@@ -262,7 +275,8 @@ __device__ __forceinline__ void epilogue_loop(const HeadFwdParams& p, const Epil
 template <bool kTokW>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
-                const HeadFwdParams p) {
+                const __grid_constant__ CUtensorMap tmap_h64, const __grid_constant__ CUtensorMap tmap_h128,
+                const __grid_constant__ CUtensorMap tmap_h192, const HeadFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
@@ -279,6 +293,11 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_h);
+    if (p.trim_rows) {
+      tma_prefetch_desc(&tmap_h64);
+      tma_prefetch_desc(&tmap_h128);
+      tma_prefetch_desc(&tmap_h192);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -306,13 +325,23 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       uint32_t stage = 0, phase = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const TileCoord t = tile_coord(p, item);
+        // Tail trimming: with one document per tile only ceil64(n16) token rows are fetched.
+        const CUtensorMap* hmap = &tmap_h;
+        uint32_t tx_bytes = p.stage_tx_bytes;
+        if (p.trim_rows) {
+          const int n16 = __ldg(&p.tile_n16[item % p.n_tt]);
+          const int sel = (n16 + 63) / 64;  // 1..4
+          const int rows = min(p.s_box, 64 * sel);
+          hmap = sel == 1 ? &tmap_h64 : (sel == 2 ? &tmap_h128 : (sel == 3 ? &tmap_h192 : &tmap_h));
+          tx_bytes = static_cast<uint32_t>(A_BYTES + rows * BLOCK_K * 2);
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* a_dst = smem + stage * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_2d(a_dst, &tmap_w, &full_bar[stage], kb * BLOCK_K, t.vt * BLOCK_V);
-          tma_load_3d(b_dst, &tmap_h, &full_bar[stage], kb * BLOCK_K, t.s0, t.b0);
+          tma_load_3d(b_dst, hmap, &full_bar[stage], kb * BLOCK_K, t.s0, t.b0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -323,11 +352,13 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16_f32(BLOCK_V, static_cast<uint32_t>(p.umma_n));
       uint32_t stage = 0, phase = 0, it = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const uint32_t acc = it & 1u;
         const uint32_t acc_phase = (it >> 1) & 1u;
+        // UMMA N of this tile: columns after the last valid token are never computed (MMA time ~ N)
+        const uint32_t idesc =
+            make_idesc_bf16_f32(BLOCK_V, static_cast<uint32_t>(__ldg(&p.tile_n16[item % p.n_tt])));
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_T;
@@ -563,7 +594,8 @@ size_t head_fwd_workspace_bytes(int B, int S, int V, bool want_tokw) {
   if (B <= 0 || S <= 0) return 0;
   int s_box, b_box, cpd, n_tt, umma_n;
   head_fwd_plan(B, S, &s_box, &b_box, &cpd, &n_tt, &umma_n);
-  size_t bytes = align256(static_cast<size_t>(n_tt) * 8 * sizeof(uint32_t));
+  size_t bytes = align256(static_cast<size_t>(n_tt) * 8 * sizeof(uint32_t)) +
+                 align256(static_cast<size_t>(n_tt) * sizeof(int32_t));
   if (S > BLOCK_T) bytes += align256(static_cast<size_t>(B) * V * sizeof(uint32_t));
   if (want_tokw) bytes += align256(static_cast<size_t>(B) * S * sizeof(uint32_t));
   return bytes;
@@ -606,6 +638,9 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
   uint32_t* tile_masks = reinterpret_cast<uint32_t*>(ws);
   p.tile_masks = tile_masks;
   ws += align256(static_cast<size_t>(p.n_tt) * 8 * sizeof(uint32_t));
+  int32_t* tile_n16 = reinterpret_cast<int32_t*>(ws);
+  p.tile_n16 = tile_n16;
+  ws += align256(static_cast<size_t>(p.n_tt) * sizeof(int32_t));
   if (p.chunks_per_doc > 1) {
     p.packed = reinterpret_cast<uint32_t*>(ws);
     const size_t n = static_cast<size_t>(B) * V * sizeof(uint32_t);
@@ -621,7 +656,7 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
   const int cols = p.s_box * p.b_box;
   bool use_pair = pair_enabled() && (sm_count() % 2 == 0) && (cols % 16 == 0) &&
                   ((p.b_box % 2 == 0) || (p.b_box == 1 && p.s_box % 16 == 0));
-  CUtensorMap tmap_w, tmap_h;
+  CUtensorMap tmap_w, tmap_h, tmap_trim[3];
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(H), static_cast<uint64_t>(V)};
     const uint64_t strides[1] = {static_cast<uint64_t>(H) * 2};
@@ -643,9 +678,17 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
     }
     rc = encode_tmap_bf16(&tmap_h, hidden, 3, dims, strides, box);
     if (rc != kOk) return rc;
+    // Trimmed boxes (64 / 128 / 192 token rows) for tiles whose document ends early; single-CTA kernel only.
+    p.trim_rows = (!use_pair && p.b_box == 1 && p.s_box > 64) ? 1 : 0;
+    for (int i = 0; i < 3; ++i) {
+      uint32_t tbox[3] = {BLOCK_K, static_cast<uint32_t>(p.trim_rows ? std::min(p.s_box, 64 * (i + 1)) : p.s_box),
+                          static_cast<uint32_t>(p.b_box)};
+      rc = encode_tmap_bf16(&tmap_trim[i], hidden, 3, dims, strides, tbox);
+      if (rc != kOk) return rc;
+    }
   }
 
-  build_tile_masks_kernel<<<p.n_tt, 256, 0, stream>>>(p, tile_masks);
+  build_tile_masks_kernel<<<p.n_tt, 256, 0, stream>>>(p, tile_masks, tile_n16);
   SPLADE_CUDA_OK(cudaGetLastError());
 
   if (use_pair) {
@@ -659,7 +702,7 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
     const int grid = std::min(sm_count(), total_items);
     auto kernel = tokw ? head_fwd_kernel<true> : head_fwd_kernel<false>;
     SPLADE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmap_w, tmap_h, p);
+    kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmap_w, tmap_h, tmap_trim[0], tmap_trim[1], tmap_trim[2], p);
   }
   SPLADE_CUDA_OK(cudaGetLastError());
 
