@@ -412,6 +412,33 @@ def run_ours(args):
         train["sparse_regime"] = run_train_leg(dev, world, rank, steps=max(3, min(20, K)), warmup=3, k_neg=1,
                                                gather=(world > 1 and args.gather_negatives), bias_offset=-2.0)
 
+    gpu_ref = None
+    if world == 1 and rank == 0 and not args.no_gpu_reference:
+        # the fair GPU baseline: the reference's own chain (cuBLAS bf16 GEMM + ATen relu/log1p/mul/max under
+        # autocast, oracle/torch_reference.py) on the same device and the same inputs
+        try:
+            from oracle import torch_reference as TR
+            h, w, b, m = sets[0]
+            hf, wf = h.float(), w.float()
+            with torch.no_grad():
+                for _ in range(2):
+                    TR.head_chain_autocast(hf, wf, b, m)
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                for _ in range(5):
+                    TR.head_chain_autocast(hf, wf, b, m)
+                r1.record()
+                torch.cuda.synchronize()
+            ref_ms = r0.elapsed_time(r1) / 5
+            gpu_ref = {"ms_per_step": ref_ms, "docs_per_s": B_DOCS / ref_ms * 1e3,
+                       "what": "reference head chain under torch.autocast(bf16) on the same GPU (cuBLAS + ATen)",
+                       "speedup_of_fused_head": ref_ms / (total_ms / K)}
+            del hf, wf
+            torch.cuda.empty_cache()
+        except Exception as e:
+            gpu_ref = {"error": repr(e)[:200]}
+
     full = None
     if world == 1 and rank == 0 and not args.no_full_model:
         try:
@@ -474,6 +501,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "train": train,
         "full_encode": full,
+        "gpu_reference_chain": gpu_ref,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -489,6 +517,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step leg")
     ap.add_argument("--no-full-model", action="store_true", help="skip the trunk+head context leg")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-chain-on-GPU context leg")
     ap.add_argument("--gather-negatives", action="store_true",
                     help="training leg: all-gather positives across ranks (north-star extension)")
     args = ap.parse_args()

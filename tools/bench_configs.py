@@ -163,6 +163,14 @@ def main():
                                   "projected_seconds_for_1M_docs": 1e6 / (n_total / dt),
                                   "d2h_bytes_per_doc": 64 * 8 + 4}
 
+    # ---------------- N1 check: what the un-fused head prologue (dense 768x768 -> GELU -> LayerNorm) costs
+    x = torch.randn(64, 256, H, generator=g).to(dev)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ms_pro = cuda_time(lambda: model.model.head(x).to(torch.bfloat16), 20)
+    out["head_prologue_hf"] = {"ms": ms_pro, "shape": "[64,256,768]",
+                               "note": "HF ModernBertPredictionHead under autocast + the bf16 cast; fusing it into "
+                                       "the projection (SURVEY 8(f) N1) could save at most this per encoder call"}
+
     # ---------------- config 3 again, full model (trunk + head + top-k)
     q_ids = torch.randint(6, V - 1, (Bq, Sq), generator=g).to(dev)
     q_mask = torch.ones(Bq, Sq, dtype=torch.int64, device=dev)
