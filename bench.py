@@ -35,6 +35,7 @@ B_DOCS, SEQ, HIDDEN, VOCAB = 64, 256, 768, 50000
 WORKLOAD = "C2: SPLADE-max head encode, A.X-Encoder-base head shape (hidden 768 -> vocab 50000), batch 64 x L=256"
 FLOP_PER_STEP = 2.0 * B_DOCS * SEQ * HIDDEN * VOCAB          # 76.8 MFLOP per token
 N_ROTATE = 3                                                 # distinct input sets (see config.l2)
+LAUNCHES_PER_STEP = 7                                        # kernels per splade_head_fwd call (see gpu_launches)
 
 
 def load_peaks():
@@ -304,6 +305,49 @@ def run_full_encode_leg(dev, steps=5, warmup=2):
     out["speedup"] = out["reference_chain"]["ms_per_batch"] / out["ours"]["ms_per_batch"]
     return out
 
+def run_ragged_leg(dev, iters=20):
+    """Right-padded batches as the reference's collator produces them (dynamic padding to the longest member,
+    src/train/data/dataloader.py:46-164): the padded tiling vs the packed variable-length tiling
+    (splade_head_fwd_mode) vs the device-side auto plan, for documents (C2 shape) and queries (C3 shape).
+    FLOP are counted on REAL tokens only."""
+    import torch
+
+    import splade_b200
+    out = {}
+    g = torch.Generator().manual_seed(3)
+    W = (torch.randn(VOCAB, HIDDEN, generator=g) * 0.0176).to(torch.bfloat16).to(dev)
+    bias = (torch.randn(VOCAB, generator=g) * 0.02).to(torch.bfloat16).float().to(dev)
+    cases = (("docs_64x256_len_U[32,256]", 64, 256, 32, 256), ("queries_512x64_len_U[4,24]", 512, 64, 4, 24))
+    for name, B, S, lo, hi in cases:
+        hidden = torch.randn(B, S, HIDDEN, generator=g).to(torch.bfloat16).to(dev)
+        lens = torch.randint(lo, hi + 1, (B,), generator=g)
+        mask = (torch.arange(S)[None, :] < lens[:, None]).to(torch.int32).to(dev)
+        toks = int(lens.sum())
+        row = {"real_tokens": toks, "real_frac": toks / (B * S)}
+        plan = torch.zeros(4, dtype=torch.int32, device=dev)
+        for label, mode in (("padded", 0), ("packed", 1), ("auto", -1)):
+            def fn():
+                return splade_b200.head_forward(hidden, W, bias, mask, False, pack_mode=mode, plan_out=plan)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            row[label + "_ms"] = ms
+            row[label + "_tflops_on_real_tokens"] = 2.0 * toks * HIDDEN * VOCAB / ms / 1e9
+        row["auto_picked"] = "packed" if int(plan[0]) == 1 else "padded"
+        row["docs_per_s_auto"] = B / row["auto_ms"] * 1e3
+        row["speedup_packed_over_padded"] = row["padded_ms"] / row["packed_ms"]
+        out[name] = row
+        del hidden
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
@@ -439,6 +483,13 @@ def run_ours(args):
         except Exception as e:
             gpu_ref = {"error": repr(e)[:200]}
 
+    ragged = None
+    if world == 1 and rank == 0 and not args.no_ragged:
+        try:
+            ragged = run_ragged_leg(dev)
+        except Exception as e:  # context only
+            ragged = {"error": repr(e)[:200]}
+
     full = None
     if world == 1 and rank == 0 and not args.no_full_model:
         try:
@@ -496,10 +547,16 @@ def run_ours(args):
                        "host buffers (H2D, fused head, D2H enqueued on the slot's stream; 2 slots / 2 streams)",
                 "checksum": checksum,
                 "numa_bound": numa_bound},
-        "gpu_launches": K,  # one head_fwd_kernel launch per step in the device-resident region (e2e: +K)
+        # kernels of libsplade_b200.so launched per step in the device-resident timed region (splade_head_fwd, auto
+        # tiling policy): build_tile_masks, varlen_count, varlen_plan, varlen_pack (exits: padded tiling chosen),
+        # head_fwd_kernel, head_fwd_varlen_kernel (exits), finalize_varlen (exits).  The e2e region adds 2 per step
+        # (build_tile_masks + head_fwd_kernel: splade_head_fwd_host decides the tiling on the host).
+        "gpu_launches": LAUNCHES_PER_STEP * K,
+        "gpu_launches_per_step": LAUNCHES_PER_STEP,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "train": train,
+        "ragged": ragged,
         "full_encode": full,
         "gpu_reference_chain": gpu_ref,
     }
@@ -517,6 +574,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step leg")
     ap.add_argument("--no-full-model", action="store_true", help="skip the trunk+head context leg")
+    ap.add_argument("--no-ragged", action="store_true", help="skip the ragged-batch (packed tiling) context leg")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-chain-on-GPU context leg")
     ap.add_argument("--gather-negatives", action="store_true",
                     help="training leg: all-gather positives across ranks (north-star extension)")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPLADE_B200_ABI_VERSION 1
+#define SPLADE_B200_ABI_VERSION 2
 
 /* error codes */
 #define SPLADE_OK 0
@@ -66,6 +66,26 @@ size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k);
 int splade_head_fwd(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S, int H,
                     int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
                     void* stream);
+
+/*
+ * splade_head_fwd with an explicit token-layout policy.  Right-padded batches (the reference's collator pads every
+ * batch to its longest member, src/train/data/dataloader.py:46-164; queries are ~10 real tokens in S=64) spend
+ * tensor-core time on padding.  The packed layout gathers the REAL tokens of the batch back to back ([T,H],
+ * T = sum of lengths) and tiles those; results are bit-identical to the padded layout.
+ *   pack_mode  SPLADE_PACK_AUTO: a device-side plan compares the cost of both tilings and picks one - no host
+ *              synchronisation, both kernels are enqueued and the one not chosen exits immediately;
+ *              SPLADE_PACK_OFF / SPLADE_PACK_ON pin the padded / packed tiling.
+ *   plan_out   optional DEVICE int32[4]: {tiling used (0 padded, 1 packed), real tokens T, packed 256-token
+ *              tiles, UMMA N of the last packed tile}; all zero when the packed path was not considered.
+ * splade_head_fwd itself uses the policy in the environment variable SPLADE_B200_PACK (auto | 0 | 1, default
+ * auto).  The packed path needs B <= 32767 and B*S <= 2^30; other shapes silently use the padded tiling.
+ */
+#define SPLADE_PACK_AUTO (-1)
+#define SPLADE_PACK_OFF 0
+#define SPLADE_PACK_ON 1
+int splade_head_fwd_mode(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S,
+                         int H, int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
+                         int pack_mode, int32_t* plan_out, void* stream);
 
 /*
  * Host-buffer form of splade_head_fwd for callers whose activations live in host memory (and for the end-to-end

@@ -108,12 +108,11 @@ int splade_abi_version(void) { return SPLADE_B200_ABI_VERSION; }
 const char* splade_last_error(void) { return g_last_error; }
 
 size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k) {
-  (void)H;
   switch (op) {
     case SPLADE_OP_HEAD_FWD:
-      return head_fwd_workspace_bytes(B, S, V, /*want_tokw=*/false);
+      return head_fwd_workspace_bytes(B, S, H, V, /*want_tokw=*/false);
     case SPLADE_OP_HEAD_FWD_TOKW:
-      return head_fwd_workspace_bytes(B, S, V, /*want_tokw=*/true);
+      return head_fwd_workspace_bytes(B, S, H, V, /*want_tokw=*/true);
     case SPLADE_OP_HEAD_BWD:
       return head_bwd_workspace_bytes(B, S, V);
     case SPLADE_OP_FLOPS_NNZ:
@@ -131,7 +130,14 @@ int splade_head_fwd(const void* hidden, const void* W, const float* bias, const 
                     int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
                     void* stream) {
   return head_fwd_launch(hidden, W, bias, mask, B, S, H, V, rep, argmax, tokw, workspace, ws_bytes,
-                         static_cast<cudaStream_t>(stream));
+                         pack_mode_from_env(), nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int splade_head_fwd_mode(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S,
+                         int H, int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
+                         int pack_mode, int32_t* plan_out, void* stream) {
+  return head_fwd_launch(hidden, W, bias, mask, B, S, H, V, rep, argmax, tokw, workspace, ws_bytes, pack_mode,
+                         plan_out, static_cast<cudaStream_t>(stream));
 }
 
 int splade_head_fwd_host(const void* hidden_host, const int32_t* mask_host, const void* W, const float* bias, int B,
@@ -147,7 +153,7 @@ int splade_head_fwd_host(const void* hidden_host, const int32_t* mask_host, cons
   SPLADE_CUDA_OK(cudaMemcpyAsync(hidden_dev, hidden_host, tokens * H * 2, cudaMemcpyHostToDevice, st));
   SPLADE_CUDA_OK(cudaMemcpyAsync(mask_dev, mask_host, tokens * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   const int rc = head_fwd_launch(hidden_dev, W, bias, mask_dev, B, S, H, V, rep_dev, argmax_dev, nullptr, workspace,
-                                 ws_bytes, st);
+                                 ws_bytes, head_fwd_pack_mode_host(mask_host, B, S), nullptr, st);
   if (rc != kOk) return rc;
   const size_t out = static_cast<size_t>(B) * V;
   if (rep_host) SPLADE_CUDA_OK(cudaMemcpyAsync(rep_host, rep_dev, out * sizeof(float), cudaMemcpyDeviceToHost, st));

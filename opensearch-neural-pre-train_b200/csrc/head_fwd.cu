@@ -68,6 +68,8 @@ struct HeadFwdParams {
   // CTA-pair kernel only: how the token rows of a tile are split between the two CTAs
   int pair_split_docs;   // 1: each CTA takes b_box/2 documents; 0: each CTA takes half of one document's rows
   int pair_half_rows;    // token rows per CTA (= umma_n / 2)
+  const int32_t* plan_mode;  // device flag written by varlen_plan_kernel (nullptr: padded path unconditionally);
+                             // != 0 means the packed kernel owns this call and the padded kernels exit at once
 };
 
 struct TileCoord {
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                 const __grid_constant__ CUtensorMap tmap_h64, const __grid_constant__ CUtensorMap tmap_h128,
                 const __grid_constant__ CUtensorMap tmap_h192, const HeadFwdParams p) {
+  if (p.plan_mode != nullptr && __ldg(p.plan_mode) != 0) return;  // grid-uniform: the packed kernel runs instead
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
@@ -546,7 +549,8 @@ head_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
 
 // packed (bf16 bits << 16 | 0xFFFF - pos) -> fp32 log1p weight + int32 argmax (documents longer than one tile)
 __global__ void finalize_packed_kernel(const uint32_t* __restrict__ packed, float* __restrict__ rep,
-                                       int32_t* __restrict__ argmax, size_t n) {
+                                       int32_t* __restrict__ argmax, size_t n, const int32_t* plan_mode) {
+  if (plan_mode != nullptr && __ldg(plan_mode) != 0) return;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t k = packed[i];
@@ -560,6 +564,493 @@ __global__ void finalize_tokw_kernel(const uint32_t* __restrict__ bits, float* _
   if (i >= n) return;
   tokw[i] = log1pf(bf16_bits_to_float(bits[i]));
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed (variable-length) path.  Right-padded batches waste tensor-core time on padding: a batch of queries
+// padded to S=64 with ~10 real tokens each is 85 % zeros.  Here the REAL tokens of the whole batch are packed
+// back to back into [T, H], the token operand is a plain 2-D TMA tile of 256 consecutive packed tokens, and the
+// epilogue follows the document boundaries inside the tile: every thread still owns one vocabulary entry and
+// walks its columns left to right, but it flushes (doc, term) whenever the column's document changes.
+//
+//   * Every document starts at a multiple of 8 packed columns; the <= 7 filler columns behind its last token are
+//     REPLICAS of that token (same hidden row, same (doc, position) descriptor).  A replica can never change a
+//     maximum, loses every tie to the original (it sits to its right) and sends token_weights the value the
+//     original already sent - so the epilogue needs no per-column masks, and document boundaries fall on the
+//     static 8-column groups of a 32-column window.
+//   * Eight epilogue warps: warps 4-7 drain columns 0-127 of the accumulator, warps 8-11 columns 128-255 (two
+//     warps per SM sub-partition hide each other's latencies).  A document that lies inside one 128-column half
+//     is stored directly; one that straddles halves is merged through the same 32-bit atomicMax key as the
+//     S > 256 padded path and decoded by a finalize pass.
+//
+// Everything is decided ON THE DEVICE (no host synchronisation): a plan kernel compares the MMA/L2 cost of the
+// padded tiling with the packed one and sets plan.mode; both main kernels are launched and the one that is not
+// selected exits at its first instruction.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int VL_ALIGN = 8;                 // packed columns per document are rounded up to this
+constexpr int VL_HALF = BLOCK_T / 2;        // columns drained by one epilogue warp group
+constexpr int VL_THREADS = 384;             // producer, MMA, TMEM-alloc, idle + 2 x 4 epilogue warps
+constexpr uint32_t VL_SPAN_BIT = 0x80000000u;
+
+struct VarlenPlan {
+  int32_t mode;      // 0: padded kernel runs, 1: packed kernel runs
+  int32_t T;         // packed columns in the batch (real tokens + replicas)
+  int32_t n_tt;      // packed token tiles = ceil(T / 256)
+  int32_t n16_last;  // UMMA N of the last packed tile
+  int32_t T_real;    // real tokens in the batch
+};
+
+struct VarlenParams {
+  const float* bias;
+  const VarlenPlan* plan;
+  const uint32_t* meta;   // [rows]: (straddles << 31) | (doc << 16) | position of every packed column
+  const uint8_t* spans;   // [B]: 1 = the document's columns straddle a 128-column half-tile boundary
+  const int32_t* len;     // [B]: real tokens per document
+  float* rep;             // [B,V]
+  int32_t* argmax;        // [B,V]
+  uint32_t* keys;         // [B,V] (bf16 bits << 16 | 0xFFFF - pos) merge buffer of straddling documents
+  uint32_t* tokw_bits;    // [B,S] or nullptr
+  int B, S, H, V, n_vt;
+};
+
+// len[b] = number of unmasked positions of document b (one warp per document)
+__global__ void __launch_bounds__(256)
+varlen_count_kernel(const int32_t* __restrict__ mask, int B, int S, int32_t* __restrict__ len) {
+  const int b = blockIdx.x * 8 + static_cast<int>(threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = static_cast<int>(threadIdx.x & 31u);
+  int c = 0;
+  for (int s = lane; s < S; s += 32) c += mask[static_cast<size_t>(b) * S + s] != 0 ? 1 : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0) len[b] = c;
+}
+
+// One CTA: exclusive scan of the 8-aligned lengths (packed offset of every document), straddle flags, and the
+// decision.  Cost model in "operand rows streamed from L2 per (vocab tile, token tile)": 128 vocabulary rows +
+// the token rows the tile loads (the kernel is within a few percent of both its tensor and its L2->SM limit, so
+// a tile with fewer columns still pays for its vocabulary rows).
+__global__ void __launch_bounds__(1024)
+varlen_plan_kernel(const int32_t* __restrict__ len, int B, const int32_t* __restrict__ tile_n16, int n_tt_pad,
+                   int trim_rows, int pad_cols, int force_mode, int32_t* __restrict__ off,
+                   uint8_t* __restrict__ spans, VarlenPlan* __restrict__ plan, int32_t* __restrict__ plan_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  __shared__ int s_real;
+  __shared__ unsigned long long s_cost;
+  const int tid = static_cast<int>(threadIdx.x);
+  const int lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    s_carry = 0;
+    s_real = 0;
+    s_cost = 0ull;
+  }
+  __syncthreads();
+  int real = 0;
+  for (int base = 0; base < B; base += 1024) {
+    const int i = base + tid;
+    const int l = i < B ? len[i] : 0;
+    real += l;
+    const int x = (l + VL_ALIGN - 1) / VL_ALIGN * VL_ALIGN;
+    int incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = s_warp[lane];
+      int wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += y;
+      }
+      s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int excl = carry + s_warp[warp] + incl - x;
+    if (i < B) {
+      off[i] = excl;
+      spans[i] = (x > 0 && (excl / VL_HALF) != ((excl + x - 1) / VL_HALF)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid == 1023) s_carry = excl + x;
+    __syncthreads();
+  }
+  real = __reduce_add_sync(0xffffffffu, real);
+  if (lane == 0 && real) atomicAdd(&s_real, real);
+  unsigned long long cost = 0;
+  for (int t = tid; t < n_tt_pad; t += 1024) {
+    const int rows = trim_rows ? min(pad_cols, (tile_n16[t] + 63) / 64 * 64) : pad_cols;
+    cost += static_cast<unsigned long long>(BLOCK_V + rows);
+  }
+  for (int d = 16; d > 0; d >>= 1) cost += __shfl_down_sync(0xffffffffu, cost, d);
+  if (lane == 0 && cost) atomicAdd(&s_cost, cost);
+  __syncthreads();
+  if (tid == 0) {
+    const int T = s_carry;
+    off[B] = T;
+    const int n_tt = (T + BLOCK_T - 1) / BLOCK_T;
+    const int tail = T - BLOCK_T * (n_tt - 1);
+    const int n16_last = T > 0 ? max(16, (tail + 15) / 16 * 16) : 16;
+    const unsigned long long cost_packed = static_cast<unsigned long long>(n_tt) * (BLOCK_V + BLOCK_T);
+    // packing, the merge keys and the finalize pass cost a few percent of a full batch: ask for a 7 % win
+    int mode = (T > 0 && cost_packed * 107ull < s_cost * 100ull) ? 1 : 0;
+    if (force_mode >= 0) mode = force_mode;
+    plan->mode = mode;
+    plan->T = T;
+    plan->n_tt = n_tt;
+    plan->n16_last = n16_last;
+    plan->T_real = s_real;
+    if (plan_out != nullptr) {
+      plan_out[0] = mode;
+      plan_out[1] = s_real;
+      plan_out[2] = n_tt;
+      plan_out[3] = n16_last;
+    }
+  }
+}
+
+// grid (ceil(S/256), B): copy the unmasked rows of 256 positions of one document to their packed place and record
+// the descriptor of every packed column.  The CTA of chunk 0 also writes the replicas of the document's last token
+// behind it (up to the next multiple of 8 columns) and clears the merge keys if the document straddles half-tiles.
+__global__ void __launch_bounds__(256)
+varlen_pack_kernel(const uint4* __restrict__ hidden, const int32_t* __restrict__ mask,
+                   const int32_t* __restrict__ len, const int32_t* __restrict__ off,
+                   const uint8_t* __restrict__ spans, const VarlenPlan* __restrict__ plan, int S, int H, int V,
+                   uint4* __restrict__ packed, uint32_t* __restrict__ meta, uint32_t* __restrict__ keys) {
+  if (plan->mode == 0) return;
+  __shared__ int s_cnt[8];
+  __shared__ int s_red[8];
+  __shared__ int s_src[256];
+  __shared__ int s_last;
+  const int b = static_cast<int>(blockIdx.y);
+  const int c0 = static_cast<int>(blockIdx.x) * 256;
+  const int tid = static_cast<int>(threadIdx.x);
+  const int lane = tid & 31, warp = tid >> 5;
+  const int32_t* mrow = mask + static_cast<size_t>(b) * S;
+  const int L = len[b];
+  if (L == 0) return;
+  const uint32_t tag = (spans[b] ? VL_SPAN_BIT : 0u) | (static_cast<uint32_t>(b) << 16);
+  const int row_u4 = H / 8;
+  if (blockIdx.x == 0) {
+    if (spans[b]) {
+      uint32_t* krow = keys + static_cast<size_t>(b) * V;
+      for (int v = tid; v < V; v += 256) krow[v] = 0u;
+    }
+    const int fill = (L + VL_ALIGN - 1) / VL_ALIGN * VL_ALIGN - L;  // replicas of the last real token
+    if (fill > 0) {
+      if (tid == 0) s_last = -1;
+      __syncthreads();
+      int last = -1;
+      for (int s = tid; s < S; s += 256) last = mrow[s] != 0 ? s : last;
+      last = __reduce_max_sync(0xffffffffu, last);
+      if (lane == 0 && last >= 0) atomicMax(&s_last, last);
+      __syncthreads();
+      last = s_last;
+      const uint4* src = hidden + (static_cast<size_t>(b) * S + last) * row_u4;
+      for (int r = warp; r < fill; r += 8) {
+        const size_t row = static_cast<size_t>(off[b] + L + r);
+        uint4* dst = packed + row * row_u4;
+        for (int i = lane; i < row_u4; i += 32) dst[i] = __ldg(&src[i]);
+        if (lane == 0) meta[row] = tag | static_cast<uint32_t>(last);
+      }
+    }
+  }
+  // unmasked positions of this document before this chunk
+  int before = 0;
+  for (int s = tid; s < c0; s += 256) before += mrow[s] != 0 ? 1 : 0;
+  before = __reduce_add_sync(0xffffffffu, before);
+  if (lane == 0) s_red[warp] = before;
+  const int s = c0 + tid;
+  const bool ok = s < S && mrow[s] != 0;
+  const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) s_cnt[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, wpre = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    base += s_red[w];
+    wpre += w < warp ? s_cnt[w] : 0;
+    total += s_cnt[w];
+  }
+  const int dst0 = off[b] + base;  // packed row of this chunk's first unmasked position
+  if (ok) {
+    const int r = wpre + __popc(bal & ((1u << lane) - 1u));
+    s_src[r] = s;
+    meta[dst0 + r] = tag | static_cast<uint32_t>(s);
+  }
+  __syncthreads();
+  for (int r = warp; r < total; r += 8) {
+    const uint4* src = hidden + (static_cast<size_t>(b) * S + s_src[r]) * row_u4;
+    uint4* dst = packed + static_cast<size_t>(dst0 + r) * row_u4;
+    for (int i = lane; i < row_u4; i += 32) dst[i] = __ldg(&src[i]);
+  }
+}
+
+template <bool kTokW>
+__global__ void __launch_bounds__(VL_THREADS, 1)
+head_fwd_varlen_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                       const VarlenParams p) {
+  if (__ldg(&p.plan->mode) == 0) return;  // grid-uniform: the padded kernel owns this call
+  const int T = __ldg(&p.plan->T);
+  const int n_tt = __ldg(&p.plan->n_tt);
+  const int n16_last = __ldg(&p.plan->n16_last);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint32_t* meta_smem = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 256);  // [8 warps][4][32]
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_items = p.n_vt * n_tt;
+  const int num_kb = p.H / BLOCK_K;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int vt = item / n_tt;
+        const int tt = item - vt * n_tt;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* a_dst = smem + stage * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(a_dst, &tmap_w, &full_bar[stage], kb * BLOCK_K, vt * BLOCK_V);
+          tma_load_2d(b_dst, &tmap_x, &full_bar[stage], kb * BLOCK_K, tt * BLOCK_T);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        const int tt = item % n_tt;
+        const uint32_t idesc =
+            make_idesc_bf16_f32(BLOCK_V, static_cast<uint32_t>(tt == n_tt - 1 ? n16_last : BLOCK_T));
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_T;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
+            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (2 groups x 4 warps)
+    const uint32_t q = warp & 3u;           // TMEM lane quarter
+    const uint32_t grp = (warp - 4u) >> 2;  // column half of the accumulator
+    uint32_t* my_meta = meta_smem + (warp - 4u) * 128u;  // this warp's 128 column descriptors
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int vt = item / n_tt;
+      const int tt = item - vt * n_tt;
+      const int v = vt * BLOCK_V + static_cast<int>(q * 32u + lane);
+      const float bias_v = v < p.V ? __ldg(&p.bias[v]) : 0.f;
+      const int col0 = static_cast<int>(grp) * VL_HALF;                  // first column of this group
+      const int ncols = min(VL_HALF, T - tt * BLOCK_T - col0);           // multiple of 8, may be <= 0
+      // column descriptors of the half-tile: fetched before the accumulator wait, whose latency hides them
+      __syncwarp();
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        my_meta[w * 32 + lane] = __ldg(&p.meta[static_cast<size_t>(tt) * BLOCK_T + col0 + w * 32 + lane]);
+      __syncwarp();
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_lane = tmem_base + ((q * 32u) << 16) + acc * BLOCK_T + static_cast<uint32_t>(col0);
+
+      uint32_t cur_tag = 0xFFFFFFFFu;  // (straddle bit | doc) of the running document, none yet
+      int best_val = 0, best_pos = 0;
+      auto flush = [&]() {
+        if (cur_tag != 0xFFFFFFFFu && v < p.V) {
+          const size_t o = static_cast<size_t>(cur_tag & 0x7FFFu) * p.V + v;
+          if (cur_tag & 0x8000u) {
+            atomicMax(&p.keys[o], (static_cast<uint32_t>(best_val) << 16) | (0xFFFFu - static_cast<uint32_t>(best_pos)));
+          } else {
+            p.rep[o] = log1pf(bf16_bits_to_float(static_cast<uint32_t>(best_val)));
+            p.argmax[o] = best_pos;
+          }
+        }
+      };
+      const int nwin = (ncols + 31) >> 5;
+      for (int w = 0; w < nwin; ++w) {
+        const int ngrp = min(4, (ncols - 32 * w) >> 3);  // valid 8-column groups of this window
+        const uint32_t m = my_meta[w * 32 + lane];
+        const uint32_t tag_j = m >> 16;
+        // group g (columns 8g..8g+7) opens a new document when its tag differs from the running one; inside a
+        // group the tag is constant by construction (documents start at multiples of 8 columns)
+        const uint32_t tag0 = __shfl_sync(0xffffffffu, tag_j, 0);
+        const uint32_t tag1 = __shfl_sync(0xffffffffu, tag_j, 8);
+        const uint32_t tag2 = __shfl_sync(0xffffffffu, tag_j, 16);
+        const uint32_t tag3 = __shfl_sync(0xffffffffu, tag_j, 24);
+
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(32 * w), r);
+        tmem_ld_wait();
+        // signed keys (bf16(acc + bias) << 16) | (31 - j), in place
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float x0 = __uint_as_float(r[j]) + bias_v;
+          const float x1 = __uint_as_float(r[j + 1]) + bias_v;
+          const uint32_t pk = cvt_bf16x2(x1, x0);
+          r[j] = (pk << 16) | static_cast<uint32_t>(31 - j);
+          r[j + 1] = (pk & 0xFFFF0000u) | static_cast<uint32_t>(30 - j);
+        }
+        if (kTokW) {
+          int tok_mine = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int t = warp_max_s32(static_cast<int>(r[j]));
+            tok_mine = (lane == static_cast<uint32_t>(j)) ? t : tok_mine;
+          }
+          const int tv = tok_mine >> 16;
+          if (tv > 0 && static_cast<int>(lane) < 8 * ngrp) {
+            atomicMax(&p.tokw_bits[static_cast<size_t>(tag_j & 0x7FFFu) * p.S + (m & 0xFFFFu)],
+                      static_cast<uint32_t>(tv));
+          }
+        }
+        int k[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          int kk = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) kk = max(kk, static_cast<int>(r[8 * g + j]));
+          k[g] = kk;
+        }
+        if (ngrp == 4 && tag0 == cur_tag && tag1 == tag0 && tag2 == tag0 && tag3 == tag0) {
+          // the common case for long documents: the whole window continues the running document
+          const int wkey = max(max(k[0], k[1]), max(k[2], k[3]));
+          const uint32_t mm = __shfl_sync(0xffffffffu, m, 31 - (wkey & 31));
+          if ((wkey >> 16) > best_val) {
+            best_val = wkey >> 16;
+            best_pos = static_cast<int>(mm & 0xFFFFu);
+          }
+        } else {
+          const uint32_t tags[4] = {tag0, tag1, tag2, tag3};
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < ngrp) {  // warp-uniform
+              if (tags[g] != cur_tag) {
+                flush();
+                cur_tag = tags[g];
+                best_val = 0;
+                best_pos = 0;
+              }
+              const uint32_t mm = __shfl_sync(0xffffffffu, m, 31 - (k[g] & 31));
+              if ((k[g] >> 16) > best_val) {  // strict: the earliest position wins ties
+                best_val = k[g] >> 16;
+                best_pos = static_cast<int>(mm & 0xFFFFu);
+              }
+            }
+          }
+        }
+      }
+      flush();
+      tcgen05_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Rows of straddling documents are decoded from the merge keys, rows of documents with no real token are zero;
+// every other row was stored by the epilogue.  Fixed-size grid striding over (document, 1024-term slab) items, so
+// that the launch costs nothing when the padded tiling was chosen (a grid proportional to B*V of immediately
+// exiting CTAs costs ~0.1 ms at B=512).
+__global__ void __launch_bounds__(256)
+finalize_varlen_kernel(const VarlenPlan* __restrict__ plan, const int32_t* __restrict__ len,
+                       const uint8_t* __restrict__ spans, const uint32_t* __restrict__ keys,
+                       float* __restrict__ rep, int32_t* __restrict__ argmax, int B, int V) {
+  if (plan->mode == 0) return;
+  const int slabs = (V + 1023) / 1024;
+  const long long items = static_cast<long long>(B) * slabs;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = static_cast<int>(item / slabs);
+    const int L = len[b];
+    if (L != 0 && spans[b] == 0) continue;
+    const int v0 = static_cast<int>(item - static_cast<long long>(b) * slabs) * 1024;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v = v0 + u * 256 + static_cast<int>(threadIdx.x);
+      if (v >= V) continue;
+      const size_t o = static_cast<size_t>(b) * V + v;
+      if (L == 0) {
+        rep[o] = 0.f;
+        argmax[o] = 0;
+      } else {
+        const uint32_t k = keys[o];
+        rep[o] = log1pf(bf16_bits_to_float(k >> 16));
+        argmax[o] = static_cast<int32_t>(0xFFFFu - (k & 0xFFFFu));
+      }
+    }
+  }
+}
+
+constexpr int VARLEN_SMEM_BYTES = SMEM_BYTES + 8 * 128 * 4;
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
@@ -590,20 +1081,89 @@ void head_fwd_plan(int B, int S, int* s_box, int* b_box, int* chunks_per_doc, in
   *umma_n = std::max(16, (cols + 15) / 16 * 16);
 }
 
-size_t head_fwd_workspace_bytes(int B, int S, int V, bool want_tokw) {
+// Shapes the packed path can take: (doc, position) of a column fit 16 bits each, offsets fit int32.
+bool varlen_shape_ok(int B, int S) {
+  return B >= 1 && B <= 32767 && S >= 1 && S <= 65535 && static_cast<size_t>(B) * S <= (static_cast<size_t>(1) << 30);
+}
+
+// rows of the packed token buffer: every document rounded up to 8 columns, a whole number of 256-token tiles
+size_t varlen_rows(int B, int S) {
+  const size_t rows = static_cast<size_t>(B) * ((static_cast<size_t>(S) + VL_ALIGN - 1) / VL_ALIGN * VL_ALIGN);
+  return (rows + BLOCK_T - 1) / BLOCK_T * BLOCK_T;
+}
+
+size_t head_fwd_workspace_bytes(int B, int S, int H, int V, bool want_tokw) {
   if (B <= 0 || S <= 0) return 0;
   int s_box, b_box, cpd, n_tt, umma_n;
   head_fwd_plan(B, S, &s_box, &b_box, &cpd, &n_tt, &umma_n);
   size_t bytes = align256(static_cast<size_t>(n_tt) * 8 * sizeof(uint32_t)) +
                  align256(static_cast<size_t>(n_tt) * sizeof(int32_t));
-  if (S > BLOCK_T) bytes += align256(static_cast<size_t>(B) * V * sizeof(uint32_t));
+  const bool varlen = varlen_shape_ok(B, S);
+  if (S > BLOCK_T || varlen) bytes += align256(static_cast<size_t>(B) * V * sizeof(uint32_t));
   if (want_tokw) bytes += align256(static_cast<size_t>(B) * S * sizeof(uint32_t));
+  if (varlen) {
+    bytes += 256;                                                          // VarlenPlan
+    bytes += align256(static_cast<size_t>(B) * sizeof(int32_t));           // len
+    bytes += align256((static_cast<size_t>(B) + 1) * sizeof(int32_t));     // off
+    bytes += align256(static_cast<size_t>(B));                             // spans
+    bytes += align256(varlen_rows(B, S) * sizeof(uint32_t));               // meta
+    bytes += align256(varlen_rows(B, S) * static_cast<size_t>(H) * 2);     // packed tokens (bf16)
+  }
   return bytes;
+}
+
+// SPLADE_B200_PACK = auto (default) | 0 | 1: token layout policy of splade_head_fwd (see splade_head_fwd_mode).
+int pack_mode_from_env() {
+  static const int mode = [] {
+    const char* e = std::getenv("SPLADE_B200_PACK");
+    if (e == nullptr) return -1;
+    if (e[0] == '0') return 0;
+    if (e[0] == '1') return 1;
+    return -1;
+  }();
+  return mode;
+}
+
+// The same decision as varlen_plan_kernel, for callers whose attention mask is still in HOST memory
+// (splade_head_fwd_host): the tiling is pinned before anything is enqueued, so no gated no-op kernels are launched.
+int head_fwd_pack_mode_host(const int32_t* mask_host, int B, int S) {
+  const int env = pack_mode_from_env();
+  if (env >= 0) return env;
+  if (!varlen_shape_ok(B, S) || pair_enabled()) return 0;
+  int s_box, b_box, cpd, n_tt, umma_n;
+  head_fwd_plan(B, S, &s_box, &b_box, &cpd, &n_tt, &umma_n);
+  const bool trim = b_box == 1 && s_box > 64;
+  unsigned long long cost = 0, T = 0;
+  for (int tt = 0; tt < n_tt; ++tt) {
+    int rows = s_box * b_box;
+    if (trim) {  // one document (chunk) per tile: rows up to the last unmasked position, rounded up to 64
+      const int b = tt / cpd;
+      const int s0 = (tt - b * cpd) * BLOCK_T;
+      const int ns = std::min(BLOCK_T, S - s0);
+      int last = -1;
+      for (int s = ns - 1; s >= 0; --s) {
+        if (mask_host[static_cast<size_t>(b) * S + s0 + s] != 0) {
+          last = s;
+          break;
+        }
+      }
+      const int n16 = std::min(umma_n, std::max(16, (last + 1 + 15) / 16 * 16));
+      rows = std::min(s_box, (n16 + 63) / 64 * 64);
+    }
+    cost += static_cast<unsigned long long>(BLOCK_V + rows);
+  }
+  for (int b = 0; b < B; ++b) {
+    unsigned long long l = 0;
+    for (int s = 0; s < S; ++s) l += mask_host[static_cast<size_t>(b) * S + s] != 0 ? 1 : 0;
+    T += (l + VL_ALIGN - 1) / VL_ALIGN * VL_ALIGN;
+  }
+  const unsigned long long n_tp = (T + BLOCK_T - 1) / BLOCK_T;
+  return (T > 0 && n_tp * (BLOCK_V + BLOCK_T) * 107ull < cost * 100ull) ? 1 : 0;
 }
 
 int head_fwd_launch(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S,
                     int H, int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
-                    cudaStream_t stream) {
+                    int pack_mode, int32_t* plan_out, cudaStream_t stream) {
   if (B == 0) return kOk;
   if (!hidden || !W || !bias || !mask || !rep || !argmax)
     return set_error(kErrInvalidArg, "splade_head_fwd: null pointer argument");
@@ -631,7 +1191,9 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
   p.n_vt = (V + BLOCK_V - 1) / BLOCK_V;
   p.stage_tx_bytes = static_cast<uint32_t>(A_BYTES + p.s_box * p.b_box * BLOCK_K * 2);
 
-  const size_t need = head_fwd_workspace_bytes(B, S, V, tokw != nullptr);
+  if (pack_mode < -1 || pack_mode > 1)
+    return set_error(kErrInvalidArg, "splade_head_fwd: pack_mode must be -1 (auto), 0 (padded) or 1 (packed)");
+  const size_t need = head_fwd_workspace_bytes(B, S, H, V, tokw != nullptr);
   if (need > 0 && (!workspace || ws_bytes < need))
     return set_error(kErrWorkspace, "splade_head_fwd: workspace too small (%zu < %zu bytes)", ws_bytes, need);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -641,21 +1203,51 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
   int32_t* tile_n16 = reinterpret_cast<int32_t*>(ws);
   p.tile_n16 = tile_n16;
   ws += align256(static_cast<size_t>(p.n_tt) * sizeof(int32_t));
-  if (p.chunks_per_doc > 1) {
-    p.packed = reinterpret_cast<uint32_t*>(ws);
+  const bool varlen_shape = varlen_shape_ok(B, S);
+  uint32_t* keys = nullptr;
+  if (p.chunks_per_doc > 1 || varlen_shape) {
+    keys = reinterpret_cast<uint32_t*>(ws);
     const size_t n = static_cast<size_t>(B) * V * sizeof(uint32_t);
-    SPLADE_CUDA_OK(cudaMemsetAsync(p.packed, 0, n, stream));
+    if (p.chunks_per_doc > 1) {  // (the packed path clears only the rows of straddling documents, on the device)
+      p.packed = keys;
+      SPLADE_CUDA_OK(cudaMemsetAsync(keys, 0, n, stream));
+    }
     ws += align256(n);
   }
   if (tokw) {
     p.tokw_bits = reinterpret_cast<uint32_t*>(ws);
     SPLADE_CUDA_OK(cudaMemsetAsync(p.tokw_bits, 0, static_cast<size_t>(B) * S * sizeof(uint32_t), stream));
+    ws += align256(static_cast<size_t>(B) * S * sizeof(uint32_t));
+  }
+  VarlenPlan* plan = nullptr;
+  int32_t* vl_len = nullptr;
+  int32_t* vl_off = nullptr;
+  uint8_t* vl_spans = nullptr;
+  uint32_t* vl_meta = nullptr;
+  void* vl_packed = nullptr;
+  if (varlen_shape) {
+    plan = reinterpret_cast<VarlenPlan*>(ws);
+    ws += 256;
+    vl_len = reinterpret_cast<int32_t*>(ws);
+    ws += align256(static_cast<size_t>(B) * sizeof(int32_t));
+    vl_off = reinterpret_cast<int32_t*>(ws);
+    ws += align256((static_cast<size_t>(B) + 1) * sizeof(int32_t));
+    vl_spans = reinterpret_cast<uint8_t*>(ws);
+    ws += align256(static_cast<size_t>(B));
+    vl_meta = reinterpret_cast<uint32_t*>(ws);
+    ws += align256(varlen_rows(B, S) * sizeof(uint32_t));
+    vl_packed = ws;
   }
 
   // CTA-pair (cta_group::2) path: needs the tile's token rows to split evenly between two CTAs.
   const int cols = p.s_box * p.b_box;
   bool use_pair = pair_enabled() && (sm_count() % 2 == 0) && (cols % 16 == 0) &&
                   ((p.b_box % 2 == 0) || (p.b_box == 1 && p.s_box % 16 == 0));
+  // The packed path is considered unless the caller (or the CTA-pair experiment) pins the padded one.
+  const bool varlen = varlen_shape && !use_pair && pack_mode != 0;
+  if (plan_out != nullptr && !varlen) {
+    SPLADE_CUDA_OK(cudaMemsetAsync(plan_out, 0, 4 * sizeof(int32_t), stream));
+  }
   CUtensorMap tmap_w, tmap_h, tmap_trim[3];
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(H), static_cast<uint64_t>(V)};
@@ -691,7 +1283,29 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
   build_tile_masks_kernel<<<p.n_tt, 256, 0, stream>>>(p, tile_masks, tile_n16);
   SPLADE_CUDA_OK(cudaGetLastError());
 
-  if (use_pair) {
+  CUtensorMap tmap_x;
+  if (varlen) {
+    varlen_count_kernel<<<(B + 7) / 8, 256, 0, stream>>>(mask, B, S, vl_len);
+    SPLADE_CUDA_OK(cudaGetLastError());
+    varlen_plan_kernel<<<1, 1024, 0, stream>>>(vl_len, B, tile_n16, p.n_tt, p.trim_rows,
+                                               p.trim_rows ? p.s_box : cols, pack_mode, vl_off, vl_spans, plan,
+                                               plan_out);
+    SPLADE_CUDA_OK(cudaGetLastError());
+    varlen_pack_kernel<<<dim3((S + 255) / 256, B), 256, 0, stream>>>(
+        static_cast<const uint4*>(hidden), mask, vl_len, vl_off, vl_spans, plan, S, H, V,
+        static_cast<uint4*>(vl_packed), vl_meta, keys);
+    SPLADE_CUDA_OK(cudaGetLastError());
+    const uint64_t dims[2] = {static_cast<uint64_t>(H), static_cast<uint64_t>(varlen_rows(B, S))};
+    const uint64_t strides[1] = {static_cast<uint64_t>(H) * 2};
+    const uint32_t box[2] = {BLOCK_K, BLOCK_T};
+    rc = encode_tmap_bf16(&tmap_x, vl_packed, 2, dims, strides, box);
+    if (rc != kOk) return rc;
+    p.plan_mode = &plan->mode;
+  }
+
+  if (varlen && pack_mode == 1) {
+    // the caller pinned the packed path: the padded kernel is not even launched
+  } else if (use_pair) {
     const int total_pairs = ((p.n_vt + 1) / 2) * p.n_tt;
     const int grid = 2 * std::min(sm_count() / 2, total_pairs);
     auto kernel = tokw ? head_fwd_pair_kernel<true> : head_fwd_pair_kernel<false>;
@@ -706,9 +1320,38 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
   }
   SPLADE_CUDA_OK(cudaGetLastError());
 
-  if (p.chunks_per_doc > 1) {
+  if (p.chunks_per_doc > 1 && !(varlen && pack_mode == 1)) {
     const size_t n = static_cast<size_t>(B) * V;
-    finalize_packed_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p.packed, rep, argmax, n);
+    finalize_packed_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p.packed, rep, argmax, n,
+                                                                                       p.plan_mode);
+    SPLADE_CUDA_OK(cudaGetLastError());
+  }
+  if (varlen) {
+    VarlenParams q{};
+    q.bias = bias;
+    q.plan = plan;
+    q.meta = vl_meta;
+    q.spans = vl_spans;
+    q.len = vl_len;
+    q.rep = rep;
+    q.argmax = argmax;
+    q.keys = keys;
+    q.tokw_bits = p.tokw_bits;
+    q.B = B;
+    q.S = S;
+    q.H = H;
+    q.V = V;
+    q.n_vt = p.n_vt;
+    // persistent over (vocab tile, packed token tile); the tile count is only known on the device
+    auto kernel = tokw ? head_fwd_varlen_kernel<true> : head_fwd_varlen_kernel<false>;
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VARLEN_SMEM_BYTES));
+    kernel<<<sm_count(), VL_THREADS, VARLEN_SMEM_BYTES, stream>>>(tmap_w, tmap_x, q);
+    SPLADE_CUDA_OK(cudaGetLastError());
+    {
+      const long long items = static_cast<long long>(B) * ((V + 1023) / 1024);
+      const int grid = static_cast<int>(std::min<long long>(items, 8ll * sm_count()));
+      finalize_varlen_kernel<<<grid, 256, 0, stream>>>(plan, vl_len, vl_spans, keys, rep, argmax, B, V);
+    }
     SPLADE_CUDA_OK(cudaGetLastError());
   }
   if (tokw) {

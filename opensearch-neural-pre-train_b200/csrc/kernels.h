@@ -19,10 +19,14 @@ int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_
 
 // head_fwd.cu
 void head_fwd_plan(int B, int S, int* s_box, int* b_box, int* chunks_per_doc, int* n_tt, int* umma_n);
-size_t head_fwd_workspace_bytes(int B, int S, int V, bool want_tokw);
+size_t head_fwd_workspace_bytes(int B, int S, int H, int V, bool want_tokw);
+int pack_mode_from_env();
+int head_fwd_pack_mode_host(const int32_t* mask_host, int B, int S);
+// pack_mode: -1 decide on the device, 0 padded tiling, 1 packed (variable-length) tiling; plan_out: optional
+// device int32[4] = {mode chosen, real tokens, packed tiles, UMMA N of the last packed tile}
 int head_fwd_launch(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S,
                     int H, int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
-                    cudaStream_t stream);
+                    int pack_mode, int32_t* plan_out, cudaStream_t stream);
 
 // head_bwd.cu
 size_t head_bwd_workspace_bytes(int B, int S, int V);

@@ -45,9 +45,14 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 # raw ops
 # ------------------------------------------------------------------------------------------------
 def head_forward(hidden: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, mask: torch.Tensor,
-                 want_token_weights: bool = True):
+                 want_token_weights: bool = True, pack_mode: Optional[int] = None,
+                 plan_out: Optional[torch.Tensor] = None):
     """hidden [B,S,H] bf16, weight [V,H] bf16, bias [V] fp32, mask [B,S] int32 ->
-    (rep [B,V] fp32, argmax [B,V] int32, token_weights [B,S] fp32 | None)."""
+    (rep [B,V] fp32, argmax [B,V] int32, token_weights [B,S] fp32 | None).
+
+    ``pack_mode``: None = the library default (env SPLADE_B200_PACK, "auto": a device-side plan picks the padded
+    or the packed variable-length tiling without a host sync); -1 auto, 0 padded, 1 packed (``splade_head_fwd_mode``).
+    ``plan_out``: optional int32[4] CUDA tensor receiving {tiling used, real tokens, packed tiles, last-tile N}."""
     lib = load_library()
     for n, t in (("hidden", hidden), ("weight", weight), ("bias", bias), ("mask", mask)):
         _require_cuda(t, n)
@@ -65,9 +70,17 @@ def head_forward(hidden: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
         op = _lib.OP_HEAD_FWD_TOKW if want_token_weights else _lib.OP_HEAD_FWD
         nbytes = lib.splade_workspace_bytes(op, B, S, H, V, 0)
         ws, ws_ptr = _ws(nbytes, dev)
-        check(lib.splade_head_fwd(hidden.data_ptr(), weight.data_ptr(), bias.data_ptr(), mask.data_ptr(),
-                                  B, S, H, V, rep.data_ptr(), argmax.data_ptr(), _ptr(tokw), ws_ptr, nbytes,
-                                  _stream(hidden)), "splade_head_fwd")
+        if pack_mode is None and plan_out is None:
+            check(lib.splade_head_fwd(hidden.data_ptr(), weight.data_ptr(), bias.data_ptr(), mask.data_ptr(),
+                                      B, S, H, V, rep.data_ptr(), argmax.data_ptr(), _ptr(tokw), ws_ptr, nbytes,
+                                      _stream(hidden)), "splade_head_fwd")
+        else:
+            if plan_out is not None:
+                assert plan_out.is_cuda and plan_out.dtype == torch.int32 and plan_out.numel() >= 4
+            check(lib.splade_head_fwd_mode(hidden.data_ptr(), weight.data_ptr(), bias.data_ptr(), mask.data_ptr(),
+                                           B, S, H, V, rep.data_ptr(), argmax.data_ptr(), _ptr(tokw), ws_ptr,
+                                           nbytes, -1 if pack_mode is None else int(pack_mode), _ptr(plan_out),
+                                           _stream(hidden)), "splade_head_fwd_mode")
     return rep, argmax, tokw
 
 

@@ -25,10 +25,18 @@ def make_head_inputs(B, S, H, V, seed, device, ragged=True, bias_offset=0.0, hol
     return hidden.to(device), W.to(device), bias.to(device), mask.to(device)
 
 
-def run_head(hidden, W, bias, mask, want_tokw=True):
+def run_head(hidden, W, bias, mask, want_tokw=True, pack_mode=None, plan_out=None):
     import splade_b200
     return splade_b200.head_forward(hidden.to(torch.bfloat16).contiguous(), W.to(torch.bfloat16).contiguous(),
-                                    bias.float().contiguous(), mask.to(torch.int32).contiguous(), want_tokw)
+                                    bias.float().contiguous(), mask.to(torch.int32).contiguous(), want_tokw,
+                                    pack_mode=pack_mode, plan_out=plan_out)
+
+
+def query_like_mask(B, S, lo, hi, seed, device):
+    """Right-padded batch whose documents hold U[lo, hi] real tokens (queries: a handful of tokens in S=64)."""
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(lo, hi + 1, (B,), generator=g)
+    return (torch.arange(S)[None, :] < lengths[:, None]).to(torch.int32).to(device)
 
 
 def assert_argmax_parity(got_arg, ref_arg, near_tie, what=""):

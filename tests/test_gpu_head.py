@@ -6,13 +6,14 @@ import torch
 
 from oracle import splade_oracle as O
 from oracle import torch_reference as TR
-from tests.gpu_util import assert_argmax_parity, assert_weights_parity, make_head_inputs, run_head
+from tests.gpu_util import (assert_argmax_parity, assert_weights_parity, make_head_inputs, query_like_mask,
+                            run_head)
 
 pytestmark = pytest.mark.gpu
 
 
-def _check_forward(hidden, W, bias, mask, want_tokw=True, what=""):
-    rep, arg, tokw = run_head(hidden, W, bias, mask, want_tokw)
+def _check_forward(hidden, W, bias, mask, want_tokw=True, what="", pack_mode=None):
+    rep, arg, tokw = run_head(hidden, W, bias, mask, want_tokw, pack_mode=pack_mode)
     torch.cuda.synchronize()
     h, w, b, m = (t.cpu().numpy() for t in (hidden, W, bias, mask))
     ref_rep, ref_arg, ref_tokw = O.head_forward(h, w, b, m, mode="bf16")
@@ -156,6 +157,88 @@ def test_autograd_function_matches_torch_chain(cuda_device):
         scale = float(r.abs().max())
         err = float((a - r).abs().max())
         assert err <= 1e-2 * scale + 1e-6, (name, err, scale)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# packed (variable-length) token layout: splade_head_fwd_mode
+# ---------------------------------------------------------------------------------------------------------
+def _both_layouts(hidden, W, bias, mask, want_tokw=True):
+    plans, outs = [], []
+    for mode in (0, 1):
+        plan = torch.full((4,), -7, dtype=torch.int32, device=hidden.device)
+        outs.append(run_head(hidden, W, bias, mask, want_tokw, pack_mode=mode, plan_out=plan))
+        plans.append(plan.cpu().tolist())
+    return outs, plans
+
+
+@pytest.mark.parametrize("B,S,H,V,kw", [
+    (1, 1, 64, 1, {}),
+    (3, 7, 64, 130, {}),                       # 21 tokens: one partial packed tile holding three documents
+    (8, 64, 128, 50000, {}),                   # config 1 head shape, ragged
+    (5, 100, 64, 777, {"holes": True}),        # non-suffix mask: positions come from the column descriptors
+    (9, 250, 192, 1000, {}),                   # documents straddle packed tiles (merge keys)
+    (2, 300, 64, 260, {}),                     # S > 256
+    (2, 700, 128, 200, {"bias_offset": -1.0}),
+    (4, 256, 768, 2048, {"bias_offset": -2.0}),
+    (40, 33, 64, 300, {}),                     # many short documents per tile, several boundaries per window
+])
+def test_packed_layout_bit_identical_to_padded(cuda_device, B, S, H, V, kw):
+    """The packed tiling computes the same bf16 logits (same K order per column), so sparse_repr, argmax and
+    token_weights must be BIT-identical to the padded tiling, and both must match the oracle."""
+    hidden, W, bias, mask = make_head_inputs(B, S, H, V, seed=B * 1000 + S + 1, device=cuda_device, **kw)
+    if B >= 3:
+        mask[1] = 0                            # a document with no real token between two real ones
+    for want_tokw in (True, False):
+        (pad, pk), plans = _both_layouts(hidden, W, bias, mask, want_tokw)
+        assert plans[0][0] == 0 and plans[1][0] == 1, plans
+        assert plans[1][1] == int(mask.sum()), plans
+        assert torch.equal(pad[0], pk[0]), "sparse_repr differs between the padded and the packed tiling"
+        assert torch.equal(pad[1], pk[1]), "argmax differs between the padded and the packed tiling"
+        if want_tokw:
+            assert torch.equal(pad[2], pk[2]), "token_weights differ between the padded and the packed tiling"
+    _check_forward(hidden, W, bias, mask, what=f"packed B{B} S{S} H{H} V{V}", pack_mode=1)
+
+
+def test_packed_layout_golden(cuda_device, golden):
+    for name in ("head_bf16", "head_sparse", "head_s300"):
+        g = golden(name)
+        t = {k: torch.from_numpy(v).to(cuda_device) for k, v in g.items()}
+        rep, arg, tokw = run_head(t["hidden"], t["W"], t["bias"], t["mask"], pack_mode=1)
+        near = O.near_tie_mask(g["hidden"], g["W"], g["bias"], g["mask"], mode="bf16")
+        assert_argmax_parity(arg.cpu().numpy(), g["argmax"], near, name)
+        assert_weights_parity(rep.cpu().numpy(), g["sparse_repr"], name)
+        assert_weights_parity(tokw.cpu().numpy(), g["token_weights"], name + " token_weights", max_flip_frac=1e-3)
+
+
+def test_device_side_plan_picks_the_cheaper_tiling(cuda_device):
+    """pack_mode=-1: no host sync; the plan kernel keeps the padded tiling for full batches and switches to the
+    packed one for query-like batches (a handful of real tokens in S=64).  Either way the results are the same."""
+    B, S, H, V = 64, 64, 128, 3000
+    hidden, W, bias, _ = make_head_inputs(B, S, H, V, seed=77, device=cuda_device)
+    full = torch.ones(B, S, dtype=torch.int32, device=cuda_device)
+    short = query_like_mask(B, S, 4, 12, seed=5, device=cuda_device)
+    for mask, want_mode in ((full, 0), (short, 1)):
+        plan = torch.zeros(4, dtype=torch.int32, device=cuda_device)
+        rep, arg, tokw = run_head(hidden, W, bias, mask, True, pack_mode=-1, plan_out=plan)
+        assert plan.cpu().tolist()[0] == want_mode and plan.cpu().tolist()[1] == int(mask.sum())
+        rep0, arg0, tokw0 = run_head(hidden, W, bias, mask, True, pack_mode=0)
+        assert torch.equal(rep, rep0) and torch.equal(arg, arg0) and torch.equal(tokw, tokw0)
+    # the default entry point (splade_head_fwd, policy from the environment: auto) takes the same decision
+    rep, arg, tokw = run_head(hidden, W, bias, short, True)
+    assert torch.equal(rep, rep0) and torch.equal(arg, arg0) and torch.equal(tokw, tokw0)
+
+
+def test_packed_layout_full_size_queries(cuda_device):
+    """BASELINE config 3 shape (512 queries x S=64, hidden 768 -> 50 000 terms) with realistic query lengths:
+    the packed tiling works on ~1/5 of the columns and must reproduce the padded result bit for bit."""
+    B, S, H, V = 512, 64, 768, 50000
+    hidden, W, bias, _ = make_head_inputs(B, S, H, V, seed=8, device=cuda_device, ragged=False)
+    mask = query_like_mask(B, S, 4, 24, seed=9, device=cuda_device)
+    (pad, pk), plans = _both_layouts(hidden, W, bias, mask, want_tokw=True)
+    assert plans[1][0] == 1 and plans[1][1] == int(mask.sum())
+    assert torch.equal(pad[0], pk[0]) and torch.equal(pad[1], pk[1]) and torch.equal(pad[2], pk[2])
+    lengths = mask.sum(1)
+    assert bool((pk[1] < lengths[:, None]).all())
 
 
 def test_cta_pair_kernel_passes_the_same_parity_suite(cuda_device):
