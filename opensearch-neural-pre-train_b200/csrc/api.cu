@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 namespace splade {
@@ -32,23 +33,40 @@ int check_cuda(cudaError_t e, const char* what) {
   return set_error(kErrCuda, "CUDA error %s (%s) at: %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
 }
 
+// Device properties are immutable: look them up once per device (these sit on every launch path).
+namespace {
+constexpr int kMaxDevices = 64;
+std::atomic<int> g_cc_major[kMaxDevices];  // 0 = not queried yet
+std::atomic<int> g_sm_count[kMaxDevices];
+}  // namespace
+
 int require_sm100(const char* who) {
   int dev = 0;
   SPLADE_CUDA_OK(cudaGetDevice(&dev));
-  int major = 0, minor = 0;
-  SPLADE_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-  SPLADE_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
-  if (major != 10)
+  int major = (dev >= 0 && dev < kMaxDevices) ? g_cc_major[dev].load(std::memory_order_relaxed) : 0;
+  if (major == 0) {
+    SPLADE_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (dev >= 0 && dev < kMaxDevices) g_cc_major[dev].store(major, std::memory_order_relaxed);
+  }
+  if (major != 10) {
+    int minor = 0;
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
     return set_error(kErrUnsupportedDevice,
                      "%s: device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", who, dev,
                      major, minor);
+  }
   return kOk;
 }
 
 int sm_count() {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < kMaxDevices) {
+    n = g_sm_count[dev].load(std::memory_order_relaxed);
+    if (n > 0) return n;
+  }
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  if (dev >= 0 && dev < kMaxDevices) g_sm_count[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 
