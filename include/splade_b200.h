@@ -43,6 +43,9 @@ extern "C" {
 #define SPLADE_OP_FLOPS_NNZ 3     /* (B=N rows, V)        FLOPS regulariser + nonzero count           */
 #define SPLADE_OP_SCORES 4        /* (B=Bq, k=N docs, V)  q.d score matrix                            */
 #define SPLADE_OP_V33_LOSS_FWD 5  /* (B=Bq, S=N docs, V, k) whole SPLADELossV33 forward               */
+#define SPLADE_OP_TRUNK_ENCODE 6  /* (B,S,H,V, k = intermediate size) native trunk + head encode      */
+#define SPLADE_OP_TRUNK_GEMM 7    /* (B = rows, S = max_pos)  splade_trunk_gemm scratch               */
+#define SPLADE_OP_TRUNK_ATTN 8    /* (B,S,-,V=1)              splade_trunk_attn scratch               */
 
 int splade_abi_version(void);
 const char* splade_last_error(void);
@@ -226,6 +229,70 @@ int splade_topk(const float* rep, int B, int V, const uint8_t* blocklist, int k,
 int splade_emit_json(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B, int k,
                      const char* token_bytes, const int64_t* token_offsets, int n_tokens, int round_decimals,
                      char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed);
+
+/*
+ * ---------------------------------------------------------------------------------------------------------------
+ * Native variable-length ModernBERT trunk for inference.  The reference runs
+ * transformers' ModernBertForMaskedLM (src/model/splade_modern.py:38,69-73) on right-padded batches; this entry
+ * runs the same network - embeddings, n_layers x (LayerNorm, Wqkv + RoPE, global / +-local_window attention, Wo,
+ * LayerNorm, GeGLU MLP), final_norm, head.dense + GELU + head.norm - on the REAL tokens only, packed back to
+ * back, followed by the fused SPLADE head, in one call and with no host synchronisation.  Arithmetic = the
+ * reference under torch.autocast(bf16): bf16 Linear outputs, fp32 residual stream / LayerNorm / softmax / RoPE.
+ * Weights: the caller passes bf16 copies of the nn.Linear matrices and the fp32 LayerNorm weights / embeddings.
+ * Needs hidden % 64 == 0 and >= 256, 64-wide heads, intermediate % 128 == 0, B <= 32767, S <= 65535.
+ */
+typedef struct splade_trunk_layer {
+  const float* attn_norm; /* [H] fp32, NULL = Identity (layer 0, modeling_modernbert.py:318-319) */
+  const void* wqkv;       /* [3H,H] bf16 attn.Wqkv.weight                                        */
+  const void* wo;         /* [H,H]  bf16 attn.Wo.weight                                          */
+  const float* mlp_norm;  /* [H] fp32                                                            */
+  const void* wi;         /* [2I,H] bf16 mlp.Wi.weight (rows [0,I) input, [I,2I) gate)           */
+  const void* wo2;        /* [H,I]  bf16 mlp.Wo.weight                                           */
+  int32_t is_global;      /* 1: full attention + global rope theta, 0: sliding window + local    */
+  int32_t reserved;
+} splade_trunk_layer;
+
+typedef struct splade_trunk_args {
+  int32_t B, S, H, I, V, n_heads, n_layers;
+  int32_t local_window;             /* keys with |pos_q - pos_k| <= local_window (config.local_attention / 2) */
+  float norm_eps, global_theta, local_theta, reserved_f;
+  const int64_t* input_ids;         /* [B,S] int64 (device) */
+  const int32_t* mask;              /* [B,S] int32 (device), nonzero = real token */
+  const float* tok_emb;             /* [V,H] fp32 embeddings.tok_embeddings.weight (tied to decoder.weight) */
+  const float* emb_norm;            /* [H] */
+  const splade_trunk_layer* layers; /* HOST array of n_layers entries (device pointers inside) */
+  const float* final_norm;          /* [H] */
+  const void* head_dense;           /* [H,H] bf16 head.dense.weight */
+  const float* head_norm;           /* [H] */
+  const void* dec_w;                /* [V,H] bf16 decoder.weight */
+  const float* dec_bias;            /* [V] fp32 (pre-rounded to bf16 to mirror autocast) */
+  float* rep;                       /* [B,V] out */
+  int32_t* argmax;                  /* [B,V] out */
+  void* hidden_out;                 /* optional [rows,H] bf16: the packed head input (rows from the workspace op) */
+  uint32_t* meta_out;               /* optional [rows]: (straddles<<31 | doc<<16 | position) of every packed row */
+  int32_t* plan_out;                /* optional int32[5]: {1, packed rows T, tiles, last-tile N, real tokens} */
+  void* workspace;                  /* splade_workspace_bytes(SPLADE_OP_TRUNK_ENCODE, B, S, H, V, I) */
+  size_t ws_bytes;
+} splade_trunk_args;
+
+int splade_trunk_encode(const splade_trunk_args* args, void* stream);
+
+/* rows of the packed buffers for a (B,S) batch: every document rounded up to 8 tokens, whole 256-row tiles */
+size_t splade_packed_rows(int B, int S);
+
+/*
+ * Building blocks of the trunk, exported for unit tests and reuse.
+ * splade_trunk_gemm: out = epilogue(A [rows,K] bf16 x W[N,K]^T bf16), rows >= 128.
+ *   epi 0 bf16 [rows,N]; 1 GELU -> bf16; 2 out (fp32 [rows,N]) += bf16(acc); 3 GeGLU: W is [2N,K], out bf16 [rows,N];
+ *   4 RoPE on features < rope_cols (64-wide heads, theta, positions pos[rows] int32) -> bf16.
+ * splade_trunk_attn: qkv_packed [rows,3H] bf16 (RoPE applied) -> out_packed [rows,H] bf16 in the packed layout of
+ *   `mask`; window < 0 = global.  meta_out as above.
+ */
+int splade_trunk_gemm(int epi, const void* A, int rows, const void* W, int N, int K, void* out, int ldo,
+                      const int32_t* pos, float rope_theta, int rope_cols, int max_pos, void* workspace,
+                      size_t ws_bytes, void* stream);
+int splade_trunk_attn(const void* qkv_packed, const int32_t* mask, int B, int S, int H, int n_heads, int window,
+                      void* out_packed, uint32_t* meta_out, void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

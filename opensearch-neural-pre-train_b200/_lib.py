@@ -21,6 +21,12 @@ OP_HEAD_BWD = 2
 OP_FLOPS_NNZ = 3
 OP_SCORES = 4
 OP_V33_LOSS_FWD = 5
+OP_TRUNK_ENCODE = 6
+OP_TRUNK_GEMM = 7
+OP_TRUNK_ATTN = 8
+
+# epilogues of splade_trunk_gemm
+EPI_BF16, EPI_GELU, EPI_RESID, EPI_GEGLU, EPI_QKV_ROPE = 0, 1, 2, 3, 4
 
 
 class V33ScalarArgs(Structure):
@@ -55,6 +61,31 @@ class V33FwdArgs(Structure):
     ]
 
 
+class TrunkLayer(Structure):
+    """Mirror of ``splade_trunk_layer`` (include/splade_b200.h)."""
+
+    _fields_ = [
+        ("attn_norm", c_void_p), ("wqkv", c_void_p), ("wo", c_void_p), ("mlp_norm", c_void_p),
+        ("wi", c_void_p), ("wo2", c_void_p), ("is_global", c_int32), ("reserved", c_int32),
+    ]
+
+
+class TrunkArgs(Structure):
+    """Mirror of ``splade_trunk_args`` (include/splade_b200.h)."""
+
+    _fields_ = [
+        ("B", c_int32), ("S", c_int32), ("H", c_int32), ("I", c_int32), ("V", c_int32),
+        ("n_heads", c_int32), ("n_layers", c_int32), ("local_window", c_int32),
+        ("norm_eps", c_float), ("global_theta", c_float), ("local_theta", c_float), ("reserved_f", c_float),
+        ("input_ids", c_void_p), ("mask", c_void_p), ("tok_emb", c_void_p), ("emb_norm", c_void_p),
+        ("layers", POINTER(TrunkLayer)),
+        ("final_norm", c_void_p), ("head_dense", c_void_p), ("head_norm", c_void_p),
+        ("dec_w", c_void_p), ("dec_bias", c_void_p), ("rep", c_void_p), ("argmax", c_void_p),
+        ("hidden_out", c_void_p), ("meta_out", c_void_p), ("plan_out", c_void_p),
+        ("workspace", c_void_p), ("ws_bytes", c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/splade_b200.h declares
 EXPORTS = {
     "splade_abi_version": (c_int, []),
@@ -80,6 +111,12 @@ EXPORTS = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "splade_emit_json": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                  c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
+    "splade_trunk_encode": (c_int, [POINTER(TrunkArgs), c_void_p]),
+    "splade_packed_rows": (c_size_t, [c_int, c_int]),
+    "splade_trunk_gemm": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_float,
+                                  c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "splade_trunk_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
     "splade_topk": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -591,14 +591,6 @@ constexpr int VL_HALF = BLOCK_T / 2;        // columns drained by one epilogue w
 constexpr int VL_THREADS = 384;             // producer, MMA, TMEM-alloc, idle + 2 x 4 epilogue warps
 constexpr uint32_t VL_SPAN_BIT = 0x80000000u;
 
-struct VarlenPlan {
-  int32_t mode;      // 0: padded kernel runs, 1: packed kernel runs
-  int32_t T;         // packed columns in the batch (real tokens + replicas)
-  int32_t n_tt;      // packed token tiles = ceil(T / 256)
-  int32_t n16_last;  // UMMA N of the last packed tile
-  int32_t T_real;    // real tokens in the batch
-};
-
 struct VarlenParams {
   const float* bias;
   const VarlenPlan* plan;
@@ -750,11 +742,13 @@ varlen_pack_kernel(const uint4* __restrict__ hidden, const int32_t* __restrict__
       if (lane == 0 && last >= 0) atomicMax(&s_last, last);
       __syncthreads();
       last = s_last;
-      const uint4* src = hidden + (static_cast<size_t>(b) * S + last) * row_u4;
       for (int r = warp; r < fill; r += 8) {
         const size_t row = static_cast<size_t>(off[b] + L + r);
-        uint4* dst = packed + row * row_u4;
-        for (int i = lane; i < row_u4; i += 32) dst[i] = __ldg(&src[i]);
+        if (hidden != nullptr) {
+          const uint4* src = hidden + (static_cast<size_t>(b) * S + last) * row_u4;
+          uint4* dst = packed + row * row_u4;
+          for (int i = lane; i < row_u4; i += 32) dst[i] = __ldg(&src[i]);
+        }
         if (lane == 0) meta[row] = tag | static_cast<uint32_t>(last);
       }
     }
@@ -783,6 +777,7 @@ varlen_pack_kernel(const uint4* __restrict__ hidden, const int32_t* __restrict__
     meta[dst0 + r] = tag | static_cast<uint32_t>(s);
   }
   __syncthreads();
+  if (hidden == nullptr) return;  // descriptors only: the caller (the native trunk) produces the packed rows itself
   for (int r = warp; r < total; r += 8) {
     const uint4* src = hidden + (static_cast<size_t>(b) * S + s_src[r]) * row_u4;
     uint4* dst = packed + static_cast<size_t>(dst0 + r) * row_u4;
@@ -1122,6 +1117,94 @@ int pack_mode_from_env() {
     return -1;
   }();
   return mode;
+}
+
+size_t varlen_rows_public(int B, int S) { return varlen_rows(B, S); }
+
+size_t varlen_layout_bytes(int B, int S, int V) {
+  if (!varlen_shape_ok(B, S)) return 0;
+  return 256 + align256(static_cast<size_t>(B) * sizeof(int32_t)) +
+         align256((static_cast<size_t>(B) + 1) * sizeof(int32_t)) + align256(static_cast<size_t>(B)) +
+         align256(varlen_rows(B, S) * sizeof(uint32_t)) + align256(static_cast<size_t>(B) * V * sizeof(uint32_t));
+}
+
+// Packed layout of a batch from its attention mask alone (count -> plan -> column descriptors), pinned to the
+// packed tiling.  Used by the native trunk, whose kernels all work on the packed rows.
+int varlen_layout_build(const int32_t* mask, int B, int S, int V, void* workspace, size_t ws_bytes,
+                        VarlenLayout* out, cudaStream_t stream) {
+  if (!varlen_shape_ok(B, S))
+    return set_error(kErrUnsupportedShape, "packed layout: needs B <= 32767, S <= 65535, B*S <= 2^30 (B=%d S=%d)", B, S);
+  if (!workspace || ws_bytes < varlen_layout_bytes(B, S, V))
+    return set_error(kErrWorkspace, "packed layout: workspace too small");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  out->plan = reinterpret_cast<VarlenPlan*>(ws);
+  ws += 256;
+  out->len = reinterpret_cast<int32_t*>(ws);
+  ws += align256(static_cast<size_t>(B) * sizeof(int32_t));
+  out->off = reinterpret_cast<int32_t*>(ws);
+  ws += align256((static_cast<size_t>(B) + 1) * sizeof(int32_t));
+  out->spans = ws;
+  ws += align256(static_cast<size_t>(B));
+  out->meta = reinterpret_cast<uint32_t*>(ws);
+  ws += align256(varlen_rows(B, S) * sizeof(uint32_t));
+  out->keys = reinterpret_cast<uint32_t*>(ws);
+  out->rows = varlen_rows(B, S);
+  varlen_count_kernel<<<(B + 7) / 8, 256, 0, stream>>>(mask, B, S, out->len);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  varlen_plan_kernel<<<1, 1024, 0, stream>>>(out->len, B, nullptr, 0, 0, 0, /*force_mode=*/1, out->off, out->spans,
+                                             out->plan, nullptr);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  varlen_pack_kernel<<<dim3((S + 255) / 256, B), 256, 0, stream>>>(nullptr, mask, out->len, out->off, out->spans,
+                                                                    out->plan, S, 64, V, nullptr, out->meta,
+                                                                    out->keys);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+// Fused head on rows that are ALREADY in the packed layout `lay` (hidden_packed [lay.rows, H] bf16).
+int head_fwd_packed_launch(const void* hidden_packed, const VarlenLayout& lay, const void* W, const float* bias,
+                           int B, int S, int H, int V, float* rep, int32_t* argmax, cudaStream_t stream) {
+  if (H % BLOCK_K != 0)
+    return set_error(kErrUnsupportedShape, "splade_head_fwd: hidden size %d is not a multiple of %d", H, BLOCK_K);
+  CUtensorMap tmap_w, tmap_x;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(H), static_cast<uint64_t>(V)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(H) * 2};
+    const uint32_t box[2] = {BLOCK_K, BLOCK_V};
+    const int rc = encode_tmap_bf16(&tmap_w, W, 2, dims, strides, box);
+    if (rc != kOk) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(H), static_cast<uint64_t>(lay.rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(H) * 2};
+    const uint32_t box[2] = {BLOCK_K, BLOCK_T};
+    const int rc = encode_tmap_bf16(&tmap_x, hidden_packed, 2, dims, strides, box);
+    if (rc != kOk) return rc;
+  }
+  VarlenParams q{};
+  q.bias = bias;
+  q.plan = lay.plan;
+  q.meta = lay.meta;
+  q.spans = lay.spans;
+  q.len = lay.len;
+  q.rep = rep;
+  q.argmax = argmax;
+  q.keys = lay.keys;
+  q.tokw_bits = nullptr;
+  q.B = B;
+  q.S = S;
+  q.H = H;
+  q.V = V;
+  q.n_vt = (V + BLOCK_V - 1) / BLOCK_V;
+  auto kernel = head_fwd_varlen_kernel<false>;
+  SPLADE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VARLEN_SMEM_BYTES));
+  kernel<<<sm_count(), VL_THREADS, VARLEN_SMEM_BYTES, stream>>>(tmap_w, tmap_x, q);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  const long long items = static_cast<long long>(B) * ((V + 1023) / 1024);
+  const int grid = static_cast<int>(std::min<long long>(items, 8ll * sm_count()));
+  finalize_varlen_kernel<<<grid, 256, 0, stream>>>(lay.plan, lay.len, lay.spans, lay.keys, rep, argmax, B, V);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
 }
 
 // The same decision as varlen_plan_kernel, for callers whose attention mask is still in HOST memory

@@ -8,6 +8,7 @@
 
 struct splade_v33_scalar_args;
 struct splade_v33_fwd_args;
+struct splade_trunk_args;
 
 namespace splade {
 
@@ -27,6 +28,49 @@ int head_fwd_pack_mode_host(const int32_t* mask_host, int B, int S);
 int head_fwd_launch(const void* hidden, const void* W, const float* bias, const int32_t* mask, int B, int S,
                     int H, int V, float* rep, int32_t* argmax, float* tokw, void* workspace, size_t ws_bytes,
                     int pack_mode, int32_t* plan_out, cudaStream_t stream);
+
+// Packed (variable-length) token layout shared by the head and the native trunk (head_fwd.cu)
+struct VarlenPlan {
+  int32_t mode;      // 0: padded kernel runs, 1: packed kernel runs
+  int32_t T;         // packed columns in the batch (real tokens + replicas)
+  int32_t n_tt;      // packed token tiles = ceil(T / 256)
+  int32_t n16_last;  // UMMA N of the last packed tile
+  int32_t T_real;    // real tokens in the batch
+};
+struct VarlenLayout {
+  VarlenPlan* plan;   // device
+  int32_t* len;       // [B] real tokens per document
+  int32_t* off;       // [B+1] first packed row of every document (multiples of 8)
+  uint8_t* spans;     // [B]
+  uint32_t* meta;     // [rows] (straddles << 31) | (doc << 16) | position
+  uint32_t* keys;     // [B,V] merge buffer of straddling documents
+  size_t rows;        // rows of the packed buffers (a whole number of 256-row tiles)
+};
+size_t varlen_layout_bytes(int B, int S, int V);
+int varlen_layout_build(const int32_t* mask, int B, int S, int V, void* workspace, size_t ws_bytes,
+                        VarlenLayout* out, cudaStream_t stream);
+int head_fwd_packed_launch(const void* hidden_packed, const VarlenLayout& lay, const void* W, const float* bias,
+                           int B, int S, int H, int V, float* rep, int32_t* argmax, cudaStream_t stream);
+
+// trunk_gemm.cu: tcgen05 GEMM with the trunk's fused epilogues
+enum TrunkEpilogue { EPI_BF16 = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_GEGLU = 3, EPI_QKV_ROPE = 4 };
+int trunk_gemm_launch(int epi, const void* A, int rows_cap, const void* W, int N, int K, const int32_t* t_rows,
+                      void* out, int ldo, const uint32_t* meta, const float2* rope, int rope_cols, int max_pos,
+                      cudaStream_t stream);
+
+// trunk.cu: embedding / LayerNorm / attention kernels and the layer loop
+struct TrunkAttnArgs;
+int trunk_rope_table_launch(float2* table, int max_pos, float theta, cudaStream_t stream);
+int trunk_embed_ln_launch(const int64_t* input_ids, const float* tok_emb, const float* gamma, float eps,
+                          const VarlenLayout& lay, int S, int H, float* x, void* xb, cudaStream_t stream);
+int trunk_ln_launch(const void* in, int in_is_bf16, const float* gamma, float eps, const int32_t* t_rows,
+                    int rows_cap, int H, void* out_bf16, cudaStream_t stream);
+int trunk_attn_launch(const void* qkv, void* out, const VarlenLayout& lay, int B, int S, int H, int n_heads,
+                      int window, cudaStream_t stream);
+
+size_t trunk_workspace_bytes(int B, int S, int H, int I, int V);
+int trunk_encode_launch(const struct splade_trunk_args* a, cudaStream_t stream);
+size_t varlen_rows_public(int B, int S);
 
 // head_bwd.cu
 size_t head_bwd_workspace_bytes(int B, int S, int V);

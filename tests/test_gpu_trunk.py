@@ -1,0 +1,180 @@
+"""-m gpu: native variable-length ModernBERT trunk (splade_trunk_encode and its building blocks) against plain
+torch restatements of the same arithmetic and against transformers' ModernBertForMaskedLM on the same device."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _close(got, ref, what, atol, rtol=2e-2, frac=1e-3):
+    got, ref = got.float(), ref.float()
+    bad = (got - ref).abs() > atol + rtol * ref.abs()
+    assert float(bad.float().mean()) <= frac, (what, int(bad.sum()), bad.numel(), float((got - ref).abs().max()))
+
+
+@pytest.mark.parametrize("rows,K,N", [(300, 256, 512), (128, 64, 256), (1000, 768, 768), (257, 1152, 768)])
+def test_trunk_gemm_epilogues(cuda_device, rows, K, N):
+    import splade_b200
+    from splade_b200 import _lib as L
+    g = torch.Generator().manual_seed(rows + K)
+    A = _bf(torch.randn(rows, K, generator=g)).to(cuda_device)
+    W = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_device)
+    acc = A.float() @ W.float().t()
+    ref = _bf(acc)
+    out = splade_b200.trunk_gemm(L.EPI_BF16, A, W)
+    _close(out, ref, "bf16", atol=2e-2)
+    out = splade_b200.trunk_gemm(L.EPI_GELU, A, W)
+    _close(out, _bf(torch.nn.functional.gelu(ref.float())), "gelu", atol=2e-2)
+    x0 = torch.randn(rows, N, generator=g).to(cuda_device)
+    x = x0.clone()
+    splade_b200.trunk_gemm(L.EPI_RESID, A, W, out=x)
+    _close(x, x0 + ref.float(), "resid", atol=2e-2)
+    # GeGLU: W = [input rows | gate rows]
+    Wg = _bf(torch.randn(2 * N, K, generator=g) / math.sqrt(K)).to(cuda_device)
+    a2 = _bf(A.float() @ Wg.float().t())
+    refg = _bf(_bf(torch.nn.functional.gelu(a2[:, :N].float())).float() * a2[:, N:].float())
+    out = splade_b200.trunk_gemm(L.EPI_GEGLU, A, Wg)
+    _close(out, refg, "geglu", atol=2e-2)
+
+
+def test_trunk_gemm_rope(cuda_device):
+    import splade_b200
+    from splade_b200 import _lib as L
+    rows, H, max_pos, theta = 300, 256, 200, 160000.0
+    g = torch.Generator().manual_seed(5)
+    A = _bf(torch.randn(rows, H, generator=g)).to(cuda_device)
+    W = _bf(torch.randn(3 * H, H, generator=g) / math.sqrt(H)).to(cuda_device)
+    pos = torch.randint(0, max_pos, (rows,), generator=g).to(torch.int32).to(cuda_device)
+    out = splade_b200.trunk_gemm(L.EPI_QKV_ROPE, A, W, pos=pos, rope_theta=theta, rope_cols=2 * H, max_pos=max_pos)
+    qkv = _bf(A.float() @ W.float().t()).float().view(rows, 3, H // 64, 64)
+    inv = 1.0 / (theta ** (torch.arange(0, 64, 2, device=cuda_device).float() / 64))
+    ang = pos.float()[:, None] * inv[None, :]
+    cos, sin = torch.cat([ang.cos(), ang.cos()], -1)[:, None, :], torch.cat([ang.sin(), ang.sin()], -1)[:, None, :]
+
+    def rot(x):
+        return torch.cat([-x[..., 32:], x[..., :32]], -1)
+    ref = qkv.clone()
+    for i in (0, 1):
+        ref[:, i] = qkv[:, i] * cos + rot(qkv[:, i]) * sin
+    _close(out, _bf(ref.view(rows, 3 * H)), "rope", atol=2e-2)
+
+
+def _pack_rows(x_pad, lens, rows):
+    """[B,S,C] padded -> [rows,C] in the packed layout: documents start at multiples of 8 rows, fillers behind a
+    document replicate its last token."""
+    out = torch.zeros(rows, x_pad.shape[-1], dtype=x_pad.dtype, device=x_pad.device)
+    starts, o = [], 0
+    for b, L in enumerate(lens):
+        starts.append(o)
+        if L:
+            L8 = (L + 7) // 8 * 8
+            out[o:o + L] = x_pad[b, :L]
+            out[o + L:o + L8] = x_pad[b, L - 1]
+            o += L8
+    return out, starts
+
+
+@pytest.mark.parametrize("window", [-1, 64])
+def test_trunk_attention_vs_torch(cuda_device, window):
+    import splade_b200
+    B, S, nh = 6, 200, 4
+    H = nh * 64
+    g = torch.Generator().manual_seed(11 + window)
+    lens = [200, 1, 0, 77, 130, 64]
+    mask = (torch.arange(S)[None, :] < torch.tensor(lens)[:, None]).to(torch.int32).to(cuda_device)
+    qkv = _bf(torch.randn(B, S, 3 * H, generator=g)).to(cuda_device)
+    rows = splade_b200.load_library().splade_packed_rows(B, S)
+    packed, starts = _pack_rows(qkv, lens, rows)
+    out, meta = splade_b200.trunk_attention(packed.contiguous(), mask, nh, window)
+    for b, L in enumerate(lens):
+        if L == 0:
+            continue
+        x = qkv[b, :L].float().view(L, 3, nh, 64)
+        q, k, v = (x[:, i].transpose(0, 1) for i in range(3))           # [nh, L, 64]
+        s = q @ k.transpose(1, 2) * 0.125
+        if window >= 0:
+            i = torch.arange(L, device=cuda_device)
+            s = s.masked_fill(((i[:, None] - i[None, :]).abs() > window)[None], float("-inf"))
+        ref = (torch.softmax(s, -1) @ v).transpose(0, 1).reshape(L, H)
+        got = out[starts[b]:starts[b] + L]
+        _close(got, ref, f"attention doc {b} window {window}", atol=2e-2)
+        L8 = (L + 7) // 8 * 8
+        if L8 > L:  # replicas reproduce the last token's output exactly
+            assert torch.equal(out[starts[b] + L:starts[b] + L8], out[starts[b] + L - 1].expand(L8 - L, -1))
+        m = meta[starts[b]:starts[b] + L].cpu().numpy()
+        assert np.array_equal(m & 0xFFFF, np.arange(L)) and np.all(((m >> 16) & 0x7FFF) == b)
+
+
+def _tiny_mlm(device, layers=4):
+    from transformers import AutoModelForMaskedLM, ModernBertConfig
+    cfg = ModernBertConfig(vocab_size=3000, hidden_size=256, intermediate_size=384, num_hidden_layers=layers,
+                           num_attention_heads=4, pad_token_id=2999, bos_token_id=0, eos_token_id=1, cls_token_id=0,
+                           sep_token_id=1, max_position_embeddings=1024, global_attn_every_n_layers=3,
+                           local_attention=128)
+    torch.manual_seed(0)
+    mlm = AutoModelForMaskedLM.from_config(cfg).to(device).eval()
+    with torch.no_grad():
+        mlm.decoder.bias.normal_(0.0, 0.02)
+        for n, p_ in mlm.named_parameters():
+            if n.endswith("norm.weight"):
+                p_.add_(0.1 * torch.randn_like(p_))   # LayerNorm weights away from 1 so that they are exercised
+    return mlm, cfg
+
+
+def test_native_trunk_vs_transformers(cuda_device):
+    """Whole network on a small ModernBERT (4 layers: global, local, local, global): the packed head input and the
+    pooled sparse vectors against transformers' own forward under autocast(bf16) on the same device."""
+    import splade_b200
+    mlm, cfg = _tiny_mlm(cuda_device)
+    B, S = 7, 160
+    g = torch.Generator().manual_seed(3)
+    lens = torch.tensor([160, 5, 33, 97, 128, 1, 150])
+    ids = torch.randint(6, cfg.vocab_size - 1, (B, S), generator=g)
+    mask = (torch.arange(S)[None, :] < lens[:, None]).to(torch.int64)
+    ids = torch.where(mask.bool(), ids, torch.full_like(ids, cfg.pad_token_id)).to(cuda_device)
+    mask = mask.to(cuda_device)
+    trunk = splade_b200.NativeTrunk(mlm)
+    rep, dbg = trunk.encode(ids, mask, debug=True)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ref_hidden = mlm.head(mlm.model(input_ids=ids, attention_mask=mask)[0]).float()
+        ref_rep, _ = splade_b200.splade_head(ref_hidden, mlm.decoder.weight, mlm.decoder.bias, mask,
+                                             want_token_weights=False)
+    plan = dbg["plan"].cpu().tolist()
+    assert plan[0] == 1 and plan[4] == int(lens.sum())
+    meta = dbg["meta"].cpu().numpy().astype(np.int64)
+    T = plan[1]
+    doc, pos = (meta[:T] >> 16) & 0x7FFF, meta[:T] & 0xFFFF
+    got = dbg["hidden_packed"][:T].float()
+    want = ref_hidden[torch.from_numpy(doc).to(cuda_device), torch.from_numpy(pos).to(cuda_device)]
+    err = (got - want).abs()
+    # bf16 Linear outputs through 4 layers: a few 1e-3 of noise on unit-scale (post-LayerNorm) activations
+    assert float(err.mean()) < 1e-2 and float(err.max()) < 0.25, (float(err.mean()), float(err.max()))
+    cos = torch.nn.functional.cosine_similarity(rep, ref_rep, dim=1)
+    assert float(cos.min()) > 0.999, cos
+    np.testing.assert_allclose(rep.cpu().numpy(), ref_rep.cpu().numpy(), atol=3e-2, rtol=3e-2)
+    assert float(rep[torch.where(lens == 0)[0]].abs().sum()) == 0.0
+
+
+def test_native_trunk_is_padding_and_batch_invariant(cuda_device):
+    """A document's vector does not depend on its neighbours, on the padded width, or on what sits at padded ids."""
+    import splade_b200
+    mlm, cfg = _tiny_mlm(cuda_device, layers=3)
+    trunk = splade_b200.NativeTrunk(mlm)
+    g = torch.Generator().manual_seed(4)
+    B, S = 5, 96
+    lens = torch.tensor([96, 17, 40, 8, 64])
+    ids = torch.randint(6, cfg.vocab_size - 1, (B, S), generator=g).to(cuda_device)
+    mask = (torch.arange(S)[None, :] < lens[:, None]).to(torch.int64).to(cuda_device)
+    rep = trunk.encode(ids, mask)
+    rep2 = trunk.encode(ids[[2, 0]].contiguous(), mask[[2, 0]].contiguous())
+    assert torch.equal(rep2[0], rep[2]) and torch.equal(rep2[1], rep[0])
+    wide_ids = torch.cat([ids, torch.randint(6, 100, (B, 32), generator=g).to(cuda_device)], 1)
+    wide_mask = torch.cat([mask, torch.zeros(B, 32, dtype=mask.dtype, device=cuda_device)], 1)
+    assert torch.equal(trunk.encode(wide_ids, wide_mask), rep)
