@@ -44,7 +44,7 @@ extern "C" {
 #define SPLADE_OP_SCORES 4        /* (B=Bq, k=N docs, V)  q.d score matrix                            */
 #define SPLADE_OP_V33_LOSS_FWD 5  /* (B=Bq, S=N docs, V, k) whole SPLADELossV33 forward               */
 #define SPLADE_OP_TRUNK_ENCODE 6  /* (B,S,H,V, k = intermediate size) native trunk + head encode      */
-#define SPLADE_OP_TRUNK_GEMM 7    /* (B = rows, S = max_pos)  splade_trunk_gemm scratch               */
+#define SPLADE_OP_TRUNK_GEMM 7    /* (-)                      splade_trunk_gemm scratch               */
 #define SPLADE_OP_TRUNK_ATTN 8    /* (B,S,-,V=1)              splade_trunk_attn scratch               */
 
 int splade_abi_version(void);
@@ -282,17 +282,17 @@ size_t splade_packed_rows(int B, int S);
 
 /*
  * Building blocks of the trunk, exported for unit tests and reuse.
- * splade_trunk_gemm: out = epilogue(A [rows,K] bf16 x W[N,K]^T bf16), rows >= 128.
- *   epi 0 bf16 [rows,N]; 1 GELU -> bf16; 2 out (fp32 [rows,N]) += bf16(acc); 3 GeGLU: W is [2N,K], out bf16 [rows,N];
- *   4 RoPE on features < rope_cols (64-wide heads, theta, positions pos[rows] int32) -> bf16.
- * splade_trunk_attn: qkv_packed [rows,3H] bf16 (RoPE applied) -> out_packed [rows,H] bf16 in the packed layout of
- *   `mask`; window < 0 = global.  meta_out as above.
+ * splade_trunk_gemm: out = epilogue(A [rows,K] bf16 x W[N,K]^T bf16), rows >= 128, K % 64 == 0, N % 128 == 0.
+ *   epi 0 bf16 [rows,N]; 1 GELU -> bf16; 2 out (fp32 [rows,N]) += bf16(acc); 3 GeGLU: W is [2N,K], out bf16 [rows,N].
+ * splade_trunk_attn: qkv_packed [rows,3H] bf16 -> out_packed [rows,H] bf16 in the packed layout of `mask`;
+ *   window < 0 = global attention, otherwise keys with |pos_q - pos_k| <= window; rope_theta > 0 first rotates
+ *   q and k IN PLACE in qkv_packed (the trunk's RoPE kernel, that base), <= 0 means they are already rotated.
  */
 int splade_trunk_gemm(int epi, const void* A, int rows, const void* W, int N, int K, void* out, int ldo,
-                      const int32_t* pos, float rope_theta, int rope_cols, int max_pos, void* workspace,
-                      size_t ws_bytes, void* stream);
-int splade_trunk_attn(const void* qkv_packed, const int32_t* mask, int B, int S, int H, int n_heads, int window,
-                      void* out_packed, uint32_t* meta_out, void* workspace, size_t ws_bytes, void* stream);
+                      void* workspace, size_t ws_bytes, void* stream);
+int splade_trunk_attn(void* qkv_packed, const int32_t* mask, int B, int S, int H, int n_heads, int window,
+                      float rope_theta, void* out_packed, uint32_t* meta_out, void* workspace, size_t ws_bytes,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ OP_TRUNK_GEMM = 7
 OP_TRUNK_ATTN = 8
 
 # epilogues of splade_trunk_gemm
-EPI_BF16, EPI_GELU, EPI_RESID, EPI_GEGLU, EPI_QKV_ROPE = 0, 1, 2, 3, 4
+EPI_BF16, EPI_GELU, EPI_RESID, EPI_GEGLU = 0, 1, 2, 3
 
 
 class V33ScalarArgs(Structure):
@@ -113,10 +113,10 @@ EXPORTS = {
                                  c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
     "splade_trunk_encode": (c_int, [POINTER(TrunkArgs), c_void_p]),
     "splade_packed_rows": (c_size_t, [c_int, c_int]),
-    "splade_trunk_gemm": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_float,
-                                  c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "splade_trunk_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                  c_void_p, c_size_t, c_void_p]),
+    "splade_trunk_gemm": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
+                                  c_size_t, c_void_p]),
+    "splade_trunk_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "splade_topk": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -142,9 +142,10 @@ size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k) {
     case SPLADE_OP_TRUNK_ENCODE:
       return trunk_workspace_bytes(B, S, H, k, V);
     case SPLADE_OP_TRUNK_GEMM:
-      return 512 + static_cast<size_t>(S > 0 ? S : 1) * 32 * sizeof(float2);
+      return 256;
     case SPLADE_OP_TRUNK_ATTN:
-      return varlen_layout_bytes(B, S, 1);
+      return ((varlen_layout_bytes(B, S, 1) + 255) & ~static_cast<size_t>(255)) +
+             static_cast<size_t>(S > 0 ? S : 1) * 32 * sizeof(float2);
     default:
       return 0;
   }
@@ -231,35 +232,37 @@ int splade_trunk_encode(const splade_trunk_args* args, void* stream) {
 size_t splade_packed_rows(int B, int S) { return varlen_rows_public(B, S); }
 
 int splade_trunk_gemm(int epi, const void* A, int rows, const void* W, int N, int K, void* out, int ldo,
-                      const int32_t* pos, float rope_theta, int rope_cols, int max_pos, void* workspace,
-                      size_t ws_bytes, void* stream) {
+                      void* workspace, size_t ws_bytes, void* stream) {
   if (!A || !W || !out || rows < 1) return set_error(kErrInvalidArg, "splade_trunk_gemm: bad argument");
-  const size_t need = 512 + static_cast<size_t>(max_pos > 0 ? max_pos : 1) * 32 * sizeof(float2);
-  if (!workspace || ws_bytes < need) return set_error(kErrWorkspace, "splade_trunk_gemm: workspace too small");
+  if (!workspace || ws_bytes < 256) return set_error(kErrWorkspace, "splade_trunk_gemm: workspace too small");
   int rc = require_sm100("splade_trunk_gemm");
   if (rc != kOk) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int32_t* t_rows = static_cast<int32_t*>(workspace);
   SPLADE_CUDA_OK(cudaMemcpyAsync(t_rows, &rows, sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  float2* rope = reinterpret_cast<float2*>(static_cast<uint8_t*>(workspace) + 512);
-  if (epi == EPI_QKV_ROPE) {
-    if (!pos || max_pos < 1) return set_error(kErrInvalidArg, "splade_trunk_gemm: RoPE needs positions");
-    rc = trunk_rope_table_launch(rope, max_pos, rope_theta, st);
-    if (rc != kOk) return rc;
-  }
-  return trunk_gemm_launch(epi, A, rows, W, N, K, t_rows, out, ldo, reinterpret_cast<const uint32_t*>(pos), rope,
-                           rope_cols, max_pos, st);
+  return trunk_gemm_launch(epi, A, rows, W, N, K, t_rows, out, ldo, st);
 }
 
-int splade_trunk_attn(const void* qkv_packed, const int32_t* mask, int B, int S, int H, int n_heads, int window,
-                      void* out_packed, uint32_t* meta_out, void* workspace, size_t ws_bytes, void* stream) {
+int splade_trunk_attn(void* qkv_packed, const int32_t* mask, int B, int S, int H, int n_heads, int window,
+                      float rope_theta, void* out_packed, uint32_t* meta_out, void* workspace, size_t ws_bytes,
+                      void* stream) {
   if (!qkv_packed || !mask || !out_packed) return set_error(kErrInvalidArg, "splade_trunk_attn: null pointer");
   int rc = require_sm100("splade_trunk_attn");
   if (rc != kOk) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t lay_bytes = (varlen_layout_bytes(B, S, 1) + 255) & ~static_cast<size_t>(255);
+  const size_t need = lay_bytes + static_cast<size_t>(S) * 32 * sizeof(float2);
+  if (!workspace || ws_bytes < need) return set_error(kErrWorkspace, "splade_trunk_attn: workspace too small");
   VarlenLayout lay{};
-  rc = varlen_layout_build(mask, B, S, 1, workspace, ws_bytes, &lay, st);
+  rc = varlen_layout_build(mask, B, S, 1, workspace, lay_bytes, &lay, st);
   if (rc != kOk) return rc;
+  if (rope_theta > 0.f) {  // the trunk's own RoPE kernel, in place on the q and k thirds
+    float2* rope = reinterpret_cast<float2*>(static_cast<uint8_t*>(workspace) + lay_bytes);
+    rc = trunk_rope_table_launch(rope, S, rope_theta, st);
+    if (rc != kOk) return rc;
+    rc = trunk_rope_launch(qkv_packed, rope, lay, H, st);
+    if (rc != kOk) return rc;
+  }
   if (meta_out)
     SPLADE_CUDA_OK(cudaMemcpyAsync(meta_out, lay.meta, lay.rows * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   return trunk_attn_launch(qkv_packed, out_packed, lay, B, S, H, n_heads, window, st);

@@ -53,10 +53,9 @@ int head_fwd_packed_launch(const void* hidden_packed, const VarlenLayout& lay, c
                            int B, int S, int H, int V, float* rep, int32_t* argmax, cudaStream_t stream);
 
 // trunk_gemm.cu: tcgen05 GEMM with the trunk's fused epilogues
-enum TrunkEpilogue { EPI_BF16 = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_GEGLU = 3, EPI_QKV_ROPE = 4 };
+enum TrunkEpilogue { EPI_BF16 = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_GEGLU = 3 };
 int trunk_gemm_launch(int epi, const void* A, int rows_cap, const void* W, int N, int K, const int32_t* t_rows,
-                      void* out, int ldo, const uint32_t* meta, const float2* rope, int rope_cols, int max_pos,
-                      cudaStream_t stream);
+                      void* out, int ldo, cudaStream_t stream);
 
 // trunk.cu: embedding / LayerNorm / attention kernels and the layer loop
 struct TrunkAttnArgs;
@@ -65,6 +64,7 @@ int trunk_embed_ln_launch(const int64_t* input_ids, const float* tok_emb, const 
                           const VarlenLayout& lay, int S, int H, float* x, void* xb, cudaStream_t stream);
 int trunk_ln_launch(const void* in, int in_is_bf16, const float* gamma, float eps, const int32_t* t_rows,
                     int rows_cap, int H, void* out_bf16, cudaStream_t stream);
+int trunk_rope_launch(void* qkv, const float2* rope, const VarlenLayout& lay, int H, cudaStream_t stream);
 int trunk_attn_launch(const void* qkv, void* out, const VarlenLayout& lay, int B, int S, int H, int n_heads,
                       int window, cudaStream_t stream);
 

@@ -70,20 +70,86 @@ __device__ __forceinline__ void warp_layernorm_row(const InT* __restrict__ src, 
   }
 }
 
-template <typename InT>
+// Register-resident row (H = 128 * kV4 floats: each lane holds kV4 float4s, every global access of the warp is a
+// contiguous 512 B): one read of the row, statistics and the normalised output all from registers.
+template <int kV4>
+__device__ __forceinline__ void warp_layernorm_regs(const float4 (&v)[kV4], const float* __restrict__ gamma, float eps,
+                                                    int lane, float* __restrict__ out_f32,
+                                                    __nv_bfloat16* __restrict__ out_bf16) {
+  constexpr int H = 128 * kV4;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  const float mean = sum * (1.0f / H);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    var += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+  const float rstd = rsqrtf(var * (1.0f / H) + eps);
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const int c4 = lane + 32 * i;  // float4 index inside the row
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x;
+    y.y = (v[i].y - mean) * rstd * g.y;
+    y.z = (v[i].z - mean) * rstd * g.z;
+    y.w = (v[i].w - mean) * rstd * g.w;
+    if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32)[c4] = y;
+    if (out_bf16 != nullptr) {
+      uint2 o;
+      o.x = cvt_bf16x2(y.y, y.x);
+      o.y = cvt_bf16x2(y.w, y.z);
+      reinterpret_cast<uint2*>(out_bf16)[c4] = o;
+    }
+  }
+}
+
+template <int kV4>
+__device__ __forceinline__ void load_row_regs(const float* __restrict__ src, int lane, float4 (&v)[kV4]) {
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src) + lane + 32 * i);
+}
+template <int kV4>
+__device__ __forceinline__ void load_row_regs(const __nv_bfloat16* __restrict__ src, int lane, float4 (&v)[kV4]) {
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(src) + lane + 32 * i);
+    v[i].x = __uint_as_float(u.x << 16);
+    v[i].y = __uint_as_float(u.x & 0xFFFF0000u);
+    v[i].z = __uint_as_float(u.y << 16);
+    v[i].w = __uint_as_float(u.y & 0xFFFF0000u);
+  }
+}
+
+// kV4 = 0: generic three-pass version for hidden sizes that are not 256 / 768 / 1024
+template <typename InT, int kV4>
 __global__ void __launch_bounds__(256)
 trunk_ln_kernel(const InT* __restrict__ in, const float* __restrict__ gamma, float eps,
                 const int32_t* __restrict__ t_rows, int H, __nv_bfloat16* __restrict__ out) {
   const int T = __ldg(t_rows);
   const int lane = static_cast<int>(threadIdx.x & 31u);
   for (int row = blockIdx.x * 8 + static_cast<int>(threadIdx.x >> 5); row < T; row += gridDim.x * 8) {
-    warp_layernorm_row<InT>(in + static_cast<size_t>(row) * H, gamma, eps, H, lane, nullptr,
-                            out + static_cast<size_t>(row) * H);
+    if (kV4 > 0) {
+      float4 v[kV4 > 0 ? kV4 : 1];
+      load_row_regs<(kV4 > 0 ? kV4 : 1)>(in + static_cast<size_t>(row) * H, lane, v);
+      warp_layernorm_regs<(kV4 > 0 ? kV4 : 1)>(v, gamma, eps, lane, nullptr, out + static_cast<size_t>(row) * H);
+    } else {
+      warp_layernorm_row<InT>(in + static_cast<size_t>(row) * H, gamma, eps, H, lane, nullptr,
+                              out + static_cast<size_t>(row) * H);
+    }
   }
 }
 
 // x = LayerNorm(tok_embeddings[input_ids[doc, pos]]) for every packed column (replicas included: they carry the
 // descriptor of the document's last token, so they stay exact duplicates of it through the whole trunk)
+template <int kV4>
 __global__ void __launch_bounds__(256)
 trunk_embed_ln_kernel(const int64_t* __restrict__ input_ids, const float* __restrict__ tok_emb,
                       const float* __restrict__ gamma, float eps, const int32_t* __restrict__ t_rows,
@@ -95,19 +161,55 @@ trunk_embed_ln_kernel(const int64_t* __restrict__ input_ids, const float* __rest
     const uint32_t m = __ldg(&meta[row]);
     const int doc = static_cast<int>((m >> 16) & 0x7FFFu), pos = static_cast<int>(m & 0xFFFFu);
     const long long id = input_ids[static_cast<size_t>(doc) * S + pos];
-    warp_layernorm_row<float>(tok_emb + static_cast<size_t>(id) * H, gamma, eps, H, lane,
-                              x + static_cast<size_t>(row) * H, xb + static_cast<size_t>(row) * H);
+    const float* src = tok_emb + static_cast<size_t>(id) * H;
+    if (kV4 > 0) {
+      float4 v[kV4 > 0 ? kV4 : 1];
+      load_row_regs<(kV4 > 0 ? kV4 : 1)>(src, lane, v);
+      warp_layernorm_regs<(kV4 > 0 ? kV4 : 1)>(v, gamma, eps, lane, x + static_cast<size_t>(row) * H,
+                                                xb + static_cast<size_t>(row) * H);
+    } else {
+      warp_layernorm_row<float>(src, gamma, eps, H, lane, x + static_cast<size_t>(row) * H,
+                                xb + static_cast<size_t>(row) * H);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RoPE
+// In place on the q and k thirds of qkv [T, 3H]: x*cos + rotate_half(x)*sin in fp32 on the bf16 Linear output,
+// rounded back to bf16 (apply_rotary_pos_emb, modeling_modernbert.py:205-228).  One thread per (row, head of q or
+// k, 2 dims): a warp covers one 64-wide head = 128 contiguous bytes; qkv of a layer is L2-resident.
+__global__ void __launch_bounds__(256)
+trunk_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float2* __restrict__ rope, const uint32_t* __restrict__ meta,
+                  const int32_t* __restrict__ t_rows, int H) {
+  const int T = __ldg(t_rows);
+  const int heads2 = 2 * H / 64;  // q heads then k heads
+  const long long total = static_cast<long long>(T) * heads2 * 16;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int d2 = static_cast<int>(i & 15);  // dims 2*d2, 2*d2+1 and their partners 32 above
+    const long long rh = i >> 4;
+    const int hd = static_cast<int>(rh % heads2);
+    const int row = static_cast<int>(rh / heads2);
+    const int pos = static_cast<int>(__ldg(&meta[row]) & 0xFFFFu);
+    const float2 c0 = __ldg(&rope[pos * 32 + 2 * d2]);
+    const float2 c1 = __ldg(&rope[pos * 32 + 2 * d2 + 1]);
+    uint32_t* plo = reinterpret_cast<uint32_t*>(qkv + static_cast<size_t>(row) * 3 * H + hd * 64 + 2 * d2);
+    uint32_t* phi = plo + 16;
+    const uint32_t lo = *plo, hi = *phi;
+    const float a0 = __uint_as_float(lo << 16), a1 = __uint_as_float(lo & 0xFFFF0000u);
+    const float b0 = __uint_as_float(hi << 16), b1 = __uint_as_float(hi & 0xFFFF0000u);
+    *plo = cvt_bf16x2(a1 * c1.x - b1 * c1.y, a0 * c0.x - b0 * c0.y);
+    *phi = cvt_bf16x2(b1 * c1.x + a1 * c1.y, b0 * c0.x + a0 * c0.y);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-constexpr int AT_BQ = 64;   // queries per CTA (4 warps x 16 rows)
 constexpr int AT_BK = 64;   // keys per step
 constexpr int AT_D = 64;    // head dim
 constexpr int AT_LD = 72;   // smem row stride in bf16 (144 B: conflict-free 32-bit fragment loads)
 
 struct AttnParams {
-  const __nv_bfloat16* qkv;  // [T, 3H]: q | k | v, RoPE already applied to q and k
+  const __nv_bfloat16* qkv;  // [T, 3H]: q | k | v (heads of 64), RoPE already applied to q and k
   __nv_bfloat16* out;        // [T, H]
   const int32_t* len;
   const int32_t* off;
@@ -124,11 +226,38 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(128)
+// 16-byte asynchronous global -> shared copy; `valid == false` writes zeros (source size 0)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+
+// kWarps x 16 query rows per CTA (8 warps = 128 queries for documents, 4 warps for query-length batches).  K and V
+// tiles of 64 keys are double-buffered in shared memory with cp.async (the next tile streams in while the tensor
+// cores work on the current one), stay row-major, and every fragment comes from one ldmatrix.x4 (V through .trans,
+// so there is no transposition pass).
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32)
 trunk_attn_kernel(const AttnParams p) {
+  constexpr int BQ = kWarps * 16;
+  constexpr int NT = kWarps * 32;
   const int b = static_cast<int>(blockIdx.z);
   const int h = static_cast<int>(blockIdx.y);
-  const int q0 = static_cast<int>(blockIdx.x) * AT_BQ;
+  const int q0 = static_cast<int>(blockIdx.x) * BQ;
   const int L = __ldg(&p.len[b]);
   if (L == 0) return;
   const int L8 = (L + 7) & ~7;  // real tokens + replicas of the last one (they are queries, never keys)
@@ -136,45 +265,63 @@ trunk_attn_kernel(const AttnParams p) {
   const int base = __ldg(&p.off[b]);
   const int H3 = 3 * p.H;
 
-  __shared__ __align__(16) __nv_bfloat16 Qs[AT_BQ][AT_LD];
-  __shared__ __align__(16) __nv_bfloat16 Ks[AT_BK][AT_LD];
-  __shared__ __align__(16) __nv_bfloat16 Vt[AT_D][AT_LD];  // transposed: [dim][key]
-  __shared__ int kpos[AT_BK];
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  typedef __nv_bfloat16 (*Tile)[AT_LD];
+  Tile Qs = reinterpret_cast<Tile>(attn_smem);
+  Tile Kbuf = reinterpret_cast<Tile>(attn_smem + BQ * AT_LD * 2);                     // [2][AT_BK] rows
+  Tile Vbuf = reinterpret_cast<Tile>(attn_smem + (BQ + 2 * AT_BK) * AT_LD * 2);       // [2][AT_BK] rows
+  int* kpos_buf = reinterpret_cast<int*>(attn_smem + (BQ + 4 * AT_BK) * AT_LD * 2);  // [2][AT_BK]
 
   const int tid = static_cast<int>(threadIdx.x);
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  for (int i = 0; i < 4; ++i) {
-    const int c = tid + 128 * i;
-    const int r = c >> 3, ch = c & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (q0 + r < L8)
-      v = __ldg(reinterpret_cast<const uint4*>(p.qkv + static_cast<size_t>(base + q0 + r) * H3 + h * AT_D + ch * 8));
-    *reinterpret_cast<uint4*>(&Qs[r][ch * 8]) = v;
+  // visible key blocks: all of them (global) or the contiguous range that intersects the queries' windows
+  const int n_kv = (L + AT_BK - 1) / AT_BK;
+  int kb_lo = 0, kb_hi = n_kv;
+  if (p.window >= 0) {
+    const int qmin = static_cast<int>(__ldg(&p.meta[base + q0]) & 0xFFFFu);
+    const int qmax = static_cast<int>(__ldg(&p.meta[base + min(q0 + BQ - 1, L8 - 1)]) & 0xFFFFu);
+    while (kb_lo < kb_hi &&
+           static_cast<int>(__ldg(&p.meta[base + min(kb_lo * AT_BK + AT_BK - 1, L - 1)]) & 0xFFFFu) < qmin - p.window)
+      ++kb_lo;
+    while (kb_hi > kb_lo &&
+           static_cast<int>(__ldg(&p.meta[base + (kb_hi - 1) * AT_BK]) & 0xFFFFu) > qmax + p.window)
+      --kb_hi;
   }
-  __syncthreads();
-  uint32_t qa[4][4];
-  {
-    const int r0 = warp * 16 + g;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      qa[ks][0] = *reinterpret_cast<const uint32_t*>(&Qs[r0][ks * 16 + 2 * t]);
-      qa[ks][1] = *reinterpret_cast<const uint32_t*>(&Qs[r0 + 8][ks * 16 + 2 * t]);
-      qa[ks][2] = *reinterpret_cast<const uint32_t*>(&Qs[r0][ks * 16 + 8 + 2 * t]);
-      qa[ks][3] = *reinterpret_cast<const uint32_t*>(&Qs[r0 + 8][ks * 16 + 8 + 2 * t]);
+
+  auto issue_kv = [&](int kb, int buf) {
+    const int kv0 = kb * AT_BK;
+    Tile Ks = Kbuf + buf * AT_BK;
+    Tile Vs = Vbuf + buf * AT_BK;
+    for (int c = tid; c < AT_BK * 8; c += NT) {
+      const int r = c >> 3, ch = c & 7;
+      const bool ok = kv0 + r < L;
+      const __nv_bfloat16* src = p.qkv + static_cast<size_t>(base + (ok ? kv0 + r : 0)) * H3 + h * AT_D + ch * 8;
+      cp_async16(&Ks[r][ch * 8], src + p.H, ok);
+      cp_async16(&Vs[r][ch * 8], src + 2 * p.H, ok);
     }
+    if (tid < AT_BK) {
+      const int key = kv0 + tid;
+      kpos_buf[buf * AT_BK + tid] = key < L ? static_cast<int>(__ldg(&p.meta[base + key]) & 0xFFFFu) : 0x3FFFFFFF;
+    }
+  };
+
+  for (int c = tid; c < BQ * 8; c += NT) {
+    const int r = c >> 3, ch = c & 7;
+    const bool ok = q0 + r < L8;
+    cp_async16(&Qs[r][ch * 8], p.qkv + static_cast<size_t>(base + (ok ? q0 + r : 0)) * H3 + h * AT_D + ch * 8, ok);
   }
+  if (kb_lo < kb_hi) issue_kv(kb_lo, 0);
+  cp_async_commit();
+
+  const bool warp_active = q0 + warp * 16 < L8;  // warps whose 16 rows are all past the document only help loading
+  uint32_t qa[4][4];
   int qpos[2];
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const int row = min(q0 + warp * 16 + g + 8 * e, L8 - 1);
     qpos[e] = static_cast<int>(__ldg(&p.meta[base + row]) & 0xFFFFu);
-  }
-  int qmin = 0, qmax = 0;
-  if (p.window >= 0) {
-    qmin = static_cast<int>(__ldg(&p.meta[base + q0]) & 0xFFFFu);
-    qmax = static_cast<int>(__ldg(&p.meta[base + min(q0 + AT_BQ - 1, L8 - 1)]) & 0xFFFFu);
   }
 
   float m_run[2] = {-INFINITY, -INFINITY};
@@ -185,41 +332,23 @@ trunk_attn_kernel(const AttnParams p) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
 
-  const int n_kv = (L + AT_BK - 1) / AT_BK;
-  for (int kb = 0; kb < n_kv; ++kb) {
+  const float sl2 = p.scale * 1.4426950408889634f;  // softmax in base 2: exp(x) = exp2(x * log2 e)
+  for (int kb = kb_lo; kb < kb_hi; ++kb) {
+    const int buf = (kb - kb_lo) & 1;
     const int kv0 = kb * AT_BK;
-    if (p.window >= 0) {  // CTA-uniform: the whole key block is outside every query's window
-      const int kfirst = static_cast<int>(__ldg(&p.meta[base + kv0]) & 0xFFFFu);
-      const int klast = static_cast<int>(__ldg(&p.meta[base + min(kv0 + AT_BK - 1, L - 1)]) & 0xFFFFu);
-      if (klast < qmin - p.window || kfirst > qmax + p.window) continue;
-    }
-    __syncthreads();  // everyone is done with the previous K / V tiles
-    for (int i = 0; i < 4; ++i) {
-      const int c = tid + 128 * i;
-      {  // K rows: 16-byte chunks, chunk index fastest (coalesced)
-        const int r = c >> 3, ch = c & 7;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (kv0 + r < L)
-          v = __ldg(reinterpret_cast<const uint4*>(p.qkv + static_cast<size_t>(base + kv0 + r) * H3 + p.H +
-                                                   h * AT_D + ch * 8));
-        *reinterpret_cast<uint4*>(&Ks[r][ch * 8]) = v;
-      }
-      {  // V rows, stored transposed: key index fastest so that the 2-byte stores of a warp are contiguous
-        const int r = c & 63, ch = c >> 6;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (kv0 + r < L)
-          v = __ldg(reinterpret_cast<const uint4*>(p.qkv + static_cast<size_t>(base + kv0 + r) * H3 + 2 * p.H +
-                                                   h * AT_D + ch * 8));
-        const __nv_bfloat16* e8 = reinterpret_cast<const __nv_bfloat16*>(&v);
+    cp_async_wait_all();
+    __syncthreads();  // tile kb has landed for everyone, and everyone is done with the other buffer
+    if (kb + 1 < kb_hi) issue_kv(kb + 1, buf ^ 1);
+    cp_async_commit();
+    if (kb == kb_lo) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Vt[ch * 8 + j][r] = e8[j];
-      }
+      for (int ks = 0; ks < 4; ++ks)
+        ldmatrix_x4(qa[ks], &Qs[warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][ks * 16 + (lane >> 4) * 8]);
     }
-    if (tid < AT_BK) {
-      const int key = kv0 + tid;
-      kpos[tid] = key < L ? static_cast<int>(__ldg(&p.meta[base + key]) & 0xFFFFu) : 0x3FFFFFFF;
-    }
-    __syncthreads();
+    if (!warp_active) continue;
+    Tile Ks = Kbuf + buf * AT_BK;
+    Tile Vs = Vbuf + buf * AT_BK;
+    const int* kpos = kpos_buf + buf * AT_BK;
 
     // S = Q K^T  (16 x 64 per warp)
     float s[8][4];
@@ -228,10 +357,11 @@ trunk_attn_kernel(const AttnParams p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) s[nt][e] = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + 8 + 2 * t]);
-        mma_bf16_16816(s[nt], qa[ks], b0, b1);
+      for (int kp = 0; kp < 2; ++kp) {  // two 16-dim steps per ldmatrix.x4
+        uint32_t kf[4];
+        ldmatrix_x4(kf, &Ks[nt * 8 + (lane & 7)][kp * 32 + (lane >> 3) * 8]);
+        mma_bf16_16816(s[nt], qa[2 * kp], kf[0], kf[1]);
+        mma_bf16_16816(s[nt], qa[2 * kp + 1], kf[2], kf[3]);
       }
     }
     // scale, mask (document end, sliding window), running maximum
@@ -247,7 +377,7 @@ trunk_attn_kernel(const AttnParams p) {
           const int d = qpos[r] - kpos[col];
           ok = ok && d <= p.window && d >= -p.window;
         }
-        s[nt][e] = ok ? s[nt][e] * p.scale : -INFINITY;
+        s[nt][e] = ok ? s[nt][e] * sl2 : -INFINITY;
         mx[r] = fmaxf(mx[r], s[nt][e]);
       }
     }
@@ -257,18 +387,18 @@ trunk_attn_kernel(const AttnParams p) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float mnew = fmaxf(m_run[r], mx[r]);
-      moff[r] = mnew == -INFINITY ? 0.f : mnew;  // nothing visible yet: keep exp() finite
-      corr[r] = __expf(m_run[r] - moff[r]);      // exp(-inf) = 0 on the first visible block
+      moff[r] = mnew == -INFINITY ? 0.f : mnew;  // nothing visible yet: keep exp2() finite
+      corr[r] = exp2f(m_run[r] - moff[r]);       // exp2(-inf) = 0 on the first visible block
       m_run[r] = mnew;
       l_run[r] *= corr[r];
     }
     uint32_t pa[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = __expf(s[nt][0] - moff[0]);
-      const float p1 = __expf(s[nt][1] - moff[0]);
-      const float p2 = __expf(s[nt][2] - moff[1]);
-      const float p3 = __expf(s[nt][3] - moff[1]);
+      const float p0 = exp2f(s[nt][0] - moff[0]);
+      const float p1 = exp2f(s[nt][1] - moff[0]);
+      const float p2 = exp2f(s[nt][2] - moff[1]);
+      const float p3 = exp2f(s[nt][3] - moff[1]);
       l_run[0] += p0 + p1;
       l_run[1] += p2 + p3;
       const int ks = nt >> 1;
@@ -286,14 +416,19 @@ trunk_attn_kernel(const AttnParams p) {
       o[dt][1] *= corr[0];
       o[dt][2] *= corr[1];
       o[dt][3] *= corr[1];
+    }
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {  // two 8-dim output tiles per ldmatrix.x4.trans
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[dt * 8 + g][ks * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[dt * 8 + g][ks * 16 + 8 + 2 * t]);
-        mma_bf16_16816(o[dt], pa[ks], b0, b1);
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, &Vs[ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)][dp * 16 + (lane >> 4) * 8]);
+        mma_bf16_16816(o[2 * dp], pa[ks], vf[0], vf[1]);
+        mma_bf16_16816(o[2 * dp + 1], pa[ks], vf[2], vf[3]);
       }
     }
   }
+  if (!warp_active) return;
 
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -326,8 +461,35 @@ int trunk_rope_table_launch(float2* table, int max_pos, float theta, cudaStream_
 
 int trunk_embed_ln_launch(const int64_t* input_ids, const float* tok_emb, const float* gamma, float eps,
                           const VarlenLayout& lay, int S, int H, float* x, void* xb, cudaStream_t stream) {
-  trunk_embed_ln_kernel<<<4 * sm_count(), 256, 0, stream>>>(input_ids, tok_emb, gamma, eps, &lay.plan->T, lay.meta, S,
-                                                            H, x, static_cast<__nv_bfloat16*>(xb));
+  const int grid = 8 * sm_count();
+  __nv_bfloat16* xb16 = static_cast<__nv_bfloat16*>(xb);
+  const int32_t* t_rows = &lay.plan->T;
+  if (H == 768) {
+    trunk_embed_ln_kernel<6><<<grid, 256, 0, stream>>>(input_ids, tok_emb, gamma, eps, t_rows, lay.meta, S, H, x, xb16);
+  } else if (H == 256) {
+    trunk_embed_ln_kernel<2><<<grid, 256, 0, stream>>>(input_ids, tok_emb, gamma, eps, t_rows, lay.meta, S, H, x, xb16);
+  } else if (H == 1024) {
+    trunk_embed_ln_kernel<8><<<grid, 256, 0, stream>>>(input_ids, tok_emb, gamma, eps, t_rows, lay.meta, S, H, x, xb16);
+  } else {
+    trunk_embed_ln_kernel<0><<<grid, 256, 0, stream>>>(input_ids, tok_emb, gamma, eps, t_rows, lay.meta, S, H, x, xb16);
+  }
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+template <typename InT>
+int ln_launch_typed(const InT* in, const float* gamma, float eps, const int32_t* t_rows, int H, __nv_bfloat16* out,
+                    cudaStream_t stream) {
+  const int grid = 8 * sm_count();
+  if (H == 768) {
+    trunk_ln_kernel<InT, 6><<<grid, 256, 0, stream>>>(in, gamma, eps, t_rows, H, out);
+  } else if (H == 256) {
+    trunk_ln_kernel<InT, 2><<<grid, 256, 0, stream>>>(in, gamma, eps, t_rows, H, out);
+  } else if (H == 1024) {
+    trunk_ln_kernel<InT, 8><<<grid, 256, 0, stream>>>(in, gamma, eps, t_rows, H, out);
+  } else {
+    trunk_ln_kernel<InT, 0><<<grid, 256, 0, stream>>>(in, gamma, eps, t_rows, H, out);
+  }
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }
@@ -335,13 +497,14 @@ int trunk_embed_ln_launch(const int64_t* input_ids, const float* tok_emb, const 
 int trunk_ln_launch(const void* in, int in_is_bf16, const float* gamma, float eps, const int32_t* t_rows,
                     int rows_cap, int H, void* out_bf16, cudaStream_t stream) {
   (void)rows_cap;
-  if (in_is_bf16) {
-    trunk_ln_kernel<__nv_bfloat16><<<4 * sm_count(), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(in), gamma, eps, t_rows, H, static_cast<__nv_bfloat16*>(out_bf16));
-  } else {
-    trunk_ln_kernel<float><<<4 * sm_count(), 256, 0, stream>>>(static_cast<const float*>(in), gamma, eps, t_rows, H,
-                                                               static_cast<__nv_bfloat16*>(out_bf16));
-  }
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
+  if (in_is_bf16) return ln_launch_typed(static_cast<const __nv_bfloat16*>(in), gamma, eps, t_rows, H, out, stream);
+  return ln_launch_typed(static_cast<const float*>(in), gamma, eps, t_rows, H, out, stream);
+}
+
+int trunk_rope_launch(void* qkv, const float2* rope, const VarlenLayout& lay, int H, cudaStream_t stream) {
+  trunk_rope_kernel<<<8 * sm_count(), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(qkv), rope, lay.meta,
+                                                        &lay.plan->T, H);
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }
@@ -359,7 +522,15 @@ int trunk_attn_launch(const void* qkv, void* out, const VarlenLayout& lay, int B
   p.window = window;
   p.scale = 0.125f;  // head_dim ** -0.5
   const int s8 = (S + 7) & ~7;
-  trunk_attn_kernel<<<dim3((s8 + AT_BQ - 1) / AT_BQ, n_heads, B), 128, 0, stream>>>(p);
+  if (s8 <= 64) {
+    constexpr int smem = (64 + 4 * AT_BK) * AT_LD * 2 + 2 * AT_BK * 4;
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(trunk_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    trunk_attn_kernel<4><<<dim3(1, n_heads, B), 128, smem, stream>>>(p);
+  } else {
+    constexpr int smem = (128 + 4 * AT_BK) * AT_LD * 2 + 2 * AT_BK * 4;
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(trunk_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    trunk_attn_kernel<8><<<dim3((s8 + 127) / 128, n_heads, B), 256, smem, stream>>>(p);
+  }
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }
@@ -424,23 +595,21 @@ int trunk_encode_launch(const splade_trunk_args* a, cudaStream_t stream) {
     if (ly.attn_norm != nullptr) {
       if ((rc = trunk_ln_launch(x, 0, ly.attn_norm, a->norm_eps, t_rows, rows_i, H, xb, stream)) != kOk) return rc;
     }
-    if ((rc = trunk_gemm_launch(EPI_QKV_ROPE, xb, rows_i, ly.wqkv, 3 * H, H, t_rows, qkv, 3 * H, lay.meta,
-                                ly.is_global ? rope_g : rope_l, 2 * H, S, stream)) != kOk)
-      return rc;
+    if ((rc = trunk_gemm_launch(EPI_BF16, xb, rows_i, ly.wqkv, 3 * H, H, t_rows, qkv, 3 * H, stream)) != kOk) return rc;
+    if ((rc = trunk_rope_launch(qkv, ly.is_global ? rope_g : rope_l, lay, H, stream)) != kOk) return rc;
     if ((rc = trunk_attn_launch(qkv, ab, lay, B, S, H, a->n_heads, ly.is_global ? -1 : a->local_window, stream)) != kOk)
       return rc;
-    if ((rc = trunk_gemm_launch(EPI_RESID, ab, rows_i, ly.wo, H, H, t_rows, x, H, nullptr, nullptr, 0, 0, stream)) != kOk)
+    if ((rc = trunk_gemm_launch(EPI_RESID, ab, rows_i, ly.wo, H, H, t_rows, x, H, stream)) != kOk)
       return rc;
     if ((rc = trunk_ln_launch(x, 0, ly.mlp_norm, a->norm_eps, t_rows, rows_i, H, xb, stream)) != kOk) return rc;
-    if ((rc = trunk_gemm_launch(EPI_GEGLU, xb, rows_i, ly.wi, I, H, t_rows, gg, I, nullptr, nullptr, 0, 0, stream)) != kOk)
+    if ((rc = trunk_gemm_launch(EPI_GEGLU, xb, rows_i, ly.wi, I, H, t_rows, gg, I, stream)) != kOk)
       return rc;
-    if ((rc = trunk_gemm_launch(EPI_RESID, gg, rows_i, ly.wo2, H, I, t_rows, x, H, nullptr, nullptr, 0, 0, stream)) != kOk)
+    if ((rc = trunk_gemm_launch(EPI_RESID, gg, rows_i, ly.wo2, H, I, t_rows, x, H, stream)) != kOk)
       return rc;
   }
   // final_norm -> head.dense -> GELU -> head.norm  (ModernBertPredictionHead)
   if ((rc = trunk_ln_launch(x, 0, a->final_norm, a->norm_eps, t_rows, rows_i, H, xb, stream)) != kOk) return rc;
-  if ((rc = trunk_gemm_launch(EPI_GELU, xb, rows_i, a->head_dense, H, H, t_rows, ab, H, nullptr, nullptr, 0, 0,
-                              stream)) != kOk)
+  if ((rc = trunk_gemm_launch(EPI_GELU, xb, rows_i, a->head_dense, H, H, t_rows, ab, H, stream)) != kOk)
     return rc;
   if ((rc = trunk_ln_launch(ab, 1, a->head_norm, a->norm_eps, t_rows, rows_i, H, xb, stream)) != kOk) return rc;
   if (a->hidden_out != nullptr) {

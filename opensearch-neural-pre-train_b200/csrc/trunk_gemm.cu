@@ -4,15 +4,16 @@
 // round trip.  Reference arithmetic (transformers modeling_modernbert.py, under torch.autocast(bf16) as the
 // trainer runs it, src/train/cli/train_v33_ddp.py:339): every nn.Linear returns bf16, the residual stream is fp32.
 //
-//   EPI_QKV_ROPE   attn.Wqkv (:278) + apply_rotary_pos_emb (:205-228) on the q and k heads -> bf16 [T, 3H]
+//   EPI_BF16       attn.Wqkv (:278)  (RoPE is applied by the attention kernel's loader)      -> bf16 [T, 3H]
 //   EPI_RESID      attn.Wo (:309) / mlp.Wo (:91) + residual add (:341-342)                -> fp32 x [T, H] (in place)
 //   EPI_GEGLU      mlp.Wi (:90) + act(input) * gate (:91)                                  -> bf16 [T, I]
 //   EPI_GELU       head.dense + GELU (:502)                                                -> bf16 [T, H]
 //
 // Orientation: UMMA M = 128 tokens (TMEM lanes), UMMA N = 256 output features (TMEM columns), K in 64-element
 // (128-byte swizzle) blocks through a 4-stage TMA ring, two 128x256 fp32 accumulators so the epilogue of one tile
-// overlaps the MMAs of the next.  An epilogue thread owns ONE token and walks its output features, so RoPE pairs
-// (d, d+32 of a head) and GeGLU pairs (input n, gate n) are both in the same thread's registers.  The number of
+// overlaps the MMAs of the next.  An epilogue thread owns ONE token and walks its output features, so the GeGLU
+// pair (input n, gate n) is in the same thread's registers; results leave through a per-warp shared-memory
+// transpose so that global accesses are row-coalesced.  The number of
 // token rows T is only known on the device (it comes from the attention mask): the kernel is persistent and reads
 // it from the packed-layout plan.
 #include "common.cuh"
@@ -33,7 +34,10 @@ constexpr int G_B_BYTES = G_BN * G_BK * 2;
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_THREADS = 384;  // producer, MMA, TMEM alloc, idle, 2 x 4 epilogue warps
 constexpr int G_TMEM_COLS = 512;
-constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + 256 + 1024;
+constexpr int G_EPI_WARPS = 8;
+constexpr int G_STAGE_LD = 33;  // fp32 words per staged row (conflict-free row writes and column reads)
+constexpr int G_EPI_STAGE_BYTES = 32 * G_STAGE_LD * 4;
+constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + 256 + G_EPI_WARPS * G_EPI_STAGE_BYTES + 1024;
 
 struct GemmParams {
   const int32_t* t_rows;  // device: number of valid token rows (packed columns) T
@@ -41,16 +45,38 @@ struct GemmParams {
   int K;
   void* out;              // bf16 [T, ldo] or fp32 x [T, ldo] (EPI_RESID, read-modify-write)
   int ldo;
-  const uint32_t* meta;   // packed column descriptors (position in the low 16 bits), EPI_QKV_ROPE
-  const float2* rope;     // [max_pos][32] (cos, sin), EPI_QKV_ROPE
-  int rope_cols;          // output features below this get RoPE (q and k: 2*H)
-  int max_pos;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// An epilogue thread owns one token ROW of the accumulator, but global memory wants a warp to touch one row at a
+// time.  Every 32 x 32 block therefore goes through a per-warp shared-memory stage: thread `lane` writes its 32
+// values as row `lane` (bank = lane + j: conflict-free), then the warp reads the block back one row per
+// instruction (bank = row + lane: conflict-free) and issues fully coalesced global accesses.
+__device__ __forceinline__ void stage_rows(float* stage, uint32_t lane, const float (&y)[32]) {
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stage[lane * G_STAGE_LD + j] = y[j];
+  __syncwarp();
+}
+
+// x[row][n0 + lane] += bf16(acc): the Linear's bf16 output added to the fp32 residual stream, as fire-and-forget
+// reductions (REDG.ADD.F32, one coalesced 128-byte line per instruction).  Every element receives exactly ONE add
+// per GEMM, so the result is the same single rounding as a load-add-store.  Measured alternatives at
+// [16384,768]x[768,768]: thread-per-row float4 load/add/store 58 us, this 39 us, coalesced load/add/store with the
+// loads prefetched one / two blocks ahead 52 / 47 us (the load latency stays exposed at 4 blocks per tile).
+__device__ __forceinline__ void emit_resid_block(const float* stage, uint32_t lane, float* x, int ldo, int row0,
+                                                 int n0, int T) {
+  float* px = x + static_cast<size_t>(row0) * ldo + n0 + lane;
+#pragma unroll 8
+  for (int rr = 0; rr < 32; ++rr) {
+    if (row0 + rr < T) atomicAdd(px + static_cast<size_t>(rr) * ldo, bf16_round(stage[rr * G_STAGE_LD + lane]));
+  }
+}
+
+// direct form for bf16 outputs: the thread's 32 features of its own row are 64 contiguous bytes (two full sectors)
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&y)[32]) {
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
@@ -170,22 +196,22 @@ trunk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp >= 4) {
     const uint32_t q = warp & 3u;           // TMEM lane quarter = 32 token rows
     const uint32_t grp = (warp - 4u) >> 2;  // which half of the tile's output features
+    float* stage = reinterpret_cast<float*>(smem + G_STAGES * G_STAGE_BYTES + 256) +
+                   (warp - 4u) * (G_EPI_STAGE_BYTES / 4);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int mt = tile / n_tiles;
       const int nt = tile - mt * n_tiles;
-      const int row = mt * G_BM + static_cast<int>(q * 32u + lane);
-      const bool row_ok = row < T;
+      const int row0 = mt * G_BM + static_cast<int>(q * 32u);  // first token row of this warp
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_lane = tmem_base + ((q * 32u) << 16) + acc * G_BN;
 
       if (kEpi == EPI_GEGLU) {
         // this group: input columns [64 grp, 64 grp + 64) and the gate columns 128 above them
-        __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           const int col = static_cast<int>(grp) * 64 + c * 32;
           uint32_t a[32], g[32];
@@ -193,7 +219,7 @@ trunk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(G_BN / 2 + col), g);
           tmem_ld_wait();
           const int n0 = nt * (G_BN / 2) + col;
-          if (row_ok && n0 < p.N) {
+          if (n0 < p.N) {  // warp-uniform
             float y[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -201,74 +227,43 @@ trunk_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               const float gate = bf16_round(__uint_as_float(g[j]));
               y[j] = bf16_round(gelu_erf(in)) * gate;
             }
-            store_bf16x32(orow + n0, y);
+            if (row0 + static_cast<int>(lane) < T)
+              store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row0 + lane) * p.ldo + n0, y);
           }
         }
-      } else if (kEpi == EPI_QKV_ROPE) {
-        __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo;
-        const int pos = row_ok ? min(static_cast<int>(__ldg(&p.meta[row]) & 0xFFFFu), p.max_pos - 1) : 0;
-        const float2* cs = p.rope + static_cast<size_t>(pos) * 32;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int col = static_cast<int>(grp) * 128 + hh * 64;  // one 64-wide head
-          uint32_t lo[32], hi[32];
-          tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(col), lo);
-          tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(col + 32), hi);
+      } else if (kEpi == EPI_RESID) {
+        float* x = static_cast<float*>(p.out);
+        const int nbase = nt * G_BN + static_cast<int>(grp) * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int n0 = nbase + c * 32;
+          uint32_t a[32];
+          tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(grp * 128u + c * 32), a);
           tmem_ld_wait();
-          const int n0 = nt * G_BN + col;
-          if (row_ok && n0 < p.N) {
-            float y1[32], y2[32];
-            if (n0 < p.rope_cols) {
+          if (n0 < p.N) {  // warp-uniform
+            float y[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float2 c = __ldg(&cs[j]);
-                const float x1 = bf16_round(__uint_as_float(lo[j]));  // the Linear's bf16 output, then .float()
-                const float x2 = bf16_round(__uint_as_float(hi[j]));
-                y1[j] = x1 * c.x - x2 * c.y;                          // q*cos + rotate_half(q)*sin
-                y2[j] = x2 * c.x + x1 * c.y;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                y1[j] = __uint_as_float(lo[j]);
-                y2[j] = __uint_as_float(hi[j]);
-              }
-            }
-            store_bf16x32(orow + n0, y1);
-            store_bf16x32(orow + n0 + 32, y2);
+            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(a[j]);
+            stage_rows(stage, lane, y);
+            emit_resid_block(stage, lane, x, p.ldo, row0, n0, T);
           }
         }
       } else {
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           const int col = static_cast<int>(grp) * 128 + c * 32;
           uint32_t a[32];
           tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(col), a);
           tmem_ld_wait();
           const int n0 = nt * G_BN + col;
-          if (row_ok && n0 < p.N) {
-            if (kEpi == EPI_RESID) {
-              float* xrow = static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + n0;
-              float4* x4 = reinterpret_cast<float4*>(xrow);
+          if (n0 < p.N && row0 + static_cast<int>(lane) < T) {
+            float y[32];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float4 v = x4[i];
-                v.x += bf16_round(__uint_as_float(a[4 * i + 0]));
-                v.y += bf16_round(__uint_as_float(a[4 * i + 1]));
-                v.z += bf16_round(__uint_as_float(a[4 * i + 2]));
-                v.w += bf16_round(__uint_as_float(a[4 * i + 3]));
-                x4[i] = v;
-              }
-            } else {
-              __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo;
-              float y[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float v = __uint_as_float(a[j]);
-                y[j] = (kEpi == EPI_GELU) ? gelu_erf(bf16_round(v)) : v;
-              }
-              store_bf16x32(orow + n0, y);
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(a[j]);
+              y[j] = (kEpi == EPI_GELU) ? gelu_erf(bf16_round(v)) : v;
             }
+            store_bf16x32(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row0 + lane) * p.ldo + n0, y);
           }
         }
       }
@@ -299,14 +294,11 @@ int launch_one(const CUtensorMap& tmap_a, const CUtensorMap& tmap_w, const GemmP
 
 // A [rows_cap, K] bf16 (rows_cap >= 128, a whole number of 256-row tiles in the trunk), W [w_rows, K] bf16.
 int trunk_gemm_launch(int epi, const void* A, int rows_cap, const void* W, int N, int K, const int32_t* t_rows,
-                      void* out, int ldo, const uint32_t* meta, const float2* rope, int rope_cols, int max_pos,
-                      cudaStream_t stream) {
+                      void* out, int ldo, cudaStream_t stream) {
   if (K % G_BK != 0 || K < G_BK)
     return set_error(kErrUnsupportedShape, "trunk gemm: K=%d is not a multiple of %d", K, G_BK);
   if (N % 128 != 0 || (epi != EPI_GEGLU && N < G_BN))
     return set_error(kErrUnsupportedShape, "trunk gemm: N=%d must be a multiple of 128 (and >= 256)", N);
-  if (epi == EPI_QKV_ROPE && (rope_cols % 64 != 0 || N % 64 != 0))
-    return set_error(kErrUnsupportedShape, "trunk gemm: RoPE needs 64-wide heads");
   if (rows_cap < G_BM) return set_error(kErrUnsupportedShape, "trunk gemm: fewer than %d activation rows", G_BM);
   const int w_rows = epi == EPI_GEGLU ? 2 * N : N;
   CUtensorMap tmap_a, tmap_w;
@@ -330,10 +322,6 @@ int trunk_gemm_launch(int epi, const void* A, int rows_cap, const void* W, int N
   p.K = K;
   p.out = out;
   p.ldo = ldo;
-  p.meta = meta;
-  p.rope = rope;
-  p.rope_cols = rope_cols;
-  p.max_pos = max_pos;
   const int grid = sm_count();
   switch (epi) {
     case EPI_BF16:
@@ -344,8 +332,6 @@ int trunk_gemm_launch(int epi, const void* A, int rows_cap, const void* W, int N
       return launch_one<EPI_RESID>(tmap_a, tmap_w, p, grid, stream);
     case EPI_GEGLU:
       return launch_one<EPI_GEGLU>(tmap_a, tmap_w, p, grid, stream);
-    case EPI_QKV_ROPE:
-      return launch_one<EPI_QKV_ROPE>(tmap_a, tmap_w, p, grid, stream);
     default:
       return set_error(kErrInvalidArg, "trunk gemm: unknown epilogue %d", epi);
   }

@@ -127,9 +127,7 @@ class NativeTrunk:
         return rep
 
 
-def trunk_gemm(epi: int, A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None,
-               pos: Optional[torch.Tensor] = None, rope_theta: float = 10000.0, rope_cols: int = 0,
-               max_pos: int = 0) -> torch.Tensor:
+def trunk_gemm(epi: int, A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Unit-test entry: out = epilogue(A [rows,K] bf16 @ W^T) (``splade_trunk_gemm``)."""
     lib = load_library()
     rows, K = A.shape
@@ -138,17 +136,18 @@ def trunk_gemm(epi: int, A: torch.Tensor, W: torch.Tensor, out: Optional[torch.T
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((rows, N), dtype=torch.bfloat16, device=dev)
-        nbytes = lib.splade_workspace_bytes(_lib.OP_TRUNK_GEMM, rows, max(max_pos, 1), 0, 0, 0)
+        nbytes = lib.splade_workspace_bytes(_lib.OP_TRUNK_GEMM, 0, 0, 0, 0, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         check(lib.splade_trunk_gemm(epi, A.data_ptr(), rows, W.data_ptr(), N, K, out.data_ptr(), out.shape[1],
-                                    None if pos is None else pos.data_ptr(), rope_theta, rope_cols, max_pos,
                                     ws.data_ptr(), nbytes, torch.cuda.current_stream(dev).cuda_stream),
               "splade_trunk_gemm")
     return out
 
 
-def trunk_attention(qkv_packed: torch.Tensor, mask: torch.Tensor, n_heads: int, window: int):
-    """Unit-test entry: packed qkv [rows,3H] bf16 -> (packed attention output [rows,H] bf16, meta [rows] int32)."""
+def trunk_attention(qkv_packed: torch.Tensor, mask: torch.Tensor, n_heads: int, window: int,
+                    rope_theta: float = 0.0):
+    """Unit-test entry: packed qkv [rows,3H] bf16 -> (packed attention output [rows,H] bf16, meta [rows] int32);
+    ``rope_theta > 0`` rotates q and k inside the kernel."""
     lib = load_library()
     B, S = mask.shape
     rows, H3 = qkv_packed.shape
@@ -161,6 +160,7 @@ def trunk_attention(qkv_packed: torch.Tensor, mask: torch.Tensor, n_heads: int, 
         nbytes = lib.splade_workspace_bytes(_lib.OP_TRUNK_ATTN, B, S, 0, 1, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         check(lib.splade_trunk_attn(qkv_packed.data_ptr(), mask.to(torch.int32).contiguous().data_ptr(), B, S, H,
-                                    n_heads, window, out.data_ptr(), meta.data_ptr(), ws.data_ptr(), nbytes,
-                                    torch.cuda.current_stream(dev).cuda_stream), "splade_trunk_attn")
+                                    n_heads, window, float(rope_theta), out.data_ptr(), meta.data_ptr(),
+                                    ws.data_ptr(), nbytes, torch.cuda.current_stream(dev).cuda_stream),
+              "splade_trunk_attn")
     return out, meta

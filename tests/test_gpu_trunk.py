@@ -44,28 +44,6 @@ def test_trunk_gemm_epilogues(cuda_device, rows, K, N):
     _close(out, refg, "geglu", atol=2e-2)
 
 
-def test_trunk_gemm_rope(cuda_device):
-    import splade_b200
-    from splade_b200 import _lib as L
-    rows, H, max_pos, theta = 300, 256, 200, 160000.0
-    g = torch.Generator().manual_seed(5)
-    A = _bf(torch.randn(rows, H, generator=g)).to(cuda_device)
-    W = _bf(torch.randn(3 * H, H, generator=g) / math.sqrt(H)).to(cuda_device)
-    pos = torch.randint(0, max_pos, (rows,), generator=g).to(torch.int32).to(cuda_device)
-    out = splade_b200.trunk_gemm(L.EPI_QKV_ROPE, A, W, pos=pos, rope_theta=theta, rope_cols=2 * H, max_pos=max_pos)
-    qkv = _bf(A.float() @ W.float().t()).float().view(rows, 3, H // 64, 64)
-    inv = 1.0 / (theta ** (torch.arange(0, 64, 2, device=cuda_device).float() / 64))
-    ang = pos.float()[:, None] * inv[None, :]
-    cos, sin = torch.cat([ang.cos(), ang.cos()], -1)[:, None, :], torch.cat([ang.sin(), ang.sin()], -1)[:, None, :]
-
-    def rot(x):
-        return torch.cat([-x[..., 32:], x[..., :32]], -1)
-    ref = qkv.clone()
-    for i in (0, 1):
-        ref[:, i] = qkv[:, i] * cos + rot(qkv[:, i]) * sin
-    _close(out, _bf(ref.view(rows, 3 * H)), "rope", atol=2e-2)
-
-
 def _pack_rows(x_pad, lens, rows):
     """[B,S,C] padded -> [rows,C] in the packed layout: documents start at multiples of 8 rows, fillers behind a
     document replicate its last token."""
@@ -81,8 +59,19 @@ def _pack_rows(x_pad, lens, rows):
     return out, starts
 
 
-@pytest.mark.parametrize("window", [-1, 64])
-def test_trunk_attention_vs_torch(cuda_device, window):
+def _rope(x, theta):
+    """apply_rotary_pos_emb on [L, nh, 64] (positions 0..L-1), fp32 math on bf16 inputs, rounded back to bf16."""
+    L = x.shape[0]
+    inv = 1.0 / (theta ** (torch.arange(0, 64, 2, device=x.device).float() / 64))
+    ang = torch.arange(L, device=x.device).float()[:, None] * inv[None, :]
+    cos = torch.cat([ang.cos(), ang.cos()], -1)[:, None, :]
+    sin = torch.cat([ang.sin(), ang.sin()], -1)[:, None, :]
+    rot = torch.cat([-x[..., 32:], x[..., :32]], -1)
+    return _bf(x * cos + rot * sin).float()
+
+
+@pytest.mark.parametrize("window,theta", [(-1, 0.0), (64, 0.0), (-1, 160000.0), (64, 10000.0)])
+def test_trunk_attention_vs_torch(cuda_device, window, theta):
     import splade_b200
     B, S, nh = 6, 200, 4
     H = nh * 64
@@ -92,11 +81,13 @@ def test_trunk_attention_vs_torch(cuda_device, window):
     qkv = _bf(torch.randn(B, S, 3 * H, generator=g)).to(cuda_device)
     rows = splade_b200.load_library().splade_packed_rows(B, S)
     packed, starts = _pack_rows(qkv, lens, rows)
-    out, meta = splade_b200.trunk_attention(packed.contiguous(), mask, nh, window)
+    out, meta = splade_b200.trunk_attention(packed.contiguous(), mask, nh, window, rope_theta=theta)
     for b, L in enumerate(lens):
         if L == 0:
             continue
         x = qkv[b, :L].float().view(L, 3, nh, 64)
+        if theta > 0:
+            x = torch.stack([_rope(x[:, 0], theta), _rope(x[:, 1], theta), x[:, 2]], 1)
         q, k, v = (x[:, i].transpose(0, 1) for i in range(3))           # [nh, L, 64]
         s = q @ k.transpose(1, 2) * 0.125
         if window >= 0:
