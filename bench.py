@@ -265,9 +265,11 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
 # ------------------------------------------------------------------------------------------------------
 def run_full_encode_leg(dev, steps=5, warmup=2):
     """SPLADEModernBERT.encode on a random-init A.X-Encoder-base-shaped model (22 layers, hidden 768, vocab
-    50 000; config restated from huggingface/v33/config.json), batch 64 x L=256, under autocast(bf16): the
-    drop-in encoder vs the reference's statement (HF logits -> relu -> log1p -> mask -> max) on the same
-    device.  The trunk is identical on both sides; this shows what the fused head buys end to end."""
+    50 000; config restated from huggingface/v33/config.json), batch 64 x L=256, under autocast(bf16):
+      ours               the reference's transformers trunk + the fused head (the drop-in default),
+      ours_native_trunk  the native packed-token trunk + fused head in one C-ABI call (splade_trunk_encode),
+      reference_chain    the reference's statement (HF logits -> relu -> log1p -> mask -> max)
+    on the same device, plus how closely the native trunk's vectors agree with the transformers trunk's."""
     import tempfile
 
     import torch
@@ -289,8 +291,18 @@ def run_full_encode_leg(dev, steps=5, warmup=2):
     ids = torch.randint(6, VOCAB - 1, (B_DOCS, SEQ), generator=g).to(dev)
     mask = torch.ones(B_DOCS, SEQ, dtype=torch.int64, device=dev)
     out = {"params": sum(p.numel() for p in ours.parameters()), "batch": B_DOCS, "seq_len": SEQ}
+    native = splade_b200.NativeTrunk(ours.model)
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-        for name, fn in (("ours", lambda: ours.encode(ids, mask)), ("reference_chain", lambda: ref(ids, mask)[0])):
+        a, b = native.encode(ids, mask), ours.encode(ids, mask)
+        ta, tb = a.topk(64, dim=1).indices.tolist(), b.topk(64, dim=1).indices.tolist()
+        out["native_vs_transformers_trunk"] = {
+            "cosine_min": float(torch.nn.functional.cosine_similarity(a, b, dim=1).min()),
+            "max_abs_diff": float((a - b).abs().max()),
+            "top64_overlap": sum(len(set(x) & set(y)) for x, y in zip(ta, tb)) / (64.0 * B_DOCS)}
+        del a, b
+        for name, fn in (("ours", lambda: ours.encode(ids, mask)),
+                         ("ours_native_trunk", lambda: native.encode(ids, mask)),
+                         ("reference_chain", lambda: ref(ids, mask)[0])):
             for _ in range(warmup):
                 fn()
             torch.cuda.synchronize()
@@ -303,6 +315,7 @@ def run_full_encode_leg(dev, steps=5, warmup=2):
             ms = e0.elapsed_time(e1) / steps
             out[name] = {"ms_per_batch": ms, "docs_per_s": B_DOCS / ms * 1e3}
     out["speedup"] = out["reference_chain"]["ms_per_batch"] / out["ours"]["ms_per_batch"]
+    out["speedup_native_trunk"] = out["reference_chain"]["ms_per_batch"] / out["ours_native_trunk"]["ms_per_batch"]
     return out
 
 def run_ragged_leg(dev, iters=20):

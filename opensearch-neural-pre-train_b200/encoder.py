@@ -10,9 +10,16 @@ tcgen05 kernel (``splade_head_fwd``); the backward is the gather-driven sparse k
 Numerics: the head always computes like the reference under ``torch.autocast("cuda", bfloat16)`` — bf16
 operands, fp32 accumulate, logits rounded once to bf16 before relu/log1p/max — whether or not autocast is
 active (outside autocast the reference is fp32; the difference is bounded by bf16 rounding).
+
+Inference can additionally run the NATIVE trunk (``trunk.NativeTrunk``): the whole
+encoder on packed real tokens in one C-ABI call, 3-12x faster than the transformers trunk on this GPU.  It is
+opt-in for ``encode`` (``model.use_native_trunk(True)`` or ``SPLADE_B200_NATIVE_TRUNK=1``) because its bf16
+arithmetic differs from the transformers trunk by rounding noise (cosine > 0.99999, top-64 overlap ~99.4 %);
+``forward`` (the training path, which needs autograd through the trunk) always uses the reference trunk.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -31,6 +38,20 @@ class SPLADEModernBERT(nn.Module):
         self.model = AutoModelForMaskedLM.from_pretrained(model_name)
         self.config = self.model.config
         self.relu = nn.ReLU()  # kept for attribute / state_dict parity; the fused kernel applies relu itself
+        # plain Python state (not parameters / buffers: state_dict keys must not change)
+        self._native_trunk = None
+        self._native_trunk_enabled = os.environ.get("SPLADE_B200_NATIVE_TRUNK", "0") == "1"
+
+    def use_native_trunk(self, enabled: bool = True) -> "SPLADEModernBERT":
+        """Route ``encode`` (inference, no autograd) through the native packed-token trunk."""
+        self._native_trunk_enabled = bool(enabled)
+        return self
+
+    def _native(self):
+        if getattr(self, "_native_trunk", None) is None:
+            from .trunk import NativeTrunk
+            self._native_trunk = NativeTrunk(self.model)
+        return self._native_trunk
 
     @property
     def vocab_size(self) -> int:
@@ -66,6 +87,8 @@ class SPLADEModernBERT(nn.Module):
     def encode(self, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
         """Inference shortcut: the reference discards token_weights here (splade_modern.py:96), so the
         per-position reduction is not computed at all."""
+        if getattr(self, "_native_trunk_enabled", False) and input_ids.is_cuda and not torch.is_grad_enabled():
+            return self._native().encode(input_ids, attention_mask)
         sparse_repr, _ = self._forward_impl(input_ids, attention_mask, False)
         return sparse_repr
 

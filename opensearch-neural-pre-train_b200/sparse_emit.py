@@ -132,13 +132,22 @@ class SparseEmitter:
 @torch.no_grad()
 def bulk_encode(model, input_ids: torch.Tensor, attention_mask: torch.Tensor, top_k: int,
                 emitter: Optional[SparseEmitter] = None, batch_size: int = 64, group=None,
-                autocast_dtype: Optional[torch.dtype] = torch.bfloat16):
+                autocast_dtype: Optional[torch.dtype] = torch.bfloat16, native_trunk: Optional[bool] = None):
     """Encode this rank's contiguous shard of a corpus (BASELINE config 5) and return compact top-k buffers.
 
     ``input_ids`` / ``attention_mask`` are the FULL corpus tensors [N,S] (host or device); rank r encodes rows
     ``shard_range(N, r, W)``.  No collective on the data path; callers concatenate the per-rank results in rank
     order.  Returns (ids [n,k] int32, weights [n,k] fp32, counts [n] int32, (lo, hi)).
+    ``native_trunk``: True / False pins the native packed-token trunk on / off for this call, None keeps the
+    model's own setting (``SPLADEModernBERT.use_native_trunk``).
     """
+    if native_trunk is not None and hasattr(model, "use_native_trunk"):
+        previous = getattr(model, "_native_trunk_enabled", False)
+        model.use_native_trunk(native_trunk)
+        try:
+            return bulk_encode(model, input_ids, attention_mask, top_k, emitter, batch_size, group, autocast_dtype)
+        finally:
+            model.use_native_trunk(previous)
     rank, world = world_info(group)
     lo, hi = shard_range(input_ids.shape[0], rank, world)
     emitter = emitter or SparseEmitter()

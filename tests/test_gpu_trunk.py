@@ -169,3 +169,37 @@ def test_native_trunk_is_padding_and_batch_invariant(cuda_device):
     wide_ids = torch.cat([ids, torch.randint(6, 100, (B, 32), generator=g).to(cuda_device)], 1)
     wide_mask = torch.cat([mask, torch.zeros(B, 32, dtype=mask.dtype, device=cuda_device)], 1)
     assert torch.equal(trunk.encode(wide_ids, wide_mask), rep)
+
+
+def test_dropin_encoder_and_bulk_encode_use_the_native_trunk(cuda_device, tmp_path):
+    """``SPLADEModernBERT.use_native_trunk`` / ``bulk_encode(native_trunk=True)``: same interface, vectors that agree
+    with the transformers-trunk path to bf16 noise, identical ``state_dict`` keys, and ``forward`` (training) keeps
+    the reference trunk."""
+    import splade_b200
+    mlm, cfg = _tiny_mlm(cuda_device, layers=3)
+    mlm.save_pretrained(tmp_path)
+    model = splade_b200.SPLADEModernBERT(model_name=str(tmp_path)).to(cuda_device).eval()
+    keys = set(model.state_dict().keys())
+    g = torch.Generator().manual_seed(8)
+    N, S = 24, 64
+    lens = torch.randint(3, S + 1, (N,), generator=g)
+    ids = torch.randint(6, cfg.vocab_size - 1, (N, S), generator=g)
+    mask = (torch.arange(S)[None, :] < lens[:, None]).to(torch.int64)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ref = model.encode(ids.to(cuda_device), mask.to(cuda_device))
+        model.use_native_trunk(True)
+        nat = model.encode(ids.to(cuda_device), mask.to(cuda_device))
+    assert set(model.state_dict().keys()) == keys
+    assert float(torch.nn.functional.cosine_similarity(nat, ref, dim=1).min()) > 0.999
+    # training path: autograd through the reference trunk even when the native trunk is enabled for encode
+    rep, tokw = model(ids[:4].to(cuda_device), mask[:4].to(cuda_device))
+    rep.sum().backward()
+    assert model.model.decoder.weight.grad is not None and tokw.shape == (4, S)
+    model.use_native_trunk(False)
+    i0, v0, c0, _ = splade_b200.bulk_encode(model, ids, mask, 16, batch_size=8, native_trunk=False)
+    i1, v1, c1, _ = splade_b200.bulk_encode(model, ids, mask, 16, batch_size=8, native_trunk=True)
+    assert model._native_trunk_enabled is False
+    assert torch.equal(c0, c1)
+    overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / 16.0 for a, b in zip(i0.cpu(), i1.cpu())])
+    assert overlap > 0.9, overlap
+    np.testing.assert_allclose(v1[:, 0].cpu().numpy(), v0[:, 0].cpu().numpy(), rtol=3e-2, atol=3e-2)

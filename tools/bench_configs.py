@@ -60,6 +60,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--docs-per-gpu", type=int, default=8192)
     ap.add_argument("--out", default="gpurun_out/configs.json")
+    ap.add_argument("--native-trunk", action="store_true", help="config 5 / config 3 full model through the native trunk")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -131,6 +132,8 @@ def main():
 
     # ---------------- config 5: bulk encode, full model, sharded, top-k emit
     model = build_model(dev)
+    if args.native_trunk:
+        model.use_native_trunk(True)   # packed-token trunk + head in one C-ABI call
     n_local = args.docs_per_gpu
     n_total = n_local * world
     ids_all = torch.randint(6, V - 1, (n_local, 256), generator=g)       # this rank's shard of the id stream
@@ -161,7 +164,9 @@ def main():
     out["config5_bulk_encode"] = {"docs_total": n_total, "docs_per_gpu": n_local, "seq_len": 256, "top_k": 64,
                                   "seconds": dt, "docs_per_s": n_total / dt, "mean_terms_emitted": nnz,
                                   "projected_seconds_for_1M_docs": 1e6 / (n_total / dt),
-                                  "d2h_bytes_per_doc": 64 * 8 + 4}
+                                  "d2h_bytes_per_doc": 64 * 8 + 4,
+                                  "trunk": "native packed-token trunk (splade_trunk_encode)" if args.native_trunk
+                                  else "transformers trunk (reference) + fused head"}
 
     # ---------------- N1 check: what the un-fused head prologue (dense 768x768 -> GELU -> LayerNorm) costs
     x = torch.randn(64, 256, H, generator=g).to(dev)
