@@ -90,9 +90,9 @@ EncodeTiledFn get_encode_fn() {
 }
 }  // namespace
 
-// bf16 tensor, innermost dimension contiguous, 128-byte swizzle, out-of-bounds elements read as zero.
-int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box) {
+// tensor with a contiguous innermost dimension, 128-byte swizzle, out-of-bounds elements read as zero / not written.
+static int encode_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* gptr, int rank,
+                             const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(kErrDriver, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gdim[5];
@@ -105,7 +105,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_
     estr[i] = 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
-  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+  const CUresult r = fn(out, dtype, static_cast<cuuint32_t>(rank),
                         const_cast<void*>(gptr), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -113,6 +113,16 @@ int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_
     return set_error(kErrDriver, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", static_cast<int>(r),
                      rank);
   return kOk;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, gptr, rank, dims, strides_bytes, box);
+}
+
+int encode_tmap_f32(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, gptr, rank, dims, strides_bytes, box);
 }
 
 }  // namespace splade
@@ -240,7 +250,8 @@ int splade_trunk_gemm(int epi, const void* A, int rows, const void* W, int N, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int32_t* t_rows = static_cast<int32_t*>(workspace);
   SPLADE_CUDA_OK(cudaMemcpyAsync(t_rows, &rows, sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  return trunk_gemm_launch(epi, A, rows, W, N, K, t_rows, out, ldo, st);
+  if (epi == EPI_QKV_ROPE) return set_error(kErrInvalidArg, "splade_trunk_gemm: epilogue 4 (RoPE) is internal to splade_trunk_encode");
+  return trunk_gemm_launch(epi, A, rows, W, N, K, t_rows, out, ldo, nullptr, 0.f, 0, st);
 }
 
 int splade_trunk_attn(void* qkv_packed, const int32_t* mask, int B, int S, int H, int n_heads, int window,

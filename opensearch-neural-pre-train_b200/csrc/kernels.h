@@ -17,6 +17,8 @@ int require_sm100(const char* who);
 int sm_count();
 int encode_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box);
+int encode_tmap_f32(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box);
 
 // head_fwd.cu
 void head_fwd_plan(int B, int S, int* s_box, int* b_box, int* chunks_per_doc, int* n_tt, int* umma_n);
@@ -53,9 +55,10 @@ int head_fwd_packed_launch(const void* hidden_packed, const VarlenLayout& lay, c
                            int B, int S, int H, int V, float* rep, int32_t* argmax, cudaStream_t stream);
 
 // trunk_gemm.cu: tcgen05 GEMM with the trunk's fused epilogues
-enum TrunkEpilogue { EPI_BF16 = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_GEGLU = 3 };
+enum TrunkEpilogue { EPI_BF16 = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_GEGLU = 3, EPI_QKV_ROPE = 4 };
 int trunk_gemm_launch(int epi, const void* A, int rows_cap, const void* W, int N, int K, const int32_t* t_rows,
-                      void* out, int ldo, cudaStream_t stream);
+                      void* out, int ldo, const uint32_t* meta, float rope_theta, int rope_cols,
+                      cudaStream_t stream);
 
 // trunk.cu: embedding / LayerNorm / attention kernels and the layer loop
 struct TrunkAttnArgs;

@@ -585,8 +585,8 @@ int trunk_encode_launch(const splade_trunk_args* a, cudaStream_t stream) {
   const int32_t* t_rows = &lay.plan->T;
   const int rows_i = static_cast<int>(rows);
 
-  if ((rc = trunk_rope_table_launch(rope_g, S, a->global_theta, stream)) != kOk) return rc;
-  if ((rc = trunk_rope_table_launch(rope_l, S, a->local_theta, stream)) != kOk) return rc;
+  (void)rope_g;
+  (void)rope_l;
   if ((rc = trunk_embed_ln_launch(a->input_ids, a->tok_emb, a->emb_norm, a->norm_eps, lay, S, H, x, xb, stream)) != kOk)
     return rc;
 
@@ -595,21 +595,23 @@ int trunk_encode_launch(const splade_trunk_args* a, cudaStream_t stream) {
     if (ly.attn_norm != nullptr) {
       if ((rc = trunk_ln_launch(x, 0, ly.attn_norm, a->norm_eps, t_rows, rows_i, H, xb, stream)) != kOk) return rc;
     }
-    if ((rc = trunk_gemm_launch(EPI_BF16, xb, rows_i, ly.wqkv, 3 * H, H, t_rows, qkv, 3 * H, stream)) != kOk) return rc;
-    if ((rc = trunk_rope_launch(qkv, ly.is_global ? rope_g : rope_l, lay, H, stream)) != kOk) return rc;
+    // Wqkv with RoPE on the q / k heads fused into the epilogue (the separate trunk_rope_kernel cost 25 us a layer)
+    if ((rc = trunk_gemm_launch(EPI_QKV_ROPE, xb, rows_i, ly.wqkv, 3 * H, H, t_rows, qkv, 3 * H, lay.meta,
+                                ly.is_global ? a->global_theta : a->local_theta, 2 * H, stream)) != kOk)
+      return rc;
     if ((rc = trunk_attn_launch(qkv, ab, lay, B, S, H, a->n_heads, ly.is_global ? -1 : a->local_window, stream)) != kOk)
       return rc;
-    if ((rc = trunk_gemm_launch(EPI_RESID, ab, rows_i, ly.wo, H, H, t_rows, x, H, stream)) != kOk)
+    if ((rc = trunk_gemm_launch(EPI_RESID, ab, rows_i, ly.wo, H, H, t_rows, x, H, nullptr, 0.f, 0, stream)) != kOk)
       return rc;
     if ((rc = trunk_ln_launch(x, 0, ly.mlp_norm, a->norm_eps, t_rows, rows_i, H, xb, stream)) != kOk) return rc;
-    if ((rc = trunk_gemm_launch(EPI_GEGLU, xb, rows_i, ly.wi, I, H, t_rows, gg, I, stream)) != kOk)
+    if ((rc = trunk_gemm_launch(EPI_GEGLU, xb, rows_i, ly.wi, I, H, t_rows, gg, I, nullptr, 0.f, 0, stream)) != kOk)
       return rc;
-    if ((rc = trunk_gemm_launch(EPI_RESID, gg, rows_i, ly.wo2, H, I, t_rows, x, H, stream)) != kOk)
+    if ((rc = trunk_gemm_launch(EPI_RESID, gg, rows_i, ly.wo2, H, I, t_rows, x, H, nullptr, 0.f, 0, stream)) != kOk)
       return rc;
   }
   // final_norm -> head.dense -> GELU -> head.norm  (ModernBertPredictionHead)
   if ((rc = trunk_ln_launch(x, 0, a->final_norm, a->norm_eps, t_rows, rows_i, H, xb, stream)) != kOk) return rc;
-  if ((rc = trunk_gemm_launch(EPI_GELU, xb, rows_i, a->head_dense, H, H, t_rows, ab, H, stream)) != kOk)
+  if ((rc = trunk_gemm_launch(EPI_GELU, xb, rows_i, a->head_dense, H, H, t_rows, ab, H, nullptr, 0.f, 0, stream)) != kOk)
     return rc;
   if ((rc = trunk_ln_launch(ab, 1, a->head_norm, a->norm_eps, t_rows, rows_i, H, xb, stream)) != kOk) return rc;
   if (a->hidden_out != nullptr) {
