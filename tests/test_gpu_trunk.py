@@ -70,13 +70,20 @@ def _rope(x, theta):
     return _bf(x * cos + rot * sin).float()
 
 
-@pytest.mark.parametrize("window,theta", [(-1, 0.0), (64, 0.0), (-1, 160000.0), (64, 10000.0)])
-def test_trunk_attention_vs_torch(cuda_device, window, theta):
+@pytest.mark.parametrize("window,theta,S,lens", [
+    (-1, 0.0, 200, [200, 1, 0, 77, 130, 64]),            # every tile fits 256 keys: tcgen05 kernel
+    (64, 0.0, 200, [200, 1, 0, 77, 130, 64]),
+    (-1, 160000.0, 200, [200, 1, 0, 77, 130, 64]),
+    (64, 10000.0, 200, [200, 1, 0, 77, 130, 64]),
+    (-1, 0.0, 600, [600, 256, 257, 3, 0, 411]),          # global over > 256 tokens: mma.sync kernel for those docs
+    (64, 10000.0, 600, [600, 256, 257, 3, 0, 411]),      # sliding window: tcgen05 kernel for any length
+    (-1, 0.0, 48, [48, 1, 17, 40, 8, 33]),               # query-length batch
+])
+def test_trunk_attention_vs_torch(cuda_device, window, theta, S, lens):
     import splade_b200
-    B, S, nh = 6, 200, 4
+    B, nh = len(lens), 4
     H = nh * 64
-    g = torch.Generator().manual_seed(11 + window)
-    lens = [200, 1, 0, 77, 130, 64]
+    g = torch.Generator().manual_seed(11 + window + S)
     mask = (torch.arange(S)[None, :] < torch.tensor(lens)[:, None]).to(torch.int32).to(cuda_device)
     qkv = _bf(torch.randn(B, S, 3 * H, generator=g)).to(cuda_device)
     rows = splade_b200.load_library().splade_packed_rows(B, S)
