@@ -64,7 +64,11 @@ class NativeTrunk:
              "head_norm": f32(m.head.norm.weight), "dec_w": bf(m.decoder.weight),
              # autocast hands F.linear a bf16 bias
              "dec_bias": m.decoder.bias.detach().to(device).to(torch.bfloat16).float().contiguous(), "layers": []}
-        layer_types = list(cfg.layer_types)
+        layer_types = getattr(cfg, "layer_types", None)
+        if layer_types is None:  # transformers < 4.56: global attention every n-th layer (modeling_modernbert.py)
+            n = int(cfg.global_attn_every_n_layers)
+            layer_types = ["full_attention" if i % n == 0 else "sliding_attention" for i in range(len(m.model.layers))]
+        layer_types = list(layer_types)
         arr = (_lib.TrunkLayer * len(m.model.layers))()
         for i, layer in enumerate(m.model.layers):
             t = {"attn_norm": f32(layer.attn_norm.weight) if isinstance(layer.attn_norm, torch.nn.LayerNorm) else None,
@@ -76,9 +80,13 @@ class NativeTrunk:
                 wo=t["wo"].data_ptr(), mlp_norm=t["mlp_norm"].data_ptr(), wi=t["wi"].data_ptr(),
                 wo2=t["wo2"].data_ptr(), is_global=int(layer_types[i] == "full_attention"), reserved=0)
         c["layer_array"] = arr
-        rp = cfg.rope_parameters
-        c["global_theta"] = float(rp["full_attention"]["rope_theta"])
-        c["local_theta"] = float(rp["sliding_attention"]["rope_theta"])
+        rp = getattr(cfg, "rope_parameters", None)
+        if rp is not None and "full_attention" in rp:
+            c["global_theta"] = float(rp["full_attention"]["rope_theta"])
+            c["local_theta"] = float(rp["sliding_attention"]["rope_theta"])
+        else:  # older configs carry the two bases as plain attributes (huggingface/v33/config.json:17,25)
+            c["global_theta"] = float(cfg.global_rope_theta)
+            c["local_theta"] = float(getattr(cfg, "local_rope_theta", None) or cfg.global_rope_theta)
         self._cache, self._versions = c, versions
         return c
 

@@ -69,3 +69,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_packed_layout_and_trunk_sizes_without_a_gpu():
+    """Host-only entry points of the packed layout / native trunk: row counts, workspace sizes, argument checks."""
+    import ctypes
+
+    import splade_b200
+    from splade_b200 import _lib as L
+    lib = splade_b200.load_library()
+    # every document rounded up to 8 tokens, whole 256-row tiles
+    assert lib.splade_packed_rows(64, 256) == 16384
+    assert lib.splade_packed_rows(3, 7) == 256
+    assert lib.splade_packed_rows(512, 60) == 512 * 64
+    head = lib.splade_workspace_bytes(L.OP_HEAD_FWD, 64, 256, 768, 50000, 0)
+    assert head >= 64 * 256 * 768 * 2 + 64 * 50000 * 4          # packed token copy + merge keys
+    assert lib.splade_workspace_bytes(L.OP_HEAD_FWD_TOKW, 64, 256, 768, 50000, 0) >= head + 64 * 256 * 4
+    trunk = lib.splade_workspace_bytes(L.OP_TRUNK_ENCODE, 64, 256, 768, 50000, 1152)
+    rows = 16384
+    assert trunk >= rows * (768 * 4 + 768 * 2 + 3 * 768 * 2 + 768 * 2 + 1152 * 2)
+    assert ctypes.sizeof(L.TrunkLayer) == 56 and ctypes.sizeof(L.TrunkArgs) % 8 == 0
+    assert lib.splade_trunk_encode(None, None) == 1               # SPLADE_ERR_INVALID_ARG, no crash
+    assert b"null pointer" in lib.splade_last_error()
