@@ -377,6 +377,8 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     numa_bound = splade_b200.distributed.bind_to_device_numa_node(local_rank) if world > 1 else False
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner out of stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, max(args.warmup, 3)
 

@@ -224,6 +224,13 @@ struct AttnParams {
   int skip_tc_tiles;  // mma.sync kernel: 1 = tiles the tcgen05 kernel handles are skipped
 };
 
+// 2^x on the SFU in one instruction (fast_exp2() adds a denormal-range fix-up around it that softmax does not need)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -394,17 +401,17 @@ trunk_attn_kernel(const AttnParams p) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float mnew = fmaxf(m_run[r], mx[r]);
       moff[r] = mnew == -INFINITY ? 0.f : mnew;  // nothing visible yet: keep exp2() finite
-      corr[r] = exp2f(m_run[r] - moff[r]);       // exp2(-inf) = 0 on the first visible block
+      corr[r] = fast_exp2(m_run[r] - moff[r]);       // exp2(-inf) = 0 on the first visible block
       m_run[r] = mnew;
       l_run[r] *= corr[r];
     }
     uint32_t pa[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f(s[nt][0] - moff[0]);
-      const float p1 = exp2f(s[nt][1] - moff[0]);
-      const float p2 = exp2f(s[nt][2] - moff[1]);
-      const float p3 = exp2f(s[nt][3] - moff[1]);
+      const float p0 = fast_exp2(s[nt][0] - moff[0]);
+      const float p1 = fast_exp2(s[nt][1] - moff[0]);
+      const float p2 = fast_exp2(s[nt][2] - moff[1]);
+      const float p3 = fast_exp2(s[nt][3] - moff[1]);
       l_run[0] += p0 + p1;
       l_run[1] += p2 + p3;
       const int ks = nt >> 1;
@@ -622,13 +629,13 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        pv[j] = exp2f(fmaf(__uint_as_float(r[j]), sl2, -moff));
+        pv[j] = fast_exp2(fmaf(__uint_as_float(r[j]), sl2, -moff));
         sum += pv[j];
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        pv[j] = (c0 + j >= lo && c0 + j < hi) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -moff)) : 0.f;
+        pv[j] = (c0 + j >= lo && c0 + j < hi) ? fast_exp2(fmaf(__uint_as_float(r[j]), sl2, -moff)) : 0.f;
         sum += pv[j];
       }
     }
