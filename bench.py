@@ -35,7 +35,7 @@ B_DOCS, SEQ, HIDDEN, VOCAB = 64, 256, 768, 50000
 WORKLOAD = "C2: SPLADE-max head encode, A.X-Encoder-base head shape (hidden 768 -> vocab 50000), batch 64 x L=256"
 FLOP_PER_STEP = 2.0 * B_DOCS * SEQ * HIDDEN * VOCAB          # 76.8 MFLOP per token
 N_ROTATE = 3                                                 # distinct input sets (see config.l2)
-LAUNCHES_PER_STEP = 7                                        # kernels per splade_head_fwd call (see gpu_launches)
+LAUNCHES_PER_STEP = 6                                        # kernels per splade_head_fwd call (see gpu_launches)
 
 
 def load_peaks():
@@ -563,7 +563,7 @@ def run_ours(args):
                 "checksum": checksum,
                 "numa_bound": numa_bound},
         # kernels of libsplade_b200.so launched per step in the device-resident timed region (splade_head_fwd, auto
-        # tiling policy): build_tile_masks, varlen_count, varlen_plan, varlen_pack (exits: padded tiling chosen),
+        # tiling policy): build_tile_masks, varlen_plan (counts + plans), varlen_pack (exits: padded tiling chosen),
         # head_fwd_kernel, head_fwd_varlen_kernel (exits), finalize_varlen (exits).  The e2e region adds 2 per step
         # (build_tile_masks + head_fwd_kernel: splade_head_fwd_host decides the tiling on the host).
         "gpu_launches": LAUNCHES_PER_STEP * K,

@@ -621,9 +621,12 @@ varlen_count_kernel(const int32_t* __restrict__ mask, int B, int S, int32_t* __r
 // the token rows the tile loads (the kernel is within a few percent of both its tensor and its L2->SM limit, so
 // a tile with fewer columns still pays for its vocabulary rows).
 __global__ void __launch_bounds__(1024)
-varlen_plan_kernel(const int32_t* __restrict__ len, int B, const int32_t* __restrict__ tile_n16, int n_tt_pad,
+varlen_plan_kernel(int32_t* __restrict__ len, int B, const int32_t* __restrict__ tile_n16, int n_tt_pad,
                    int trim_rows, int pad_cols, int force_mode, int32_t* __restrict__ off,
-                   uint8_t* __restrict__ spans, VarlenPlan* __restrict__ plan, int32_t* __restrict__ plan_out) {
+                   uint8_t* __restrict__ spans, VarlenPlan* __restrict__ plan, int32_t* __restrict__ plan_out,
+                   const int32_t* __restrict__ mask, int S) {
+  // mask != nullptr: the lengths are counted here as well (small batches: saves the varlen_count_kernel launch)
+  __shared__ int s_len[1024];
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   __shared__ int s_real;
@@ -639,7 +642,20 @@ varlen_plan_kernel(const int32_t* __restrict__ len, int B, const int32_t* __rest
   int real = 0;
   for (int base = 0; base < B; base += 1024) {
     const int i = base + tid;
-    const int l = i < B ? len[i] : 0;
+    if (mask != nullptr) {  // one warp per document, 32 documents per warp and chunk
+      for (int d = warp; d < 1024 && base + d < B; d += 32) {
+        const int32_t* mrow = mask + static_cast<size_t>(base + d) * S;
+        int c = 0;
+        for (int s = lane; s < S; s += 32) c += mrow[s] != 0 ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) {
+          s_len[d] = c;
+          len[base + d] = c;
+        }
+      }
+      __syncthreads();
+    }
+    const int l = i < B ? (mask != nullptr ? s_len[tid] : len[i]) : 0;
     real += l;
     const int x = (l + VL_ALIGN - 1) / VL_ALIGN * VL_ALIGN;
     int incl = x;
@@ -1149,10 +1165,13 @@ int varlen_layout_build(const int32_t* mask, int B, int S, int V, void* workspac
   ws += align256(varlen_rows(B, S) * sizeof(uint32_t));
   out->keys = reinterpret_cast<uint32_t*>(ws);
   out->rows = varlen_rows(B, S);
-  varlen_count_kernel<<<(B + 7) / 8, 256, 0, stream>>>(mask, B, S, out->len);
-  SPLADE_CUDA_OK(cudaGetLastError());
+  const bool count_inline = static_cast<size_t>(B) * S <= 131072;
+  if (!count_inline) {
+    varlen_count_kernel<<<(B + 7) / 8, 256, 0, stream>>>(mask, B, S, out->len);
+    SPLADE_CUDA_OK(cudaGetLastError());
+  }
   varlen_plan_kernel<<<1, 1024, 0, stream>>>(out->len, B, nullptr, 0, 0, 0, /*force_mode=*/1, out->off, out->spans,
-                                             out->plan, nullptr);
+                                             out->plan, nullptr, count_inline ? mask : nullptr, S);
   SPLADE_CUDA_OK(cudaGetLastError());
   varlen_pack_kernel<<<dim3((S + 255) / 256, B), 256, 0, stream>>>(nullptr, mask, out->len, out->off, out->spans,
                                                                     out->plan, S, 64, V, nullptr, out->meta,
@@ -1368,11 +1387,14 @@ int head_fwd_launch(const void* hidden, const void* W, const float* bias, const 
 
   CUtensorMap tmap_x;
   if (varlen) {
-    varlen_count_kernel<<<(B + 7) / 8, 256, 0, stream>>>(mask, B, S, vl_len);
-    SPLADE_CUDA_OK(cudaGetLastError());
+    const bool count_inline = static_cast<size_t>(B) * S <= 131072;  // small batch: the plan kernel counts itself
+    if (!count_inline) {
+      varlen_count_kernel<<<(B + 7) / 8, 256, 0, stream>>>(mask, B, S, vl_len);
+      SPLADE_CUDA_OK(cudaGetLastError());
+    }
     varlen_plan_kernel<<<1, 1024, 0, stream>>>(vl_len, B, tile_n16, p.n_tt, p.trim_rows,
                                                p.trim_rows ? p.s_box : cols, pack_mode, vl_off, vl_spans, plan,
-                                               plan_out);
+                                               plan_out, count_inline ? mask : nullptr, S);
     SPLADE_CUDA_OK(cudaGetLastError());
     varlen_pack_kernel<<<dim3((S + 255) / 256, B), 256, 0, stream>>>(
         static_cast<const uint4*>(hidden), mask, vl_len, vl_off, vl_spans, plan, S, H, V,

@@ -160,6 +160,49 @@ def test_native_trunk_vs_transformers(cuda_device):
     assert float(rep[torch.where(lens == 0)[0]].abs().sum()) == 0.0
 
 
+def _hf_vs_native(cuda_device, lens, S, hole_at=None, seed=3):
+    import splade_b200
+    mlm, cfg = _tiny_mlm(cuda_device)
+    B = len(lens)
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.tensor(lens)
+    ids = torch.randint(6, cfg.vocab_size - 1, (B, S), generator=g)
+    mask = (torch.arange(S)[None, :] < lens[:, None]).to(torch.int64)
+    if hole_at is not None:
+        mask[:, hole_at] = 0                      # non-suffix masks: positions keep counting across the holes
+    ids = torch.where(mask.bool(), ids, torch.full_like(ids, cfg.pad_token_id)).to(cuda_device)
+    mask = mask.to(cuda_device)
+    rep, dbg = splade_b200.NativeTrunk(mlm).encode(ids, mask, debug=True)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ref_hidden = mlm.head(mlm.model(input_ids=ids, attention_mask=mask)[0]).float()
+        ref_rep, _ = splade_b200.splade_head(ref_hidden, mlm.decoder.weight, mlm.decoder.bias, mask,
+                                             want_token_weights=False)
+    plan = dbg["plan"].cpu().tolist()
+    assert plan[4] == int(mask.sum())
+    meta = dbg["meta"].cpu().numpy().astype(np.int64)
+    T = plan[1]
+    doc, pos = (meta[:T] >> 16) & 0x7FFF, meta[:T] & 0xFFFF
+    assert bool(mask[torch.from_numpy(doc).to(cuda_device), torch.from_numpy(pos).to(cuda_device)].all())
+    got = dbg["hidden_packed"][:T].float()
+    want = ref_hidden[torch.from_numpy(doc).to(cuda_device), torch.from_numpy(pos).to(cuda_device)]
+    err = (got - want).abs()
+    assert float(err.mean()) < 1e-2 and float(err.max()) < 0.3, (float(err.mean()), float(err.max()))
+    live = mask.sum(1) > 0
+    cos = torch.nn.functional.cosine_similarity(rep[live], ref_rep[live], dim=1)
+    assert float(cos.min()) > 0.999, cos
+    assert float(rep[~live].abs().sum()) == 0.0
+
+
+def test_native_trunk_long_documents_use_both_attention_kernels(cuda_device):
+    """Documents longer than 256 tokens: global layers fall to the mma.sync kernel for those documents while the
+    short ones of the same batch (and every sliding-window layer) run on the tcgen05 kernel."""
+    _hf_vs_native(cuda_device, [700, 300, 257, 9, 256, 0], 700)
+
+
+def test_native_trunk_with_holes_in_the_mask(cuda_device):
+    _hf_vs_native(cuda_device, [90, 12, 64, 33], 96, hole_at=5, seed=6)
+
+
 def test_native_trunk_is_padding_and_batch_invariant(cuda_device):
     """A document's vector does not depend on its neighbours, on the padded width, or on what sits at padded ids."""
     import splade_b200
