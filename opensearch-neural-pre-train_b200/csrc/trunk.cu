@@ -475,7 +475,7 @@ trunk_attn_kernel(const AttnParams p) {
 //   O[128 q, 64] = P V            tcgen05.mma with V as the MN-major B operand (the TMA-loaded [key][dim] tile as
 //                                 it is: dims contiguous), accumulator in the TMEM columns S no longer needs
 // 96 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, so one tile's loads / softmax overlap the
-// other's MMAs.  Tiles that do not qualify (global attention over > 256 tokens) are left to the mma.sync kernel.
+// other's MMAs; 256 threads, two per query row (each sweeps half of the row's 32-column chunks).  Tiles that do not qualify (global attention over > 256 tokens) are left to the mma.sync kernel.
 constexpr int TA_BQ = 128;
 constexpr int TA_BKV = 256;
 constexpr int TA_Q_OFF = 0;                    // 128 rows x 128 B
@@ -483,7 +483,8 @@ constexpr int TA_K_OFF = 16384;                // 256 rows x 128 B
 constexpr int TA_V_OFF = 65536;                // 256 rows x 128 B (16 KB of padding before it: P needs 64 KB)
 constexpr int TA_BAR_OFF = 98304;
 constexpr int TA_KPOS_OFF = TA_BAR_OFF + 64;
-constexpr int TA_SMEM_BYTES = TA_KPOS_OFF + TA_BKV * 4 + 1024;
+constexpr int TA_XCHG_OFF = TA_KPOS_OFF + TA_BKV * 4;
+constexpr int TA_SMEM_BYTES = TA_XCHG_OFF + 2 * 128 * 4 + 1024;
 constexpr int TA_TMEM_COLS = 256;
 
 __host__ __device__ inline bool attn_tc_eligible(int L, int window) {
@@ -501,7 +502,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr) 
   return d;
 }
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                      const AttnParams p) {
   const int b = static_cast<int>(blockIdx.z);
@@ -523,10 +524,15 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_load + 2);
   int* kpos = reinterpret_cast<int*>(smem + TA_KPOS_OFF);
+  float* xchg = reinterpret_cast<float*>(smem + TA_XCHG_OFF);  // [2][128]: row maxima, then row sums, per half
 
+  // 256 threads: thread t and thread t + 128 share query row (t & 127) = TMEM lane; `half` 0 takes the low 32-column
+  // chunks of the row, half 1 the high ones (two warps per SM sub-partition instead of one: the softmax is
+  // latency-bound, not issue-bound)
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5;
-  const uint32_t lane = lane_id();
+  const uint32_t row_t = tid & 127u;
+  const uint32_t half = tid >> 7;
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
@@ -540,9 +546,9 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tma_load_2d(smem + TA_V_OFF, &tmap_kv, bar_load, 2 * p.H + h * AT_D, base + kstart);
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, TA_TMEM_COLS);
-  for (int i = static_cast<int>(tid); i < TA_BKV; i += 128) {
-    const int key = kstart + i;
-    kpos[i] = key < kend ? static_cast<int>(__ldg(&p.meta[base + key]) & 0xFFFFu) : 0x3FFFFFFF;
+  {
+    const int key = kstart + static_cast<int>(tid);
+    kpos[tid] = key < kend ? static_cast<int>(__ldg(&p.meta[base + key]) & 0xFFFFu) : 0x3FFFFFFF;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -565,11 +571,12 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   mbar_wait(bar_mma, 0);
   tcgen05_fence_after();
 
-  // ---- softmax: one query row per thread.  Positions grow with the column index, so the keys a row may see are a
-  // contiguous column range [lo, hi): found once per row (two binary searches over the staged key positions for
-  // the sliding window), and every 32-column chunk is then, for the whole warp, fully visible (no mask arithmetic
-  // at all: the common case), invisible (skipped; its P columns are zero) or mixed (two integer compares per score).
-  const int qrow = min(q0 + static_cast<int>(tid), L8 - 1);
+  // ---- softmax: one query row per thread pair.  Positions grow with the column index, so the keys a row may see
+  // are a contiguous column range [lo, hi): found once per row (two binary searches over the staged key positions
+  // for the sliding window), and every 32-column chunk is then, for the whole warp, fully visible (no mask
+  // arithmetic at all: the common case), invisible (skipped; its P columns are zero) or mixed (two integer compares
+  // per score).
+  const int qrow = min(q0 + static_cast<int>(row_t), L8 - 1);
   const int qpos = static_cast<int>(__ldg(&p.meta[base + qrow]) & 0xFFFFu);
   int lo = 0, hi = nkeys;
   if (p.window >= 0) {
@@ -586,11 +593,13 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
     hi = l;
   }
-  const uint32_t t_lane = tmem + ((warp * 32u) << 16);
+  const uint32_t t_lane = tmem + (((warp & 3u) * 32u) << 16);
   const int nchunks = (nkeys + 31) >> 5;
+  const int c_mid = (nchunks + 1) >> 1;
+  const int c_beg = half == 0 ? 0 : c_mid, c_end = half == 0 ? c_mid : nchunks;
   const float sl2 = p.scale * 1.4426950408889634f;
   float mx = -INFINITY;
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = c_beg; c < c_end; ++c) {
     const int c0 = 32 * c;
     if (__all_sync(0xffffffffu, hi <= c0 || lo >= c0 + 32)) continue;
     const bool full = __all_sync(0xffffffffu, lo <= c0 && hi >= c0 + 32);
@@ -605,19 +614,22 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       for (int j = 0; j < 32; ++j) mx = (c0 + j >= lo && c0 + j < hi) ? fmaxf(mx, __uint_as_float(r[j])) : mx;
     }
   }
+  xchg[half * 128u + row_t] = mx;
+  __syncthreads();
+  mx = fmaxf(mx, xchg[(half ^ 1u) * 128u + row_t]);
   if (mx == -INFINITY) mx = 0.f;  // rows past the document (never stored)
   const float moff = mx * sl2;
   float sum = 0.f;
   // P overwrites the Q / K tiles (the first MMA has completed): [64-key block][row][128 B], chunk c of row r at
   // chunk position c ^ (r & 7)
-  for (int c = 0; c < nchunks; ++c) {
+  for (int c = c_beg; c < c_end; ++c) {
     const int c0 = 32 * c;
-    uint8_t* prow = smem + (c >> 1) * 16384 + tid * 128u;
+    uint8_t* prow = smem + (c >> 1) * 16384 + row_t * 128u;
     if (__all_sync(0xffffffffu, hi <= c0 || lo >= c0 + 32)) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + i);
-        *reinterpret_cast<uint4*>(prow + ((chunk ^ (tid & 7u)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(prow + ((chunk ^ (row_t & 7u)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
       }
       continue;
     }
@@ -647,7 +659,7 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       v.z = cvt_bf16x2(pv[8 * i + 5], pv[8 * i + 4]);
       v.w = cvt_bf16x2(pv[8 * i + 7], pv[8 * i + 6]);
       const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + i);
-      *reinterpret_cast<uint4*>(prow + ((chunk ^ (tid & 7u)) << 4)) = v;
+      *reinterpret_cast<uint4*>(prow + ((chunk ^ (row_t & 7u)) << 4)) = v;
     }
   }
   // The second MMA reads ceil(nkeys / 16) 16-key steps: all inside written P chunks (their tail columns are zero).
@@ -658,6 +670,8 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (tid < 128 && vrow < ((nkeys + 15) & ~15))
       *reinterpret_cast<uint4*>(smem + TA_V_OFF + vrow * 128 + (tid & 7u) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
+  __syncthreads();                      // both halves have read the exchanged maxima
+  xchg[half * 128u + row_t] = sum;      // row sums, exchanged after the next sync
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -673,18 +687,19 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 make_smem_desc_sw128_mn(v_addr + ks * 2048), idesc, ks != 0 ? 1u : 0u);
     umma_commit(bar_mma);
   }
+  sum += xchg[(half ^ 1u) * 128u + row_t];
   mbar_wait(bar_mma, 1);
   tcgen05_fence_after();
 
+  // each half stores 32 of the 64 output dims of its row
   const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-  const int row = q0 + static_cast<int>(tid);
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
+  const int row = q0 + static_cast<int>(row_t);
+  {
     uint32_t r[32];
-    tmem_ld_32x32b_x32(t_lane + static_cast<uint32_t>(32 * c), r);
+    tmem_ld_32x32b_x32(t_lane + 32u * half, r);
     tmem_ld_wait();
     if (row < L8) {
-      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(base + row) * p.H + h * AT_D + 32 * c);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(base + row) * p.H + h * AT_D + 32 * half);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 v;
@@ -802,7 +817,7 @@ int trunk_attn_launch(const void* qkv, void* out, const VarlenLayout& lay, int B
     if (rc != kOk) return rc;
     SPLADE_CUDA_OK(cudaFuncSetAttribute(trunk_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         TA_SMEM_BYTES));
-    trunk_attn_tc_kernel<<<dim3((s8 + TA_BQ - 1) / TA_BQ, n_heads, B), 128, TA_SMEM_BYTES, stream>>>(tmap_q, tmap_kv, p);
+    trunk_attn_tc_kernel<<<dim3((s8 + TA_BQ - 1) / TA_BQ, n_heads, B), 256, TA_SMEM_BYTES, stream>>>(tmap_q, tmap_kv, p);
     SPLADE_CUDA_OK(cudaGetLastError());
   }
   if (!tc_covers_all) {

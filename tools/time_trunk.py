@@ -46,6 +46,19 @@ for name, B, S, lo, hi in (("docs 64x256 full", 64, 256, 256, 256), ("docs 64x25
         row["max_abs_diff"] = float((a - b).abs().max())
         top_a, top_b = a.topk(64, dim=1).indices, b.topk(64, dim=1).indices
         row["top64_overlap"] = float(sum(len(set(x.tolist()) & set(y.tolist())) for x, y in zip(top_a, top_b)) / (64 * B))
+        if name.startswith("docs 64x256 full"):
+            # the reference's inference path is fp32 without autocast (benchmark/encoders.py:309-318)
+            with torch.autocast("cuda", enabled=False):
+                c = ref(ids, mask)[0]
+            row["cosine_min_vs_fp32_reference_chain"] = float(torch.nn.functional.cosine_similarity(a, c, dim=1).min())
+            row["cosine_min_transformers_bf16_vs_fp32_reference_chain"] = float(
+                torch.nn.functional.cosine_similarity(b, c, dim=1).min())
+            top_c = c.topk(64, dim=1).indices
+            row["top64_overlap_vs_fp32_reference_chain"] = float(
+                sum(len(set(x.tolist()) & set(y.tolist())) for x, y in zip(top_a, top_c)) / (64 * B))
+            row["top64_overlap_transformers_bf16_vs_fp32"] = float(
+                sum(len(set(x.tolist()) & set(y.tolist())) for x, y in zip(top_b, top_c)) / (64 * B))
+            del c
         row["native_ms"] = timed(lambda: trunk.encode(ids, mask), 10)
         row["reference_trunk_plus_fused_head_ms"] = timed(lambda: ours.encode(ids, mask), 5)
         row["reference_chain_ms"] = timed(lambda: ref(ids, mask)[0], 3)
