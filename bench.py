@@ -192,7 +192,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------
 # secondary metric: training-step tokens/s of the hot path (BASELINE config 4)
 # ------------------------------------------------------------------------------------------------------
-def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_offset=-1.0):
+def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_offset=-1.0, exchange="peer"):
     """One C4 micro-step of the HOT PATH per rank: fused head forward for query (64x64), positive (64x256)
     and k negatives (64k x 256) hidden states, SPLADELossV33 (InfoNCE + FLOPS, optional cross-GPU negatives),
     backward through the loss and the sparse head backward, then the gradient all-reduce DDP would do for the
@@ -211,7 +211,19 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
     bias = (torch.randn(VOCAB, generator=g) * 0.02 + bias_offset).to(dev).requires_grad_(True)
     ones = lambda n, s: torch.ones(n, s, dtype=torch.int64, device=dev)  # noqa: E731
     mq, mp, mn = ones(Bq, 64), ones(Bq, SEQ), ones(Bq * k_neg, SEQ)
-    loss_fn = splade_b200.SPLADELossV33(gather_negatives=gather)
+    # cross-GPU negatives: through NVLink peer memory inside the loss kernels (PeerExchange) unless asked for / forced
+    # back to the NCCL all-gather + reduce-scatter statement; every rank takes the same branch
+    exchange_used, exchange_obj = "none", None
+    if gather and world > 1:
+        exchange_used = "nccl"
+        if exchange == "peer":
+            try:  # construction fails on EVERY rank or on none (peer_exchange.py)
+                exchange_obj = splade_b200.PeerExchange(Bq, VOCAB)
+                exchange_used = "peer"
+            except RuntimeError as e:  # e.g. CUDA IPC not permitted in this container
+                exchange_obj = None
+                exchange_used = f"nccl (peer exchange unavailable: {str(e)[:200]})"
+    loss_fn = splade_b200.SPLADELossV33(gather_negatives=gather, exchange=exchange_obj)
 
     def step(i):
         for t in (hq, hp, hn, W, bias):
@@ -233,6 +245,8 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
 
     for i in range(warmup):
         d = step(i)
+    if exchange_obj is not None:
+        exchange_obj.check()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -245,6 +259,9 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
         dist.barrier()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    if exchange_obj is not None:
+        exchange_obj.check()
+        exchange_obj.close()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -257,7 +274,7 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
                         f"decoder matrix and bias grads; trunk excluded",
             "head_fwd_tflop_per_step_per_gpu": head_flop / 1e12, "nonzero_d": d["nonzero_d"],
             "regime": f"decoder.bias offset {bias_offset}: {d['nonzero_d']:.0f} active terms per document",
-            "scaling": "weak"}
+            "negatives_exchange": exchange_used, "scaling": "weak"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -465,11 +482,16 @@ def run_ours(args):
     train = None
     if not args.no_train:
         del sets[1:], host_in, host_out, slots
-        train = run_train_leg(dev, world, rank, steps=max(3, min(20, K)), warmup=3, k_neg=1,
-                              gather=(world > 1 and args.gather_negatives))
-        # the same step in the trained-like sparse regime (bias offset sweeps the density)
-        train["sparse_regime"] = run_train_leg(dev, world, rank, steps=max(3, min(20, K)), warmup=3, k_neg=1,
-                                               gather=(world > 1 and args.gather_negatives), bias_offset=-2.0)
+        gather = world > 1 and not args.local_negatives
+        n_train = max(3, min(20, K))
+        try:
+            train = run_train_leg(dev, world, rank, steps=n_train, warmup=3, k_neg=1, gather=gather,
+                                  exchange=args.exchange)
+            # the same step in the trained-like sparse regime (bias offset sweeps the density)
+            train["sparse_regime"] = run_train_leg(dev, world, rank, steps=n_train, warmup=3, k_neg=1, gather=gather,
+                                                   bias_offset=-2.0, exchange=args.exchange)
+        except RuntimeError as e:  # secondary leg: never lose the headline line over it
+            train = dict(train or {}, error=f"{type(e).__name__}: {e}"[:400])
 
     gpu_ref = None
     if world == 1 and rank == 0 and not args.no_gpu_reference:
@@ -592,7 +614,13 @@ def main():
     ap.add_argument("--no-ragged", action="store_true", help="skip the ragged-batch (packed tiling) context leg")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-chain-on-GPU context leg")
     ap.add_argument("--gather-negatives", action="store_true",
-                    help="training leg: all-gather positives across ranks (north-star extension)")
+                    help="(default for N > 1, kept for old command lines) training leg: every rank's positives are "
+                         "in-batch negatives for every query (BASELINE config 4, north-star extension)")
+    ap.add_argument("--local-negatives", action="store_true",
+                    help="training leg: per-rank negatives only, the reference's own semantics (no exchange step)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="how the positives travel for N > 1: 'peer' = NVLink peer-memory loads inside the loss "
+                         "kernels (PeerExchange), 'nccl' = all-gather forward / reduce-scatter backward")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

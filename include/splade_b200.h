@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPLADE_B200_ABI_VERSION 2
+#define SPLADE_B200_ABI_VERSION 3
 
 /* error codes */
 #define SPLADE_OK 0
@@ -46,6 +46,7 @@ extern "C" {
 #define SPLADE_OP_TRUNK_ENCODE 6  /* (B,S,H,V, k = intermediate size) native trunk + head encode      */
 #define SPLADE_OP_TRUNK_GEMM 7    /* (-)                      splade_trunk_gemm scratch               */
 #define SPLADE_OP_TRUNK_ATTN 8    /* (B,S,-,V=1)              splade_trunk_attn scratch               */
+#define SPLADE_OP_PEER_LOSS_BWD 9 /* (B=Bq, k=world)          splade_peer_loss_bwd scratch            */
 
 int splade_abi_version(void);
 const char* splade_last_error(void);
@@ -229,6 +230,65 @@ int splade_topk(const float* rep, int B, int V, const uint8_t* blocklist, int k,
 int splade_emit_json(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B, int k,
                      const char* token_bytes, const int64_t* token_offsets, int n_tokens, int round_decimals,
                      char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed);
+
+/*
+ * ---------------------------------------------------------------------------------------------------------------
+ * Cross-GPU negatives without NCCL on the data path (north_star multi-GPU step).
+ * The reference has local negatives only (src/model/losses.py:136-181 sees one rank's batch); the extension
+ * scores every rank's queries against ALL ranks' positives.  Instead of all-gather -> GEMM and GEMM ->
+ * reduce-scatter, the exchange is folded into the kernels themselves over NVLink peer memory:
+ *
+ *   forward : every rank publishes q and its positives in an "exchange window" (device memory it exports with
+ *             CUDA IPC); after a flag barrier written straight into the peers' windows, ONE kernel pulls the
+ *             other ranks' positives over NVLink, casts them to the bf16 operand of the tcgen05 score GEMM and
+ *             keeps the fp32 copy for backward - the gathered fp32 tensor never takes a separate pass;
+ *   backward: ddocs of the LOCAL positives only, = sum over ranks s of gl_s * G_s[:, my columns]^T q_s, computed
+ *             by a kernel that reads q_s directly from the peers' windows (G_s, gl_s are pulled by the barrier
+ *             kernel).  The [W*Bq, V] gradient of the gathered tensor and its reduce-scatter never exist.
+ *
+ * Windows are double-buffered by the parity of `epoch` (a counter the ranks advance together, first call = 1),
+ * so one flag barrier per phase is enough.  A barrier that is not answered within the timeout
+ * (env SPLADE_B200_PEER_TIMEOUT_MS, default 20000) sets the window's status word instead of hanging the GPU.
+ * ---------------------------------------------------------------------------------------------------------------
+ */
+#define SPLADE_MAX_PEERS 16
+
+typedef struct splade_peer_group {
+  int32_t rank, world; /* world <= SPLADE_MAX_PEERS */
+  int32_t Bq, V;       /* the shapes every window was sized for (splade_peer_window_bytes) */
+  void* window[SPLADE_MAX_PEERS]; /* window[s] = base of rank s's window as mapped in THIS process */
+} splade_peer_group;
+
+size_t splade_peer_window_bytes(int Bq, int V, int world);
+/* window memory: cudaMalloc'ed and zeroed by the library on the current device because CUDA IPC exports whole
+ * allocations (the one exception to "PyTorch owns every buffer"); the caller frees it with splade_peer_free. */
+int splade_peer_alloc(size_t bytes, void** dptr);
+int splade_peer_free(void* dptr);
+int splade_peer_export(const void* dptr, void* handle_out /* 64 bytes, cudaIpcMemHandle_t */);
+int splade_peer_open(const void* handle /* 64 bytes from another process */, void** dptr_out);
+int splade_peer_close(void* dptr);
+/* synchronous read of the local window's status word: 0 = every barrier so far was answered */
+int splade_peer_status(const splade_peer_group* group, int32_t* status_host);
+
+/*
+ * SPLADELossV33 forward with gathered positives.  `args` as for splade_v33_loss_fwd with args->docs = the
+ * LOCAL positives [Bq,V] and args->N = Bq; labels are rank*Bq + i; args->g_inbatch is ignored (the [Bq, W*Bq]
+ * gradient lives in the window, where the peers read it); args->workspace is sized by
+ * splade_workspace_bytes(SPLADE_OP_V33_LOSS_FWD, Bq, world*Bq, 0, V, k).  KL-KD is not available (teacher
+ * scores are [Bq,Bq]).  docs_all [world*Bq, V] fp32 (out) must be kept for splade_peer_loss_bwd.  V % 4 == 0.
+ */
+int splade_peer_v33_loss_fwd(const splade_v33_fwd_args* args, const splade_peer_group* group, uint32_t epoch,
+                             float* docs_all, void* stream);
+
+/*
+ * Backward of the same (formulas of splade_loss_bwd); ddocs_local [Bq,V] is the gradient of the LOCAL positives
+ * summed over every rank's queries.  workspace: splade_workspace_bytes(SPLADE_OP_PEER_LOSS_BWD, Bq,0,0,0, world).
+ */
+int splade_peer_loss_bwd(const splade_peer_group* group, uint32_t epoch, const float* q, const float* docs_all,
+                         const float* negs, int Bq, int k, int V, const float* g_hard, const float* colmean_q,
+                         const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
+                         const float* g_loss, float* dq, float* ddocs_local, float* dnegs, void* workspace,
+                         size_t ws_bytes, void* stream);
 
 /*
  * ---------------------------------------------------------------------------------------------------------------

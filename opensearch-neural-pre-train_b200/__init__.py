@@ -10,12 +10,13 @@ from .distributed import all_gather_documents, shard_range  # noqa: F401
 from .encoder import SPLADEModernBERT  # noqa: F401
 from .ops import (HostEncodeSlot, flops_nnz, head_backward, head_forward, head_forward_host, rowdot, scores,  # noqa: F401
                   splade_head, topk)
+from .peer_exchange import PeerExchange  # noqa: F401
 from .sparse_emit import SparseEmitter, build_blocklist, bulk_encode  # noqa: F401
 from .trunk import NativeTrunk, trunk_attention, trunk_gemm  # noqa: F401
 from .v33_loss import SPLADELossV33  # noqa: F401
 
 __all__ = [
-    "SPLADEModernBERT", "SPLADELossV33", "SparseEmitter", "build_blocklist", "bulk_encode",
+    "SPLADEModernBERT", "SPLADELossV33", "PeerExchange", "SparseEmitter", "build_blocklist", "bulk_encode",
     "splade_head", "head_forward", "head_forward_host", "HostEncodeSlot", "head_backward", "flops_nnz", "scores", "rowdot", "topk",
     "NativeTrunk", "trunk_gemm", "trunk_attention", "all_gather_documents", "shard_range", "load_library", "LIB_PATH", "ABI_VERSION",
 ]

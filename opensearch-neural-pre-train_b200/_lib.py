@@ -8,11 +8,11 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p)
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_uint32, c_void_p)
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libsplade_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # op ids for splade_workspace_bytes (include/splade_b200.h)
 OP_HEAD_FWD = 0
@@ -24,6 +24,8 @@ OP_V33_LOSS_FWD = 5
 OP_TRUNK_ENCODE = 6
 OP_TRUNK_GEMM = 7
 OP_TRUNK_ATTN = 8
+OP_PEER_LOSS_BWD = 9
+MAX_PEERS = 16
 
 # epilogues of splade_trunk_gemm
 EPI_BF16, EPI_GELU, EPI_RESID, EPI_GEGLU = 0, 1, 2, 3
@@ -86,6 +88,13 @@ class TrunkArgs(Structure):
     ]
 
 
+class PeerGroup(Structure):
+    """Mirror of ``splade_peer_group`` (include/splade_b200.h)."""
+
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("Bq", c_int32), ("V", c_int32),
+                ("window", c_void_p * MAX_PEERS)]
+
+
 # name -> (restype, argtypes); every symbol include/splade_b200.h declares
 EXPORTS = {
     "splade_abi_version": (c_int, []),
@@ -118,6 +127,17 @@ EXPORTS = {
     "splade_trunk_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "splade_topk": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "splade_peer_window_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "splade_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "splade_peer_free": (c_int, [c_void_p]),
+    "splade_peer_export": (c_int, [c_void_p, c_void_p]),
+    "splade_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "splade_peer_close": (c_int, [c_void_p]),
+    "splade_peer_status": (c_int, [POINTER(PeerGroup), POINTER(c_int32)]),
+    "splade_peer_v33_loss_fwd": (c_int, [POINTER(V33FwdArgs), POINTER(PeerGroup), c_uint32, c_void_p, c_void_p]),
+    "splade_peer_loss_bwd": (c_int, [POINTER(PeerGroup), c_uint32, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

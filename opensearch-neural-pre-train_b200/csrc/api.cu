@@ -156,6 +156,8 @@ size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k) {
     case SPLADE_OP_TRUNK_ATTN:
       return ((varlen_layout_bytes(B, S, 1) + 255) & ~static_cast<size_t>(255)) +
              static_cast<size_t>(S > 0 ? S : 1) * 32 * sizeof(float2);
+    case SPLADE_OP_PEER_LOSS_BWD:
+      return peer_loss_bwd_workspace_bytes(B, k);
     default:
       return 0;
   }

@@ -87,11 +87,15 @@ int flops_nnz_launch(const float* rep, int N, int V, float* colmean, float* out2
                      size_t ws_bytes, cudaStream_t stream);
 size_t scores_workspace_bytes(int Bq, int N, int V);
 int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int round_bf16, float* raw,
-                  void* workspace, size_t ws_bytes, cudaStream_t stream);
+                  void* workspace, size_t ws_bytes, cudaStream_t stream, bool docs_prepacked = false);
 int rowdot_launch(const float* q, const float* docs, int Bq, int k, int V, float* out, cudaStream_t stream);
 int v33_scalars_launch(const struct splade_v33_scalar_args* args, cudaStream_t stream);
 size_t v33_loss_fwd_workspace_bytes(int Bq, int N, int V, int k);
-int v33_loss_fwd_launch(const struct splade_v33_fwd_args* args, cudaStream_t stream);
+int v33_loss_fwd_launch(const struct splade_v33_fwd_args* args, cudaStream_t stream, bool docs_prepacked = false);
+void* v33_loss_fwd_scores_ws(const struct splade_v33_fwd_args* args);
+int loss_bwd_dq_launch(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,
+                       const float* g_inbatch, const float* g_hard, const float* colmean_q, const float* colmean_n,
+                       float cq, float cn, const float* g_loss, float* dq, float* dnegs, cudaStream_t stream);
 int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,
                     int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
                     const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
@@ -100,7 +104,13 @@ int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq
 // scores_tc.cu (tcgen05 path used when round_bf16 != 0)
 size_t scores_tc_workspace_bytes(int Bq, int N, int V);
 int scores_tc_launch(const float* q, int Bq, const float* docs, int N, int V, void* workspace, size_t ws_bytes,
-                     float** partial_out, int* ksplit_out, cudaStream_t stream);
+                     float** partial_out, int* ksplit_out, bool docs_prepacked, cudaStream_t stream);
+void* scores_tc_docs16(void* workspace, int Bq, int N, int V, int* Vp_out);
+
+// peer.cu: cross-GPU negatives over NVLink peer memory (include/splade_b200.h, splade_peer_*)
+struct PeerGroupView;
+size_t peer_window_bytes(int Bq, int V, int world);
+size_t peer_loss_bwd_workspace_bytes(int Bq, int world);
 
 // topk.cu
 int topk_launch(const float* rep, int B, int V, const uint8_t* blocklist, int k, int32_t* ids, float* vals,

@@ -662,7 +662,7 @@ size_t scores_workspace_bytes(int Bq, int N, int V) {
 }
 
 int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int round_bf16, float* raw,
-                  void* workspace, size_t ws_bytes, cudaStream_t stream) {
+                  void* workspace, size_t ws_bytes, cudaStream_t stream, bool docs_prepacked) {
   if (!q || !docs || !raw) return set_error(kErrInvalidArg, "splade_scores: null pointer argument");
   if (Bq < 1 || N < 1 || V < 1) return set_error(kErrInvalidArg, "splade_scores: bad sizes Bq=%d N=%d V=%d", Bq, N, V);
   const size_t n_out = static_cast<size_t>(Bq) * N;
@@ -670,7 +670,7 @@ int scores_launch(const float* q, int Bq, const float* docs, int N, int V, int r
     // autocast mode: bf16 operands, fp32 accumulate -> tcgen05 tensor-core path (scores_tc.cu)
     float* tc_partial = nullptr;
     int tc_ksplit = 0;
-    const int rc = scores_tc_launch(q, Bq, docs, N, V, workspace, ws_bytes, &tc_partial, &tc_ksplit, stream);
+    const int rc = scores_tc_launch(q, Bq, docs, N, V, workspace, ws_bytes, &tc_partial, &tc_ksplit, docs_prepacked, stream);
     if (rc != kOk) return rc;
     scores_reduce_kernel<<<static_cast<unsigned>((n_out + 7) / 8), 256, 0, stream>>>(tc_partial, tc_ksplit, n_out,
                                                                                    raw);
@@ -731,7 +731,14 @@ size_t v33_loss_fwd_workspace_bytes(int Bq, int N, int V, int k) {
          align256(static_cast<size_t>(Bq) * 4) + align256(6 * 4) + align256(static_cast<size_t>(3) * Bq * 4);
 }
 
-int v33_loss_fwd_launch(const splade_v33_fwd_args* a, cudaStream_t stream) {
+// The scores workspace inside the forward workspace (layout of v33_loss_fwd_launch below).
+void* v33_loss_fwd_scores_ws(const splade_v33_fwd_args* a) {
+  const size_t flops_ws =
+      align256(std::max(flops_workspace_bytes(a->Bq, a->V), flops_workspace_bytes(a->Bq * a->k, a->V)));
+  return static_cast<uint8_t*>(a->workspace) + flops_ws;
+}
+
+int v33_loss_fwd_launch(const splade_v33_fwd_args* a, cudaStream_t stream, bool docs_prepacked) {
   if (!a) return set_error(kErrInvalidArg, "splade_v33_loss_fwd: null args");
   if (a->Bq < 1 || a->N < 1 || a->k < 1 || a->V < 1)
     return set_error(kErrInvalidArg, "splade_v33_loss_fwd: bad sizes Bq=%d N=%d k=%d V=%d", a->Bq, a->N, a->k, a->V);
@@ -768,7 +775,8 @@ int v33_loss_fwd_launch(const splade_v33_fwd_args* a, cudaStream_t stream) {
   rc = flops_nnz_launch(a->negs, Bq * k, V, a->colmean + 2 * static_cast<size_t>(V), flops3 + 4, w_flops, flops_ws,
                         stream);
   if (rc != kOk) return rc;
-  rc = scores_launch(a->q, Bq, a->docs, N, V, a->round_bf16, raw_in, w_scores, scores_ws, stream);
+  rc = scores_launch(a->q, Bq, a->docs, N, V, a->round_bf16, raw_in, w_scores, scores_ws, stream,
+                     docs_prepacked && a->round_bf16);
   if (rc != kOk) return rc;
   rc = rowdot_launch(a->q, a->negs, Bq, k, V, raw_hard, stream);
   if (rc != kOk) return rc;
@@ -829,6 +837,23 @@ int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq
                                                          g_hard, colmean_q, colmean_d, colmean_n, cq, cd, cn,
                                                          g_loss, dq, ddocs, dnegs);
   }
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+// dq and dnegs only (vectorised kernel): the peer exchange computes ddocs itself (peer.cu).
+int loss_bwd_dq_launch(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,
+                       const float* g_inbatch, const float* g_hard, const float* colmean_q, const float* colmean_n,
+                       float cq, float cn, const float* g_loss, float* dq, float* dnegs, cudaStream_t stream) {
+  if (!q || !docs || !negs || !g_inbatch || !g_hard || !colmean_q || !colmean_n || !g_loss || !dq || !dnegs)
+    return set_error(kErrInvalidArg, "splade_peer_loss_bwd: null pointer argument");
+  auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+  if (V % 4 != 0 || !aligned16(q) || !aligned16(docs) || !aligned16(negs) || !aligned16(dq) || !aligned16(dnegs) ||
+      !aligned16(colmean_q) || !aligned16(colmean_n))
+    return set_error(kErrUnsupportedShape, "splade_peer_loss_bwd: V %% 4 == 0 and 16-byte aligned rows are required");
+  const unsigned cx = static_cast<unsigned>((V / 4 + 127) / 128);
+  loss_bwd_dq_kernel<<<dim3(cx, (Bq + VT - 1) / VT), 128, 0, stream>>>(q, docs, negs, Bq, N, k, V, g_inbatch, g_hard,
+                                                                      colmean_q, colmean_n, cq, cn, g_loss, dq, dnegs);
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }

@@ -191,9 +191,18 @@ size_t scores_tc_workspace_bytes(int Bq, int N, int V) {
          align256(static_cast<size_t>(ksplit) * Bq * N * sizeof(float));
 }
 
+// Where scores_tc_launch keeps the bf16 document operand inside its workspace ([N, *Vp] bf16): the peer gather
+// kernel (peer.cu) writes it there directly and then launches with docs_prepacked = true.
+void* scores_tc_docs16(void* workspace, int Bq, int N, int V, int* Vp_out) {
+  int Vp, n_tile, m_tiles, n_tiles, kb_total, kb_per_cta, ksplit;
+  plan(Bq, N, V, &Vp, &n_tile, &m_tiles, &n_tiles, &kb_total, &kb_per_cta, &ksplit);
+  *Vp_out = Vp;
+  return static_cast<uint8_t*>(workspace) + align256(static_cast<size_t>(Bq) * Vp * 2);
+}
+
 // Returns the number of k-splits written to `*partial_out` ([ksplit][Bq][N]); the caller reduces them.
 int scores_tc_launch(const float* q, int Bq, const float* docs, int N, int V, void* workspace, size_t ws_bytes,
-                     float** partial_out, int* ksplit_out, cudaStream_t stream) {
+                     float** partial_out, int* ksplit_out, bool docs_prepacked, cudaStream_t stream) {
   int rc = require_sm100("splade_scores");
   if (rc != kOk) return rc;
   int Vp, n_tile, m_tiles, n_tiles, kb_total, kb_per_cta, ksplit;
@@ -210,7 +219,7 @@ int scores_tc_launch(const float* q, int Bq, const float* docs, int N, int V, vo
 
   const unsigned chunks = static_cast<unsigned>((Vp / 8 + 255) / 256);
   pack_bf16_kernel<<<dim3(chunks, Bq), 256, 0, stream>>>(q, V, Vp, q16);
-  pack_bf16_kernel<<<dim3(chunks, N), 256, 0, stream>>>(docs, V, Vp, d16);
+  if (!docs_prepacked) pack_bf16_kernel<<<dim3(chunks, N), 256, 0, stream>>>(docs, V, Vp, d16);
   SPLADE_CUDA_OK(cudaGetLastError());
 
   CUtensorMap tmap_q, tmap_d;

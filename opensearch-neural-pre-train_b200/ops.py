@@ -341,3 +341,78 @@ class V33LossFunction(torch.autograd.Function):
                                       gl.data_ptr(), dq.data_ptr(), ddocs.data_ptr(), dnegs.data_ptr(),
                                       _stream(q)), "splade_loss_bwd")
         return dq.to(qd), ddocs.to(dd), dnegs.view(nshape).to(nd), None, None, None, None
+
+
+class V33PeerLossFunction(torch.autograd.Function):
+    """``V33LossFunction`` with the positives of every rank as in-batch documents, exchanged through
+    ``PeerExchange`` windows by the kernels themselves (``splade_peer_v33_loss_fwd`` / ``splade_peer_loss_bwd``):
+    no NCCL all-gather forward, no ``[W*B, V]`` gradient and no reduce-scatter backward.  Returns the gradient
+    of the LOCAL positives summed over every rank's queries - what all-gather + reduce-scatter(sum) produce."""
+
+    @staticmethod
+    def forward(ctx, anchor, docs_local, negatives, teacher_pos, teacher_neg, cfg: dict, exchange):
+        lib = load_library()
+        _require_cuda(anchor, "anchor_repr")
+        dev = anchor.device
+        q = _f32c(anchor)
+        d = _f32c(docs_local)
+        n = _f32c(negatives)
+        Bq, V = q.shape
+        k = n.shape[1]
+        W = exchange.world
+        if (Bq, V) != (exchange.batch, exchange.vocab) or tuple(d.shape) != (Bq, V):
+            raise RuntimeError(f"SPLADELossV33: the peer exchange was built for batch {exchange.batch} x vocabulary "
+                               f"{exchange.vocab}, got queries {tuple(q.shape)} / positives {tuple(d.shape)}")
+        round_bf16 = bool(cfg["round_bf16"])
+        has_mmse = teacher_pos is not None and teacher_neg is not None and cfg["lambda_mmse"] > 0
+        epoch = exchange.next_epoch()
+        with torch.cuda.device(dev):
+            colmean = torch.empty((3, V), dtype=torch.float32, device=dev)
+            scalars = torch.empty((16,), dtype=torch.float32, device=dev)
+            g_hard = torch.empty((Bq, k), dtype=torch.float32, device=dev)
+            docs_all = torch.empty((W * Bq, V), dtype=torch.float32, device=dev)
+            t_pos = _f32c(teacher_pos).view(Bq) if has_mmse else None
+            t_neg = _f32c(teacher_neg).view(Bq, k) if has_mmse else None
+            nbytes = lib.splade_workspace_bytes(_lib.OP_V33_LOSS_FWD, Bq, W * Bq, 0, V, k)
+            ws, ws_ptr = _ws(nbytes, dev)
+            args = _lib.V33FwdArgs(
+                Bq=Bq, N=Bq, k=k, V=V, label_offset=0, round_bf16=int(round_bf16), has_kd=0,
+                has_mmse=int(has_mmse),
+                temperature=cfg["temperature"], kd_temperature=cfg["kd_temperature"],
+                lambda_q=cfg["lambda_q"], lambda_d=cfg["lambda_d"], lambda_neg=cfg["lambda_neg"],
+                lambda_kd=0.0, lambda_mmse=cfg["lambda_mmse"], reserved_f=0.0,
+                q=q.data_ptr(), docs=d.data_ptr(), negs=n.data_ptr(),
+                teacher_kd=None, teacher_pos=_ptr(t_pos), teacher_neg=_ptr(t_neg),
+                colmean=colmean.data_ptr(), scalars=scalars.data_ptr(), g_inbatch=None,
+                g_hard=g_hard.data_ptr(), workspace=ws_ptr, ws_bytes=nbytes)
+            check(lib.splade_peer_v33_loss_fwd(ctypes.byref(args), ctypes.byref(exchange.group_struct), epoch,
+                                               docs_all.data_ptr(), _stream(q)), "splade_peer_v33_loss_fwd")
+        ctx.save_for_backward(q, docs_all, n, g_hard, colmean)
+        ctx.exchange, ctx.epoch = exchange, epoch
+        ctx.meta = (Bq, k, V, cfg["lambda_q"], cfg["lambda_d"], cfg["lambda_neg"],
+                    anchor.dtype, docs_local.dtype, negatives.dtype, tuple(negatives.shape))
+        loss = scalars[0].clone()
+        ctx.mark_non_differentiable(scalars)
+        return loss, scalars
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_scalars):
+        lib = load_library()
+        q, docs_all, n, g_hard, colmean = ctx.saved_tensors
+        Bq, k, V, lq, ld, ln, qd, dd, nd, nshape = ctx.meta
+        x = ctx.exchange
+        dev = q.device
+        gl = _f32c(g_loss).reshape(1)
+        with torch.cuda.device(dev):
+            dq = torch.empty_like(q)
+            ddocs = torch.empty_like(q)
+            dnegs = torch.empty_like(n)
+            nbytes = lib.splade_workspace_bytes(_lib.OP_PEER_LOSS_BWD, Bq, 0, 0, 0, x.world)
+            ws, ws_ptr = _ws(nbytes, dev)
+            check(lib.splade_peer_loss_bwd(ctypes.byref(x.group_struct), ctx.epoch, q.data_ptr(),
+                                           docs_all.data_ptr(), n.data_ptr(), Bq, k, V, g_hard.data_ptr(),
+                                           colmean[0].data_ptr(), colmean[1].data_ptr(), colmean[2].data_ptr(),
+                                           2.0 * lq / Bq, 2.0 * ld / Bq, 2.0 * ln / (Bq * k), gl.data_ptr(),
+                                           dq.data_ptr(), ddocs.data_ptr(), dnegs.data_ptr(), ws_ptr, nbytes,
+                                           _stream(q)), "splade_peer_loss_bwd")
+        return dq.to(qd), ddocs.to(dd), dnegs.view(nshape).to(nd), None, None, None, None

@@ -17,7 +17,7 @@ from typing import Dict, Optional, Tuple
 import torch
 import torch.nn as nn
 
-from .ops import V33LossFunction
+from .ops import V33LossFunction, V33PeerLossFunction
 
 _SCALAR_KEYS = ("loss", "infonce", "flops_q", "flops_d", "flops_neg", "kd", "margin_mse", "nonzero_q",
                 "nonzero_d")
@@ -39,6 +39,7 @@ class SPLADELossV33(nn.Module):
         lambda_neg: float = 0.0,
         gather_negatives: Optional[bool] = None,
         process_group=None,
+        exchange=None,
     ):
         super().__init__()
         self.lambda_q = lambda_q
@@ -55,6 +56,11 @@ class SPLADELossV33(nn.Module):
             gather_negatives = os.environ.get("SPLADE_B200_GATHER_NEGATIVES", "0") == "1"
         self.gather_negatives = bool(gather_negatives)
         self.process_group = process_group
+        # a PeerExchange (peer_exchange.py): gathered negatives through NVLink peer memory inside the loss
+        # kernels instead of NCCL all-gather / reduce-scatter around them
+        self.exchange = exchange
+        if exchange is not None:
+            self.gather_negatives = True
 
         # Monitoring state (losses.py:53-55)
         self._avg_nonzero_q = 0.0
@@ -89,12 +95,13 @@ class SPLADELossV33(nn.Module):
             teacher_neg_scores = teacher_neg_scores.unsqueeze(1)
 
         docs, label_offset = positive_repr, 0
-        if self.gather_negatives:
+        use_peer = self.exchange is not None and self.exchange.world > 1
+        if self.gather_negatives and not use_peer:
             from .distributed import all_gather_documents
             docs, label_offset = all_gather_documents(positive_repr, self.process_group)
 
         use_kd = self.lambda_kd > 0 and teacher_scores is not None
-        if use_kd and docs.shape[0] != anchor_repr.shape[0]:
+        if use_kd and (use_peer or docs.shape[0] != anchor_repr.shape[0]):
             raise RuntimeError("SPLADELossV33: KL-KD teacher_scores [B,B] cannot be combined with gathered negatives")
         use_mmse = (self.lambda_margin_mse > 0 and teacher_pos_scores is not None
                     and teacher_neg_scores is not None)
@@ -108,13 +115,21 @@ class SPLADELossV33(nn.Module):
             lambda_kd=float(self.lambda_kd) if use_kd else 0.0,
             lambda_mmse=float(self.lambda_margin_mse) if use_mmse else 0.0,
         )
-        loss, scalars = V33LossFunction.apply(
-            anchor_repr, docs, negs,
-            teacher_scores if use_kd else None,
-            teacher_pos_scores if use_mmse else None,
-            teacher_neg_scores if use_mmse else None,
-            cfg,
-        )
+        if use_peer:
+            loss, scalars = V33PeerLossFunction.apply(
+                anchor_repr, positive_repr, negs,
+                teacher_pos_scores if use_mmse else None,
+                teacher_neg_scores if use_mmse else None,
+                cfg, self.exchange,
+            )
+        else:
+            loss, scalars = V33LossFunction.apply(
+                anchor_repr, docs, negs,
+                teacher_scores if use_kd else None,
+                teacher_pos_scores if use_mmse else None,
+                teacher_neg_scores if use_mmse else None,
+                cfg,
+            )
 
         vals = scalars[: len(_SCALAR_KEYS)].tolist()  # the single device->host sync of this step
         s = dict(zip(_SCALAR_KEYS, vals))

@@ -49,6 +49,23 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(V33FwdArgs) == 8 * 4 + 8 * 4 + 11 * 8 + 8
 
 
+def test_peer_exchange_sizing_and_struct():
+    """Host-only pieces of the NVLink peer exchange: struct mirror, window and workspace sizes (no device call)."""
+    import ctypes
+    import splade_b200
+    from splade_b200 import _lib
+    lib = splade_b200.load_library()
+    assert ctypes.sizeof(_lib.PeerGroup) == 4 * 4 + _lib.MAX_PEERS * 8
+    B, V, W = 64, 50000, 8
+    rep, g = B * V * 4, B * W * B * 4
+    # header + 2 parities x (Q, P, G, gl), every region 256-byte aligned
+    assert lib.splade_peer_window_bytes(B, V, W) == 512 + 2 * (2 * rep + g + 256)
+    assert lib.splade_peer_window_bytes(B, V, _lib.MAX_PEERS + 1) == 0
+    assert lib.splade_workspace_bytes(_lib.OP_PEER_LOSS_BWD, B, 0, 0, 0, W) == W * B * B * 4
+    with pytest.raises(RuntimeError, match="process group"):
+        splade_b200.PeerExchange(B, V)
+
+
 def test_product_refuses_cpu_tensors():
     import torch
     import splade_b200
