@@ -19,7 +19,8 @@
 //     D2D   g_loss -> gl                                                   (publish)
 //     K3    loss_bwd_dq_kernel       dq, dnegs from the local docs_all copy (loss.cu)
 //     K4    peer_bwd_sync_kernel     CTA s: flag e into peer s's slot 1, wait for its flag, pull gl_s * G_s[:, mine]
-//     K5    peer_ddocs_kernel        ddocs_local = sum_s (gl_s G_s[:, mine])^T q_s, q_s read from peer s's window
+//     K5    peer_ddocs_kernel        ddocs_local = sum_s (gl_s G_s[:, mine])^T q_s, q_s TMA-bulk-copied from peer
+//                                    s's window into shared memory (3-stage mbarrier pipeline)
 //
 // Double buffering makes one barrier per phase sufficient: a window half is rewritten at epoch e+2, after its
 // owner passed the epoch e+1 barrier, which every peer only signals after its epoch e kernels (stream order).
@@ -131,14 +132,18 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerPtrs g, int 
 // ---------------------------------------------------------------------------------------------
 struct GatherParams {
   const float* seg[kMaxPeers];
+  int W, rank;
   int rows, V, Vp;
   float* out32;            // [W*rows, V]
   __nv_bfloat16* out16;    // [W*rows, Vp] or nullptr
 };
 
 __global__ void __launch_bounds__(256) peer_gather_kernel(const GatherParams p) {
-  const int row = blockIdx.y;
-  const int s = row / p.rows, r = row - s * p.rows;
+  // Consecutive CTAs read from DIFFERENT ranks, and rank r starts its rotation at r+1: at any moment every
+  // rank's requests are spread over all peers, so no peer's NVLink egress serves W-1 readers while the rest idle.
+  const int r = blockIdx.y / p.W;
+  const int s = (p.rank + 1 + static_cast<int>(blockIdx.y % p.W)) % p.W;
+  const int row = s * p.rows + r;
   const int v0 = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (v0 >= p.Vp) return;
   const float* src = p.seg[s] + static_cast<size_t>(r) * p.V;
@@ -190,76 +195,149 @@ __global__ void __launch_bounds__(256) peer_bwd_sync_kernel(const BwdParams p) {
   const float* Gs = reinterpret_cast<const float*>(p.g.win[s] + p.g_off);
   const float gls = ld_f1(reinterpret_cast<const float*>(p.g.win[s] + p.gl_off));
   float* out = p.gloc + static_cast<size_t>(s) * Bq * Bq;
-  for (int e = threadIdx.x; e < Bq * Bq; e += blockDim.x) {
-    const int i = e / Bq, j = e - i * Bq;
-    out[e] = gls * ld_f1(Gs + static_cast<size_t>(i) * N + p.g.rank * Bq + j);
+  for (int base = 0; base < Bq * Bq; base += 256 * 8) {  // eight remote loads in flight per thread
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = base + u * 256 + static_cast<int>(threadIdx.x);
+      const int i = e / Bq, j = e - i * Bq;
+      v[u] = (e < Bq * Bq) ? ld_f1(Gs + static_cast<size_t>(i) * N + p.g.rank * Bq + j) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = base + u * 256 + static_cast<int>(threadIdx.x);
+      if (e < Bq * Bq) out[e] = gls * v[u];
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // K5: ddocs_local[j, :] = sum_s sum_i Gloc[s][i][j] * q_s[i, :] + gl_rank * cd * colmean_d
-// Each thread owns two vocabulary columns and PD local documents (accumulators in registers); q rows are read
-// straight from the owning rank's window, eight 8-byte loads in flight per thread, each element exactly once.
+// A CTA owns 256 vocabulary columns and PD local documents; each thread two columns, accumulators in
+// registers.  The q rows come straight out of the owning rank's window: one elected thread issues TMA bulk
+// copies (cp.async.bulk, 1 KB per row, 16 rows per stage, 3 stages) that land in shared memory and complete
+// on an mbarrier, so ~32 KB per CTA are in flight over NVLink while the previous tile is being multiplied.
+// Every q element crosses the link exactly once.  CTAs start their rotation over the ranks at different
+// peers (rank + 1 + blockIdx.x), which spreads the reads over all links at all times.
 // ---------------------------------------------------------------------------------------------
-constexpr int PD = 64;   // local documents per CTA
-constexpr int PK = 16;   // queries per staged tile of G
-constexpr int PKP = 20;  // padded row of the staged tile (keeps 16-byte alignment, spreads banks)
+constexpr int PD = 64;        // local documents per CTA
+constexpr int PK = 16;        // query rows per stage
+constexpr int PKP = 20;       // padded row of the staged G tile (keeps 16-byte alignment, spreads banks)
+constexpr int PCOLS = 256;    // vocabulary columns per CTA
+constexpr int PSTAGES = 3;
+constexpr int PSTAGE_BYTES = PK * PCOLS * 4;
+constexpr int PDDOCS_SMEM = PSTAGES * PSTAGE_BYTES + PD * PKP * 4 + PSTAGES * 8 + 128;
+
+__device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// mbar_wait of common.cuh reports a timeout with printf, which gives the kernel a stack frame; the first launch of
+// a kernel with a larger local-memory footprint than any before it makes the driver synchronise the device, and
+// that must not happen while a peer's barrier kernel is waiting for this rank.  Same bound, no message.
+__device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(addr, parity)) {
+    if (clock64() - t0 > SPLADE_MBAR_TIMEOUT_CYCLES) __trap();
+  }
+}
 
 __global__ void __launch_bounds__(128) peer_ddocs_kernel(const BwdParams p) {
-  __shared__ __align__(16) float Gt[PD][PKP];  // Gt[jj][ii] = Gloc[s][i0+ii][j0+jj]
-  const int Bq = p.Bq, n2 = p.V >> 1;
-  const int c2 = blockIdx.x * 128 + threadIdx.x;
-  const bool live = c2 < n2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  float* stage_base = reinterpret_cast<float*>(smem);                                   // [PSTAGES][PK][PCOLS]
+  float(*Gt)[PKP] = reinterpret_cast<float(*)[PKP]>(smem + PSTAGES * PSTAGE_BYTES);    // Gt[jj][ii]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PSTAGES * PSTAGE_BYTES + PD * PKP * 4);
+
+  const int Bq = p.Bq, V = p.V, W = p.g.world;
+  const int c0 = blockIdx.x * PCOLS;
+  const int cols = min(PCOLS, V - c0);            // multiple of 4 (V % 4 == 0)
+  const uint32_t row_bytes = static_cast<uint32_t>(cols) * 4u;
+  const int c = c0 + 2 * static_cast<int>(threadIdx.x);
+  const bool live = 2 * static_cast<int>(threadIdx.x) < cols;
   const int j0 = blockIdx.y * PD;
+  const int tiles_per_rank = (Bq + PK - 1) / PK;
+  const int T = W * tiles_per_rank;
+  const int s_first = (p.g.rank + 1 + static_cast<int>(blockIdx.x)) % W;
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < PSTAGES; ++st) mbar_init(&full_bar[st], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // thread 0 only; a macro-like helper without a closure object (the kernel must not need a stack frame: the
+  // first launch of a kernel with a larger local-memory footprint synchronises the device)
+#define SPLADE_PEER_ISSUE(t_)                                                                                     \
+  do {                                                                                                            \
+    const int t__ = (t_);                                                                                         \
+    const int s__ = (s_first + t__ / tiles_per_rank) % W;                                                         \
+    const int i__ = (t__ % tiles_per_rank) * PK;                                                                  \
+    const int rows__ = min(PK, Bq - i__);                                                                         \
+    const int st__ = t__ % PSTAGES;                                                                               \
+    const float* src__ =                                                                                          \
+        reinterpret_cast<const float*>(p.g.win[s__] + p.q_off) + static_cast<size_t>(i__) * V + c0;               \
+    float* dst__ = stage_base + static_cast<size_t>(st__) * PK * PCOLS;                                           \
+    mbar_arrive_expect_tx(&full_bar[st__], row_bytes * static_cast<uint32_t>(rows__));                            \
+    for (int r__ = 0; r__ < rows__; ++r__)                                                                        \
+      bulk_load_row(dst__ + r__ * PCOLS, src__ + static_cast<size_t>(r__) * V, row_bytes, &full_bar[st__]);       \
+  } while (0)
+
+  if (threadIdx.x == 0)
+    for (int t = 0; t < PSTAGES - 1 && t < T; ++t) SPLADE_PEER_ISSUE(t);
+
   float2 acc[PD];
 #pragma unroll
   for (int jj = 0; jj < PD; ++jj) acc[jj] = make_float2(0.f, 0.f);
 
-  for (int s = 0; s < p.g.world; ++s) {
-    const float* qs = reinterpret_cast<const float*>(p.g.win[s] + p.q_off) + 2 * static_cast<size_t>(c2);
+  for (int t = 0; t < T; ++t) {
+    const int s = (s_first + t / tiles_per_rank) % W;
+    const int i0 = (t % tiles_per_rank) * PK;
+    const int st = t % PSTAGES;
+    __syncthreads();  // everyone is done with tile t-1: its stage and Gt may be overwritten
+    if (threadIdx.x == 0 && t + PSTAGES - 1 < T) SPLADE_PEER_ISSUE(t + PSTAGES - 1);
     const float* gl = p.gloc + static_cast<size_t>(s) * Bq * Bq;
-    for (int i0 = 0; i0 < Bq; i0 += PK) {
-      __syncthreads();
-      for (int e = threadIdx.x; e < PD * PK; e += 128) {
-        const int ii = e / PD, jj = e - ii * PD;  // consecutive threads -> consecutive local documents
-        Gt[jj][ii] = (i0 + ii < Bq && j0 + jj < Bq) ? gl[static_cast<size_t>(i0 + ii) * Bq + j0 + jj] : 0.f;
-      }
-      __syncthreads();
+    for (int e = threadIdx.x; e < PD * PK; e += 128) {
+      const int ii = e / PD, jj = e - ii * PD;  // consecutive threads -> consecutive local documents
+      Gt[jj][ii] = (i0 + ii < Bq && j0 + jj < Bq) ? gl[static_cast<size_t>(i0 + ii) * Bq + j0 + jj] : 0.f;
+    }
+    __syncthreads();
+    mbar_wait_quiet(&full_bar[st], static_cast<uint32_t>((t / PSTAGES) & 1));
+    const float* xs = stage_base + static_cast<size_t>(st) * PK * PCOLS + 2 * threadIdx.x;
 #pragma unroll
-      for (int h = 0; h < PK; h += 8) {
-        float2 x[8];
+    for (int h = 0; h < PK; h += 4) {
+      float2 x[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          x[u] = (live && i0 + h + u < Bq) ? ld_f2(qs + static_cast<size_t>(i0 + h + u) * p.V) : make_float2(0.f, 0.f);
+      for (int u = 0; u < 4; ++u)  // rows past the batch were not loaded: never touch their (stale) bytes
+        x[u] = (live && i0 + h + u < Bq) ? *reinterpret_cast<const float2*>(xs + (h + u) * PCOLS) : make_float2(0.f, 0.f);
 #pragma unroll
-        for (int jj = 0; jj < PD; ++jj) {
-          const float4 ga = *reinterpret_cast<const float4*>(&Gt[jj][h]);
-          const float4 gb = *reinterpret_cast<const float4*>(&Gt[jj][h + 4]);
-          float2 a = acc[jj];
-          a.x = fmaf(ga.x, x[0].x, a.x); a.y = fmaf(ga.x, x[0].y, a.y);
-          a.x = fmaf(ga.y, x[1].x, a.x); a.y = fmaf(ga.y, x[1].y, a.y);
-          a.x = fmaf(ga.z, x[2].x, a.x); a.y = fmaf(ga.z, x[2].y, a.y);
-          a.x = fmaf(ga.w, x[3].x, a.x); a.y = fmaf(ga.w, x[3].y, a.y);
-          a.x = fmaf(gb.x, x[4].x, a.x); a.y = fmaf(gb.x, x[4].y, a.y);
-          a.x = fmaf(gb.y, x[5].x, a.x); a.y = fmaf(gb.y, x[5].y, a.y);
-          a.x = fmaf(gb.z, x[6].x, a.x); a.y = fmaf(gb.z, x[6].y, a.y);
-          a.x = fmaf(gb.w, x[7].x, a.x); a.y = fmaf(gb.w, x[7].y, a.y);
-          acc[jj] = a;
-        }
+      for (int jj = 0; jj < PD; ++jj) {
+        const float4 g = *reinterpret_cast<const float4*>(&Gt[jj][h]);
+        float2 a = acc[jj];
+        a.x = fmaf(g.x, x[0].x, a.x); a.y = fmaf(g.x, x[0].y, a.y);
+        a.x = fmaf(g.y, x[1].x, a.x); a.y = fmaf(g.y, x[1].y, a.y);
+        a.x = fmaf(g.z, x[2].x, a.x); a.y = fmaf(g.z, x[2].y, a.y);
+        a.x = fmaf(g.w, x[3].x, a.x); a.y = fmaf(g.w, x[3].y, a.y);
+        acc[jj] = a;
       }
     }
   }
   if (!live) return;
   const float glr = ld_f1(reinterpret_cast<const float*>(p.g.win[p.g.rank] + p.gl_off));
-  const float2 md = *reinterpret_cast<const float2*>(p.cm_d + 2 * static_cast<size_t>(c2));
+  const float2 md = *reinterpret_cast<const float2*>(p.cm_d + c);
   const float fx = glr * p.cd * md.x, fy = glr * p.cd * md.y;
 #pragma unroll
   for (int jj = 0; jj < PD; ++jj) {
     const int j = j0 + jj;
     if (j < Bq)
-      *reinterpret_cast<float2*>(p.ddocs + static_cast<size_t>(j) * p.V + 2 * static_cast<size_t>(c2)) =
-          make_float2(acc[jj].x + fx, acc[jj].y + fy);
+      *reinterpret_cast<float2*>(p.ddocs + static_cast<size_t>(j) * V + c) = make_float2(acc[jj].x + fx, acc[jj].y + fy);
   }
+#undef SPLADE_PEER_ISSUE
 }
 
 unsigned long long timeout_ns_from_env() {
@@ -322,6 +400,9 @@ int splade_peer_alloc(size_t bytes, void** dptr) {
   SPLADE_CUDA_OK(cudaFuncGetAttributes(&fa, peer_gather_kernel));
   SPLADE_CUDA_OK(cudaFuncGetAttributes(&fa, peer_bwd_sync_kernel));
   SPLADE_CUDA_OK(cudaFuncGetAttributes(&fa, peer_ddocs_kernel));
+  // ... and configure them here for the same reason (the first cudaFuncSetAttribute on a function may block
+  // behind running kernels); windows are allocated on every device that will launch these kernels.
+  SPLADE_CUDA_OK(cudaFuncSetAttribute(peer_ddocs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PDDOCS_SMEM));
   void* p = nullptr;
   SPLADE_CUDA_OK(cudaMalloc(&p, bytes));
   cudaError_t e = cudaMemset(p, 0, bytes);
@@ -414,6 +495,8 @@ int splade_peer_v33_loss_fwd(const splade_v33_fwd_args* args, const splade_peer_
 
   GatherParams gp{};
   for (int s = 0; s < W; ++s) gp.seg[s] = reinterpret_cast<const float*>(ptrs.win[s] + L.p[b]);
+  gp.W = W;
+  gp.rank = group->rank;
   gp.rows = Bq;
   gp.V = V;
   gp.out32 = docs_all;
@@ -472,8 +555,9 @@ int splade_peer_loss_bwd(const splade_peer_group* group, uint32_t epoch, const f
   p.cd = cd;
   p.ddocs = ddocs_local;
   peer_bwd_sync_kernel<<<W, 256, 0, stream>>>(p);
-  const unsigned cx = static_cast<unsigned>((V / 2 + 127) / 128);
-  peer_ddocs_kernel<<<dim3(cx, static_cast<unsigned>((Bq + PD - 1) / PD)), 128, 0, stream>>>(p);
+  // (the kernel's dynamic shared memory limit is raised once per device in splade_peer_alloc)
+  const unsigned cx = static_cast<unsigned>((V + PCOLS - 1) / PCOLS);
+  peer_ddocs_kernel<<<dim3(cx, static_cast<unsigned>((Bq + PD - 1) / PD)), 128, PDDOCS_SMEM, stream>>>(p);
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }

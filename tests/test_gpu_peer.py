@@ -39,7 +39,7 @@ def _expected(q_all, p_all, n_all, W, Bq, k, cfg, scale):
         n = n_all[sl].clone().requires_grad_(True)
         loss, s = V33LossFunction.apply(q, docs, n, None, None, None, dict(cfg, label_offset=r * Bq))
         (loss * scale[r]).backward()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         scal.append(s[:9].cpu().numpy())
         dq.append(q.grad.clone())
         dn.append(n.grad.clone())
