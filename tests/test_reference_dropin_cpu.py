@@ -45,7 +45,7 @@ def test_signatures_equal_the_reference(ref):
     ours = _public_sig(splade_b200.SPLADELossV33.__init__)
     theirs = _public_sig(RefLoss.__init__)
     assert ours[:len(theirs)] == theirs            # same leading parameters; ours appends two opt-in keywords
-    assert [n for n, _, _ in ours[len(theirs):]] == ["gather_negatives", "process_group"]
+    assert [n for n, _, _ in ours[len(theirs):]] == ["gather_negatives", "process_group", "exchange"]
     for prop in ("vocab_size", "hidden_size"):
         assert isinstance(getattr(splade_b200.SPLADEModernBERT, prop), property)
         assert isinstance(getattr(RefModel, prop), property)
