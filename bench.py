@@ -223,9 +223,21 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
             except RuntimeError as e:  # e.g. CUDA IPC not permitted in this container
                 exchange_obj = None
                 exchange_used = f"nccl (peer exchange unavailable: {str(e)[:200]})"
-    loss_fn = splade_b200.SPLADELossV33(gather_negatives=gather, exchange=exchange_obj)
+    loss_box = [splade_b200.SPLADELossV33(gather_negatives=gather, exchange=exchange_obj)]
+
+    def exchange_ok():
+        """Collective: True when no rank saw a peer barrier time out (every rank gets the same answer)."""
+        ok = 1.0
+        try:
+            exchange_obj.check()
+        except RuntimeError:
+            ok = 0.0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item() > 0.5)
 
     def step(i):
+        loss_fn = loss_box[0]
         for t in (hq, hp, hn, W, bias):
             t.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -245,8 +257,14 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
 
     for i in range(warmup):
         d = step(i)
-    if exchange_obj is not None:
-        exchange_obj.check()
+    if exchange_obj is not None and not exchange_ok():
+        # every rank switches to the NCCL statement of the exchange together and warms up again
+        exchange_obj.close()
+        exchange_obj = None
+        exchange_used = "nccl (a peer-exchange barrier timed out during warm-up)"
+        loss_box[0] = splade_b200.SPLADELossV33(gather_negatives=gather)
+        for i in range(warmup):
+            d = step(i)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -259,13 +277,16 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
         dist.barrier()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    exchange_failed = False
     if exchange_obj is not None:
-        exchange_obj.check()
+        exchange_failed = not exchange_ok()
         exchange_obj.close()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if exchange_failed:
+        raise RuntimeError("a peer-exchange barrier timed out inside the timed region; the training leg is invalid")
     tokens = world * Bq * (64 + SEQ + SEQ * k_neg) * steps
     head_flop = 2.0 * HIDDEN * VOCAB * Bq * (64 + SEQ + SEQ * k_neg)
     return {"tokens_per_s": tokens / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
