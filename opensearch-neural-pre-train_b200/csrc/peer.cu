@@ -450,6 +450,8 @@ int splade_peer_status(const splade_peer_group* group, int32_t* status_host) {
   int rc = check_group(group, "splade_peer_status");
   if (rc != kOk) return rc;
   if (!status_host) return set_error(kErrInvalidArg, "splade_peer_status: null pointer argument");
+  // the caller's streams may be non-blocking ones the legacy-stream memcpy would not wait for
+  SPLADE_CUDA_OK(cudaDeviceSynchronize());
   SPLADE_CUDA_OK(cudaMemcpy(status_host, static_cast<uint8_t*>(group->window[group->rank]) + kStatusOffset,
                             sizeof(int32_t), cudaMemcpyDeviceToHost));
   return kOk;
