@@ -115,11 +115,15 @@ class PeerExchange:
 
     # -- per-step -----------------------------------------------------------------------------------------
     def next_epoch(self) -> int:
+        if not (self._own and self._own.value):
+            raise RuntimeError("PeerExchange used after close()")
         self.epoch += 1
         return self.epoch
 
     def check(self) -> None:
         """Raise if any barrier of this rank timed out (synchronises the device)."""
+        if not (self._own and self._own.value):
+            raise RuntimeError("PeerExchange.check() after close()")
         st = ctypes.c_int32(0)
         with torch.cuda.device(self.device):
             check(load_library().splade_peer_status(ctypes.byref(self.group_struct), ctypes.byref(st)),
@@ -147,6 +151,8 @@ class PeerExchange:
         """Collective for a distributed exchange (every rank calls it): mappings are closed, then a barrier, then
         the owners free their windows."""
         lib = load_library()
+        if not (self._own and self._own.value):
+            return  # already closed
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)
             for p in self._opened:
