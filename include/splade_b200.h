@@ -232,6 +232,26 @@ int splade_emit_json(const int32_t* ids_host, const float* vals_host, const int3
                      char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed);
 
 /*
+ * HOST-side: the body of an OpenSearch `_bulk` request for B documents - per document the action line and the
+ * source line that opensearch-py's helpers.bulk serialises from the reference's actions
+ *   benchmark/indexer.py:112-138            {"_index", "_id", "_source": {"doc_id", "content", "sparse_embedding"}}
+ *   scripts/neural_sparse_search_aws.py:993-1013  "_source": {"title", "content", "category", "sparse_embedding"},
+ *                                                 documents whose vector is empty are skipped (skip_empty != 0)
+ * namely
+ *   {"index":{"_index":"<index_name>","_id":"<id>"}}\n
+ *   {<head>,"<field_name>":{"term":w,...}}\n
+ * Document ids are UTF-8 strings (id_bytes / id_offsets [B+1]); `head` (head_bytes / head_offsets [B+1], or both
+ * NULL) is the caller-serialised leading members of _source WITHOUT the braces (the per-document strings are the
+ * caller's; the per-term work is done here).  The sparse object and the sizing protocol are splade_emit_json's;
+ * out_offsets [B+1] delimit each document's two lines (an empty range for a skipped document).
+ */
+int splade_emit_bulk(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B, int k,
+                     const char* token_bytes, const int64_t* token_offsets, int n_tokens, int round_decimals,
+                     const char* index_name, const char* field_name, const char* id_bytes,
+                     const int64_t* id_offsets, const char* head_bytes, const int64_t* head_offsets, int skip_empty,
+                     char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed);
+
+/*
  * ---------------------------------------------------------------------------------------------------------------
  * Cross-GPU negatives without NCCL on the data path (north_star multi-GPU step).
  * The reference has local negatives only (src/model/losses.py:136-181 sees one rank's batch); the extension

@@ -68,7 +68,11 @@ class SparseEmitter:
             d = {}
             for tid, w in zip(row_ids[:n], row_vals[:n]):
                 key = self.token_lookup[tid] if self.token_lookup is not None else str(tid)
-                d[key] = round(w, round_decimals) if round_decimals is not None else w
+                if round_decimals is not None:
+                    w = round(w, round_decimals)
+                    if w <= 0.0:  # scripts/neural_sparse_search_aws.py:753-755
+                        continue
+                d[key] = w
             out.append(d)
         return out
 
@@ -127,6 +131,71 @@ class SparseEmitter:
             check(rc, "splade_emit_json")
         raw = out.raw
         return [raw[offsets[b]:offsets[b + 1]] for b in range(B)]
+
+    def to_bulk(self, ids: torch.Tensor, vals: torch.Tensor, counts: torch.Tensor, index_name: str,
+                doc_ids: Sequence[str], sources: Optional[Sequence[Dict[str, object]]] = None,
+                field: str = "sparse_embedding", round_decimals: Optional[int] = None,
+                skip_empty: bool = False) -> bytes:
+        """The body of an OpenSearch ``_bulk`` request for these documents: per document the action line and the
+        source line opensearch-py's ``helpers.bulk`` would serialise from the reference's actions
+        (benchmark/indexer.py:112-138 ``{"doc_id", "content", "sparse_embedding"}``;
+        scripts/neural_sparse_search_aws.py:993-1013 ``{"title", "content", "category", "sparse_embedding"}`` with
+        ``skip_empty=True``).  ``sources[i]`` holds the leading members of ``_source`` (serialised here, once per
+        document); the per-term object comes from the C emitter ``splade_emit_bulk``."""
+        import ctypes
+        import json
+
+        import numpy as np
+
+        from ._lib import check, load_library
+        lib = load_library()
+        ids_h = np.ascontiguousarray(ids.cpu().numpy(), dtype=np.int32)
+        vals_h = np.ascontiguousarray(vals.cpu().numpy(), dtype=np.float32)
+        counts_h = np.ascontiguousarray(counts.cpu().numpy(), dtype=np.int32)
+        B, k = ids_h.shape
+        if len(doc_ids) != B or (sources is not None and len(sources) != B):
+            raise ValueError(f"to_bulk: {B} documents, {len(doc_ids)} ids, "
+                             f"{None if sources is None else len(sources)} sources")
+
+        def pack(chunks):
+            enc = [c.encode("utf-8") for c in chunks]
+            off = np.zeros(len(enc) + 1, dtype=np.int64)
+            np.cumsum([len(e) for e in enc], out=off[1:])
+            blob = b"".join(enc)
+            return ctypes.create_string_buffer(blob, len(blob) + 1), off
+
+        id_buf, id_off = pack([str(d) for d in doc_ids])
+        head_ptr = head_off_ptr = None
+        if sources is not None:
+            heads = [json.dumps(dict(src), ensure_ascii=False, separators=(",", ":"))[1:-1] for src in sources]
+            head_buf, head_off = pack(heads)
+            head_ptr, head_off_ptr = ctypes.addressof(head_buf), head_off.ctypes.data
+        table = self._token_table()
+        tok_ptr = off_ptr = None
+        n_tok = 0
+        if table is not None:
+            tok_buf = ctypes.create_string_buffer(table[0], len(table[0]) + 1)
+            tok_ptr, off_ptr, n_tok = ctypes.addressof(tok_buf), table[1].ctypes.data, len(table[1]) - 1
+        offsets = np.zeros(B + 1, dtype=np.int64)
+        need = ctypes.c_size_t(0)
+        dec = -1 if round_decimals is None else int(round_decimals)
+        cap = 0  # first call sizes the buffer, second fills it
+        rc = 0
+        for _ in range(2):
+            out = ctypes.create_string_buffer(max(cap, 1))
+            rc = lib.splade_emit_bulk(ids_h.ctypes.data, vals_h.ctypes.data, counts_h.ctypes.data, B, k, tok_ptr,
+                                      off_ptr, n_tok, dec, index_name.encode("utf-8"), field.encode("utf-8"),
+                                      ctypes.addressof(id_buf), id_off.ctypes.data, head_ptr, head_off_ptr,
+                                      int(skip_empty), ctypes.addressof(out) if cap else None, cap,
+                                      offsets.ctypes.data, ctypes.byref(need))
+            if rc == 0:
+                break
+            if need.value > cap:
+                cap = need.value
+                continue
+            break
+        check(rc, "splade_emit_bulk")
+        return out.raw[: need.value]
 
 
 @torch.no_grad()

@@ -119,3 +119,88 @@ def test_c_emitter_json_matches_python_dicts():
         assert list(g.keys()) == list(w.keys())
         assert all(abs(g[k_] - w[k_]) <= 1e-4 for k_ in g)
     assert objs4[0].startswith(b'{"3": 1.4142, "1": 0.7049')
+
+
+def _bulk_fixture():
+    tokens = ["plain", 'quo"te', "back\\slash", "한국어", "tab\there", "nl\nx", "ctl\x01", "", "last"]
+    ids = torch.tensor([[3, 1, 0, 8], [4, 5, 6, 2], [0, -1, -1, -1], [-1, -1, -1, -1]], dtype=torch.int32)
+    vals = torch.tensor([[1.4142135, 0.7049465, 0.33333334, 1e-7], [0.5, 0.25, 0.125, 3.0],
+                         [0.1, 0, 0, 0], [0, 0, 0, 0]], dtype=torch.float32)
+    counts = torch.tensor([4, 4, 1, 0], dtype=torch.int32)
+    return tokens, ids, vals, counts
+
+
+def _expand_like_opensearch_py(actions):
+    """What opensearch-py's helpers.bulk puts on the wire for `index` actions (helpers/actions.py expand_action +
+    JSONSerializer: compact separators, ensure_ascii=False): an action line and a source line per document."""
+    import json
+    lines = []
+    for a in actions:
+        lines.append(json.dumps({"index": {"_index": a["_index"], "_id": a["_id"]}}, ensure_ascii=False,
+                                separators=(",", ":")))
+        lines.append(json.dumps(a["_source"], ensure_ascii=False, separators=(",", ":")))
+    return lines
+
+
+def test_c_emitter_bulk_body_is_what_the_indexer_sends():
+    """splade_emit_bulk (host code): the `_bulk` body for the reference's rank_features actions
+    (benchmark/indexer.py:112-138) - parsed back line by line it equals the actions' expansion; strings that need
+    escaping survive in ids, index name, content and tokens; weights round-trip fp32 exactly."""
+    import json
+
+    import numpy as np
+
+    import splade_b200
+    tokens, ids, vals, counts = _bulk_fixture()
+    em = splade_b200.SparseEmitter(None, tokens)
+    doc_ids = ["a", 'b"2', "c\\3", "d 4"]
+    contents = ['안녕 "x"\n', "", "tab\there", "plain"]
+    dicts = em.to_dicts(ids, vals, counts)
+    actions = [{"_index": "bench-한", "_id": d, "_source": {"doc_id": d, "content": c, "sparse_embedding": v}}
+               for d, c, v in zip(doc_ids, contents, dicts)]
+    body = em.to_bulk(ids, vals, counts, "bench-한", doc_ids,
+                      [{"doc_id": d, "content": c} for d, c in zip(doc_ids, contents)])
+    assert body.endswith(b"\n")
+    got = body.decode("utf-8").split("\n")[:-1]
+    want = _expand_like_opensearch_py(actions)
+    assert len(got) == len(want) == 8
+    for g, w in zip(got, want):
+        g, w = json.loads(g), json.loads(w)
+        if "sparse_embedding" in w:
+            assert list(g) == list(w) and g["doc_id"] == w["doc_id"] and g["content"] == w["content"]
+            assert list(g["sparse_embedding"]) == list(w["sparse_embedding"])
+            assert all(np.float32(g["sparse_embedding"][t]) == np.float32(w["sparse_embedding"][t])
+                       for t in w["sparse_embedding"])
+        else:
+            assert g == w
+    # action lines are byte-identical to opensearch-py's serialisation (no floats in them)
+    assert got[0::2] == want[0::2]
+    assert got[7] == '{"doc_id":"d 4","content":"plain","sparse_embedding":{}}'
+
+
+def test_c_emitter_bulk_sparse_vector_format_skips_empty_documents():
+    """The AWS script's variant (scripts/neural_sparse_search_aws.py:745-770, 993-1013): "<term id>" keys, weights
+    rounded to 4 decimals, terms that round to zero dropped, documents left without a term skipped."""
+    import json
+
+    import splade_b200
+    _, ids, vals, counts = _bulk_fixture()
+    vals = vals.clone()
+    vals[2, 0] = 2e-5  # document 2's only term rounds to 0.0000 -> the whole document is skipped
+    em = splade_b200.SparseEmitter(None, None)
+    sources = [{"title": f"t{i}", "content": f"c{i}", "category": "x"} for i in range(4)]
+    body = em.to_bulk(ids, vals, counts, "aws", [str(i) for i in range(4)], sources, round_decimals=4,
+                      skip_empty=True)
+    lines = [json.loads(x) for x in body.decode().split("\n") if x]
+    assert [x["index"]["_id"] for x in lines[0::2]] == ["0", "1"]
+    assert lines[1] == {"title": "t0", "content": "c0", "category": "x",
+                        "sparse_embedding": {"3": 1.4142, "1": 0.7049, "0": 0.3333}}
+    assert lines[3]["sparse_embedding"] == {"4": 0.5, "5": 0.25, "6": 0.125, "2": 3.0}
+    want = em.to_dicts(ids, vals, counts, round_decimals=4)
+    assert want[2] == {} and want[0] == lines[1]["sparse_embedding"]
+    # without skip_empty every document is present; without sources the field stands alone
+    body_all = em.to_bulk(ids, vals, counts, "aws", ["0", "1", "2", "3"], None, round_decimals=4)
+    tail = body_all.decode().split("\n")
+    assert len(tail) == 9 and tail[5] == '{"sparse_embedding":{}}' and tail[7] == '{"sparse_embedding":{}}'
+    with pytest.raises(ValueError):
+        em.to_bulk(ids, vals, counts, "aws", ["0"], None)

@@ -102,3 +102,56 @@ def test_reference_train_epoch_reaches_our_kernel_boundary(ref, tmp_path):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         trainer.train_epoch(model, loader, loss_fn, opt, None, cfg, epoch=0, global_step=0,
                             device=torch.device("cpu"))
+
+
+def test_bulk_body_equals_the_reference_indexers_actions():
+    """The reference's own `bulk_actions_sparse` (benchmark/indexer.py:112-138, loaded unmodified; its sibling
+    modules, which need opensearch-py / AWS credentials helpers that are not installed, are stubbed) builds the
+    actions; `SparseEmitter.to_bulk` must produce the same documents line for line."""
+    import json
+
+    import numpy as np
+
+    import splade_b200
+    saved = {k: sys.modules.get(k) for k in ("benchmark", "benchmark.config", "benchmark.data_loader",
+                                             "benchmark.encoders", "benchmark.index_manager")}
+    try:
+        pkg = types.ModuleType("benchmark")
+        pkg.__path__ = []
+        sys.modules["benchmark"] = pkg
+        for mod, names in (("benchmark.config", ["BenchmarkConfig"]), ("benchmark.data_loader", ["BenchmarkData"]),
+                           ("benchmark.encoders", ["BgeM3Encoder", "NeuralSparseEncoder"]),
+                           ("benchmark.index_manager", ["IndexManager"])):
+            m = types.ModuleType(mod)
+            for n in names:
+                setattr(m, n, type(n, (), {}))
+            sys.modules[mod] = m
+        ix = _load("ref_benchmark_indexer_t", f"{REF}/benchmark/indexer.py")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+    tokens = ["서울", "날씨", "##는", 'q"uote', "back\\slash", "맑음"]
+    ids = torch.tensor([[0, 5, 1], [3, 4, -1], [-1, -1, -1]], dtype=torch.int32)
+    vals = torch.tensor([[2.5, 1.25, 0.3333333], [0.1, 0.05, 0.0], [0.0, 0.0, 0.0]], dtype=torch.float32)
+    counts = torch.tensor([3, 2, 0], dtype=torch.int32)
+    em = splade_b200.SparseEmitter(None, tokens)
+    dicts = em.to_dicts(ids, vals, counts)
+    doc_ids, contents = ["d0", "d1", "d2"], ["서울 날씨는 맑음", 'he said "hi"', ""]
+    docs = [ix.EncodedDocument(doc_id=d, content=c, dense_embedding=[], sparse_embedding=v)
+            for d, c, v in zip(doc_ids, contents, dicts)]
+    actions = list(ix.bulk_actions_sparse(docs, "bench-sparse"))
+    body = em.to_bulk(ids, vals, counts, "bench-sparse", doc_ids,
+                      [{"doc_id": d, "content": c} for d, c in zip(doc_ids, contents)])
+    lines = [json.loads(x) for x in body.decode("utf-8").split("\n") if x]
+    assert len(lines) == 2 * len(actions)
+    for a, head, src in zip(actions, lines[0::2], lines[1::2]):
+        assert head == {"index": {"_index": a["_index"], "_id": a["_id"]}}
+        assert list(src) == list(a["_source"])
+        assert src["doc_id"] == a["_source"]["doc_id"] and src["content"] == a["_source"]["content"]
+        want = a["_source"]["sparse_embedding"]
+        assert list(src["sparse_embedding"]) == list(want)
+        assert all(np.float32(src["sparse_embedding"][t]) == np.float32(want[t]) for t in want)
