@@ -252,6 +252,21 @@ int splade_emit_bulk(const int32_t* ids_host, const float* vals_host, const int3
                      char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed);
 
 /*
+ * HOST-side, query leg (BASELINE config 3): the search request bodies NeuralSparseSearcher.search builds from a
+ * pruned query vector (benchmark/searchers.py:158-185) - one `rank_feature` should-clause per kept term, highest
+ * weight first, at most max_clauses (the reference keeps 64) -
+ *   {"size":<size>,"query":{"bool":{"should":[{"rank_feature":{"field":"<field_name>.<token>","boost":w}},...]}}}
+ * for B queries from splade_topk's compact buffers (already ordered by weight desc, ties by term id asc = the
+ * reference's stable sort).  msearch_index != NULL emits the `_msearch` form instead: a {"index":"<name>"} header
+ * line before and a newline after every body.  A query with no surviving term produces no bytes (the reference
+ * returns an empty response without calling OpenSearch).  Sizing protocol and out_offsets [B+1] as above.
+ */
+int splade_emit_search(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B, int k,
+                       const char* token_bytes, const int64_t* token_offsets, int n_tokens, int max_clauses,
+                       int size, const char* field_name, const char* msearch_index, char* out, size_t out_cap,
+                       int64_t* out_offsets, size_t* bytes_needed);
+
+/*
  * ---------------------------------------------------------------------------------------------------------------
  * Cross-GPU negatives without NCCL on the data path (north_star multi-GPU step).
  * The reference has local negatives only (src/model/losses.py:136-181 sees one rank's batch); the extension

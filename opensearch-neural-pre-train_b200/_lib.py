@@ -123,6 +123,8 @@ EXPORTS = {
     "splade_emit_bulk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                  c_char_p, c_char_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
+    "splade_emit_search": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_char_p, c_char_p, c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
     "splade_trunk_encode": (c_int, [POINTER(TrunkArgs), c_void_p]),
     "splade_packed_rows": (c_size_t, [c_int, c_int]),
     "splade_trunk_gemm": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,

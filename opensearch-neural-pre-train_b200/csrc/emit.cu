@@ -13,42 +13,6 @@
 #include <cstdlib>
 #include <cstring>
 
-namespace splade {
-namespace {
-
-// Append a JSON string literal (with quotes) for a UTF-8 token; returns bytes written or -1 on overflow.
-long put_json_string(char* dst, size_t cap, const char* s, size_t n) {
-  size_t o = 0;
-  auto put = [&](char c) {
-    if (o < cap) dst[o] = c;
-    ++o;
-  };
-  put('"');
-  for (size_t i = 0; i < n; ++i) {
-    const unsigned char c = static_cast<unsigned char>(s[i]);
-    switch (c) {
-      case '"': put('\\'); put('"'); break;
-      case '\\': put('\\'); put('\\'); break;
-      case '\n': put('\\'); put('n'); break;
-      case '\r': put('\\'); put('r'); break;
-      case '\t': put('\\'); put('t'); break;
-      default:
-        if (c < 0x20) {
-          char buf[8];
-          snprintf(buf, sizeof(buf), "\\u%04x", c);
-          for (int j = 0; j < 6; ++j) put(buf[j]);
-        } else {
-          put(static_cast<char>(c));  // UTF-8 bytes pass through
-        }
-    }
-  }
-  put('"');
-  return o <= cap ? static_cast<long>(o) : -1;
-}
-
-}  // namespace
-}  // namespace splade
-
 using namespace splade;
 
 namespace {
@@ -65,19 +29,44 @@ struct Sink {
     o += n;
   }
   void lit(const char* s) { raw(s, strlen(s)); }
-  void json_string(const char* s, size_t len) {
-    const long wrote = splade::put_json_string(o <= cap ? out + o : out, o <= cap ? cap - o : 0, s, len);
-    if (wrote < 0) {
-      overflow = true;
-      size_t need = 2;  // count the bytes anyway: worst case 6 per byte + the quotes
-      for (size_t i = 0; i < len; ++i) {
-        const unsigned char c = static_cast<unsigned char>(s[i]);
-        need += (c == '"' || c == '\\' || c == '\n' || c == '\r' || c == '\t') ? 2 : (c < 0x20 ? 6 : 1);
+  // JSON string escaping of UTF-8 bytes (no quotes): ", \\ and control characters; everything else passes through
+  void escaped(const char* s, size_t len) {
+    size_t run = 0;  // pending bytes that need no escaping
+    for (size_t i = 0; i < len; ++i) {
+      const unsigned char c = static_cast<unsigned char>(s[i]);
+      if (c != '"' && c != '\\' && c >= 0x20) {
+        ++run;
+        continue;
       }
-      o += need;
-    } else {
-      o += static_cast<size_t>(wrote);
+      if (run) raw(s + i - run, run);
+      run = 0;
+      switch (c) {
+        case '"': raw("\\\"", 2); break;
+        case '\\': raw("\\\\", 2); break;
+        case '\n': raw("\\n", 2); break;
+        case '\r': raw("\\r", 2); break;
+        case '\t': raw("\\t", 2); break;
+        default: {
+          char buf[8];
+          snprintf(buf, sizeof(buf), "\\u%04x", c);
+          raw(buf, 6);
+        }
+      }
     }
+    if (run) raw(s + len - run, run);
+  }
+  void json_string(const char* s, size_t len) {
+    raw("\"", 1);
+    escaped(s, len);
+    raw("\"", 1);
+  }
+  // "<prefix>.<token>" as ONE JSON string (rank_feature field paths)
+  void json_field_path(const char* prefix, size_t plen, const char* tok, size_t tlen) {
+    raw("\"", 1);
+    escaped(prefix, plen);
+    raw(".", 1);
+    escaped(tok, tlen);
+    raw("\"", 1);
   }
 };
 
@@ -197,5 +186,54 @@ extern "C" int splade_emit_bulk(const int32_t* ids_host, const float* vals_host,
   *bytes_needed = w.o;
   if (w.overflow)
     return set_error(kErrWorkspace, "splade_emit_bulk: output buffer too small (%zu < %zu bytes)", out_cap, w.o);
+  return kOk;
+}
+
+extern "C" int splade_emit_search(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
+                                  int k, const char* token_bytes, const int64_t* token_offsets, int n_tokens,
+                                  int max_clauses, int size, const char* field_name, const char* msearch_index,
+                                  char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed) {
+  if (!ids_host || !vals_host || !counts_host || !out_offsets || !bytes_needed || (!out && out_cap) || !field_name)
+    return set_error(kErrInvalidArg, "splade_emit_search: null pointer argument");
+  if (B < 0 || k < 1 || size < 0 || max_clauses < 1)
+    return set_error(kErrInvalidArg, "splade_emit_search: bad arguments B=%d k=%d size=%d max_clauses=%d", B, k, size,
+                     max_clauses);
+  if (!token_bytes || !token_offsets)
+    return set_error(kErrInvalidArg, "splade_emit_search: rank_feature field paths need the token table");
+  Sink w{out, out_cap};
+  const size_t field_len = strlen(field_name);
+  char num[64];
+  for (int b = 0; b < B; ++b) {
+    out_offsets[b] = static_cast<int64_t>(w.o);
+    int n = counts_host[b] < k ? (counts_host[b] > 0 ? counts_host[b] : 0) : k;
+    if (n > max_clauses) n = max_clauses;
+    if (n == 0) continue;  // `if not query_sparse: return SearchResponse(results=[], ...)`: no request at all
+    if (msearch_index) {
+      w.lit("{\"index\":");
+      w.json_string(msearch_index, strlen(msearch_index));
+      w.lit("}\n");
+    }
+    int m = snprintf(num, sizeof(num), "{\"size\":%d,\"query\":{\"bool\":{\"should\":[", size);
+    w.raw(num, static_cast<size_t>(m));
+    for (int j = 0; j < n; ++j) {
+      const int32_t id = ids_host[static_cast<size_t>(b) * k + j];
+      if (id < 0 || id >= n_tokens)
+        return set_error(kErrInvalidArg, "splade_emit_search: term id %d outside the token table (%d)", id, n_tokens);
+      if (j) w.raw(",", 1);
+      w.lit("{\"rank_feature\":{\"field\":");
+      w.json_field_path(field_name, field_len, token_bytes + token_offsets[id],
+                        static_cast<size_t>(token_offsets[id + 1] - token_offsets[id]));
+      w.lit(",\"boost\":");
+      m = snprintf(num, sizeof(num), "%.9g", static_cast<double>(vals_host[static_cast<size_t>(b) * k + j]));
+      w.raw(num, static_cast<size_t>(m));
+      w.lit("}}");
+    }
+    w.lit("]}}}");
+    if (msearch_index) w.raw("\n", 1);
+  }
+  out_offsets[B] = static_cast<int64_t>(w.o);
+  *bytes_needed = w.o;
+  if (w.overflow)
+    return set_error(kErrWorkspace, "splade_emit_search: output buffer too small (%zu < %zu bytes)", out_cap, w.o);
   return kOk;
 }

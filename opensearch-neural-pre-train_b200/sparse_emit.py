@@ -197,6 +197,49 @@ class SparseEmitter:
         check(rc, "splade_emit_bulk")
         return out.raw[: need.value]
 
+    def to_search_bodies(self, ids: torch.Tensor, vals: torch.Tensor, counts: torch.Tensor, size: int = 10,
+                         field: str = "sparse_embedding", max_clauses: int = 64,
+                         msearch_index: Optional[str] = None) -> List[bytes]:
+        """The request bodies ``NeuralSparseSearcher.search`` sends (benchmark/searchers.py:158-185): one
+        ``rank_feature`` should-clause per kept query term, highest weight first, at most ``max_clauses``.  One
+        ``bytes`` per query (``b""`` when no term survived - the reference then skips the request); with
+        ``msearch_index`` each is the header + body pair of an ``_msearch`` request, so ``b"".join(...)`` is the
+        whole multi-search body for the batch (C emitter ``splade_emit_search``)."""
+        import ctypes
+
+        import numpy as np
+
+        from ._lib import check, load_library
+        lib = load_library()
+        table = self._token_table()
+        if table is None:
+            raise ValueError("to_search_bodies needs a token table (rank_feature fields are named by token string)")
+        ids_h = np.ascontiguousarray(ids.cpu().numpy(), dtype=np.int32)
+        vals_h = np.ascontiguousarray(vals.cpu().numpy(), dtype=np.float32)
+        counts_h = np.ascontiguousarray(counts.cpu().numpy(), dtype=np.int32)
+        B, k = ids_h.shape
+        tok_buf = ctypes.create_string_buffer(table[0], len(table[0]) + 1)
+        offsets = np.zeros(B + 1, dtype=np.int64)
+        need = ctypes.c_size_t(0)
+        cap, rc = 0, 0
+        idx = None if msearch_index is None else msearch_index.encode("utf-8")
+        for _ in range(2):
+            out = ctypes.create_string_buffer(max(cap, 1))
+            rc = lib.splade_emit_search(ids_h.ctypes.data, vals_h.ctypes.data, counts_h.ctypes.data, B, k,
+                                        ctypes.addressof(tok_buf), table[1].ctypes.data, len(table[1]) - 1,
+                                        int(max_clauses), int(size), field.encode("utf-8"), idx,
+                                        ctypes.addressof(out) if cap else None, cap, offsets.ctypes.data,
+                                        ctypes.byref(need))
+            if rc == 0:
+                break
+            if need.value > cap:
+                cap = need.value
+                continue
+            break
+        check(rc, "splade_emit_search")
+        raw = out.raw
+        return [raw[offsets[b]:offsets[b + 1]] for b in range(B)]
+
 
 @torch.no_grad()
 def bulk_encode(model, input_ids: torch.Tensor, attention_mask: torch.Tensor, top_k: int,

@@ -204,3 +204,33 @@ def test_c_emitter_bulk_sparse_vector_format_skips_empty_documents():
     assert len(tail) == 9 and tail[5] == '{"sparse_embedding":{}}' and tail[7] == '{"sparse_embedding":{}}'
     with pytest.raises(ValueError):
         em.to_bulk(ids, vals, counts, "aws", ["0"], None)
+
+
+def test_c_emitter_search_bodies():
+    """splade_emit_search (host code, query leg): rank_feature bool queries as benchmark/searchers.py:158-185
+    builds them, at most max_clauses clauses, nothing for a query without terms, `_msearch` framing on request."""
+    import json
+
+    import numpy as np
+
+    import splade_b200
+    tokens, ids, vals, counts = _bulk_fixture()
+    em = splade_b200.SparseEmitter(None, tokens)
+    bodies = em.to_search_bodies(ids, vals, counts, size=7, max_clauses=3)
+    assert len(bodies) == 4 and bodies[3] == b""
+    q0 = json.loads(bodies[0])
+    assert q0["size"] == 7 and list(q0) == ["size", "query"]
+    clauses = q0["query"]["bool"]["should"]
+    assert [c["rank_feature"]["field"] for c in clauses] == ["sparse_embedding.한국어", 'sparse_embedding.quo"te',
+                                                             "sparse_embedding.plain"]
+    assert [np.float32(c["rank_feature"]["boost"]) for c in clauses] == [np.float32(v) for v in vals[0, :3].tolist()]
+    q1 = json.loads(bodies[1])
+    assert q1["query"]["bool"]["should"][2]["rank_feature"]["field"] == "sparse_embedding.ctl\x01"
+    ms = b"".join(em.to_search_bodies(ids, vals, counts, msearch_index="bench-한", field="emb")).decode("utf-8")
+    lines = ms.split("\n")
+    assert lines[-1] == "" and len(lines) == 7  # 3 queries x (header, body), the empty query is absent
+    assert [json.loads(x) for x in lines[0:6:2]] == [{"index": "bench-한"}] * 3
+    assert json.loads(lines[1])["query"]["bool"]["should"][3]["rank_feature"] == {
+        "field": "emb.last", "boost": pytest.approx(1e-7, rel=1e-6)}
+    with pytest.raises(ValueError):
+        splade_b200.SparseEmitter(None, None).to_search_bodies(ids, vals, counts)

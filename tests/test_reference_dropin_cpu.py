@@ -155,3 +155,81 @@ def test_bulk_body_equals_the_reference_indexers_actions():
         want = a["_source"]["sparse_embedding"]
         assert list(src["sparse_embedding"]) == list(want)
         assert all(np.float32(src["sparse_embedding"][t]) == np.float32(want[t]) for t in want)
+
+
+def test_search_bodies_equal_the_reference_searchers():
+    """The reference's own NeuralSparseSearcher.search (benchmark/searchers.py:130-185, loaded unmodified with its
+    opensearch-py / encoder imports stubbed) builds the request body from a pruned query dict;
+    `SparseEmitter.to_search_bodies` must produce the same body from the compact top-k buffers."""
+    import json
+
+    import numpy as np
+
+    import splade_b200
+    names = ("opensearchpy", "benchmark", "benchmark.config", "benchmark.encoders")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        osp = types.ModuleType("opensearchpy")
+        osp.OpenSearch = type("OpenSearch", (), {})
+        sys.modules["opensearchpy"] = osp
+        pkg = types.ModuleType("benchmark")
+        pkg.__path__ = []
+        sys.modules["benchmark"] = pkg
+        for mod, cls in (("benchmark.config", ["BenchmarkConfig"]),
+                         ("benchmark.encoders", ["BgeM3Encoder", "NeuralSparseEncoder"])):
+            m = types.ModuleType(mod)
+            for n in cls:
+                setattr(m, n, type(n, (), {}))
+            sys.modules[mod] = m
+        sr = _load("ref_benchmark_searchers_t", f"{REF}/benchmark/searchers.py")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+    tokens = ["서울", "날씨", "##는", 'q"uote', "맑음", "tie_a", "tie_b"]
+    # rows as splade_topk returns them: weight descending, ties by ascending term id
+    ids = torch.tensor([[0, 4, 5, 6, 1], [3, 2, -1, -1, -1], [-1, -1, -1, -1, -1]], dtype=torch.int32)
+    vals = torch.tensor([[2.5, 1.25, 0.5, 0.5, 0.3333333], [0.1, 0.05, 0, 0, 0], [0, 0, 0, 0, 0]],
+                        dtype=torch.float32)
+    counts = torch.tensor([5, 2, 0], dtype=torch.int32)
+    em = splade_b200.SparseEmitter(None, tokens)
+    dicts = em.to_dicts(ids, vals, counts)  # what encode_for_query returns for these queries
+
+    class Encoder:
+        class tokenizer:  # noqa: N801
+            @staticmethod
+            def get_vocab():
+                return {t: i for i, t in enumerate(tokens)}
+
+        def __init__(self):
+            self.i = -1
+
+        def encode_for_query(self, text, top_k=100):
+            self.i += 1
+            return dicts[self.i]
+
+    class Client:
+        def __init__(self):
+            self.calls = []
+
+        def search(self, index, body):
+            self.calls.append((index, body))
+            return {"hits": {"hits": [], "total": {"value": 0}}, "took": 0}
+
+    client = Client()
+    searcher = sr.NeuralSparseSearcher(client, "bench-sparse", Encoder(), top_k=10)
+    for q in ("q0", "q1", "q2"):
+        searcher.search(q)
+    assert len(client.calls) == 2  # the empty query never reaches OpenSearch
+    ours = em.to_search_bodies(ids, vals, counts, size=10)
+    assert ours[2] == b""
+    for (index, want), got in zip(client.calls, ours[:2]):
+        got = json.loads(got)
+        assert index == "bench-sparse" and list(got) == list(want) and got["size"] == want["size"]
+        gc, wc = got["query"]["bool"]["should"], want["query"]["bool"]["should"]
+        assert [c["rank_feature"]["field"] for c in gc] == [c["rank_feature"]["field"] for c in wc]
+        assert all(np.float32(a["rank_feature"]["boost"]) == np.float32(b["rank_feature"]["boost"])
+                   for a, b in zip(gc, wc))
