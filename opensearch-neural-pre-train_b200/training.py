@@ -7,7 +7,10 @@ negatives) and one loss call inside ``torch.autocast("cuda", bfloat16)``, ``(los
 then — every ``accum`` micro-steps — ``clip_grad_norm_(1.0)``, optimizer and scheduler step.
 
 Trainer hygiene the reference lacks is available behind explicit flags and OFF by
-default: ``no_sync`` on non-final accumulation micro-steps (the reference all-reduces 597 MB on every one).
+default: ``no_sync`` on non-final accumulation micro-steps (the reference all-reduces 597 MB on every one), and
+``enable_bf16_gradient_compression`` (the gradient all-reduce, 597 MB fp32 per step of which the tied
+decoder/embedding matrix alone is 153.6 MB, travels as bf16: half the NVLink bytes of the one collective the
+reference's DDP step has).
 """
 from __future__ import annotations
 
@@ -24,6 +27,14 @@ class StepConfig:
     gradient_clip: float = 1.0
     skip_allreduce_on_accumulation: bool = False  # N3: DDP.no_sync() on non-final micro-steps
     autocast_dtype: torch.dtype = torch.bfloat16
+
+
+def enable_bf16_gradient_compression(ddp_model) -> None:
+    """N3, opt-in: DDP casts every gradient bucket to bf16 for the all-reduce and back (PyTorch's stock
+    ``bf16_compress_hook``); call once after wrapping the model (src/train/cli/train_v33_ddp.py:539-544 wraps it).
+    Parameters and optimizer state stay fp32; only the averaged gradient carries bf16 rounding (relative 2^-9)."""
+    from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+    ddp_model.register_comm_hook(state=None, hook=default_hooks.bf16_compress_hook)
 
 
 def train_micro_step(model, loss_fn, optimizer, scheduler, batch: Dict[str, torch.Tensor], micro_idx: int,

@@ -80,3 +80,28 @@ def test_bulk_encode_shards_contiguously_without_collectives():
     out = _spawn("_bulk_case", 2)
     assert out[0][1] == (0, 6) and out[1][1] == (6, 11)
     assert out[0][0] + out[1][0] == [i % 16 for i in range(11)]                  # rank-order concatenation
+
+
+def _bf16_hook_case(rank, world):
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    from splade_b200.training import enable_bf16_gradient_compression
+    torch.manual_seed(0)
+    model = torch.nn.Linear(16, 8)
+    ddp = DDP(model)
+    enable_bf16_gradient_compression(ddp)
+    x = torch.full((4, 16), float(rank + 1))
+    ddp(x).sum().backward()
+    return model.weight.grad.clone(), model.bias.grad.clone()
+
+
+def test_bf16_gradient_compression_hook_averages_like_ddp():
+    """N3 (opt-in): gradients are averaged over ranks as DDP does, within bf16 rounding of the exact mean."""
+    try:
+        out = _spawn("_bf16_hook_case", 2)
+    except Exception as e:  # a gloo build without bf16 all-reduce: the hook is NCCL-only there
+        pytest.skip(f"gloo cannot all-reduce bf16 here: {type(e).__name__}")
+    # d(sum(Wx+b))/dW = sum over the batch of x = 4 * (rank+1) per input column; mean over ranks = 6; bias: 4
+    for w_grad, b_grad in out:
+        torch.testing.assert_close(w_grad, torch.full((8, 16), 6.0), rtol=2 ** -8, atol=0)
+        torch.testing.assert_close(b_grad, torch.full((8,), 4.0), rtol=2 ** -8, atol=0)
