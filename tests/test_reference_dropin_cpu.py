@@ -233,3 +233,45 @@ def test_search_bodies_equal_the_reference_searchers():
         assert [c["rank_feature"]["field"] for c in gc] == [c["rank_feature"]["field"] for c in wc]
         assert all(np.float32(a["rank_feature"]["boost"]) == np.float32(b["rank_feature"]["boost"])
                    for a, b in zip(gc, wc))
+
+
+def test_synthetic_batches_follow_the_real_collator():
+    """A17: the reference's TripletCollator (src/train/data/dataloader.py:46-164, loaded unmodified) on real text
+    with the checkpoint's tokenizer, single- and multi-negative, with teacher scores - and
+    `synthetic_triplet_batch` (what the GPU tests and benches feed the path) has the same tensor keys, dtypes,
+    shape relations, right padding with the same pad id, and `num_negatives` convention."""
+    from transformers import AutoTokenizer
+
+    from splade_b200.training import synthetic_triplet_batch
+    tok_dir = f"{REF}/huggingface/v33"
+    if not os.path.isdir(tok_dir):
+        pytest.skip("tokenizer files not present")
+    tok = AutoTokenizer.from_pretrained(tok_dir)
+    dl = _load("ref_dataloader_t", f"{REF}/src/train/data/dataloader.py")
+    coll = dl.TripletCollator(tok, query_max_length=64, doc_max_length=256)
+    single = [{"query": "서울 날씨", "positive": "서울은 오늘 맑고 따뜻합니다.", "negative": "부산 맛집 추천",
+               "teacher_pos_score": 0.9, "teacher_neg_score": 0.1},
+              {"query": "파이썬 설치 방법을 알려줘", "positive": "파이썬은 공식 홈페이지에서 내려받아 설치합니다. " * 6,
+               "negative": "자바", "teacher_pos_score": 0.8, "teacher_neg_score": 0.2}]
+    multi = [{"query": d["query"], "positive": d["positive"], "negatives": [d["negative"], "다른 문서", "또 다른 문서"],
+              "teacher_pos_score": 0.5, "teacher_neg_scores": [0.1, 0.2, 0.3]} for d in single]
+    for raw, k in ((single, 1), (multi, 3)):
+        real = coll([dict(d) for d in raw])
+        synth = synthetic_triplet_batch(len(raw), real["query_input_ids"].shape[1],
+                                        real["positive_input_ids"].shape[1], k, len(tok), tok.pad_token_id, seed=0)
+        tensor_keys = [key for key, v in real.items() if torch.is_tensor(v) and not key.startswith("teacher")]
+        assert sorted(tensor_keys) == sorted(key for key, v in synth.items() if torch.is_tensor(v))
+        assert real["num_negatives"] == synth["num_negatives"] == k
+        for key in tensor_keys:
+            assert real[key].dtype == synth[key].dtype == torch.int64, key
+            assert real[key].shape[0] == synth[key].shape[0], key          # negatives flattened to [B*k, S]
+        assert real["negative_input_ids"].shape[0] == len(raw) * k
+        for side in ("query", "positive", "negative"):
+            for batch in (real, synth):
+                m, ids = batch[f"{side}_attention_mask"], batch[f"{side}_input_ids"]
+                assert bool((m[:, :-1] >= m[:, 1:]).all())                  # right padded
+                assert bool((ids[m == 0] == tok.pad_token_id).all())       # same pad id convention
+                assert int(m.sum(1).max()) == m.shape[1]                   # padded to the longest member
+        # teacher scores keep the shapes SPLADELossV33.forward documents ([B] and [B] / [B,k])
+        assert real["teacher_pos_scores"].shape == (len(raw),)
+        assert real["teacher_neg_scores"].shape == ((len(raw),) if k == 1 else (len(raw), k))
