@@ -275,3 +275,28 @@ def test_synthetic_batches_follow_the_real_collator():
         # teacher scores keep the shapes SPLADELossV33.forward documents ([B] and [B] / [B,k])
         assert real["teacher_pos_scores"].shape == (len(raw),)
         assert real["teacher_neg_scores"].shape == ((len(raw),) if k == 1 else (len(raw), k))
+
+
+def test_blocklist_with_the_real_tokenizer_equals_the_reference_filter():
+    """A9: with the checkpoint's tokenizer, `build_blocklist` marks exactly the term ids the reference's emit loop
+    drops (benchmark/encoders.py:277-287 special ids, :332 tokens starting with '[' or '<') plus the model row
+    beyond the tokenizer's vocabulary: {0..36, 64, 95, 49999}, 40 ids."""
+    from transformers import AutoTokenizer
+
+    import splade_b200
+    tok_dir = f"{REF}/huggingface/v33"
+    if not os.path.isdir(tok_dir):
+        pytest.skip("tokenizer files not present")
+    tok = AutoTokenizer.from_pretrained(tok_dir)
+    V = 50000
+    block = splade_b200.build_blocklist(tok, V)
+    # the reference's rule, restated from its loop: id kept iff not special and its token does not start with [ or <
+    special = {tok.cls_token_id, tok.sep_token_id, tok.pad_token_id, tok.unk_token_id, tok.bos_token_id,
+               tok.eos_token_id} - {None}
+    lookup = tok.convert_ids_to_tokens(list(range(tok.vocab_size)))
+    dropped = {i for i in range(V)
+               if i in special or i >= len(lookup) or not lookup[i] or lookup[i].startswith(("[", "<"))}
+    assert set(torch.nonzero(block).flatten().tolist()) == dropped
+    assert dropped == set(range(37)) | {64, 95, 49999}
+    em = splade_b200.SparseEmitter.from_tokenizer(tok, V)
+    assert em.token_lookup[100] == lookup[100] and len(em.token_lookup) == tok.vocab_size == 49999
