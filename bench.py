@@ -27,6 +27,9 @@ import sys
 import threading
 import time
 
+# the bench falls back to NCCL when a peer-exchange barrier is not answered; do not wait NCCL-long for that
+os.environ.setdefault("SPLADE_B200_PEER_TIMEOUT_MS", "20000")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -36,6 +39,14 @@ WORKLOAD = "C2: SPLADE-max head encode, A.X-Encoder-base head shape (hidden 768 
 FLOP_PER_STEP = 2.0 * B_DOCS * SEQ * HIDDEN * VOCAB          # 76.8 MFLOP per token
 N_ROTATE = 3                                                 # distinct input sets (see config.l2)
 LAUNCHES_PER_STEP = 6                                        # kernels per splade_head_fwd call (see gpu_launches)
+
+
+def bench_config(world: int) -> dict:
+    """The `config` object of the JSON line - the SAME dict for our arm and for `--impl reference`."""
+    return {"workload": WORKLOAD, "docs_per_gpu_per_step": B_DOCS, "seq_len": SEQ, "hidden": HIDDEN,
+            "vocab": VOCAB, "sharding": f"documents sharded over {world} rank(s), no data-path collective",
+            "l2": f"inputs larger than L2: rotating {N_ROTATE} distinct (hidden, W, bias) sets, "
+                  f"{N_ROTATE} x 102 MB > 126 MB"}
 
 
 def load_peaks():
@@ -180,7 +191,7 @@ def run_reference(args):
         "impl": "reference", "metric": "splade_head_encode_docs_per_sec", "value": value, "unit": "docs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": bench_config(int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": value, "unit": "docs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -593,10 +604,7 @@ def run_ours(args):
         "metric": "splade_head_encode_docs_per_sec", "value": value, "unit": "docs/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "docs_per_gpu_per_step": B_DOCS, "seq_len": SEQ, "hidden": HIDDEN,
-                   "vocab": VOCAB, "sharding": f"documents sharded over {world} rank(s), no data-path collective",
-                   "l2": f"inputs larger than L2: rotating {N_ROTATE} distinct (hidden, W, bias) sets, "
-                         f"{N_ROTATE} x 102 MB > 126 MB"},
+        "config": bench_config(world),
         "tokens_per_s": value * SEQ,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d_bytes,

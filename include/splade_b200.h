@@ -283,7 +283,7 @@ int splade_emit_search(const int32_t* ids_host, const float* vals_host, const in
  *
  * Windows are double-buffered by the parity of `epoch` (a counter the ranks advance together, first call = 1),
  * so one flag barrier per phase is enough.  A barrier that is not answered within the timeout
- * (env SPLADE_B200_PEER_TIMEOUT_MS, default 20000) sets the window's status word instead of hanging the GPU.
+ * (env SPLADE_B200_PEER_TIMEOUT_MS, default 600000 - NCCL-like patience) sets the window's status word instead of hanging the GPU.
  * ---------------------------------------------------------------------------------------------------------------
  */
 #define SPLADE_MAX_PEERS 16

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(128) peer_ddocs_kernel(const BwdParams p) {
 unsigned long long timeout_ns_from_env() {
   static unsigned long long cached = 0;
   if (cached == 0) {
-    unsigned long long ms = 20000;
+    unsigned long long ms = 600000;  // NCCL-like patience: ranks legitimately skew by minutes (rank-0 evaluation, checkpoints)
     if (const char* e = std::getenv("SPLADE_B200_PEER_TIMEOUT_MS")) {
       const long long v = std::atoll(e);
       if (v > 0) ms = static_cast<unsigned long long>(v);
@@ -512,7 +512,14 @@ int splade_peer_v33_loss_fwd(const splade_v33_fwd_args* args, const splade_peer_
   const unsigned chunks = static_cast<unsigned>((gp.Vp / 8 + 255) / 256);
   peer_gather_kernel<<<dim3(chunks, static_cast<unsigned>(W * Bq)), 256, 0, stream>>>(gp);
   SPLADE_CUDA_OK(cudaGetLastError());
-  return v33_loss_fwd_launch(&a, stream, /*docs_prepacked=*/a.round_bf16 != 0);
+  rc = v33_loss_fwd_launch(&a, stream, /*docs_prepacked=*/a.round_bf16 != 0);
+  if (rc != kOk) return rc;
+  // The window's status word rides along with the monitoring scalars (raw int32 bits in scalars[15]): the one
+  // device->host copy SPLADELossV33.forward makes anyway tells the caller when a barrier of this rank gave up.
+  if (a.scalars)
+    SPLADE_CUDA_OK(cudaMemcpyAsync(a.scalars + 15, mine + kStatusOffset, sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                   stream));
+  return kOk;
 }
 
 int splade_peer_loss_bwd(const splade_peer_group* group, uint32_t epoch, const float* q, const float* docs_all,
@@ -533,6 +540,18 @@ int splade_peer_loss_bwd(const splade_peer_group* group, uint32_t epoch, const f
   const size_t need = peer_loss_bwd_workspace_bytes(Bq, W);
   if (!workspace || ws_bytes < need)
     return set_error(kErrWorkspace, "%s: workspace too small (%zu < %zu bytes)", who, ws_bytes, need);
+  // everything loss_bwd_dq_launch would refuse is refused HERE, before the first enqueue: a rank must never
+  // publish its gl / signal its peers and then bail out (they would be left to time out)
+  if (!q || !docs_all || !negs || !g_hard || !colmean_q || !colmean_n || !dq || !dnegs)
+    return set_error(kErrInvalidArg, "%s: null pointer argument", who);
+  {
+    auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+    if (!aligned16(q) || !aligned16(docs_all) || !aligned16(negs) || !aligned16(dq) || !aligned16(dnegs) ||
+        !aligned16(colmean_q) || !aligned16(colmean_n) || !aligned16(colmean_d) || !aligned16(ddocs_local))
+      return set_error(kErrUnsupportedShape, "%s: 16-byte aligned rows are required", who);
+  }
+  rc = require_sm100(who);
+  if (rc != kOk) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const PeerLayout L = peer_layout(Bq, V, W);
   const int b = static_cast<int>(epoch & 1u);

@@ -6,6 +6,7 @@ stream and records the autograd graph.  All arithmetic happens in ``libsplade_b2
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -210,21 +211,34 @@ def topk(rep: torch.Tensor, k: int, blocklist: Optional[torch.Tensor] = None):
 # ------------------------------------------------------------------------------------------------
 # autograd: fused head
 # ------------------------------------------------------------------------------------------------
-_WEIGHT_CACHE = {}
+_WEIGHT_CACHE = []  # at most one entry: (weakref to the parameter, _version, data_ptr, bf16 copy)
+
+
+def clear_weight_cache() -> None:
+    """Drop the cached bf16 copy (call after mutating a weight through ``.data``, which bumps no version)."""
+    _WEIGHT_CACHE.clear()
 
 
 def cached_bf16(weight: torch.Tensor) -> torch.Tensor:
     """bf16 copy of a parameter, reused until the parameter is modified in place (optimizer step).
-    Mirrors autocast's own weight-cast cache; saves two 77 MB casts per micro-step."""
+    Mirrors autocast's own weight-cast cache; saves two 77 MB casts per micro-step.
+
+    The entry is tied to the parameter OBJECT (weak reference), not to its address: a second model whose tied
+    matrix lands on the allocator address a freed model used, with the same version counter, must never see the
+    first model's weights."""
     if weight.dtype == torch.bfloat16 and weight.is_contiguous():
         return weight.detach()
-    key = (weight.data_ptr(), weight.device)
-    hit = _WEIGHT_CACHE.get(key)
-    if hit is not None and hit[0] == weight._version and hit[1].shape == weight.shape:
-        return hit[1]
+    if _WEIGHT_CACHE:
+        ref, version, ptr, w16 = _WEIGHT_CACHE[0]
+        if (ref() is weight and version == weight._version and ptr == weight.data_ptr()
+                and w16.shape == weight.shape and w16.device == weight.device):
+            return w16
     w = weight.detach().to(torch.bfloat16).contiguous()
     _WEIGHT_CACHE.clear()  # one live entry is enough (the tied decoder/embedding matrix)
-    _WEIGHT_CACHE[key] = (weight._version, w)
+    try:
+        _WEIGHT_CACHE.append((weakref.ref(weight), weight._version, weight.data_ptr(), w))
+    except TypeError:  # not weak-referenceable: do not cache
+        pass
     return w
 
 
@@ -263,10 +277,22 @@ class SpladeHeadFunction(torch.autograd.Function):
         return (d_hidden.to(hd), dW.to(wd), None if bd is None else dbias.to(bd), None, None, None)
 
 
+def autocast_is_bf16() -> bool:
+    """True inside ``torch.autocast("cuda", dtype=torch.bfloat16)`` - the only autocast mode this path mirrors
+    (src/train/cli/train_v33_ddp.py:337).  fp16 autocast is refused rather than silently computed as bf16."""
+    if not torch.is_autocast_enabled("cuda"):
+        return False
+    dt = torch.get_autocast_dtype("cuda")
+    if dt != torch.bfloat16:
+        raise RuntimeError(f"splade_b200: autocast dtype {dt} is not supported; the fused path mirrors "
+                           f"torch.autocast('cuda', dtype=torch.bfloat16) only")
+    return True
+
+
 def splade_head(hidden, weight, bias, attention_mask, want_token_weights: bool = True,
                 round_bias: Optional[bool] = None):
     if round_bias is None:
-        round_bias = torch.is_autocast_enabled("cuda") if hidden.is_cuda else False
+        round_bias = autocast_is_bf16() if hidden.is_cuda else False
     rep, tokw = SpladeHeadFunction.apply(hidden, weight, bias, attention_mask, want_token_weights, round_bias)
     return rep, (tokw if want_token_weights else None)
 

@@ -129,10 +129,14 @@ class PeerExchange:
             check(load_library().splade_peer_status(ctypes.byref(self.group_struct), ctypes.byref(st)),
                   "splade_peer_status")
         if st.value != 0:
-            phase, peer = st.value >> 8, (st.value & 0xFF) - 1
-            raise RuntimeError(f"PeerExchange: rank {self.rank} waited in vain for rank {peer} "
-                               f"({'forward' if phase == 1 else 'backward'} barrier timed out); "
-                               f"the results of that step are invalid")
+            self.raise_for_status(st.value)
+
+    def raise_for_status(self, status: int) -> None:
+        """Turn a non-zero window status word (``splade_peer_status`` / scalars[15] of the peer loss) into the error."""
+        phase, peer = status >> 8, (status & 0xFF) - 1
+        raise RuntimeError(f"PeerExchange: rank {self.rank} waited in vain for rank {peer} "
+                           f"({'forward' if phase == 1 else 'backward'} barrier timed out); "
+                           f"the results of that step are invalid")
 
     def _release_local(self) -> None:
         lib = load_library()

@@ -71,6 +71,9 @@ def train_micro_step(model, loss_fn, optimizer, scheduler, batch: Dict[str, torc
         (loss / accum).backward()
 
     if last_micro:
+        exchange = getattr(loss_fn, "exchange", None)
+        if exchange is not None and exchange.world > 1:
+            exchange.check()  # a backward barrier that gave up must not reach the optimizer
         torch.nn.utils.clip_grad_norm_(model.parameters(), cfg.gradient_clip)
         optimizer.step()
         if scheduler is not None:

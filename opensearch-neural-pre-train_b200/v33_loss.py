@@ -12,12 +12,13 @@ per-rank.  Off by default = the reference's per-GPU local negatives.
 from __future__ import annotations
 
 import os
+import struct
 from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn as nn
 
-from .ops import V33LossFunction, V33PeerLossFunction
+from .ops import V33LossFunction, V33PeerLossFunction, autocast_is_bf16
 
 _SCALAR_KEYS = ("loss", "infonce", "flops_q", "flops_d", "flops_neg", "kd", "margin_mse", "nonzero_q",
                 "nonzero_d")
@@ -109,7 +110,7 @@ class SPLADELossV33(nn.Module):
         cfg = dict(
             label_offset=label_offset,
             # autocast makes torch.mm consume and produce bf16; mirror it bit for bit
-            round_bf16=torch.is_autocast_enabled("cuda"),
+            round_bf16=autocast_is_bf16(),
             temperature=float(self.temperature), kd_temperature=float(self.kd_temperature),
             lambda_q=float(cur_lambda_q), lambda_d=float(cur_lambda_d), lambda_neg=float(cur_lambda_neg),
             lambda_kd=float(self.lambda_kd) if use_kd else 0.0,
@@ -131,7 +132,14 @@ class SPLADELossV33(nn.Module):
                 cfg,
             )
 
-        vals = scalars[: len(_SCALAR_KEYS)].tolist()  # the single device->host sync of this step
+        host = scalars.tolist()  # the single device->host sync of this step (16 floats)
+        vals = host[: len(_SCALAR_KEYS)]
+        if use_peer:
+            # scalars[15] carries the exchange window's status word (raw int32 bits): a barrier of this rank that
+            # gave up - in this forward or in an earlier backward - must stop the run, not poison it silently
+            status = struct.unpack("<i", struct.pack("<f", host[15]))[0]
+            if status != 0:
+                self.exchange.raise_for_status(status)
         s = dict(zip(_SCALAR_KEYS, vals))
         self._avg_nonzero_q = 0.9 * self._avg_nonzero_q + 0.1 * s["nonzero_q"]
         self._avg_nonzero_d = 0.9 * self._avg_nonzero_d + 0.1 * s["nonzero_d"]

@@ -234,3 +234,44 @@ def test_c_emitter_search_bodies():
         "field": "emb.last", "boost": pytest.approx(1e-7, rel=1e-6)}
     with pytest.raises(ValueError):
         splade_b200.SparseEmitter(None, None).to_search_bodies(ids, vals, counts)
+
+
+def test_bf16_weight_cache_is_tied_to_the_parameter_object_not_its_address():
+    """evaluating several checkpoints in one process frees model A and builds model B whose tied
+    matrix very likely lands on A's allocator address with the same version counter; B must never be served A's
+    bf16 copy.  Also: an in-place update (optimizer step) invalidates, an untouched parameter hits."""
+    from splade_b200 import ops
+    ops.clear_weight_cache()
+    stale = 0
+    for i in range(8):
+        w = torch.nn.Parameter(torch.full((64, 32), float(i + 1)))
+        with torch.no_grad():
+            w.mul_(1.0)                       # same version history for every "model"
+        c = ops.cached_bf16(w)
+        stale += int(float(c[0, 0]) != float(i + 1))
+        assert ops.cached_bf16(w) is c        # second call of the same step: cache hit
+        del w, c
+    assert stale == 0
+    w = torch.nn.Parameter(torch.ones(8, 8))
+    a = ops.cached_bf16(w)
+    with torch.no_grad():
+        w.add_(1.0)                           # what an optimizer step does
+    b = ops.cached_bf16(w)
+    assert a is not b and float(b[0, 0]) == 2.0
+    w.data = torch.full((8, 8), 5.0)          # re-pointed storage (load / .to()): data_ptr changes
+    assert float(ops.cached_bf16(w)[0, 0]) == 5.0
+    ops.clear_weight_cache()
+
+
+def test_only_bf16_autocast_is_mirrored(monkeypatch):
+    """SPLADELossV33 / splade_head mirror torch.autocast('cuda', bfloat16); fp16 autocast must be refused, not
+    silently computed as bf16.  (CUDA autocast cannot be entered without a device: the two torch
+    queries are patched.)"""
+    from splade_b200 import ops
+    assert ops.autocast_is_bf16() is False
+    monkeypatch.setattr(torch, "is_autocast_enabled", lambda *a: True)
+    monkeypatch.setattr(torch, "get_autocast_dtype", lambda *a: torch.bfloat16)
+    assert ops.autocast_is_bf16() is True
+    monkeypatch.setattr(torch, "get_autocast_dtype", lambda *a: torch.float16)
+    with pytest.raises(RuntimeError, match="autocast dtype"):
+        ops.autocast_is_bf16()
