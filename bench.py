@@ -203,7 +203,8 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------
 # secondary metric: training-step tokens/s of the hot path (BASELINE config 4)
 # ------------------------------------------------------------------------------------------------------
-def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_offset=-1.0, exchange="peer"):
+def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_offset=-1.0, exchange="peer",
+                  grad_bf16=False):
     """One C4 micro-step of the HOT PATH per rank: fused head forward for query (64x64), positive (64x256)
     and k negatives (64k x 256) hidden states, SPLADELossV33 (InfoNCE + FLOPS, optional cross-GPU negatives),
     backward through the loss and the sparse head backward, then the gradient all-reduce DDP would do for the
@@ -260,7 +261,12 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
             loss, d = loss_fn(a, p, n, global_step=1000 + i)
         loss.backward()
         if world > 1:
-            dist.all_reduce(W.grad, op=dist.ReduceOp.AVG)
+            if grad_bf16:  # N3: the tied matrix's gradient travels as bf16 (what DDP's bf16_compress_hook does)
+                g16 = W.grad.to(torch.bfloat16)
+                dist.all_reduce(g16, op=dist.ReduceOp.AVG)
+                W.grad.copy_(g16)
+            else:
+                dist.all_reduce(W.grad, op=dist.ReduceOp.AVG)
             dist.all_reduce(bias.grad, op=dist.ReduceOp.AVG)
         with torch.no_grad():  # stand-in for the optimizer: bumps the version so the bf16 weight copy is re-cast
             W.add_(W.grad, alpha=-1e-6)
@@ -303,7 +309,7 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
     return {"tokens_per_s": tokens / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
             "workload": f"C4 hot path per GPU: head fwd+bwd for q 64x64 / pos 64x256 / neg {64 * k_neg}x256 + "
                         f"SPLADELossV33 fwd+bwd (k={k_neg}, gather_negatives={gather}) + all-reduce of the tied "
-                        f"decoder matrix and bias grads; trunk excluded",
+                        f"decoder matrix ({'bf16-compressed' if grad_bf16 else 'fp32'}) and bias grads; trunk excluded",
             "head_fwd_tflop_per_step_per_gpu": head_flop / 1e12, "nonzero_d": d["nonzero_d"],
             "regime": f"decoder.bias offset {bias_offset}: {d['nonzero_d']:.0f} active terms per document",
             "negatives_exchange": exchange_used, "scaling": "weak"}
@@ -312,29 +318,19 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
 # ------------------------------------------------------------------------------------------------------
 # context: full encode (unchanged ModernBERT trunk + head), ours vs the reference statement on the same GPU
 # ------------------------------------------------------------------------------------------------------
-def run_full_encode_leg(dev, steps=5, warmup=2):
+def run_full_encode_leg(dev, steps=5, warmup=2, ours=None):
     """SPLADEModernBERT.encode on a random-init A.X-Encoder-base-shaped model (22 layers, hidden 768, vocab
     50 000; config restated from huggingface/v33/config.json), batch 64 x L=256, under autocast(bf16):
       ours               the reference's transformers trunk + the fused head (the drop-in default),
       ours_native_trunk  the native packed-token trunk + fused head in one C-ABI call (splade_trunk_encode),
       reference_chain    the reference's statement (HF logits -> relu -> log1p -> mask -> max)
     on the same device, plus how closely the native trunk's vectors agree with the transformers trunk's."""
-    import tempfile
-
     import torch
-    from transformers import AutoModelForMaskedLM, ModernBertConfig
 
     import splade_b200
     from oracle import torch_reference as TR
-    cfg = ModernBertConfig(vocab_size=VOCAB, hidden_size=HIDDEN, intermediate_size=1152, num_hidden_layers=22,
-                           num_attention_heads=12, pad_token_id=VOCAB - 1, bos_token_id=0, eos_token_id=1,
-                           cls_token_id=0, sep_token_id=1, max_position_embeddings=16384,
-                           global_attn_every_n_layers=3, local_attention=128)
-    torch.manual_seed(0)
-    hf = AutoModelForMaskedLM.from_config(cfg)
-    with tempfile.TemporaryDirectory() as d:
-        hf.save_pretrained(d)
-        ours = splade_b200.SPLADEModernBERT(model_name=d).to(dev).eval()
+    if ours is None:
+        ours = build_axbase_model().to(dev).eval()
     ref = TR.ReferenceSpladeModule(ours.model).eval()
     g = torch.Generator().manual_seed(1)
     ids = torch.randint(6, VOCAB - 1, (B_DOCS, SEQ), generator=g).to(dev)
@@ -366,6 +362,289 @@ def run_full_encode_leg(dev, steps=5, warmup=2):
     out["speedup"] = out["reference_chain"]["ms_per_batch"] / out["ours"]["ms_per_batch"]
     out["speedup_native_trunk"] = out["reference_chain"]["ms_per_batch"] / out["ours_native_trunk"]["ms_per_batch"]
     return out
+
+def build_axbase_model(bias_offset=None, seed=0):
+    """Random-init A.X-Encoder-base-shaped SPLADEModernBERT (22 layers, hidden 768, 12 heads, intermediate 1152,
+    vocab 50 000, 149 M parameters; config restated from huggingface/v33/config.json) through the drop-in class's
+    own constructor.  ``bias_offset`` shifts decoder.bias so that the pooled vectors are as sparse as a trained
+    model's."""
+    import tempfile
+
+    import torch
+    from transformers import AutoModelForMaskedLM, ModernBertConfig
+
+    import splade_b200
+    cfg = ModernBertConfig(vocab_size=VOCAB, hidden_size=HIDDEN, intermediate_size=1152, num_hidden_layers=22,
+                           num_attention_heads=12, pad_token_id=VOCAB - 1, bos_token_id=0, eos_token_id=1,
+                           cls_token_id=0, sep_token_id=1, max_position_embeddings=16384,
+                           global_attn_every_n_layers=3, local_attention=128)
+    torch.manual_seed(seed)
+    hf = AutoModelForMaskedLM.from_config(cfg)
+    if bias_offset is not None:
+        with torch.no_grad():
+            hf.decoder.bias.copy_(torch.randn(VOCAB, generator=torch.Generator().manual_seed(2)) * 0.02 + bias_offset)
+    with tempfile.TemporaryDirectory() as d:
+        hf.save_pretrained(d)
+        return splade_b200.SPLADEModernBERT(model_name=d)
+
+
+def run_e2e_encode_leg(dev, model, steps, warmup, world, barrier, max_over_ranks, native_trunk, top_k=64):
+    """The reference's production encode (benchmark/encoders.py:309-345) end to end through the public API: token
+    ids + attention mask in PINNED HOST memory -> H2D -> SPLADEModernBERT.encode under autocast(bf16) -> GPU top-k
+    (splade_topk) -> ids / weights / counts back to PINNED HOST memory.  Every step's copies are inside the timed
+    region; two slots on two streams so the copies of one batch overlap the compute of the other."""
+    import torch
+
+    import splade_b200
+    g = torch.Generator().manual_seed(7)
+    ids_h = [torch.randint(6, VOCAB - 1, (B_DOCS, SEQ), generator=g).pin_memory() for _ in range(2)]
+    mask_h = torch.ones(B_DOCS, SEQ, dtype=torch.int64).pin_memory()
+    out_h = [(torch.empty(B_DOCS, top_k, dtype=torch.int32).pin_memory(),
+              torch.empty(B_DOCS, top_k, dtype=torch.float32).pin_memory(),
+              torch.empty(B_DOCS, dtype=torch.int32).pin_memory()) for _ in range(2)]
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    previous = getattr(model, "_native_trunk_enabled", False)
+    model.use_native_trunk(native_trunk)
+
+    def loop(n):
+        for i in range(n):
+            j = i & 1
+            with torch.cuda.stream(streams[j]), torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                ids = ids_h[j].to(dev, non_blocking=True)
+                mask = mask_h.to(dev, non_blocking=True)
+                rep = model.encode(ids, mask)
+                ti, tv, tc = splade_b200.topk(rep, top_k)
+                out_h[j][0].copy_(ti, non_blocking=True)
+                out_h[j][1].copy_(tv, non_blocking=True)
+                out_h[j][2].copy_(tc, non_blocking=True)
+
+    try:
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream(dev))
+        loop(max(2, warmup))
+        barrier()
+        t0 = time.perf_counter()
+        loop(steps)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+    finally:
+        model.use_native_trunk(previous)
+    h2d = ids_h[0].numel() * 8 + mask_h.numel() * 8
+    d2h = sum(t.numel() * t.element_size() for t in out_h[0])
+    j = (steps - 1) & 1
+    return {"value": world * B_DOCS * steps / dt, "unit": "docs/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "trunk": "native packed-token trunk (splade_trunk_encode, opt-in)" if native_trunk
+                     else "transformers ModernBERT trunk (the drop-in default)",
+            "top_k": top_k, "checksum": float(out_h[j][1][0, :8].sum()), "counts0": int(out_h[j][2][0])}
+
+
+def run_peer_parity(dev, world, rank, exchange="peer"):
+    """Real-IPC parity of the NVLink peer exchange, run inside the N >= 2 bench so that the driver's SCALE record
+    carries it: SPLADELossV33 with exchange=PeerExchange against the NCCL all-gather / reduce-scatter statement on
+    the same seeded inputs (both window parities, autocast on and off, MarginMSE teachers included)."""
+    import torch
+    import torch.distributed as dist
+
+    import splade_b200
+    if world < 2 or exchange != "peer":
+        return None
+    try:
+        x = splade_b200.PeerExchange(B_DOCS, VOCAB)
+    except RuntimeError as e:
+        return {"error": f"peer exchange unavailable: {str(e)[:200]}"}
+    out = {"loss_bitexact": True, "dq_bitexact": True, "dnegs_bitexact": True, "ddocs_max_rel": 0.0,
+           "loss_dict_equal": True}
+    try:
+        g = torch.Generator().manual_seed(500 + rank)
+
+        def reps(n):
+            return (torch.rand(n, VOCAB, generator=g) * (torch.rand(n, VOCAB, generator=g) < 0.02)).to(dev)
+
+        q, p, n = reps(B_DOCS), reps(B_DOCS), reps(B_DOCS)
+        t_pos = torch.randn(B_DOCS, generator=g).to(dev)
+        t_neg = torch.randn(B_DOCS, generator=g).to(dev)
+        f_peer = splade_b200.SPLADELossV33(exchange=x, lambda_margin_mse=0.5)
+        f_nccl = splade_b200.SPLADELossV33(gather_negatives=True, lambda_margin_mse=0.5)
+
+        def run(fn, autocast):
+            a, b, c = (t.clone().requires_grad_(True) for t in (q, p, n))
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                loss, d = fn(a, b, c, global_step=20000, teacher_pos_scores=t_pos, teacher_neg_scores=t_neg)
+            (loss / (1 + rank)).backward()
+            return loss.detach(), d, a.grad, b.grad, c.grad
+
+        for autocast in (True, False):
+            for _ in range(2):  # both window parities
+                got, want = run(f_peer, autocast), run(f_nccl, autocast)
+                out["loss_bitexact"] &= bool(torch.equal(got[0], want[0]))
+                out["dq_bitexact"] &= bool(torch.equal(got[2], want[2]))
+                out["dnegs_bitexact"] &= bool(torch.equal(got[4], want[4]))
+                rel = float((got[3] - want[3]).abs().max()) / (float(want[3].abs().max()) + 1e-30)
+                out["ddocs_max_rel"] = max(out["ddocs_max_rel"], rel)
+                out["loss_dict_equal"] &= all(got[1][k] == want[1][k] for k in want[1])
+        x.check()
+    except RuntimeError as e:
+        out = {"error": f"{type(e).__name__}: {e}"[:300]}
+    # every rank reports; rank 0's line carries the worst case
+    flags = torch.tensor([float(out.get("loss_bitexact", False)), float(out.get("dq_bitexact", False)),
+                          float(out.get("dnegs_bitexact", False)), float(out.get("loss_dict_equal", False)),
+                          -float(out.get("ddocs_max_rel", 1.0))], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    x.close()
+    f = flags.tolist()
+    res = {"loss_bitexact": f[0] > 0.5, "dq_bitexact": f[1] > 0.5, "dnegs_bitexact": f[2] > 0.5,
+           "loss_dict_equal": f[3] > 0.5, "ddocs_max_rel": -f[4], "ranks": world,
+           "what": "SPLADELossV33(exchange=PeerExchange) vs SPLADELossV33(gather_negatives=True) [NCCL all-gather + "
+                   "reduce-scatter] on identical inputs, real CUDA-IPC windows; min / max over ranks; ddocs differs "
+                   "by the summation order over ranks only"}
+    if "error" in out:
+        res["error"] = out["error"]
+    return res
+
+
+def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=1, exchange="peer"):
+    """The FULL training step of the reference (src/train/cli/train_v33_ddp.py:337-374) on the A.X-Encoder-base
+    shape, BASELINE config 4: per GPU 64 queries x 64 + 64 positives x 256 + 64 negatives x 256 tokens through the
+    22-layer transformers trunk WITH autograd, three head calls, SPLADELossV33, (loss / accum).backward() under
+    DistributedDataParallel (:539-544) for N > 1, and - every `accum` micro-steps - clip_grad_norm_(1.0) + AdamW.
+    decoder.bias is offset so the pooled vectors are sparse like a trained model's.  Variants:
+      reference_semantics  drop-in classes, DDP all-reduces on EVERY micro-step (what the reference does)
+      no_sync              DDP.no_sync() on the non-final micro-steps of the accumulation window (N3)
+      bf16_grad_hook       + bf16 gradient compression of the all-reduce (N3)
+      peer_negatives       + cross-GPU in-batch negatives through the NVLink peer exchange (N > 1)
+      reference_statement  the reference's own head/loss statement (oracle/torch_reference.py) on the same trunk
+    tokens/s = whole job (all ranks, real padded tokens of the collator shape) / max-over-ranks CUDA-event time."""
+    import torch
+    import torch.distributed as dist
+
+    import splade_b200
+    from oracle import torch_reference as TR
+    from splade_b200.training import (StepConfig, enable_bf16_gradient_compression, synthetic_triplet_batch,
+                                      train_micro_step)
+    B = B_DOCS
+    n_micro = accum * (1 + opt_steps)
+    batches = [synthetic_triplet_batch(B, 64, SEQ, 1, VOCAB, VOCAB - 1, seed=1000 * (42 + rank) + i, ragged=False)
+               for i in range(n_micro)]
+    tokens_per_micro = world * B * (64 + SEQ + SEQ)
+    out = {"workload": "C4 full training step per GPU: q 64x64 / pos 64x256 / neg 64x256 tokens, A.X-Encoder-base "
+                       "shape (22L, 149 M params, transformers trunk with autograd) + 3 head calls + SPLADELossV33 + "
+                       f"clip + AdamW, gradient accumulation {accum}, autocast(bf16), DDP when n_gpus > 1",
+           "n_gpus": world, "accum": accum, "micro_steps_timed": accum * opt_steps,
+           "tokens_per_micro_step": tokens_per_micro, "scaling": "weak"}
+    base = build_axbase_model(bias_offset=-2.0)
+    sched = splade_b200.SPLADELossV33()
+
+    def ref_loss(anchor_repr, positive_repr, negative_repr, global_step, **kw):
+        lam = [sched._lambda_schedule(global_step, x) for x in (sched.lambda_q, sched.lambda_d, sched.lambda_neg)]
+        loss = TR.v33_loss(anchor_repr, positive_repr, negative_repr, *lam)
+        return loss, {"nonzero_d": float((positive_repr > 0).sum(1).float().mean())}
+
+    def time_variant(module, loss_fn, no_sync, bf16_hook):
+        model = module.to(dev).train()
+        if world > 1:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            model = DDP(model, device_ids=[local_rank], find_unused_parameters=False)
+            if bf16_hook:
+                enable_bf16_gradient_compression(model)
+        opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.01)
+        scfg = StepConfig(gradient_accumulation_steps=accum, skip_allreduce_on_accumulation=no_sync)
+        gs, d = 20000, {}
+        torch.cuda.reset_peak_memory_stats(dev)
+        for i in range(accum):  # one full optimizer step of warm-up
+            loss, d, gs = train_micro_step(model, loss_fn, opt, None, batches[i], i, gs, scfg, dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(accum, n_micro):
+            loss, d, gs = train_micro_step(model, loss_fn, opt, None, batches[i], i, gs, scfg, dev)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (n_micro - accum)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        res = {"ms_per_micro_step": ms, "tokens_per_s": tokens_per_micro / ms * 1e3,
+               "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30, "last_loss": float(loss),
+               "nonzero_d": d.get("nonzero_d")}
+        del opt, model
+        module.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        return res
+
+    variants = [("reference_semantics", "ours", False, False, "local")]
+    if world > 1:
+        variants += [("no_sync", "ours", True, False, "local"), ("bf16_grad_hook", "ours", True, True, "local"),
+                     ("peer_negatives", "ours", True, False, exchange)]
+    variants.append(("reference_statement", "ref", False, False, "local"))
+    ref_module = None
+    for name, side, no_sync, hook, negs in variants:
+        x = None
+        try:
+            if side == "ours":
+                module = base
+                loss_fn = splade_b200.SPLADELossV33()
+                if negs == "peer":
+                    x = splade_b200.PeerExchange(B, VOCAB)
+                    loss_fn = splade_b200.SPLADELossV33(exchange=x)
+                elif negs == "nccl":
+                    loss_fn = splade_b200.SPLADELossV33(gather_negatives=True)
+            else:
+                if ref_module is None:
+                    base.to("cpu")
+                    torch.cuda.empty_cache()
+                    ref_module = TR.ReferenceSpladeModule(base.model)
+                module, loss_fn = ref_module, ref_loss
+            out[name] = time_variant(module, loss_fn, no_sync, hook)
+        except Exception as e:  # noqa: BLE001 - keep the other variants
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if x is not None:
+            try:
+                x.check()
+                x.close()
+            except RuntimeError as e:
+                out[name]["exchange_error"] = str(e)[:200]
+    # the collective that bounds the step: DDP's bucketed fp32 all-reduce of every gradient (597 MB), timed alone
+    if world > 1:
+        nbytes = sum(p.numel() for p in base.parameters()) * 4
+        buf = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        tied = torch.empty(VOCAB * HIDDEN, dtype=torch.float32, device=dev)
+        coll = {}
+        for label, t in (("all_gradients_fp32", buf), ("tied_decoder_matrix_fp32", tied),
+                         ("all_gradients_bf16", buf.to(torch.bfloat16))):
+            for _ in range(2):
+                dist.all_reduce(t)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                dist.all_reduce(t)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            sz = t.numel() * t.element_size()
+            coll[label] = {"bytes": sz, "ms": ms, "busbw_GBps": sz * 2 * (world - 1) / world / ms / 1e6}
+        out["collectives_timed_alone"] = coll
+        a, b = out.get("reference_semantics", {}), out.get("no_sync", {})
+        if "ms_per_micro_step" in a and "ms_per_micro_step" in b:
+            out["limiting_collective"] = (
+                f"DDP bucketed all-reduce of all gradients ({nbytes / 1e6:.0f} MB fp32 per micro-step, NCCL over "
+                f"NVLink): {coll['all_gradients_fp32']['ms']:.2f} ms alone; exposed per micro-step = "
+                f"{a['ms_per_micro_step'] - b['ms_per_micro_step'] * accum / (accum - 1 + 1):.2f} ms "
+                f"(reference_semantics - no_sync, the latter still pays it on 1 of {accum} micro-steps)")
+    a, r = out.get("reference_semantics", {}), out.get("reference_statement", {})
+    if "ms_per_micro_step" in a and "ms_per_micro_step" in r:
+        out["speedup_vs_reference_statement"] = r["ms_per_micro_step"] / a["ms_per_micro_step"]
+    del base, ref_module
+    torch.cuda.empty_cache()
+    return out
+
 
 def run_ragged_leg(dev, iters=20):
     """Right-padded batches as the reference's collator produces them (dynamic padding to the longest member,
@@ -511,9 +790,30 @@ def run_ours(args):
     d2h_bytes = host_out[0].numel() * 4
     checksum = float(host_out[(n_e2e - 1) & 1][0, :8].sum())  # touch the result on the host
 
+    e2e_head = {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "steps": n_e2e,
+                "api": "splade_b200.head_forward_host = one C-ABI call splade_head_fwd_host per step on pinned "
+                       "host buffers holding HIDDEN STATES (H2D, fused head, D2H of the dense [64, 50 000] fp32 "
+                       "vectors; 2 slots / 2 streams) - round 1's e2e, PCIe-bound at 8 GPUs: hidden states never "
+                       "live on the host in the reference",
+                "checksum": checksum, "numa_bound": numa_bound}
+    del host_in, host_out, slots
+
+    # ---- (2b) the reference's real encode boundary (benchmark/encoders.py:309-345): token ids in, top-k out
+    e2e, e2e_hf, model, e2e_err = None, None, None, None
+    if not args.no_full_model:
+        try:
+            model = build_axbase_model().to(dev).eval()
+            e2e = run_e2e_encode_leg(dev, model, K, Wm, world, barrier, max_over_ranks, native_trunk=True)
+            e2e_hf = run_e2e_encode_leg(dev, model, max(3, min(K, 20)), 2, world, barrier, max_over_ranks,
+                                        native_trunk=False)
+        except Exception as e:  # noqa: BLE001 - never lose the headline line; every rank fails alike (same code)
+            e2e_err = f"{type(e).__name__}: {e}"[:300]
+    t_load3 = time.perf_counter()
+
     train = None
     if not args.no_train:
-        del sets[1:], host_in, host_out, slots
+        del sets[1:]
         gather = world > 1 and not args.local_negatives
         n_train = max(3, min(20, K))
         try:
@@ -522,8 +822,31 @@ def run_ours(args):
             # the same step in the trained-like sparse regime (bias offset sweeps the density)
             train["sparse_regime"] = run_train_leg(dev, world, rank, steps=n_train, warmup=3, k_neg=1, gather=gather,
                                                    bias_offset=-2.0, exchange=args.exchange)
+            if world > 1:  # N3 variant: the same sparse-regime step with the gradient all-reduce in bf16
+                train["sparse_regime_bf16_allreduce"] = run_train_leg(
+                    dev, world, rank, steps=n_train, warmup=3, k_neg=1, gather=gather, bias_offset=-2.0,
+                    exchange=args.exchange, grad_bf16=True)
         except RuntimeError as e:  # secondary leg: never lose the headline line over it
             train = dict(train or {}, error=f"{type(e).__name__}: {e}"[:400])
+
+    peer_parity = None
+    if world > 1 and not args.no_train and not args.local_negatives:
+        try:
+            peer_parity = run_peer_parity(dev, world, rank, args.exchange)
+        except Exception as e:  # noqa: BLE001
+            peer_parity = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    train_full = None
+    if not args.no_train_full:
+        if model is not None:
+            model.to("cpu")
+        torch.cuda.empty_cache()
+        try:
+            train_full = run_train_full_leg(dev, world, rank, local_rank, exchange=args.exchange)
+        except Exception as e:  # noqa: BLE001
+            train_full = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if model is not None and world == 1:
+            model.to(dev)
 
     gpu_ref = None
     if world == 1 and rank == 0 and not args.no_gpu_reference:
@@ -562,7 +885,7 @@ def run_ours(args):
     full = None
     if world == 1 and rank == 0 and not args.no_full_model:
         try:
-            full = run_full_encode_leg(dev)
+            full = run_full_encode_leg(dev, ours=model)
         except Exception as e:  # context only: never fail the bench line over it
             full = {"error": repr(e)[:200]}
 
@@ -607,12 +930,14 @@ def run_ours(args):
         "config": bench_config(world),
         "tokens_per_s": value * SEQ,
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "steps": n_e2e,
-                "api": "splade_b200.head_forward_host = one C-ABI call splade_head_fwd_host per step on pinned "
-                       "host buffers (H2D, fused head, D2H enqueued on the slot's stream; 2 slots / 2 streams)",
-                "checksum": checksum,
-                "numa_bound": numa_bound},
+        # e2e = the reference's production encode boundary: token ids (pinned host) -> SPLADEModernBERT.encode ->
+        # top-k ids / weights (pinned host); e2e_head = the same head call as `value` fed from host hidden states
+        "e2e": dict(e2e, api="token ids + mask in pinned host memory -> SPLADEModernBERT.encode (22-layer A.X-base "
+                             "shape, autocast bf16) -> splade_topk(k=64) -> ids / weights / counts in pinned host "
+                             "memory; 2 slots / 2 streams; every copy inside the timed region")
+               if e2e is not None else dict(e2e_head, note=f"full-encode e2e unavailable: {e2e_err or 'skipped'}"),
+        "e2e_reference_trunk": e2e_hf,
+        "e2e_head": e2e_head,
         # kernels of libsplade_b200.so launched per step in the device-resident timed region (splade_head_fwd, auto
         # tiling policy): build_tile_masks, varlen_plan (counts + plans), varlen_pack (exits: padded tiling chosen),
         # head_fwd_kernel, head_fwd_varlen_kernel (exits), finalize_varlen (exits).  The e2e region adds 2 per step
@@ -622,6 +947,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "train": train,
+        "train_full": train_full,
+        "peer_parity": peer_parity,
         "ragged": ragged,
         "full_encode": full,
         "gpu_reference_chain": gpu_ref,
@@ -639,7 +966,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step leg")
-    ap.add_argument("--no-full-model", action="store_true", help="skip the trunk+head context leg")
+    ap.add_argument("--no-full-model", action="store_true", help="skip the trunk+head legs (e2e falls back to e2e_head)")
+    ap.add_argument("--no-train-full", action="store_true", help="skip the full DDP training-step leg")
     ap.add_argument("--no-ragged", action="store_true", help="skip the ragged-batch (packed tiling) context leg")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-chain-on-GPU context leg")
     ap.add_argument("--gather-negatives", action="store_true",

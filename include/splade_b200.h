@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPLADE_B200_ABI_VERSION 3
+#define SPLADE_B200_ABI_VERSION 4
 
 /* error codes */
 #define SPLADE_OK 0
@@ -47,6 +47,8 @@ extern "C" {
 #define SPLADE_OP_TRUNK_GEMM 7    /* (-)                      splade_trunk_gemm scratch               */
 #define SPLADE_OP_TRUNK_ATTN 8    /* (B,S,-,V=1)              splade_trunk_attn scratch               */
 #define SPLADE_OP_PEER_LOSS_BWD 9 /* (B=Bq, k=world)          splade_peer_loss_bwd scratch            */
+#define SPLADE_OP_HEAD_BWD_DHIDDEN 10 /* (B,S,-,V)            splade_head_bwd_dhidden scratch (one segment)   */
+#define SPLADE_OP_HEAD_BWD_BITMAP 11  /* (B,-,-,V)            bytes of one segment's activity bitmap          */
 
 int splade_abi_version(void);
 const char* splade_last_error(void);
@@ -113,6 +115,42 @@ int splade_head_fwd_host(const void* hidden_host, const int32_t* mask_host, cons
 int splade_head_bwd(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden, const void* W,
                     int B, int S, int H, int V, float* d_hidden, float* dW, float* dbias, void* workspace,
                     size_t ws_bytes, void* stream);
+
+/*
+ * The same backward for SEVERAL head calls that share one decoder matrix.  The reference trainer runs the model
+ * three times per micro-step (query, positive, negatives: src/train/cli/train_v33_ddp.py:339-343) and
+ * back-propagates once (:364); autograd then sums three dense [V,H] gradients of the tied decoder / embedding
+ * matrix.  Here each head call is a "segment" and dW / dbias are produced by ONE sweep over the vocabulary that
+ * walks all segments (fixed order: segments as given, documents ascending => run-to-run bit-identical).
+ *   accumulate != 0: dW / dbias are ADDED to the buffers' contents (e.g. straight into tok_embeddings.weight.grad
+ *                    on the later micro-steps of a gradient-accumulation window) instead of overwriting them.
+ *   d_hidden may be NULL for a segment whose input needs no gradient.
+ * splade_head_bwd_multi does everything in three launches.  The two-phase form serves autograd, which delivers the
+ * three g_rep one after the other: splade_head_bwd_dhidden (per segment, as its g_rep arrives; uses segment.active
+ * or, when that is NULL, writes the activity bitmap uint32 [B, ceil(V/32)] into `bitmap`) and, after the last one,
+ * splade_head_bwd_dw over all segments and their bitmaps.  The backward kernels are DRIVEN by the bitmap: in the
+ * trained (sparse) regime g_rep / rep / argmax are read at the active terms only.
+ * Workspaces: splade_head_bwd_multi_workspace_bytes; SPLADE_OP_HEAD_BWD_DHIDDEN via splade_workspace_bytes.
+ */
+#define SPLADE_HEAD_BWD_MAX_SEGMENTS 8
+typedef struct splade_head_bwd_segment {
+  const float* g_rep;     /* [B,V] fp32  gradient of sparse_repr                 */
+  const float* rep;       /* [B,V] fp32  sparse_repr saved from the forward      */
+  const int32_t* argmax;  /* [B,V] int32 saved from the forward                  */
+  const void* hidden;     /* [B,S,H] bf16 the forward's input                    */
+  float* d_hidden;        /* [B,S,H] fp32 out, or NULL                           */
+  int32_t B, S;
+  const uint32_t* active; /* optional [B, ceil(V/32)]: bit j of word w = (rep[b, 32w+j] > 0), as splade_rep_bitmap
+                             writes it (cheapest right after the forward, rep is L2-hot); NULL = computed here */
+} splade_head_bwd_segment;
+int splade_rep_bitmap(const float* rep, int B, int V, uint32_t* bitmap, void* stream);
+size_t splade_head_bwd_multi_workspace_bytes(const splade_head_bwd_segment* segs, int n_segs, int V);
+int splade_head_bwd_multi(const splade_head_bwd_segment* segs, int n_segs, const void* W, int H, int V, float* dW,
+                          float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream);
+int splade_head_bwd_dhidden(const splade_head_bwd_segment* seg, const void* W, int H, int V, uint32_t* bitmap,
+                            void* workspace, size_t ws_bytes, void* stream);
+int splade_head_bwd_dw(const splade_head_bwd_segment* segs, const uint32_t* const* bitmaps, int n_segs, int H, int V,
+                       float* dW, float* dbias, int accumulate, void* stream);
 
 /*
  * FLOPS regulariser (src/model/losses.py:57-73) and nonzero monitoring (losses.py:272-273) in one pass.

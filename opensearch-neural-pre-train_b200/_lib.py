@@ -12,7 +12,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_siz
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libsplade_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # op ids for splade_workspace_bytes (include/splade_b200.h)
 OP_HEAD_FWD = 0
@@ -25,6 +25,9 @@ OP_TRUNK_ENCODE = 6
 OP_TRUNK_GEMM = 7
 OP_TRUNK_ATTN = 8
 OP_PEER_LOSS_BWD = 9
+OP_HEAD_BWD_DHIDDEN = 10
+OP_HEAD_BWD_BITMAP = 11
+HEAD_BWD_MAX_SEGMENTS = 8
 MAX_PEERS = 16
 
 # epilogues of splade_trunk_gemm
@@ -61,6 +64,13 @@ class V33FwdArgs(Structure):
         ("colmean", c_void_p), ("scalars", c_void_p), ("g_inbatch", c_void_p), ("g_hard", c_void_p),
         ("workspace", c_void_p), ("ws_bytes", c_size_t),
     ]
+
+
+class HeadBwdSegment(Structure):
+    """Mirror of ``splade_head_bwd_segment`` (include/splade_b200.h)."""
+
+    _fields_ = [("g_rep", c_void_p), ("rep", c_void_p), ("argmax", c_void_p), ("hidden", c_void_p),
+                ("d_hidden", c_void_p), ("B", c_int32), ("S", c_int32), ("active", c_void_p)]
 
 
 class TrunkLayer(Structure):
@@ -109,6 +119,14 @@ EXPORTS = {
                                      c_void_p]),
     "splade_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "splade_rep_bitmap": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "splade_head_bwd_multi_workspace_bytes": (c_size_t, [POINTER(HeadBwdSegment), c_int, c_int]),
+    "splade_head_bwd_multi": (c_int, [POINTER(HeadBwdSegment), c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                      c_int, c_void_p, c_size_t, c_void_p]),
+    "splade_head_bwd_dhidden": (c_int, [POINTER(HeadBwdSegment), c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                        c_size_t, c_void_p]),
+    "splade_head_bwd_dw": (c_int, [POINTER(HeadBwdSegment), POINTER(c_void_p), c_int, c_int, c_int, c_void_p,
+                                   c_void_p, c_int, c_void_p]),
     "splade_flops_nnz": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "splade_scores": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                               c_void_p]),

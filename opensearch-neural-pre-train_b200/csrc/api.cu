@@ -158,6 +158,10 @@ size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k) {
              static_cast<size_t>(S > 0 ? S : 1) * 32 * sizeof(float2);
     case SPLADE_OP_PEER_LOSS_BWD:
       return peer_loss_bwd_workspace_bytes(B, k);
+    case SPLADE_OP_HEAD_BWD_DHIDDEN:
+      return head_bwd_dhidden_workspace_bytes(B, S, V);
+    case SPLADE_OP_HEAD_BWD_BITMAP:
+      return head_bwd_bitmap_bytes(B, V);
     default:
       return 0;
   }
@@ -204,6 +208,30 @@ int splade_head_bwd(const float* g_rep, const float* rep, const int32_t* argmax,
                     size_t ws_bytes, void* stream) {
   return head_bwd_launch(g_rep, rep, argmax, hidden, W, B, S, H, V, d_hidden, dW, dbias, workspace, ws_bytes,
                          static_cast<cudaStream_t>(stream));
+}
+
+int splade_rep_bitmap(const float* rep, int B, int V, uint32_t* bitmap, void* stream) {
+  return rep_bitmap_launch(rep, B, V, bitmap, static_cast<cudaStream_t>(stream));
+}
+
+size_t splade_head_bwd_multi_workspace_bytes(const splade_head_bwd_segment* segs, int n_segs, int V) {
+  return head_bwd_multi_workspace_bytes(segs, n_segs, V);
+}
+
+int splade_head_bwd_multi(const splade_head_bwd_segment* segs, int n_segs, const void* W, int H, int V, float* dW,
+                          float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream) {
+  return head_bwd_multi_launch(segs, n_segs, W, H, V, dW, dbias, accumulate, workspace, ws_bytes,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int splade_head_bwd_dhidden(const splade_head_bwd_segment* seg, const void* W, int H, int V, uint32_t* bitmap,
+                            void* workspace, size_t ws_bytes, void* stream) {
+  return head_bwd_dhidden_launch(seg, W, H, V, bitmap, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int splade_head_bwd_dw(const splade_head_bwd_segment* segs, const uint32_t* const* bitmaps, int n_segs, int H, int V,
+                       float* dW, float* dbias, int accumulate, void* stream) {
+  return head_bwd_dw_launch(segs, bitmaps, n_segs, H, V, dW, dbias, accumulate, static_cast<cudaStream_t>(stream));
 }
 
 int splade_flops_nnz(const float* rep, int N, int V, float* colmean, float* out2, void* workspace, size_t ws_bytes,

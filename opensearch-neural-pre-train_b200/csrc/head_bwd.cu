@@ -1,4 +1,4 @@
-// Gather-driven sparse backward of the fused SPLADE-max head (sm_100a).
+// Gather-driven sparse backward of the fused SPLADE-max head (sm_100a), for ONE or SEVERAL head calls at once.
 //
 // The reference back-propagates through dense [B,S,V] tensors (autograd of src/model/splade_modern.py:69-83
 // run from src/train/cli/train_v33_ddp.py:364): value_selecting_reduction_backward scatters g to the argmax
@@ -10,13 +10,22 @@
 //     dbias[v]      = sum_b coef[b,v]
 //     dW[v,:]       = sum_b coef[b,v] * hidden[b, argmax[b,v], :]                 (gather of B rows per term)
 //     dHidden[b,s,:]= sum_{v : argmax[b,v]=s} coef[b,v] * W[v,:]                  (gather after bucketing by s)
-// Both gathers read 16-bit rows that live in the 126 MB L2 (hidden 25 MB, W 77 MB at the headline shape);
-// the kernels are L2-gather-bound, not tensor-core work.
 //
-// Kernels: (1) bucket_count / bucket_scan / bucket_scatter: deterministic per-document counting sort of the active
-//              terms by argmax position, one warp per (document, 1024-term chunk);
-//          (2) dhidden_kernel: one warp per (b,s) row sums coef * W[v,:] over its bucket;
-//          (3) dw_kernel: one warp per vocabulary row sums coef * hidden[b,argmax,:] over the batch.
+// The reference trainer calls the model three times per micro-step (query, positive, negatives:
+// train_v33_ddp.py:339-343) and back-propagates once (:364); all three head calls share ONE decoder matrix, so
+// their dW / dbias are one sum.  A "segment" is one head call; the kernels take up to kMaxSegs of them:
+//   (1) bwd_bucket_kernel   one CTA per document (all segments in one launch): deterministic counting sort of the
+//                           document's active terms by argmax position (count in shared memory, scan, scatter) AND
+//                           the activity bitmap [doc][V/32] the dW sweep is driven by;
+//   (2) dhidden_kernel      one warp per (doc, position) row of any segment sums coef * W[v,:] over its bucket;
+//   (3) dw_kernel           ONE sweep over the vocabulary for all segments: a CTA owns 32 consecutive terms, reads
+//                           one bitmap word per document, stages the coefficients of the active (doc, term) pairs
+//                           only, and every warp sums coef * hidden[doc, argmax, :] for 4 terms in a fixed order
+//                           (segments in call order, documents ascending) => dW / dbias written once, bit-identical
+//                           run to run.  `accumulate` adds into an existing gradient buffer instead.
+// Gathers read 16-bit rows that live in the 126 MB L2 (createpolicy evict_last); the streams that pass through once
+// (sorted lists, fp32 outputs) are marked evict_first so that they do not push W / hidden out of it.
+#include "../../include/splade_b200.h"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,95 +34,232 @@
 namespace splade {
 namespace {
 
-constexpr int kBucketThreads = 1024;
+constexpr int kMaxSegs = SPLADE_HEAD_BWD_MAX_SEGMENTS;
+constexpr int kBucketThreads = 512;
+constexpr int kBucketWarps = kBucketThreads / 32;
+constexpr int kDwDocs = 256;  // documents staged per pass of the dW sweep
+constexpr int kRowsPerWarp = 8;  // dHidden: consecutive positions of one document per warp
+
+struct Seg {
+  const float* g;
+  const float* rep;
+  const int32_t* arg;
+  const uint16_t* hidden;
+  float* dh;
+  int32_t* row_ptr;     // [B][S+1]
+  int32_t* sorted_v;    // [B][V]
+  float* sorted_c;      // [B][V]
+  uint32_t* bitmap;     // [B][words]
+  int B, S;
+  int doc0;             // first global document index of this segment
+  long long row0;       // first global row GROUP (kRowsPerWarp consecutive positions of one document) of this segment
+};
+
+struct Segs {
+  Seg s[kMaxSegs];
+  int n;
+  int total_docs;
+  long long total_rows;
+};
 
 __device__ __forceinline__ float coef_of(float g, float rep) { return rep > 0.f ? g * expf(-rep) : 0.f; }
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
-// ---------------------------------------------------------------------------------------------
-// (1) DETERMINISTIC per-document counting sort of the active (b,v) pairs by position.
-//     The vocabulary of every document is cut into chunks of kChunk terms; ONE WARP walks a chunk in term order:
-//       count   : per-(doc, chunk, position) counts            (warp-private shared-memory counters)
-//       scan    : row_ptr[b][s] and, per chunk, the first slot of each position (prefix over chunks)
-//       scatter : the same walk again; slot = chunk base + running count + rank among the lanes of the same
-//                 position (lanes are in term order)  => every bucket lists its terms in ascending term id,
-//                 so dHidden sums in a fixed order: run-to-run bit-identical.
-// ---------------------------------------------------------------------------------------------
-constexpr int kChunk = 1024;  // vocabulary entries per warp
-
-__global__ void __launch_bounds__(256)
-bucket_count_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep,
-                    const int32_t* __restrict__ argmax, int B, int S, int V, int n_chunks, int warps_per_cta,
-                    int32_t* __restrict__ chunk_counts /*[B][n_chunks][S]*/) {
-  extern __shared__ int32_t sm[];  // [warps_per_cta][S]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp >= warps_per_cta) return;
-  const long long job = static_cast<long long>(blockIdx.x) * warps_per_cta + warp;  // (b, chunk)
-  if (job >= static_cast<long long>(B) * n_chunks) return;
-  const int b = static_cast<int>(job / n_chunks), ch = static_cast<int>(job % n_chunks);
-  int32_t* cnt = sm + static_cast<size_t>(warp) * S;
-  for (int s = lane; s < S; s += 32) cnt[s] = 0;
-  __syncwarp();
-  const int v0 = ch * kChunk, v1 = min(V, v0 + kChunk);
-  const size_t base = static_cast<size_t>(b) * V;
-  for (int vb = v0; vb < v1; vb += 128) {  // four 32-term steps per trip: their loads are issued together
-    float gg[4], rr[4];
-    int pp[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int v = vb + 32 * u + lane;
-      gg[u] = rr[u] = 0.f;
-      pp[u] = 0;
-      if (v < v1) {
-        gg[u] = g_rep[base + v];
-        rr[u] = rep[base + v];
-        pp[u] = argmax[base + v];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool act = coef_of(gg[u], rr[u]) != 0.f;
-      const uint32_t am = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const uint32_t peers = __match_any_sync(am, pp[u]);
-        if (lane == __ffs(peers) - 1) cnt[pp[u]] += __popc(peers);  // one lane per distinct position: no race
-      }
-      __syncwarp();
-    }
-  }
-  int32_t* out = chunk_counts + (static_cast<size_t>(b) * n_chunks + ch) * S;
-  for (int s = lane; s < S; s += 32) out[s] = cnt[s];
+// ---- L2 residency hints ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_hint(const void* ptr, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_hint(float* ptr, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
 }
 
-// chunk_counts -> row_ptr [B][S+1] (exclusive scan over positions of the per-position totals) and, in place,
-// chunk_counts[b][ch][s] := row_ptr[b][s] + sum_{ch' < ch} counts[b][ch'][s].  One CTA per document.
+__device__ __forceinline__ int seg_of_doc(const Segs& p, int doc) {
+  int sel = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxSegs; ++i)
+    if (i < p.n && doc >= p.s[i].doc0) sel = i;
+  return sel;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (0) activity bitmap: bit j of word w of document b = (rep[b, 32w + j] > 0).  The autograd path computes it right
+//     after the forward (rep is L2-hot then); every backward kernel below is DRIVEN by it, so in the trained
+//     (sparse) regime g_rep / rep / argmax are read at the ~300 active terms of a document only, not 50 000.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rep_bitmap_kernel(const float* __restrict__ rep, int B, int V, uint32_t* __restrict__ bitmap) {
+  const int words = (V + 31) >> 5;
+  const long long total = static_cast<long long>(B) * words;
+  const int lane = threadIdx.x & 31;
+  for (long long w = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); w < total;
+       w += static_cast<long long>(gridDim.x) * 8) {
+    const int b = static_cast<int>(w / words), wi = static_cast<int>(w - static_cast<long long>(b) * words);
+    const int v = wi * 32 + lane;
+    const bool act = v < V && rep[static_cast<size_t>(b) * V + v] > 0.f;
+    const uint32_t m = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) bitmap[w] = m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (1) per-document counting sort by position.  A CLUSTER of C CTAs owns one document (C is chosen so that the grid
+//     fills the machine in one wave: 192 documents -> 2 CTAs each); every warp of the cluster owns a contiguous
+//     range of 32-term bitmap words and walks the NON-ZERO ones in term order, four words per trip (their loads are
+//     issued together):
+//       pass 1 : per-(warp, position) counts in the CTA's shared memory
+//       scan   : every CTA reads the counters of the whole cluster (its own directly, the others through
+//                distributed shared memory) -> row_ptr[s] (exclusive over positions) and the first slot of each
+//                of its (warp, position) pairs
+//       pass 2 : the same walk (operands L2-hot); slot = base + running count + rank among the lanes with the same
+//                position (lanes are in term order)
+//     => every bucket lists its terms in ascending term id, so dHidden sums in a fixed order.
+//     Shared memory: cnt [nw][S] | base [nw][S] | tot [S] int32.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_nctaid() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ int32_t ld_dsmem_s32(uint32_t cluster_addr) {
+  int32_t v;
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(cluster_addr));
+  return v;
+}
+
+// One walk over the warp's words.  kScatter = false: count into cnt[]; true: cnt[] holds the running slot of every
+// position, entries are written to the sorted lists.
+template <bool kScatter>
+__device__ __forceinline__ void bucket_walk(const float* __restrict__ g_rep, const float* __restrict__ rep,
+                                            const int32_t* __restrict__ argmax, const uint32_t* __restrict__ bm,
+                                            size_t base, int V, int w0, int w1, int lane, int32_t* cnt,
+                                            int32_t* __restrict__ sorted_v, float* __restrict__ sorted_c) {
+  for (int wc = w0; wc < w1; wc += 32) {
+    const uint32_t myw = (wc + lane < w1) ? bm[wc + lane] : 0u;
+    uint32_t nz = __ballot_sync(0xffffffffu, myw != 0u);
+    while (nz) {
+      uint32_t bits[4];
+      int widx[4];
+      float cc[4];
+      int pp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = nz ? __ffs(nz) - 1 : 0;
+        bits[u] = nz ? __shfl_sync(0xffffffffu, myw, k) : 0u;
+        widx[u] = wc + k;
+        nz &= nz - 1;  // (0 stays 0)
+        cc[u] = 0.f;
+        pp[u] = 0;
+        if ((bits[u] >> lane) & 1u) {
+          const size_t o = base + static_cast<size_t>(widx[u]) * 32 + lane;
+          cc[u] = coef_of(g_rep[o], rep[o]);
+          pp[u] = argmax[o];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool act = cc[u] != 0.f;
+        const uint32_t am = __ballot_sync(0xffffffffu, act);
+        if (am == 0u) continue;  // warp-uniform
+        uint32_t peers = 0;
+        int slot = 0;
+        if (act) {
+          peers = __match_any_sync(am, pp[u]);
+          if (kScatter) slot = cnt[pp[u]] + __popc(peers & ((1u << lane) - 1u));  // lanes are in term order
+        }
+        __syncwarp();
+        if (act) {
+          if (lane == __ffs(peers) - 1) cnt[pp[u]] += __popc(peers);  // one lane per distinct position: no race
+          if (kScatter) {
+            sorted_v[base + slot] = widx[u] * 32 + lane;
+            sorted_c[base + slot] = cc[u];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBucketThreads)
-bucket_scan_kernel(int S, int n_chunks, int32_t* __restrict__ chunk_counts, int32_t* __restrict__ row_ptr) {
+bwd_bucket_kernel(const __grid_constant__ Segs p, int V, int nw) {
+  extern __shared__ int32_t bk_smem[];
   __shared__ int32_t warp_tot[32];
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x;
-  int32_t* cc = chunk_counts + static_cast<size_t>(b) * n_chunks * S;
-  int32_t* rp = row_ptr + static_cast<size_t>(b) * (S + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = static_cast<int>(cluster_nctaid());
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int doc = blockIdx.x / C;
+  const int si = seg_of_doc(p, doc);
+  const Seg& sg = p.s[si];
+  const int b = doc - sg.doc0;
+  const int S = sg.S;
+  int32_t* cnt_all = bk_smem;                                     // [nw][S]
+  int32_t* base_all = bk_smem + static_cast<size_t>(nw) * S;      // [nw][S]
+  int32_t* tot_s = bk_smem + static_cast<size_t>(2) * nw * S;     // [S]
+  const int words = (V + 31) >> 5;
+  const int gwarps = C * nw;
+  const int wpw = (words + gwarps - 1) / gwarps;
+  const int gw = rank * nw + warp;
+  const int w0 = min(words, gw * wpw), w1 = (warp < nw) ? min(words, w0 + wpw) : w0;
+  const size_t base = static_cast<size_t>(b) * V;
+  const uint32_t* __restrict__ bm = sg.bitmap + static_cast<size_t>(b) * words;
+  int32_t* cnt = cnt_all + static_cast<size_t>(min(warp, nw - 1)) * S;
+
+  if (warp < nw)
+    for (int s = lane; s < S; s += 32) cnt[s] = 0;
+  __syncwarp();
+  bucket_walk<false>(sg.g, sg.rep, sg.arg, bm, base, V, w0, w1, lane, cnt, nullptr, nullptr);
+  cluster_sync_all();  // every counter of the cluster is final (also a CTA-wide barrier)
+
+  // ---- scan over positions (thread t owns a contiguous range of positions)
   const int per = (S + kBucketThreads - 1) / kBucketThreads;
   const int lo = min(S, tid * per), hi = min(S, lo + per);
+  const uint32_t cnt_addr = smem_u32(cnt_all);
   int tsum = 0;
   for (int s = lo; s < hi; ++s) {
-    int tot = 0;
-    for (int ch = 0; ch < n_chunks; ++ch) tot += cc[static_cast<size_t>(ch) * S + s];
-    rp[s] = tot;  // per-position total, turned into the exclusive offset below
+    int tot = 0, before = 0;
+    for (int r = 0; r < C; ++r) {
+      int part = 0;
+      if (r == rank) {
+        for (int w = 0; w < nw; ++w) part += cnt_all[static_cast<size_t>(w) * S + s];
+      } else {
+        const uint32_t remote = map_to_cta(cnt_addr, static_cast<uint32_t>(r));
+        for (int w = 0; w < nw; ++w) part += ld_dsmem_s32(remote + (static_cast<uint32_t>(w) * S + s) * 4u);
+      }
+      tot += part;
+      if (r < rank) before += part;
+    }
+    tot_s[s] = tot;
+    base_all[s] = before;  // row 0 of base_all, finalised below
     tsum += tot;
   }
+  cluster_sync_all();  // nobody reads a peer's counters after this point (a CTA may finish before its peers)
   int incl = tsum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int n = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((tid & 31) >= o) incl += n;
+    if (lane >= o) incl += n;
   }
-  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
   if (tid < 32) {
-    const int w = warp_tot[tid];
+    const int w = tid < kBucketWarps ? warp_tot[tid] : 0;
     int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -123,220 +269,571 @@ bucket_scan_kernel(int S, int n_chunks, int32_t* __restrict__ chunk_counts, int3
     warp_tot[tid] = wi - w;  // exclusive
   }
   __syncthreads();
-  int run = warp_tot[tid >> 5] + incl - tsum;
+  int32_t* rp = sg.row_ptr + static_cast<size_t>(b) * (S + 1);
+  int run = warp_tot[warp] + incl - tsum;
   for (int s = lo; s < hi; ++s) {
-    const int tot = rp[s];
-    rp[s] = run;
-    int acc = run;
-    for (int ch = 0; ch < n_chunks; ++ch) {  // first slot of position s for each chunk
-      const size_t i = static_cast<size_t>(ch) * S + s;
-      const int c = cc[i];
-      cc[i] = acc;
-      acc += c;
+    if (rank == 0) rp[s] = run;
+    int slot = run + base_all[s];  // behind the slots of the lower-ranked CTAs
+    for (int w = 0; w < nw; ++w) {  // first slot of position s for each of this CTA's warps
+      const size_t i = static_cast<size_t>(w) * S + s;
+      const int c = cnt_all[i];
+      base_all[i] = slot;
+      slot += c;
     }
-    run += tot;
+    run += tot_s[s];
   }
-  if (tid == kBucketThreads - 1) rp[S] = run;  // total number of active terms of this document
-}
+  if (rank == 0 && tid == kBucketThreads - 1) rp[S] = run;  // total number of active terms of this document
+  __syncthreads();
 
-__global__ void __launch_bounds__(256)
-bucket_scatter_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep,
-                      const int32_t* __restrict__ argmax, int B, int S, int V, int n_chunks, int warps_per_cta,
-                      const int32_t* __restrict__ chunk_base, int32_t* __restrict__ sorted_v,
-                      float* __restrict__ sorted_c) {
-  extern __shared__ int32_t sm[];  // [warps_per_cta][S] running slot per position
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp >= warps_per_cta) return;
-  const long long job = static_cast<long long>(blockIdx.x) * warps_per_cta + warp;
-  if (job >= static_cast<long long>(B) * n_chunks) return;
-  const int b = static_cast<int>(job / n_chunks), ch = static_cast<int>(job % n_chunks);
-  int32_t* cur = sm + static_cast<size_t>(warp) * S;
-  const int32_t* cb = chunk_base + (static_cast<size_t>(b) * n_chunks + ch) * S;
-  for (int s = lane; s < S; s += 32) cur[s] = cb[s];
-  __syncwarp();
-  const int v0 = ch * kChunk, v1 = min(V, v0 + kChunk);
-  const size_t base = static_cast<size_t>(b) * V;
-  for (int vb = v0; vb < v1; vb += 128) {
-    float cc4[4];
-    int pp[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int v = vb + 32 * u + lane;
-      cc4[u] = 0.f;
-      pp[u] = 0;
-      if (v < v1) {
-        cc4[u] = coef_of(g_rep[base + v], rep[base + v]);
-        pp[u] = argmax[base + v];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int v = vb + 32 * u + lane;
-      const float c = cc4[u];
-      const int pos = pp[u];
-      const bool act = c != 0.f;
-      const uint32_t am = __ballot_sync(0xffffffffu, act);
-      uint32_t peers = 0;
-      int slot = 0;
-      if (act) {
-        peers = __match_any_sync(am, pos);
-        slot = cur[pos] + __popc(peers & ((1u << lane) - 1u));  // lanes are in term order
-      }
-      __syncwarp();
-      if (act) {
-        if (lane == __ffs(peers) - 1) cur[pos] += __popc(peers);
-        sorted_v[base + slot] = v;
-        sorted_c[base + slot] = c;
-      }
-      __syncwarp();
-    }
-  }
-}
-
-// acc[8] += c * (8 bf16 packed in a uint4)
-__device__ __forceinline__ void fma_bf16x8(float (&acc)[8], float c, const uint4& u) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    acc[2 * i] = fmaf(c, __uint_as_float(w[i] << 16), acc[2 * i]);
-    acc[2 * i + 1] = fmaf(c, __uint_as_float(w[i] & 0xFFFF0000u), acc[2 * i + 1]);
-  }
-}
-
-__device__ __forceinline__ void store_row8(float* dst, const float (&acc)[8], float scale) {
-  float4 a = make_float4(acc[0] * scale, acc[1] * scale, acc[2] * scale, acc[3] * scale);
-  float4 b = make_float4(acc[4] * scale, acc[5] * scale, acc[6] * scale, acc[7] * scale);
-  reinterpret_cast<float4*>(dst)[0] = a;
-  reinterpret_cast<float4*>(dst)[1] = b;
+  int32_t* cur = base_all + static_cast<size_t>(min(warp, nw - 1)) * S;
+  bucket_walk<true>(sg.g, sg.rep, sg.arg, bm, base, V, w0, w1, lane, cur, sg.sorted_v, sg.sorted_c);
 }
 
 // ---------------------------------------------------------------------------------------------
-// (2) dHidden: one warp per (b,s) row.  kChunks = ceil(H / 256); lane l owns h = i*256 + l*8 .. +8.
+// Row fragments.  A lane owns 4 consecutive floats of every 128-float chunk of a row (h = q*128 + lane*4), so that a
+// warp's 64-bit bf16 loads cover 256 contiguous bytes and its 128-bit fp32 stores 512 contiguous bytes (whole
+// sectors - the 8-floats-per-lane layout wrote every 32-byte sector in two halves).  kQ = chunks = ceil(H / 128).
 // ---------------------------------------------------------------------------------------------
-template <int kChunks>
+__device__ __forceinline__ uint2 ldg_hint2(const void* ptr, uint64_t pol) {
+  uint2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void fma_bf16x4(float (&acc)[4], float c, const uint2& u) {
+  acc[0] = fmaf(c, __uint_as_float(u.x << 16), acc[0]);
+  acc[1] = fmaf(c, __uint_as_float(u.x & 0xFFFF0000u), acc[1]);
+  acc[2] = fmaf(c, __uint_as_float(u.y << 16), acc[2]);
+  acc[3] = fmaf(c, __uint_as_float(u.y & 0xFFFF0000u), acc[3]);
+}
+template <int kQ>
+__device__ __forceinline__ void load_row(uint2 (&u)[kQ], const uint16_t* row, int H, int lane, uint64_t pol) {
+#pragma unroll
+  for (int q = 0; q < kQ; ++q) {
+    const int h = q * 128 + lane * 4;
+    if (h < H) u[q] = ldg_hint2(row + h, pol);
+  }
+}
+template <int kQ>
+__device__ __forceinline__ void fma_row(float (&acc)[kQ][4], float c, const uint2 (&u)[kQ], int H, int lane) {
+#pragma unroll
+  for (int q = 0; q < kQ; ++q)
+    if (q * 128 + lane * 4 < H) fma_bf16x4(acc[q], c, u[q]);
+}
+template <int kQ>
+__device__ __forceinline__ void zero_acc(float (&acc)[kQ][4]) {
+#pragma unroll
+  for (int q = 0; q < kQ; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
+}
+template <int kQ>
+__device__ __forceinline__ void store_row(float* out, const float (&acc)[kQ][4], int H, int lane, uint64_t pol) {
+#pragma unroll
+  for (int q = 0; q < kQ; ++q) {
+    const int h = q * 128 + lane * 4;
+    if (h < H) stg_hint(out + h, make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]), pol);
+  }
+}
+template <int kQ>
+__device__ __forceinline__ void store_zero_row(float* out, int H, int lane, uint64_t pol) {
+#pragma unroll
+  for (int q = 0; q < kQ; ++q) {
+    const int h = q * 128 + lane * 4;
+    if (h < H) stg_hint(out + h, make_float4(0.f, 0.f, 0.f, 0.f), pol);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2) dHidden: one warp per GROUP of kRowsPerWarp consecutive positions of one document.  row_ptr is monotone over
+//     the positions of a document, so the buckets of the group are ONE contiguous range of the sorted lists: the
+//     warp reads the group's row_ptr entries (one load), stores the EMPTY positions' zero rows at once (nearly all
+//     of them in the trained regime: the write stream does not wait for the gather chain), then reads the range
+//     (coalesced) and walks it as a segmented sum, kDepth W rows in flight.  Three dependent global latencies per
+//     GROUP instead of per position.
+// ---------------------------------------------------------------------------------------------
+template <int kQ, int kDepth>
 __global__ void __launch_bounds__(256)
-dhidden_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ sorted_v,
-               const float* __restrict__ sorted_c, const uint16_t* __restrict__ W, int B, int S, int H, int V,
-               float* __restrict__ d_hidden) {
+dhidden_kernel(const __grid_constant__ Segs p, const uint16_t* __restrict__ W, int H, int V) {
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= static_cast<long long>(B) * S) return;
-  const int b = static_cast<int>(row / S);
-  const int s = static_cast<int>(row - static_cast<long long>(b) * S);
-  const int32_t* rp = row_ptr + static_cast<size_t>(b) * (S + 1);
-  const int beg = rp[s], end = rp[s + 1];
-  const size_t lbase = static_cast<size_t>(b) * V;
+  const long long grp = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (grp >= p.total_rows) return;
+  int si = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxSegs; ++i)
+    if (i < p.n && grp >= p.s[i].row0) si = i;
+  const Seg& sg = p.s[si];
+  if (sg.dh == nullptr) return;
+  const int S = sg.S;
+  const int gps = (S + kRowsPerWarp - 1) / kRowsPerWarp;
+  const long long lg = grp - sg.row0;
+  const int b = static_cast<int>(lg / gps);
+  const int s0 = static_cast<int>(lg - static_cast<long long>(b) * gps) * kRowsPerWarp;
+  const int nrows = min(kRowsPerWarp, S - s0);
+  const int32_t* rp = sg.row_ptr + static_cast<size_t>(b) * (S + 1) + s0;
+  const int my_rp = lane <= nrows ? rp[lane] : 0;
+  const int beg = __shfl_sync(0xffffffffu, my_rp, 0), end = __shfl_sync(0xffffffffu, my_rp, nrows);
+  const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
+  float* out = sg.dh + (static_cast<size_t>(b) * S + s0) * H;
 
-  float acc[kChunks][8];
-#pragma unroll
-  for (int i = 0; i < kChunks; ++i)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+  // empty positions first
+  const int my_next = __shfl_down_sync(0xffffffffu, my_rp, 1);
+  const uint32_t empty = __ballot_sync(0xffffffffu, lane < nrows && my_next == my_rp);
+  for (uint32_t m = empty; m; m &= m - 1) store_zero_row<kQ>(out + static_cast<size_t>(__ffs(m) - 1) * H, H, lane, stream);
+  if (beg == end) return;
+
+  const size_t lbase = static_cast<size_t>(b) * V;
+  const int32_t* __restrict__ sorted_v = sg.sorted_v;
+  const float* __restrict__ sorted_c = sg.sorted_c;
+  float acc[kQ][4];
+  zero_acc<kQ>(acc);
+  int row = 0;                                        // position s0 + row is being summed
+  while ((empty >> row) & 1u) ++row;                  // (beg < end: some position is not empty)
+  int row_end = __shfl_sync(0xffffffffu, my_rp, row + 1);
 
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int n = min(32, end - e0);
     int my_v = 0;
     float my_c = 0.f;
     if (lane < n) {
-      my_v = sorted_v[lbase + e0 + lane];
-      my_c = sorted_c[lbase + e0 + lane];
+      my_v = __ldcs(sorted_v + lbase + e0 + lane);
+      my_c = __ldcs(sorted_c + lbase + e0 + lane);
     }
-#pragma unroll 4
-    for (int l = 0; l < n; ++l) {
-      const int v = __shfl_sync(0xffffffffu, my_v, l);
-      const float c = __shfl_sync(0xffffffffu, my_c, l);
-      const uint16_t* wrow = W + static_cast<size_t>(v) * H;
+    for (int l = 0; l < n; l += kDepth) {
+      uint2 u[kDepth][kQ];
+      float c[kDepth];
 #pragma unroll
-      for (int i = 0; i < kChunks; ++i) {
-        const int h = i * 256 + lane * 8;
-        if (h < H) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(wrow + h));
-          fma_bf16x8(acc[i], c, u);
+      for (int k = 0; k < kDepth; ++k) {
+        const int src = min(l + k, n - 1);  // past the end: a valid row, never accumulated
+        const int v = __shfl_sync(0xffffffffu, my_v, src);
+        c[k] = __shfl_sync(0xffffffffu, my_c, src);
+        load_row<kQ>(u[k], W + static_cast<size_t>(v) * H, H, lane, keep);
+      }
+#pragma unroll
+      for (int k = 0; k < kDepth; ++k) {
+        if (l + k < n) {
+          while (e0 + l + k >= row_end) {  // warp-uniform: this position's bucket is complete
+            store_row<kQ>(out + static_cast<size_t>(row) * H, acc, H, lane, stream);
+            zero_acc<kQ>(acc);
+            ++row;
+            while ((empty >> row) & 1u) ++row;
+            row_end = __shfl_sync(0xffffffffu, my_rp, row + 1);
+          }
+          fma_row<kQ>(acc, c[k], u[k], H, lane);
         }
       }
     }
   }
-  float* out = d_hidden + static_cast<size_t>(row) * H;
-#pragma unroll
-  for (int i = 0; i < kChunks; ++i) {
-    const int h = i * 256 + lane * 8;
-    if (h < H) store_row8(out + h, acc[i], 1.f);
-  }
+  store_row<kQ>(out + static_cast<size_t>(row) * H, acc, H, lane, stream);  // the last non-empty position
 }
 
 // ---------------------------------------------------------------------------------------------
-// (3) dW + dbias.  A CTA owns 32 consecutive vocabulary rows: it first stages coef[b][32] and argmax[b][32]
-//     for the whole batch in shared memory with fully coalesced 128-byte reads (the three [B,V] arrays are read
-//     exactly once), then each of its 8 warps produces 4 rows, skipping inactive (b,v) pairs.
+// (3) dW + dbias for ALL segments in one sweep.  A CTA owns the 32 terms of one bitmap word.  Per pass of
+//     <= kDwDocs documents (one pass unless a micro-step has more head rows than that):
+//       a. one bitmap word per document -> shared memory (one load per thread, all in flight together); terms that
+//          no document activates get their zero row stored right away (the write stream does not wait for b-d);
+//       b. the set bits are compacted into a list of (document, term) pairs (shared-memory slot counter; the order
+//          of the list is irrelevant, every pair has its own staging slot);
+//       c. g / rep / argmax of the listed pairs only - one global latency for the whole CTA in the trained regime,
+//          coalesced 128-byte rows in the dense one - give coef and the hidden row index, staged as [term][doc];
+//       d. warp w owns terms 4w..4w+3: per term it walks the active documents (ballot over the bitmap words, 32
+//          documents at a time) in ascending document order, kDepth hidden rows in flight.
+//     The sum order is fixed (segments in call order, documents ascending) => run-to-run bit-identical.
 // ---------------------------------------------------------------------------------------------
-template <int kChunks>
+template <int kQ, int kDepth>
 __global__ void __launch_bounds__(256)
-dw_kernel(const float* __restrict__ g_rep, const float* __restrict__ rep, const int32_t* __restrict__ argmax,
-          const uint16_t* __restrict__ hidden, int B, int S, int H, int V, float* __restrict__ dW,
-          float* __restrict__ dbias) {
+dw_kernel(const __grid_constant__ Segs p, int H, int V, int docs_per_pass, int stride /* odd, >= docs_per_pass */,
+          float* dW, float* dbias, int accumulate) {
   extern __shared__ __align__(16) uint8_t dw_smem[];
-  float* s_c = reinterpret_cast<float*>(dw_smem);                  // [B][32]
-  int32_t* s_p = reinterpret_cast<int32_t*>(s_c + static_cast<size_t>(B) * 32);  // [B][32]
+  float* s_c = reinterpret_cast<float*>(dw_smem);                                       // [32][stride]
+  uint32_t* s_p = reinterpret_cast<uint32_t*>(s_c + static_cast<size_t>(32) * stride);  // [32][stride]
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_p + static_cast<size_t>(32) * stride);  // [32 * docs_per_pass]
+  __shared__ const uint16_t* s_hid[kMaxSegs];
+  __shared__ uint32_t s_bits[kDwDocs];
+  __shared__ int s_n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int v0 = blockIdx.x * 32;
+  const int word = blockIdx.x, v0 = word * 32;
+  const int words = (V + 31) >> 5;
+  if (threadIdx.x < kMaxSegs) s_hid[threadIdx.x] = threadIdx.x < p.n ? p.s[threadIdx.x].hidden : nullptr;
+  const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
+  const bool single_pass = p.total_docs <= docs_per_pass;
 
-  for (int idx = threadIdx.x; idx < B * 32; idx += 256) {
-    const int b = idx >> 5, j = idx & 31;
-    const int v = v0 + j;
-    float c = 0.f;
-    int pos = 0;
-    if (v < V) {
-      const size_t o = static_cast<size_t>(b) * V + v;
-      c = coef_of(g_rep[o], rep[o]);
-      pos = argmax[o];
+  for (int d0 = 0; d0 < p.total_docs; d0 += docs_per_pass) {
+    const int nb = min(docs_per_pass, p.total_docs - d0);
+    __syncthreads();  // the previous pass is done with the staging buffers (and s_hid is visible)
+    if (threadIdx.x == 0) s_n = 0;
+    if (static_cast<int>(threadIdx.x) < nb) {  // a.
+      const int doc = d0 + threadIdx.x;
+      const Seg& sg = p.s[seg_of_doc(p, doc)];
+      s_bits[threadIdx.x] = sg.bitmap[static_cast<size_t>(doc - sg.doc0) * words + word];
     }
-    s_c[idx] = c;
-    s_p[idx] = pos;
-  }
-  __syncthreads();
-
-  for (int r = 0; r < 4; ++r) {
-    const int j = warp * 4 + r;
-    const int v = v0 + j;
-    if (v >= V) break;  // warp-uniform
-    float acc[kChunks][8];
+    __syncthreads();
+    // which of this warp's four terms does some document of the pass activate?
+    uint32_t any = 0;
+    for (int c0 = 0; c0 < nb; c0 += 32) any |= (c0 + lane < nb) ? s_bits[c0 + lane] : 0u;
 #pragma unroll
-    for (int i = 0; i < kChunks; ++i)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
-    float bsum = 0.f;
-#pragma unroll 4
-    for (int b = 0; b < B; ++b) {
-      const float c = s_c[b * 32 + j];  // broadcast
-      if (c == 0.f) continue;           // warp-uniform
-      bsum += c;
-      const uint16_t* hrow = hidden + (static_cast<size_t>(b) * S + s_p[b * 32 + j]) * H;
-#pragma unroll
-      for (int i = 0; i < kChunks; ++i) {
-        const int h = i * 256 + lane * 8;
-        if (h < H) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(hrow + h));
-          fma_bf16x8(acc[i], c, u);
+    for (int o = 16; o; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
+    if (single_pass && !accumulate) {
+      for (int r = 0; r < 4; ++r) {
+        const int j = warp * 4 + r;
+        if (v0 + j < V && !((any >> j) & 1u)) {
+          store_zero_row<kQ>(dW + static_cast<size_t>(v0 + j) * H, H, lane, stream);
+          if (lane == 0) dbias[v0 + j] = 0.f;
         }
       }
     }
-    if (lane == 0) dbias[v] = bsum;
-    float* out = dW + static_cast<size_t>(v) * H;
+    for (int dl = warp; dl < nb; dl += 8) {  // b.
+      const uint32_t bits = s_bits[dl];
+      if (bits == 0u) continue;
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&s_n, __popc(bits));
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if ((bits >> lane) & 1u)
+        s_list[slot + __popc(bits & ((1u << lane) - 1u))] = static_cast<uint16_t>((dl << 5) | lane);
+    }
+    __syncthreads();
+    const int n_pairs = s_n;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n_pairs; i += 256) {  // c.
+      const int e = s_list[i];
+      const int dl = e >> 5, j = e & 31;
+      const int doc = d0 + dl;
+      const int si = seg_of_doc(p, doc);
+      const Seg& sg = p.s[si];
+      const int b = doc - sg.doc0;
+      const size_t o = static_cast<size_t>(b) * V + v0 + j;
+      s_c[j * stride + dl] = coef_of(sg.g[o], sg.rep[o]);
+      s_p[j * stride + dl] = (static_cast<uint32_t>(si) << 28) | static_cast<uint32_t>(b * sg.S + sg.arg[o]);
+    }
+    __syncthreads();
+
+    const bool first = (d0 == 0) && !accumulate;
+    const bool last = d0 + docs_per_pass >= p.total_docs;
+    for (int r = 0; r < 4; ++r) {  // d.
+      const int j = warp * 4 + r;
+      const int v = v0 + j;
+      if (v >= V) break;  // warp-uniform
+      const bool touched = (any >> j) & 1u;
+      if (!touched && (single_pass ? !accumulate : !first)) continue;  // zero row already stored / nothing to add
+      float* out = dW + static_cast<size_t>(v) * H;
+      float acc[kQ][4];
+      float bsum = 0.f;
+      if (first) {
+        zero_acc<kQ>(acc);
+      } else {  // continue this term's sum (an earlier pass of this warp, or the caller's gradient buffer)
+        if (!touched) continue;
 #pragma unroll
-    for (int i = 0; i < kChunks; ++i) {
-      const int h = i * 256 + lane * 8;
-      if (h < H) store_row8(out + h, acc[i], 1.f);
+        for (int q = 0; q < kQ; ++q) {
+          const int h = q * 128 + lane * 4;
+          if (h < H) {
+            const float4 a = *reinterpret_cast<const float4*>(out + h);
+            acc[q][0] = a.x, acc[q][1] = a.y, acc[q][2] = a.z, acc[q][3] = a.w;
+          }
+        }
+        bsum = dbias[v];
+      }
+      const float* cj = s_c + j * stride;
+      const uint32_t* pj = s_p + j * stride;
+      for (int c0 = 0; c0 < nb; c0 += 32) {
+        const uint32_t bits = (c0 + lane < nb) ? s_bits[c0 + lane] : 0u;
+        uint32_t m = __ballot_sync(0xffffffffu, (bits >> j) & 1u);
+        while (m) {  // up to kDepth active documents per trip: their hidden rows are independent loads
+          int d[kDepth];
+          float c[kDepth];
+          uint2 u[kDepth][kQ];
+#pragma unroll
+          for (int k = 0; k < kDepth; ++k) {
+            d[k] = m ? (c0 + __ffs(m) - 1) : -1;
+            m &= m - 1;  // (0 stays 0)
+            const int dk = d[k] < 0 ? d[0] : d[k];
+            c[k] = cj[dk];  // broadcast reads
+            const uint32_t pw = pj[dk];
+            load_row<kQ>(u[k], s_hid[pw >> 28] + static_cast<size_t>(pw & 0x0FFFFFFFu) * H, H, lane, keep);
+          }
+#pragma unroll
+          for (int k = 0; k < kDepth; ++k) {
+            if (d[k] >= 0) {
+              bsum += c[k];
+              fma_row<kQ>(acc, c[k], u[k], H, lane);
+            }
+          }
+        }
+      }
+      if (lane == 0) dbias[v] = bsum;
+      if (last) {
+        store_row<kQ>(out, acc, H, lane, stream);
+      } else {  // read back by this very lane in the next pass
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) {
+          const int h = q * 128 + lane * 4;
+          if (h < H) *reinterpret_cast<float4*>(out + h) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+        }
+      }
     }
   }
+}
+
+size_t bitmap_bytes(int B, int V) { return align256(static_cast<size_t>(B) * ((V + 31) / 32) * sizeof(uint32_t)); }
+
+// transient workspace of one segment's bucket + dHidden phase (row_ptr | sorted_v | sorted_c)
+size_t seg_sort_bytes(int B, int S, int V) {
+  return align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t)) +
+         2 * align256(static_cast<size_t>(B) * V * sizeof(int32_t));
+}
+
+int validate_common(const char* who, int H, int V) {
+  if (V < 1 || H < 1) return set_error(kErrInvalidArg, "%s: bad sizes H=%d V=%d", who, H, V);
+  if (H % 8 != 0 || H > 1024)
+    return set_error(kErrUnsupportedShape, "%s: hidden size %d must be a multiple of 8 and <= 1024", who, H);
+  return kOk;
+}
+
+int validate_seg(const char* who, const splade_head_bwd_segment& s, int i, bool need_dh) {
+  if (s.B < 0 || s.S < 1) return set_error(kErrInvalidArg, "%s: segment %d has bad sizes B=%d S=%d", who, i, s.B, s.S);
+  if (s.B > 0 && (!s.g_rep || !s.rep || !s.argmax || !s.hidden || (need_dh && !s.d_hidden)))
+    return set_error(kErrInvalidArg, "%s: segment %d has a null pointer argument", who, i);
+  if (static_cast<size_t>(s.S) * sizeof(int32_t) * 3 > 220 * 1024)
+    return set_error(kErrUnsupportedShape, "%s: sequence length %d too long for the bucket pass", who, s.S);
+  if (static_cast<long long>(s.B) * s.S >= (1ll << 28))
+    return set_error(kErrUnsupportedShape, "%s: segment %d has B*S >= 2^28 rows", who, i);
+  return kOk;
+}
+
+// bucket + dHidden of the segments in `p` (their row_ptr / sorted_* / bitmap pointers are set)
+int launch_sort_dhidden(const Segs& p, const void* W, int H, int V, int s_max, bool any_dh, cudaStream_t stream) {
+  if (p.total_docs == 0) return kOk;
+  // shared memory: (2 nw + 1) S counters; as many warps as fit
+  const size_t per_pos = static_cast<size_t>(s_max) * sizeof(int32_t);
+  int nw = kBucketWarps;
+  while (nw > 1 && (2 * static_cast<size_t>(nw) + 1) * per_pos > 200 * 1024) nw >>= 1;
+  const size_t smem = (2 * static_cast<size_t>(nw) + 1) * per_pos;
+  if (smem > 220 * 1024)
+    return set_error(kErrUnsupportedShape, "splade_head_bwd: sequence length %d too long for the bucket pass", s_max);
+  if (smem > 44 * 1024)
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(bwd_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+  // one wave over the machine: C CTAs per document (a cluster), C a power of two <= 8
+  int C = 1;
+  while (C < 8 && static_cast<long long>(p.total_docs) * C < 2ll * sm_count()) C <<= 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(p.total_docs) * C);
+  cfg.blockDim = dim3(kBucketThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(C);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SPLADE_CUDA_OK(cudaLaunchKernelEx(&cfg, bwd_bucket_kernel, p, V, nw));
+  SPLADE_CUDA_OK(cudaGetLastError());
+  if (!any_dh) return kOk;
+  const uint16_t* Wb = static_cast<const uint16_t*>(W);
+  const unsigned grid_h = static_cast<unsigned>((p.total_rows + 7) / 8);  // 8 warps = 8 row groups per CTA
+  switch ((H + 127) / 128) {
+    case 1: dhidden_kernel<1, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
+    case 2: dhidden_kernel<2, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
+    case 3:
+    case 4: dhidden_kernel<4, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
+    case 5:
+    case 6: dhidden_kernel<6, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
+    default: dhidden_kernel<8, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
+  }
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+template <int kQ>
+int launch_dw_t(const Segs& p, int H, int V, float* dW, float* dbias, int accumulate, cudaStream_t stream) {
+  const int docs = std::max(1, std::min(kDwDocs, p.total_docs));
+  const int stride = docs | 1;  // odd: the transposed staging writes are bank-conflict free
+  const size_t smem = static_cast<size_t>(32) * stride * 8 + static_cast<size_t>(32) * docs * sizeof(uint16_t);
+  if (smem > 44 * 1024)  // (static shared memory counts against the 48 KB default too)
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<kQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+  dw_kernel<kQ, 4><<<static_cast<unsigned>((V + 31) / 32), 256, smem, stream>>>(p, H, V, docs, stride, dW, dbias,
+                                                                                accumulate);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
+}
+
+int launch_dw(const Segs& p, int H, int V, float* dW, float* dbias, int accumulate, cudaStream_t stream) {
+  switch ((H + 127) / 128) {
+    case 1: return launch_dw_t<1>(p, H, V, dW, dbias, accumulate, stream);
+    case 2: return launch_dw_t<2>(p, H, V, dW, dbias, accumulate, stream);
+    case 3:
+    case 4: return launch_dw_t<4>(p, H, V, dW, dbias, accumulate, stream);
+    case 5:
+    case 6: return launch_dw_t<6>(p, H, V, dW, dbias, accumulate, stream);
+    default: return launch_dw_t<8>(p, H, V, dW, dbias, accumulate, stream);
+  }
+}
+
+int launch_rep_bitmap(const float* rep, int B, int V, uint32_t* bitmap, cudaStream_t stream) {
+  if (B == 0) return kOk;
+  const long long total = static_cast<long long>(B) * ((V + 31) / 32);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((total + 7) / 8, 16ll * sm_count()));
+  rep_bitmap_kernel<<<grid, 256, 0, stream>>>(rep, B, V, bitmap);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
 }
 
 }  // namespace
 
-size_t head_bwd_workspace_bytes(int B, int S, int V) {
-  const size_t n_chunks = (static_cast<size_t>(V) + kChunk - 1) / kChunk;
-  return align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t)) +
-         align256(static_cast<size_t>(B) * n_chunks * S * sizeof(int32_t)) +
-         2 * align256(static_cast<size_t>(B) * V * sizeof(int32_t));
+size_t head_bwd_bitmap_bytes(int B, int V) { return bitmap_bytes(B, V); }
+
+int rep_bitmap_launch(const float* rep, int B, int V, uint32_t* bitmap, cudaStream_t stream) {
+  if (B < 0 || V < 1) return set_error(kErrInvalidArg, "splade_rep_bitmap: bad sizes B=%d V=%d", B, V);
+  if (B > 0 && (!rep || !bitmap)) return set_error(kErrInvalidArg, "splade_rep_bitmap: null pointer argument");
+  int rc = require_sm100("splade_rep_bitmap");
+  if (rc != kOk) return rc;
+  return launch_rep_bitmap(rep, B, V, bitmap, stream);
+}
+
+size_t head_bwd_dhidden_workspace_bytes(int B, int S, int V) { return seg_sort_bytes(B, S, V); }
+
+size_t head_bwd_workspace_bytes(int B, int S, int V) { return seg_sort_bytes(B, S, V) + bitmap_bytes(B, V); }
+
+size_t head_bwd_multi_workspace_bytes(const splade_head_bwd_segment* segs, int n_segs, int V) {
+  size_t total = 0;
+  for (int i = 0; segs && i < n_segs; ++i)
+    total += seg_sort_bytes(segs[i].B, segs[i].S, V) + bitmap_bytes(segs[i].B, V);
+  return total;
+}
+
+// Phase 1 for ONE segment: bucket + dHidden; leaves the activity bitmap for phase 2.
+int head_bwd_dhidden_launch(const splade_head_bwd_segment* seg, const void* W, int H, int V, uint32_t* bitmap,
+                            void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  const char* who = "splade_head_bwd_dhidden";
+  if (!seg || !W || (!bitmap && !seg->active)) return set_error(kErrInvalidArg, "%s: null pointer argument", who);
+  int rc = validate_common(who, H, V);
+  if (rc != kOk) return rc;
+  rc = validate_seg(who, *seg, 0, /*need_dh=*/false);  // d_hidden == NULL: only the bitmap is produced
+  if (rc != kOk) return rc;
+  rc = require_sm100(who);
+  if (rc != kOk) return rc;
+  const size_t need = seg_sort_bytes(seg->B, seg->S, V);
+  if (!workspace || ws_bytes < need)
+    return set_error(kErrWorkspace, "%s: workspace too small (%zu < %zu bytes)", who, ws_bytes, need);
+  if (seg->B == 0) return kOk;
+  Segs p{};
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  Seg& s = p.s[0];
+  s.g = seg->g_rep, s.rep = seg->rep, s.arg = seg->argmax, s.hidden = static_cast<const uint16_t*>(seg->hidden);
+  s.dh = seg->d_hidden, s.B = seg->B, s.S = seg->S, s.doc0 = 0, s.row0 = 0;
+  if (seg->active) {
+    s.bitmap = const_cast<uint32_t*>(seg->active);
+  } else {  // the caller has no bitmap from the forward: one pass over rep
+    rc = launch_rep_bitmap(seg->rep, seg->B, V, bitmap, stream);
+    if (rc != kOk) return rc;
+    s.bitmap = bitmap;
+  }
+  s.row_ptr = reinterpret_cast<int32_t*>(ws);
+  ws += align256(static_cast<size_t>(s.B) * (s.S + 1) * sizeof(int32_t));
+  s.sorted_v = reinterpret_cast<int32_t*>(ws);
+  ws += align256(static_cast<size_t>(s.B) * V * sizeof(int32_t));
+  s.sorted_c = reinterpret_cast<float*>(ws);
+  p.n = 1, p.total_docs = s.B, p.total_rows = static_cast<long long>(s.B) * ((s.S + kRowsPerWarp - 1) / kRowsPerWarp);
+  return launch_sort_dhidden(p, W, H, V, s.S, s.dh != nullptr, stream);
+}
+
+// Phase 2: ONE dW / dbias sweep over every segment whose bitmap phase 1 left behind.
+int head_bwd_dw_launch(const splade_head_bwd_segment* segs, const uint32_t* const* bitmaps, int n_segs, int H, int V,
+                       float* dW, float* dbias, int accumulate, cudaStream_t stream) {
+  const char* who = "splade_head_bwd_dw";
+  if (n_segs < 0 || n_segs > kMaxSegs)
+    return set_error(kErrInvalidArg, "%s: %d segments (at most %d)", who, n_segs, kMaxSegs);
+  if ((n_segs > 0 && (!segs || !bitmaps)) || !dW || !dbias)
+    return set_error(kErrInvalidArg, "%s: null pointer argument", who);
+  int rc = validate_common(who, H, V);
+  if (rc != kOk) return rc;
+  Segs p{};
+  for (int i = 0; i < n_segs; ++i) {
+    rc = validate_seg(who, segs[i], i, /*need_dh=*/false);
+    if (rc != kOk) return rc;
+    if (segs[i].B > 0 && !bitmaps[i]) return set_error(kErrInvalidArg, "%s: segment %d has no bitmap", who, i);
+    Seg& s = p.s[i];
+    s.g = segs[i].g_rep, s.rep = segs[i].rep, s.arg = segs[i].argmax;
+    s.hidden = static_cast<const uint16_t*>(segs[i].hidden);
+    s.B = segs[i].B, s.S = segs[i].S, s.bitmap = const_cast<uint32_t*>(bitmaps[i]);
+    s.doc0 = p.total_docs, s.row0 = p.total_rows;
+    p.total_docs += s.B;
+    p.total_rows += static_cast<long long>(s.B) * ((s.S + kRowsPerWarp - 1) / kRowsPerWarp);
+  }
+  p.n = n_segs;
+  rc = require_sm100(who);
+  if (rc != kOk) return rc;
+  if (p.total_docs == 0 && !accumulate) {
+    SPLADE_CUDA_OK(cudaMemsetAsync(dW, 0, static_cast<size_t>(V) * H * sizeof(float), stream));
+    SPLADE_CUDA_OK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * sizeof(float), stream));
+    return kOk;
+  }
+  if (p.total_docs == 0) return kOk;
+  return launch_dw(p, H, V, dW, dbias, accumulate, stream);
+}
+
+// Everything for n segments in three launches: one bucket pass over all documents, one dHidden launch over all
+// rows, one dW sweep.
+int head_bwd_multi_launch(const splade_head_bwd_segment* segs, int n_segs, const void* W, int H, int V, float* dW,
+                          float* dbias, int accumulate, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  const char* who = "splade_head_bwd_multi";
+  if (n_segs < 0 || n_segs > kMaxSegs)
+    return set_error(kErrInvalidArg, "%s: %d segments (at most %d)", who, n_segs, kMaxSegs);
+  if ((n_segs > 0 && !segs) || !W || !dW || !dbias) return set_error(kErrInvalidArg, "%s: null pointer argument", who);
+  int rc = validate_common(who, H, V);
+  if (rc != kOk) return rc;
+  for (int i = 0; i < n_segs; ++i) {
+    rc = validate_seg(who, segs[i], i, /*need_dh=*/false);
+    if (rc != kOk) return rc;
+  }
+  rc = require_sm100(who);
+  if (rc != kOk) return rc;
+  const size_t need = head_bwd_multi_workspace_bytes(segs, n_segs, V);
+  if (need > 0 && (!workspace || ws_bytes < need))
+    return set_error(kErrWorkspace, "%s: workspace too small (%zu < %zu bytes)", who, ws_bytes, need);
+
+  Segs p{};
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int s_max = 1;
+  bool any_dh = false;
+  for (int i = 0; i < n_segs; ++i) {
+    Seg& s = p.s[i];
+    s.g = segs[i].g_rep, s.rep = segs[i].rep, s.arg = segs[i].argmax;
+    s.hidden = static_cast<const uint16_t*>(segs[i].hidden);
+    s.dh = segs[i].d_hidden, s.B = segs[i].B, s.S = segs[i].S;
+    s.doc0 = p.total_docs, s.row0 = p.total_rows;
+    s.row_ptr = reinterpret_cast<int32_t*>(ws);
+    ws += align256(static_cast<size_t>(s.B) * (s.S + 1) * sizeof(int32_t));
+    s.sorted_v = reinterpret_cast<int32_t*>(ws);
+    ws += align256(static_cast<size_t>(s.B) * V * sizeof(int32_t));
+    s.sorted_c = reinterpret_cast<float*>(ws);
+    ws += align256(static_cast<size_t>(s.B) * V * sizeof(int32_t));
+    uint32_t* own_bitmap = reinterpret_cast<uint32_t*>(ws);
+    ws += bitmap_bytes(s.B, V);
+    if (segs[i].active) {
+      s.bitmap = const_cast<uint32_t*>(segs[i].active);
+    } else {
+      rc = launch_rep_bitmap(s.rep, s.B, V, own_bitmap, stream);
+      if (rc != kOk) return rc;
+      s.bitmap = own_bitmap;
+    }
+    p.total_docs += s.B;
+    p.total_rows += static_cast<long long>(s.B) * ((s.S + kRowsPerWarp - 1) / kRowsPerWarp);
+    if (s.B > 0) s_max = std::max(s_max, s.S);
+    any_dh = any_dh || (s.B > 0 && s.dh != nullptr);
+  }
+  p.n = n_segs;
+  if (p.total_docs == 0) {
+    if (!accumulate) {
+      SPLADE_CUDA_OK(cudaMemsetAsync(dW, 0, static_cast<size_t>(V) * H * sizeof(float), stream));
+      SPLADE_CUDA_OK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * sizeof(float), stream));
+    }
+    return kOk;
+  }
+  rc = launch_sort_dhidden(p, W, H, V, s_max, any_dh, stream);
+  if (rc != kOk) return rc;
+  return launch_dw(p, H, V, dW, dbias, accumulate, stream);
 }
 
 int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden,
@@ -346,89 +843,10 @@ int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax,
     return set_error(kErrInvalidArg, "splade_head_bwd: null pointer argument");
   if (B < 0 || S < 1 || V < 1 || H < 1)
     return set_error(kErrInvalidArg, "splade_head_bwd: bad sizes B=%d S=%d H=%d V=%d", B, S, H, V);
-  if (H % 8 != 0 || H > 1024)
-    return set_error(kErrUnsupportedShape, "splade_head_bwd: hidden size %d must be a multiple of 8 and <= 1024",
-                     H);
-  const size_t bucket_smem = static_cast<size_t>(S) * sizeof(int32_t);
-  if (bucket_smem > 200 * 1024)
-    return set_error(kErrUnsupportedShape, "splade_head_bwd: sequence length %d too long for the bucket pass", S);
-  if (static_cast<size_t>(B) * 32 * 8 > 200 * 1024)
-    return set_error(kErrUnsupportedShape, "splade_head_bwd: batch %d too large for the dW staging buffer (<= 800)", B);
-  int rc = require_sm100("splade_head_bwd");
-  if (rc != kOk) return rc;
-  const size_t need = head_bwd_workspace_bytes(B, S, V);
-  if (!workspace || ws_bytes < need)
-    return set_error(kErrWorkspace, "splade_head_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, need);
-
-  if (B == 0) {
-    SPLADE_CUDA_OK(cudaMemsetAsync(dW, 0, static_cast<size_t>(V) * H * sizeof(float), stream));
-    SPLADE_CUDA_OK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * sizeof(float), stream));
-    return kOk;
-  }
-
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  int32_t* row_ptr = reinterpret_cast<int32_t*>(ws);
-  ws += align256(static_cast<size_t>(B) * (S + 1) * sizeof(int32_t));
-  const int n_chunks = (V + kChunk - 1) / kChunk;
-  int32_t* chunk_tab = reinterpret_cast<int32_t*>(ws);
-  ws += align256(static_cast<size_t>(B) * n_chunks * S * sizeof(int32_t));
-  int32_t* sorted_v = reinterpret_cast<int32_t*>(ws);
-  ws += align256(static_cast<size_t>(B) * V * sizeof(int32_t));
-  float* sorted_c = reinterpret_cast<float*>(ws);
-
-  // warp-private position counters live in shared memory: as many warps per CTA as fit
-  const int warps_per_cta = static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / bucket_smem)));
-  const size_t smem_cs = bucket_smem * warps_per_cta;
-  if (smem_cs > 48 * 1024) {
-    SPLADE_CUDA_OK(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem_cs)));
-    SPLADE_CUDA_OK(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem_cs)));
-  }
-  const long long jobs = static_cast<long long>(B) * n_chunks;
-  const unsigned grid_cs = static_cast<unsigned>((jobs + warps_per_cta - 1) / warps_per_cta);
-  bucket_count_kernel<<<grid_cs, 256, smem_cs, stream>>>(g_rep, rep, argmax, B, S, V, n_chunks, warps_per_cta,
-                                                        chunk_tab);
-  bucket_scan_kernel<<<B, kBucketThreads, 0, stream>>>(S, n_chunks, chunk_tab, row_ptr);
-  bucket_scatter_kernel<<<grid_cs, 256, smem_cs, stream>>>(g_rep, rep, argmax, B, S, V, n_chunks, warps_per_cta,
-                                                          chunk_tab, sorted_v, sorted_c);
-  SPLADE_CUDA_OK(cudaGetLastError());
-
-  const uint16_t* Wb = static_cast<const uint16_t*>(W);
-  const uint16_t* Hb = static_cast<const uint16_t*>(hidden);
-  const long long rows = static_cast<long long>(B) * S;
-  const unsigned grid_h = static_cast<unsigned>((rows + 7) / 8);
-  const unsigned grid_w = static_cast<unsigned>((V + 31) / 32);
-  const size_t dw_smem_bytes = static_cast<size_t>(B) * 32 * 8;
-  const int chunks = (H + 255) / 256;
-  switch (chunks) {
-    case 1:
-      dhidden_kernel<1><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
-      SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(dw_smem_bytes)));
-      dw_kernel<1><<<grid_w, 256, dw_smem_bytes, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
-      break;
-    case 2:
-      dhidden_kernel<2><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
-      SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(dw_smem_bytes)));
-      dw_kernel<2><<<grid_w, 256, dw_smem_bytes, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
-      break;
-    case 3:
-      dhidden_kernel<3><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
-      SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(dw_smem_bytes)));
-      dw_kernel<3><<<grid_w, 256, dw_smem_bytes, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
-      break;
-    default:
-      dhidden_kernel<4><<<grid_h, 256, 0, stream>>>(row_ptr, sorted_v, sorted_c, Wb, B, S, H, V, d_hidden);
-      SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(dw_smem_bytes)));
-      dw_kernel<4><<<grid_w, 256, dw_smem_bytes, stream>>>(g_rep, rep, argmax, Hb, B, S, H, V, dW, dbias);
-      break;
-  }
-  SPLADE_CUDA_OK(cudaGetLastError());
-  return kOk;
+  splade_head_bwd_segment seg{};
+  seg.g_rep = g_rep, seg.rep = rep, seg.argmax = argmax, seg.hidden = hidden, seg.d_hidden = d_hidden;
+  seg.B = B, seg.S = S;
+  return head_bwd_multi_launch(&seg, 1, W, H, V, dW, dbias, 0, workspace, ws_bytes, stream);
 }
 
 }  // namespace splade

@@ -9,6 +9,7 @@
 struct splade_v33_scalar_args;
 struct splade_v33_fwd_args;
 struct splade_trunk_args;
+struct splade_head_bwd_segment;
 
 namespace splade {
 
@@ -77,6 +78,17 @@ size_t varlen_rows_public(int B, int S);
 
 // head_bwd.cu
 size_t head_bwd_workspace_bytes(int B, int S, int V);
+size_t head_bwd_bitmap_bytes(int B, int V);
+int rep_bitmap_launch(const float* rep, int B, int V, uint32_t* bitmap, cudaStream_t stream);
+size_t head_bwd_dhidden_workspace_bytes(int B, int S, int V);
+size_t head_bwd_multi_workspace_bytes(const struct splade_head_bwd_segment* segs, int n_segs, int V);
+int head_bwd_multi_launch(const struct splade_head_bwd_segment* segs, int n_segs, const void* W, int H, int V,
+                          float* dW, float* dbias, int accumulate, void* workspace, size_t ws_bytes,
+                          cudaStream_t stream);
+int head_bwd_dhidden_launch(const struct splade_head_bwd_segment* seg, const void* W, int H, int V, uint32_t* bitmap,
+                            void* workspace, size_t ws_bytes, cudaStream_t stream);
+int head_bwd_dw_launch(const struct splade_head_bwd_segment* segs, const uint32_t* const* bitmaps, int n_segs, int H,
+                       int V, float* dW, float* dbias, int accumulate, cudaStream_t stream);
 int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden,
                     const void* W, int B, int S, int H, int V, float* d_hidden, float* dW, float* dbias,
                     void* workspace, size_t ws_bytes, cudaStream_t stream);

@@ -6,6 +6,7 @@ stream and records the autograd graph.  All arithmetic happens in ``libsplade_b2
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import Optional, Tuple
 
@@ -139,6 +140,102 @@ def head_backward(g_rep: torch.Tensor, rep: torch.Tensor, argmax: torch.Tensor, 
     return d_hidden, dW, dbias
 
 
+def _segment_struct(g_rep, rep, argmax, hidden, d_hidden, active=None):
+    B, S, _ = hidden.shape
+    return _lib.HeadBwdSegment(g_rep=g_rep.data_ptr(), rep=rep.data_ptr(), argmax=argmax.data_ptr(),
+                               hidden=hidden.data_ptr(), d_hidden=_ptr(d_hidden), B=B, S=S, active=_ptr(active))
+
+
+def rep_bitmap(rep: torch.Tensor) -> torch.Tensor:
+    """rep [B,V] fp32 -> int32 [B, ceil(V/32)], bit j of word w = (rep[b, 32w+j] > 0) (``splade_rep_bitmap``).
+    The backward kernels are driven by it; computed right after the forward, while rep is L2-hot."""
+    lib = load_library()
+    _require_cuda(rep, "rep")
+    assert rep.dtype == torch.float32 and rep.is_contiguous()
+    B, V = rep.shape
+    with torch.cuda.device(rep.device):
+        bitmap = torch.empty((B, (V + 31) // 32), dtype=torch.int32, device=rep.device)
+        check(lib.splade_rep_bitmap(rep.data_ptr(), B, V, bitmap.data_ptr(), _stream(rep)), "splade_rep_bitmap")
+    return bitmap
+
+
+def head_backward_dhidden(g_rep: torch.Tensor, rep: torch.Tensor, argmax: torch.Tensor, hidden: torch.Tensor,
+                          weight: torch.Tensor, want_d_hidden: bool = True, active: Optional[torch.Tensor] = None):
+    """Phase 1 of the multi-segment backward for ONE head call (``splade_head_bwd_dhidden``):
+    -> (d_hidden [B,S,H] fp32 | None, activity bitmap int32 [B, ceil(V/32)] for ``head_backward_dw``).
+    ``active``: the bitmap ``rep_bitmap(rep)`` made after the forward; computed here when missing."""
+    lib = load_library()
+    B, S, H = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    assert g_rep.dtype == torch.float32 and g_rep.is_contiguous()
+    with torch.cuda.device(dev):
+        d_hidden = torch.empty((B, S, H), dtype=torch.float32, device=dev) if want_d_hidden else None
+        bitmap = active if active is not None else torch.empty((B, (V + 31) // 32), dtype=torch.int32, device=dev)
+        nbytes = lib.splade_workspace_bytes(_lib.OP_HEAD_BWD_DHIDDEN, B, S, H, V, 0)
+        ws, ws_ptr = _ws(nbytes, dev)
+        seg = _segment_struct(g_rep, rep, argmax, hidden, d_hidden, active)
+        check(lib.splade_head_bwd_dhidden(ctypes.byref(seg), weight.data_ptr(), H, V, bitmap.data_ptr(), ws_ptr,
+                                          nbytes, _stream(hidden)), "splade_head_bwd_dhidden")
+    return d_hidden, bitmap
+
+
+def _grad_buffers(accumulate_into, V, H, dev):
+    if accumulate_into is None:
+        return (torch.empty((V, H), dtype=torch.float32, device=dev),
+                torch.empty((V,), dtype=torch.float32, device=dev))
+    dW, dbias = accumulate_into
+    assert dW.dtype == torch.float32 and dW.is_contiguous() and tuple(dW.shape) == (V, H)
+    assert dbias.dtype == torch.float32 and dbias.is_contiguous() and tuple(dbias.shape) == (V,)
+    return dW, dbias
+
+
+def head_backward_dw(segments, H: int, V: int, accumulate_into=None):
+    """Phase 2: ONE dW / dbias sweep over ``segments`` = [(g_rep, rep, argmax, hidden, bitmap), ...]
+    (``splade_head_bwd_dw``).  ``accumulate_into=(dW, dbias)`` adds into existing fp32 buffers."""
+    lib = load_library()
+    n = len(segments)
+    assert 1 <= n <= _lib.HEAD_BWD_MAX_SEGMENTS
+    dev = segments[0][3].device
+    with torch.cuda.device(dev):
+        dW, dbias = _grad_buffers(accumulate_into, V, H, dev)
+        segs = (_lib.HeadBwdSegment * n)()
+        maps = (ctypes.c_void_p * n)()
+        for i, (g_rep, rep, argmax, hidden, bitmap) in enumerate(segments):
+            segs[i] = _segment_struct(g_rep, rep, argmax, hidden, None)
+            maps[i] = bitmap.data_ptr()
+        check(lib.splade_head_bwd_dw(segs, maps, n, H, V, dW.data_ptr(), dbias.data_ptr(),
+                                     int(accumulate_into is not None), _stream(segments[0][3])), "splade_head_bwd_dw")
+    return dW, dbias
+
+
+def head_backward_multi(segments, weight: torch.Tensor, accumulate_into=None):
+    """All phases for several head calls in three launches (``splade_head_bwd_multi``).
+    ``segments`` = [(g_rep, rep, argmax, hidden[, active bitmap]), ...] -> ([d_hidden_i], dW, dbias)."""
+    lib = load_library()
+    n = len(segments)
+    assert 1 <= n <= _lib.HEAD_BWD_MAX_SEGMENTS
+    V, H = weight.shape
+    dev = weight.device
+    with torch.cuda.device(dev):
+        dW, dbias = _grad_buffers(accumulate_into, V, H, dev)
+        segs = (_lib.HeadBwdSegment * n)()
+        keep, d_hiddens = [], []
+        for i, seg in enumerate(segments):
+            g_rep, rep, argmax, hidden = seg[:4]
+            g_rep = _f32c(g_rep)
+            keep.append(g_rep)
+            dh = torch.empty(tuple(hidden.shape), dtype=torch.float32, device=dev)
+            d_hiddens.append(dh)
+            segs[i] = _segment_struct(g_rep, rep, argmax, hidden, dh, seg[4] if len(seg) > 4 else None)
+        nbytes = lib.splade_head_bwd_multi_workspace_bytes(segs, n, V)
+        ws, ws_ptr = _ws(nbytes, dev)
+        check(lib.splade_head_bwd_multi(segs, n, weight.data_ptr(), H, V, dW.data_ptr(), dbias.data_ptr(),
+                                        int(accumulate_into is not None), ws_ptr, nbytes, _stream(weight)),
+              "splade_head_bwd_multi")
+    return d_hiddens, dW, dbias
+
+
 def flops_nnz(rep: torch.Tensor, out2: Optional[torch.Tensor] = None):
     """rep [N,V] fp32 -> (colmean [V], out2 [2] = {sum_j mean_j^2, mean_i nnz_i})"""
     lib = load_library()
@@ -242,11 +339,94 @@ def cached_bf16(weight: torch.Tensor) -> torch.Tensor:
     return w
 
 
+class _HeadTicket:
+    """One head call whose backward is outstanding (see ``_DeferredDW``)."""
+
+    __slots__ = ("seq", "node", "task", "segment", "__weakref__")
+
+    def __init__(self, seq, node):
+        self.seq = seq           # forward call order: the fixed summation order of the dW sweep
+        self.node = node         # weakref to the autograd node (ctx) of that call
+        self.task = -1           # id of the backward pass (graph task) in which its g_rep arrived
+        self.segment = None      # (g_rep, rep, argmax, hidden, bitmap) once arrived
+
+
+class _DeferredDW:
+    """One backward, one dW.  The reference trainer calls the model three times per micro-step and back-propagates
+    once (train_v33_ddp.py:339-343, 364); all three head calls share the tied decoder matrix.  Instead of three
+    dense [V,H] gradients summed by autograd, every head backward computes its dHidden at once, parks its segment
+    here and returns NO weight gradient, until the last head node of the running backward pass arrives: that one
+    runs the single dW / dbias sweep over all parked segments (``splade_head_bwd_dw``) and returns the result.
+    "Last" is decided by asking the autograd engine which of the other outstanding head nodes it will still
+    execute in this pass (``torch._C._will_engine_execute_node``): nodes of an unrelated or abandoned graph
+    (an evaluation forward under grad mode, a recomputation) are ignored, never waited for."""
+
+    def __init__(self):
+        self._groups = {}  # id(weight parameter) -> (weakref to it, [tickets]); identity-keyed (tensors define ==)
+        self._seq = 0
+
+    def _group(self, weight, create: bool):
+        key = id(weight)
+        hit = self._groups.get(key)
+        if hit is not None and hit[0]() is weight:
+            return hit[1]
+        if not create:
+            return None
+        tickets = []
+        self._groups[key] = (weakref.ref(weight, lambda _r, k=key: self._groups.pop(k, None)), tickets)
+        return tickets
+
+    def open(self, weight, ctx) -> _HeadTicket:
+        group = self._group(weight, create=True)
+        group[:] = [t for t in group if t.node() is not None]
+        self._seq += 1
+        t = _HeadTicket(self._seq, weakref.ref(ctx))
+        group.append(t)
+        return t
+
+    def arrive(self, weight, ticket, segment):
+        """-> list of segments to sweep now (forward call order), or None when another head node of this pass
+        is still to come."""
+        task = torch._C._current_graph_task_id()
+        ticket.task, ticket.segment = task, segment
+        group = self._group(weight, create=False)
+        if group is None or task < 0:  # not inside the engine (direct call): nothing to wait for
+            ticket.segment = None
+            return [segment]
+        ready = []
+        for t in group:
+            if t is ticket:
+                ready.append(t)
+                continue
+            node = t.node()
+            if node is None:
+                continue
+            if t.segment is not None and t.task == task:
+                ready.append(t)       # arrived earlier in this pass
+            elif t.segment is not None:
+                t.segment = None      # left over from a pass that never finished (exception): drop
+            elif torch._C._will_engine_execute_node(node):
+                return None           # still to come in this pass
+        ready.sort(key=lambda t: t.seq)
+        segments = [t.segment for t in ready]
+        for t in ready:
+            t.segment = None
+        return segments
+
+
+_DEFERRED_DW = _DeferredDW()
+
+
+def _defer_dw_enabled() -> bool:
+    return os.environ.get("SPLADE_B200_DEFER_DW", "1") != "0"
+
+
 class SpladeHeadFunction(torch.autograd.Function):
     """sparse_repr, token_weights = SPLADE-max head(hidden, decoder.weight, decoder.bias, attention_mask).
 
     Replaces src/model/splade_modern.py:73-86 + the decoder Linear.  Backward is the gather-driven sparse
-    backward (splade_head_bwd)."""
+    backward: dHidden at once (``splade_head_bwd_dhidden``), dW / dbias once per backward pass for all head calls
+    that share the weight (``_DeferredDW``)."""
 
     @staticmethod
     def forward(ctx, hidden, weight, bias, attention_mask, want_token_weights: bool, round_bias: bool):
@@ -262,8 +442,15 @@ class SpladeHeadFunction(torch.autograd.Function):
             b32 = b32.to(torch.float32).contiguous()
         m32 = attention_mask.detach().to(torch.int32).contiguous()
         rep, argmax, tokw = head_forward(h16, w16, b32, m32, want_token_weights)
-        ctx.save_for_backward(rep, argmax, h16, w16)
+        active = rep_bitmap(rep) if any(ctx.needs_input_grad[:3]) else rep.new_empty((0,), dtype=torch.int32)
+        ctx.save_for_backward(rep, argmax, h16, w16, active)
         ctx.in_dtypes = (hidden.dtype, weight.dtype, None if bias is None else bias.dtype)
+        ctx.weight_ref = None
+        ctx.ticket = None
+        needs_w = ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2])
+        if needs_w and _defer_dw_enabled():
+            ctx.weight_ref = weakref.ref(weight)
+            ctx.ticket = _DEFERRED_DW.open(weight, ctx)
         if tokw is None:
             tokw = torch.zeros((0,), dtype=torch.float32, device=hidden.device)
         ctx.mark_non_differentiable(tokw)
@@ -271,10 +458,26 @@ class SpladeHeadFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rep, _g_tokw):
-        rep, argmax, h16, w16 = ctx.saved_tensors
-        d_hidden, dW, dbias = head_backward(g_rep, rep, argmax, h16, w16)
+        rep, argmax, h16, w16, active = ctx.saved_tensors
         hd, wd, bd = ctx.in_dtypes
-        return (d_hidden.to(hd), dW.to(wd), None if bd is None else dbias.to(bd), None, None, None)
+        need_h = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or (bd is not None and ctx.needs_input_grad[2])
+        g32 = _f32c(g_rep)
+        d_hidden, bitmap = head_backward_dhidden(g32, rep, argmax, h16, w16, want_d_hidden=need_h,
+                                                 active=active if active.numel() else None)
+        dW = dbias = None
+        if need_w:
+            segment = (g32, rep, argmax, h16, bitmap)
+            weight = ctx.weight_ref() if ctx.weight_ref is not None else None
+            segments = [segment]
+            if ctx.ticket is not None and weight is not None:
+                segments = _DEFERRED_DW.arrive(weight, ctx.ticket, segment)
+            if segments is not None:
+                V, H = w16.shape
+                dW, dbias = head_backward_dw(segments, H, V)
+                dW = dW.to(wd) if ctx.needs_input_grad[1] else None
+                dbias = dbias.to(bd) if (bd is not None and ctx.needs_input_grad[2]) else None
+        return (d_hidden.to(hd) if need_h else None, dW, dbias, None, None, None)
 
 
 def autocast_is_bf16() -> bool:

@@ -160,6 +160,118 @@ def test_autograd_function_matches_torch_chain(cuda_device):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# one backward, one dW: several head calls sharing the decoder matrix (splade_head_bwd_multi / _dhidden / _dw)
+# ---------------------------------------------------------------------------------------------------------
+def _segments(device, shapes, H, V, bias_offset, seed=11):
+    """[(g_rep, rep, argmax, hidden_bf16)] for head calls of different (B, S) on ONE (W, bias)."""
+    _, W, bias, _ = make_head_inputs(1, 8, H, V, seed=seed, device=device, bias_offset=bias_offset)
+    w16 = W.to(torch.bfloat16).contiguous()
+    segs = []
+    for i, (B, S) in enumerate(shapes):
+        if B == 0:  # an empty head call (e.g. a rank whose shard ran dry)
+            segs.append((torch.empty(0, V, device=device), torch.empty(0, V, device=device),
+                         torch.empty(0, V, dtype=torch.int32, device=device),
+                         torch.empty(0, S, H, dtype=torch.bfloat16, device=device)))
+            continue
+        hidden, _, _, mask = make_head_inputs(B, S, H, V, seed=seed + 1 + i, device=device)
+        rep, arg, _ = run_head(hidden, W, bias, mask, want_tokw=False)
+        g = torch.randn(B, V, generator=torch.Generator().manual_seed(seed + 100 + i)).to(device)
+        segs.append((g, rep, arg, hidden.to(torch.bfloat16).contiguous()))
+    return segs, w16
+
+
+@pytest.mark.parametrize("shapes,H,V,off", [
+    ([(4, 16), (4, 64), (8, 40)], 128, 1999, -0.5),      # q / pos / neg of different lengths, vocabulary tail
+    ([(3, 7)], 64, 33, 0.0),                             # one segment = splade_head_bwd
+    ([(2, 300), (5, 9), (1, 1), (0, 4)], 64, 1000, -1.0),  # long documents, a 1x1 call, an EMPTY segment
+    ([(150, 8), (150, 8)], 64, 520, -0.3),               # 300 documents: two staging passes of the dW sweep
+    ([(2, 64), (2, 256), (2, 256)], 768, 4096, -2.0),    # real hidden size, trained-like sparsity
+])
+def test_multi_segment_backward_equals_the_sum_of_single_calls(cuda_device, shapes, H, V, off):
+    import splade_b200
+    segs, w16 = _segments(cuda_device, shapes, H, V, off)
+    singles = [splade_b200.head_backward(g, rep, arg, h, w16) for g, rep, arg, h in segs if h.shape[0] > 0]
+    dhs, dW, dbias = splade_b200.head_backward_multi(segs, w16)
+    torch.cuda.synchronize()
+    j = 0
+    for (g, rep, arg, h), dh in zip(segs, dhs):
+        if h.shape[0] == 0:
+            continue
+        assert torch.equal(dh, singles[j][0]), "dHidden of a segment must not depend on the other segments"
+        j += 1
+    ref_dW = torch.stack([s[1].double() for s in singles]).sum(0)
+    ref_db = torch.stack([s[2].double() for s in singles]).sum(0)
+    scale = float(ref_dW.abs().max())
+    assert float((dW.double() - ref_dW).abs().max()) <= 1e-5 * scale + 1e-7
+    assert float((dbias.double() - ref_db).abs().max()) <= 1e-5 * float(ref_db.abs().max()) + 1e-7
+
+    # two-phase form (what autograd drives): bit-identical to the three-launch form, also for a NULL dHidden
+    live = [s for s in segs if s[3].shape[0] > 0]
+    phase = [splade_b200.head_backward_dhidden(g, rep, arg, h, w16, want_d_hidden=(i != 0))
+             for i, (g, rep, arg, h) in enumerate(live)]
+    assert phase[0][0] is None
+    for (dh2, _), dh in zip(phase[1:], [d for d, s in zip(dhs, segs) if s[3].shape[0] > 0][1:]):
+        assert torch.equal(dh2, dh)
+    dW2, db2 = splade_b200.head_backward_dw([(g, rep, arg, h, bm) for (g, rep, arg, h), (_, bm) in zip(live, phase)],
+                                            H, V)
+    assert torch.equal(dW2, dW) and torch.equal(db2, dbias)
+
+    # the bitmap made right after the forward (what autograd passes) gives bit-identical results to the one the
+    # library derives itself, in the three-launch and in the two-phase form
+    act = [splade_b200.rep_bitmap(s[1]) for s in segs]
+    dhs4, dW4, db4 = splade_b200.head_backward_multi([(*s, a) for s, a in zip(segs, act)], w16)
+    assert torch.equal(dW4, dW) and torch.equal(db4, dbias) and all(torch.equal(a, b) for a, b in zip(dhs4, dhs))
+    g0, rep0, arg0, h0 = live[-1]
+    act0 = splade_b200.rep_bitmap(rep0)
+    dh5, bm5 = splade_b200.head_backward_dhidden(g0, rep0, arg0, h0, w16, active=act0)
+    assert bm5 is act0 and torch.equal(bm5, phase[-1][1]) and torch.equal(dh5, [d for d, s in zip(dhs, segs) if s[3].shape[0] > 0][-1])
+
+    # accumulate: adds into the caller's gradient buffers (same sweep, starting from their contents)
+    base_W = torch.randn(V, H, generator=torch.Generator().manual_seed(5)).to(cuda_device)
+    base_b = torch.randn(V, generator=torch.Generator().manual_seed(6)).to(cuda_device)
+    acc_W, acc_b = base_W.clone(), base_b.clone()
+    splade_b200.head_backward_multi(segs, w16, accumulate_into=(acc_W, acc_b))
+    # (the sweep continues FROM the buffer's value, ((base + t1) + t2) + ..., so it differs from base + (t1 + t2 + ...)
+    # by fp32 rounding at the magnitude of base ~ N(0,1), not of the gradient)
+    torch.testing.assert_close(acc_W, base_W + dW, rtol=1e-5, atol=5e-5)
+    torch.testing.assert_close(acc_b, base_b + dbias, rtol=1e-5, atol=5e-5)
+
+    # deterministic: the same call again is bit-identical
+    dhs3, dW3, db3 = splade_b200.head_backward_multi(segs, w16)
+    assert torch.equal(dW3, dW) and torch.equal(db3, dbias) and all(torch.equal(a, b) for a, b in zip(dhs3, dhs))
+
+
+def test_three_head_calls_one_backward_one_dw_sweep(cuda_device, monkeypatch):
+    """The reference's micro-step pattern through autograd (train_v33_ddp.py:339-343, 364): three head calls on the
+    tied matrix, one backward => ONE dW sweep over three segments; gradients equal the un-deferred path."""
+    import splade_b200
+    from splade_b200 import ops
+    H, V = 128, 3000
+    _, W, bias, _ = make_head_inputs(1, 8, H, V, seed=21, device=cuda_device, bias_offset=-0.5)
+    ins = [make_head_inputs(B, S, H, V, seed=22 + i, device=cuda_device)[::3] for i, (B, S) in
+           enumerate(((4, 16), (4, 48), (8, 48)))]
+    sweeps = []
+    real_dw = ops.head_backward_dw
+    monkeypatch.setattr(ops, "head_backward_dw", lambda segs, *a, **k: (sweeps.append(len(segs)), real_dw(segs, *a, **k))[1])
+    grads = {}
+    for defer in ("1", "0"):
+        monkeypatch.setenv("SPLADE_B200_DEFER_DW", defer)
+        w = W.clone().requires_grad_(True)
+        b = bias.clone().requires_grad_(True)
+        hs = [h.clone().requires_grad_(True) for h, _ in ins]
+        sweeps.clear()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            reps = [splade_b200.splade_head(h, w, b, m)[0] for h, (_, m) in zip(hs, ins)]
+            loss = sum((r * r).sum() * (i + 1) for i, r in enumerate(reps))
+        loss.backward()
+        torch.cuda.synchronize()
+        assert sweeps == ([3] if defer == "1" else [1, 1, 1])
+        grads[defer] = [w.grad, b.grad] + [h.grad for h in hs]
+    for a, r in zip(grads["1"], grads["0"]):
+        torch.testing.assert_close(a, r, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # packed (variable-length) token layout: splade_head_fwd_mode
 # ---------------------------------------------------------------------------------------------------------
 def _both_layouts(hidden, W, bias, mask, want_tokw=True):

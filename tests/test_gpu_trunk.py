@@ -253,3 +253,66 @@ def test_dropin_encoder_and_bulk_encode_use_the_native_trunk(cuda_device, tmp_pa
     overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / 16.0 for a, b in zip(i0.cpu(), i1.cpu())])
     assert overlap > 0.9, overlap
     np.testing.assert_allclose(v1[:, 0].cpu().numpy(), v0[:, 0].cpu().numpy(), rtol=3e-2, atol=3e-2)
+
+
+def test_native_trunk_real_shape_vs_transformers_and_fp32(cuda_device):
+    """The native trunk at the REAL A.X-Encoder-base shape (22 layers, hidden 768, 12 heads, intermediate 1152,
+    vocab 50 000; the shape every native-trunk number in bench.py / profiles rests on), B = 64 x S = 256 where the
+    +-64 sliding window actually bites, full-length and ragged batches.  Two oracles, thresholds stated here:
+
+      (1) transformers' own forward under autocast(bf16) + the fused head (the drop-in default path):
+          per-document cosine >= 0.9999, max |dw| <= 2e-2, mean top-64 overlap >= 0.98, worst document >= 0.90
+      (2) the reference's fp32 inference chain (benchmark/encoders.py:309-318, no autocast): the native trunk must
+          be no further from it than the reference's OWN autocast path is (cosine and top-64 overlap within 1e-4 /
+          0.01 of that path's) - bf16 Linear outputs through 22 layers are the reference's rounding noise too.
+    """
+    import splade_b200
+    from transformers import AutoModelForMaskedLM, ModernBertConfig
+    V, H = 50000, 768
+    cfg = ModernBertConfig(vocab_size=V, hidden_size=H, intermediate_size=1152, num_hidden_layers=22,
+                           num_attention_heads=12, pad_token_id=V - 1, bos_token_id=0, eos_token_id=1, cls_token_id=0,
+                           sep_token_id=1, max_position_embeddings=16384, global_attn_every_n_layers=3,
+                           local_attention=128)
+    torch.manual_seed(0)
+    mlm = AutoModelForMaskedLM.from_config(cfg).to(cuda_device).eval()
+    with torch.no_grad():
+        mlm.decoder.bias.normal_(0.0, 0.02)
+    trunk = splade_b200.NativeTrunk(mlm)
+    B, S = 64, 256
+    g = torch.Generator().manual_seed(5)
+
+    def topk_overlap(a, b, k=64):
+        ta, tb = a.topk(k, dim=1).indices.tolist(), b.topk(k, dim=1).indices.tolist()
+        return [len(set(x) & set(y)) / k for x, y in zip(ta, tb)]
+
+    for ragged in (False, True):
+        lens = torch.randint(32, S + 1, (B,), generator=g) if ragged else torch.full((B,), S)
+        if ragged:
+            lens[0], lens[1] = S, 1
+        ids = torch.randint(6, V - 1, (B, S), generator=g)
+        mask = (torch.arange(S)[None, :] < lens[:, None]).to(torch.int64)
+        ids = torch.where(mask.bool(), ids, torch.full_like(ids, cfg.pad_token_id)).to(cuda_device)
+        mask = mask.to(cuda_device)
+        native = trunk.encode(ids, mask)
+        with torch.no_grad():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                hid = mlm.head(mlm.model(input_ids=ids, attention_mask=mask)[0]).float()
+                auto, _ = splade_b200.splade_head(hid, mlm.decoder.weight, mlm.decoder.bias, mask,
+                                                  want_token_weights=False)
+            logits = mlm(input_ids=ids, attention_mask=mask).logits            # fp32, no autocast
+            fp32 = (torch.log1p(torch.relu(logits)) * mask.unsqueeze(-1).float()).max(dim=1).values
+            del logits
+        what = "ragged" if ragged else "full"
+        # (1) against the drop-in default (transformers trunk under autocast + fused head)
+        cos = torch.nn.functional.cosine_similarity(native, auto, dim=1)
+        ov = topk_overlap(native, auto)
+        assert float(cos.min()) >= 0.9999, (what, float(cos.min()))
+        assert float((native - auto).abs().max()) <= 2e-2, (what, float((native - auto).abs().max()))
+        assert sum(ov) / len(ov) >= 0.98 and min(ov) >= 0.90, (what, sum(ov) / len(ov), min(ov))
+        # (2) against fp32: no worse than the reference's own autocast path
+        cos_n = float(torch.nn.functional.cosine_similarity(native, fp32, dim=1).min())
+        cos_a = float(torch.nn.functional.cosine_similarity(auto, fp32, dim=1).min())
+        ov_n, ov_a = topk_overlap(native, fp32), topk_overlap(auto, fp32)
+        assert cos_n >= cos_a - 1e-4, (what, cos_n, cos_a)
+        assert sum(ov_n) / len(ov_n) >= sum(ov_a) / len(ov_a) - 0.01, (what, sum(ov_n) / B, sum(ov_a) / B)
+        np.testing.assert_allclose(native.cpu().numpy(), fp32.cpu().numpy(), atol=2e-2, rtol=2e-2)

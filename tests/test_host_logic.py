@@ -275,3 +275,100 @@ def test_only_bf16_autocast_is_mirrored(monkeypatch):
     monkeypatch.setattr(torch, "get_autocast_dtype", lambda *a: torch.float16)
     with pytest.raises(RuntimeError, match="autocast dtype"):
         ops.autocast_is_bf16()
+
+
+def _fake_head_kernels(monkeypatch, calls):
+    """Plain-torch stand-ins for the three C-ABI head entry points so that the HOST logic of SpladeHeadFunction
+    (deferral of dW across head calls) can be exercised on CPU.  Test infrastructure only."""
+    from splade_b200 import ops
+
+    def fwd(h16, w16, b32, m32, want_tokw, pack_mode=None, plan_out=None):
+        logits = (h16.float() @ w16.float().t() + b32).to(torch.bfloat16).float()
+        act = torch.log1p(torch.relu(logits)) * m32[:, :, None].float()
+        rep, arg = act.max(dim=1)
+        return rep, arg.to(torch.int32), (act.max(dim=2).values if want_tokw else None)
+
+    def dhidden(g32, rep, argmax, h16, w16, want_d_hidden=True, active=None):
+        calls.append("dhidden")
+        coef = torch.where(rep > 0, g32 * torch.exp(-rep), torch.zeros_like(rep))
+        dh = None
+        if want_d_hidden:
+            B, S, H = h16.shape
+            dh = torch.zeros(B, S, H)
+            for b in range(B):
+                dh[b].index_add_(0, argmax[b].long(), coef[b][:, None] * w16.float())
+        return dh, coef  # the "bitmap" slot carries the coefficients for the fake sweep
+
+    def dw(segments, H, V, accumulate_into=None):
+        calls.append(("dw", len(segments)))
+        dW, db = torch.zeros(V, H), torch.zeros(V)
+        for g32, rep, argmax, h16, coef in segments:
+            B = h16.shape[0]
+            rows = h16.float()[torch.arange(B)[:, None], argmax.long()]          # [B,V,H]
+            dW += (coef[:, :, None] * rows).sum(0)
+            db += coef.sum(0)
+        return dW, db
+
+    monkeypatch.setattr(ops, "_require_cuda", lambda t, n: None)
+    monkeypatch.setattr(ops, "head_forward", fwd)
+    monkeypatch.setattr(ops, "rep_bitmap", lambda rep: torch.ones(1, dtype=torch.int32))
+    monkeypatch.setattr(ops, "head_backward_dhidden", dhidden)
+    monkeypatch.setattr(ops, "head_backward_dw", dw)
+
+
+def _torch_head(hidden, W, bias, mask):
+    st = lambda t: t + (t.to(torch.bfloat16).float() - t).detach()   # noqa: E731  bf16 rounding, fp32 gradient
+    logits = st(hidden) @ st(W).t() + bias
+    logits = logits + (logits.to(torch.bfloat16).float() - logits).detach()      # bf16 rounding, straight-through
+    return (torch.log1p(torch.relu(logits)) * mask[:, :, None].float()).max(dim=1).values
+
+
+def test_one_backward_one_dw_sweep_host_logic(monkeypatch):
+    """Three head calls sharing the tied decoder matrix, one backward (train_v33_ddp.py:339-343, 364): exactly ONE
+    dW sweep over three segments, returned by the last head node the engine runs; a stale forward whose graph is
+    never back-propagated is not waited for; gradients equal plain autograd; retain_graph passes work again."""
+    from splade_b200 import ops
+    calls = []
+    _fake_head_kernels(monkeypatch, calls)
+    g = torch.Generator().manual_seed(0)
+    V, H = 40, 16
+    W = torch.nn.Parameter(torch.randn(V, H, generator=g).to(torch.bfloat16).float() * 0.3)
+    bias = torch.nn.Parameter(torch.zeros(V))
+    hs = [torch.randn(b, s, H, generator=g).to(torch.bfloat16).float().requires_grad_(True)
+          for b, s in ((3, 5), (3, 7), (6, 7))]
+    ms = [torch.ones(h.shape[0], h.shape[1], dtype=torch.int64) for h in hs]
+
+    stale, _ = ops.splade_head(hs[0].detach(), W, bias, ms[0], round_bias=False)   # never back-propagated, kept alive
+    reps = [ops.splade_head(h, W, bias, m, round_bias=False)[0] for h, m in zip(hs, ms)]
+    loss = sum((r * r).sum() for r in reps)
+    loss.backward(retain_graph=True)
+    assert calls.count("dhidden") == 3 and [c for c in calls if c != "dhidden"] == [("dw", 3)]
+    got = [W.grad.clone(), bias.grad.clone()] + [h.grad.clone() for h in hs]
+
+    W2, b2 = W.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    hs2 = [h.detach().clone().requires_grad_(True) for h in hs]
+    sum((_torch_head(h, W2, b2, m) ** 2).sum() for h, m in zip(hs2, ms)).backward()
+    for a, b in zip(got, [W2.grad, b2.grad] + [h.grad for h in hs2]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+    # the same graph again (retain_graph): one more sweep over three segments, gradients accumulate to 2x
+    calls.clear()
+    loss.backward()
+    assert [c for c in calls if c != "dhidden"] == [("dw", 3)]
+    torch.testing.assert_close(W.grad, 2 * got[0], rtol=1e-5, atol=1e-6)
+
+    # only two of the three calls take part in a backward: one sweep over two segments
+    calls.clear()
+    W.grad = None
+    reps = [ops.splade_head(h, W, bias, m, round_bias=False)[0] for h, m in zip(hs, ms)]
+    (reps[0].sum() + reps[2].sum()).backward()
+    assert [c for c in calls if c != "dhidden"] == [("dw", 2)]
+    del stale
+
+    # deferral switched off: every head backward sweeps on its own (three dense gradients, summed by autograd)
+    calls.clear()
+    monkeypatch.setenv("SPLADE_B200_DEFER_DW", "0")
+    W.grad = None
+    sum((ops.splade_head(h, W, bias, m, round_bias=False)[0] ** 2).sum() for h, m in zip(hs, ms)).backward()
+    assert [c for c in calls if c != "dhidden"] == [("dw", 1)] * 3
+    torch.testing.assert_close(W.grad, got[0], rtol=1e-5, atol=1e-6)
