@@ -49,6 +49,7 @@ extern "C" {
 #define SPLADE_OP_PEER_LOSS_BWD 9 /* (B=Bq, k=world)          splade_peer_loss_bwd scratch            */
 #define SPLADE_OP_HEAD_BWD_DHIDDEN 10 /* (B,S,-,V)            splade_head_bwd_dhidden scratch (one segment)   */
 #define SPLADE_OP_HEAD_BWD_BITMAP 11  /* (B,-,-,V)            bytes of one segment's activity bitmap          */
+#define SPLADE_OP_LOSS_BWD_TC 12      /* (B=Bq, k=N docs)     splade_loss_bwd_tc scratch                      */
 
 int splade_abi_version(void);
 const char* splade_last_error(void);
@@ -244,6 +245,21 @@ int splade_loss_bwd(const float* q, const float* docs, const float* negs, int Bq
                     int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
                     const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
                     const float* g_loss, float* dq, float* ddocs, float* dnegs, void* stream);
+
+/*
+ * The same backward in autocast mode on the 5th-generation tensor cores.  Under torch.autocast the reference's
+ * backward of torch.mm(anchor, positive.t()) (src/model/losses.py:155) is a bf16 GEMM on the bf16 casts of its
+ * operands; splade_v33_loss_fwd (round_bf16 != 0) already packed those casts for the score GEMM and leaves them in
+ * its workspace: splade_v33_loss_fwd_operands returns where (q16 [Bq,Vp], d16 [N,Vp] bf16, Vp = V rounded up to 8) -
+ * keep the forward workspace alive until the backward ran.  G is rounded to bf16, accumulation and outputs are
+ * fp32.  ddocs may be NULL (dq and dnegs only).  Needs V % 4 == 0.
+ */
+int splade_v33_loss_fwd_operands(const splade_v33_fwd_args* args, const void** q16, const void** d16, int* Vp);
+int splade_loss_bwd_tc(const float* q, const float* negs, const void* q16, const void* d16, int Bq, int N, int k, int V,
+                       int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
+                       const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
+                       const float* g_loss, float* dq, float* ddocs, float* dnegs, void* workspace, size_t ws_bytes,
+                       void* stream);
 
 /*
  * Top-k pruning with the production emit semantics (benchmark/encoders.py:320-343): keep weight > 0, drop

@@ -27,6 +27,7 @@ OP_TRUNK_ATTN = 8
 OP_PEER_LOSS_BWD = 9
 OP_HEAD_BWD_DHIDDEN = 10
 OP_HEAD_BWD_BITMAP = 11
+OP_LOSS_BWD_TC = 12
 HEAD_BWD_MAX_SEGMENTS = 8
 MAX_PEERS = 16
 
@@ -136,6 +137,11 @@ EXPORTS = {
     "splade_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "splade_v33_loss_fwd_operands": (c_int, [POINTER(V33FwdArgs), POINTER(c_void_p), POINTER(c_void_p),
+                                             POINTER(c_int)]),
+    "splade_loss_bwd_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "splade_emit_json": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                  c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
     "splade_emit_bulk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,

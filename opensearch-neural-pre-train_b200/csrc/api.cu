@@ -162,6 +162,8 @@ size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k) {
       return head_bwd_dhidden_workspace_bytes(B, S, V);
     case SPLADE_OP_HEAD_BWD_BITMAP:
       return head_bwd_bitmap_bytes(B, V);
+    case SPLADE_OP_LOSS_BWD_TC:
+      return loss_bwd_tc_workspace_bytes(B, k);
     default:
       return 0;
   }
@@ -263,6 +265,27 @@ int splade_loss_bwd(const float* q, const float* docs, const float* negs, int Bq
                     const float* g_loss, float* dq, float* ddocs, float* dnegs, void* stream) {
   return loss_bwd_launch(q, docs, negs, Bq, N, k, V, label_offset, g_inbatch, g_hard, colmean_q, colmean_d,
                          colmean_n, cq, cd, cn, g_loss, dq, ddocs, dnegs, static_cast<cudaStream_t>(stream));
+}
+
+int splade_v33_loss_fwd_operands(const splade_v33_fwd_args* args, const void** q16, const void** d16, int* Vp) {
+  if (!args || !q16 || !d16 || !Vp || !args->workspace)
+    return set_error(kErrInvalidArg, "splade_v33_loss_fwd_operands: null pointer argument");
+  if (!args->round_bf16)
+    return set_error(kErrInvalidArg, "splade_v33_loss_fwd_operands: the forward packs bf16 operands in autocast mode only");
+  void* sws = v33_loss_fwd_scores_ws(args);
+  *q16 = sws;
+  *d16 = scores_tc_docs16(sws, args->Bq, args->N, args->V, Vp);
+  return kOk;
+}
+
+int splade_loss_bwd_tc(const float* q, const float* negs, const void* q16, const void* d16, int Bq, int N, int k, int V,
+                       int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
+                       const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
+                       const float* g_loss, float* dq, float* ddocs, float* dnegs, void* workspace, size_t ws_bytes,
+                       void* stream) {
+  return loss_bwd_tc_launch(q, negs, q16, d16, Bq, N, k, V, label_offset, g_inbatch, g_hard, colmean_q, colmean_d,
+                            colmean_n, cq, cd, cn, g_loss, dq, ddocs, dnegs, workspace, ws_bytes,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int splade_trunk_encode(const splade_trunk_args* args, void* stream) {

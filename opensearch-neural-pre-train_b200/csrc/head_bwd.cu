@@ -66,30 +66,6 @@ __device__ __forceinline__ float coef_of(float g, float rep) { return rep > 0.f 
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
-// ---- L2 residency hints ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint4 ldg_hint(const void* ptr, uint64_t pol) {
-  uint4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(ptr), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ void stg_hint(float* ptr, float4 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z),
-               "f"(v.w), "l"(pol)
-               : "memory");
-}
-
 __device__ __forceinline__ int seg_of_doc(const Segs& p, int doc) {
   int sel = 0;
 #pragma unroll
@@ -290,70 +266,78 @@ bwd_bucket_kernel(const __grid_constant__ Segs p, int V, int nw) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Row fragments.  A lane owns 4 consecutive floats of every 128-float chunk of a row (h = q*128 + lane*4), so that a
-// warp's 64-bit bf16 loads cover 256 contiguous bytes and its 128-bit fp32 stores 512 contiguous bytes (whole
-// sectors - the 8-floats-per-lane layout wrote every 32-byte sector in two halves).  kQ = chunks = ceil(H / 128).
+// Row fragments.  A lane owns 8 consecutive elements of every 256-element chunk of a row (h = c*256 + lane*8): one
+// 128-bit load of bf16 per chunk (64-bit loads measured 1.5x slower in the L2-gather-bound dense regime), two
+// 128-bit fp32 stores.  kC = chunks = ceil(H / 256).  (L2 eviction-priority hints on the gathers / output stores
+// and st.global.cs were measured: no difference in either regime, so plain accesses.)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint2 ldg_hint2(const void* ptr, uint64_t pol) {
-  uint2 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ void fma_bf16x4(float (&acc)[4], float c, const uint2& u) {
-  acc[0] = fmaf(c, __uint_as_float(u.x << 16), acc[0]);
-  acc[1] = fmaf(c, __uint_as_float(u.x & 0xFFFF0000u), acc[1]);
-  acc[2] = fmaf(c, __uint_as_float(u.y << 16), acc[2]);
-  acc[3] = fmaf(c, __uint_as_float(u.y & 0xFFFF0000u), acc[3]);
-}
-template <int kQ>
-__device__ __forceinline__ void load_row(uint2 (&u)[kQ], const uint16_t* row, int H, int lane, uint64_t pol) {
+__device__ __forceinline__ void fma_bf16x8(float (&acc)[8], float c, const uint4& u) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int q = 0; q < kQ; ++q) {
-    const int h = q * 128 + lane * 4;
-    if (h < H) u[q] = ldg_hint2(row + h, pol);
+  for (int i = 0; i < 4; ++i) {
+    acc[2 * i] = fmaf(c, __uint_as_float(w[i] << 16), acc[2 * i]);
+    acc[2 * i + 1] = fmaf(c, __uint_as_float(w[i] & 0xFFFF0000u), acc[2 * i + 1]);
   }
 }
-template <int kQ>
-__device__ __forceinline__ void fma_row(float (&acc)[kQ][4], float c, const uint2 (&u)[kQ], int H, int lane) {
+template <int kC>
+__device__ __forceinline__ void load_row(uint4 (&u)[kC], const uint16_t* row, int H, int lane) {
 #pragma unroll
-  for (int q = 0; q < kQ; ++q)
-    if (q * 128 + lane * 4 < H) fma_bf16x4(acc[q], c, u[q]);
-}
-template <int kQ>
-__device__ __forceinline__ void zero_acc(float (&acc)[kQ][4]) {
-#pragma unroll
-  for (int q = 0; q < kQ; ++q)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
-}
-template <int kQ>
-__device__ __forceinline__ void store_row(float* out, const float (&acc)[kQ][4], int H, int lane, uint64_t pol) {
-#pragma unroll
-  for (int q = 0; q < kQ; ++q) {
-    const int h = q * 128 + lane * 4;
-    if (h < H) stg_hint(out + h, make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]), pol);
+  for (int c = 0; c < kC; ++c) {
+    const int h = c * 256 + lane * 8;
+    if (h < H) u[c] = __ldg(reinterpret_cast<const uint4*>(row + h));
   }
 }
-template <int kQ>
-__device__ __forceinline__ void store_zero_row(float* out, int H, int lane, uint64_t pol) {
+template <int kC>
+__device__ __forceinline__ void fma_row(float (&acc)[kC][8], float coef, const uint4 (&u)[kC], int H, int lane) {
 #pragma unroll
-  for (int q = 0; q < kQ; ++q) {
-    const int h = q * 128 + lane * 4;
-    if (h < H) stg_hint(out + h, make_float4(0.f, 0.f, 0.f, 0.f), pol);
+  for (int c = 0; c < kC; ++c)
+    if (c * 256 + lane * 8 < H) fma_bf16x8(acc[c], coef, u[c]);
+}
+template <int kC>
+__device__ __forceinline__ void zero_acc(float (&acc)[kC][8]) {
+#pragma unroll
+  for (int c = 0; c < kC; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+}
+template <int kC>
+__device__ __forceinline__ void store_row(float* out, const float (&acc)[kC][8], int H, int lane) {
+#pragma unroll
+  for (int c = 0; c < kC; ++c) {
+    const int h = c * 256 + lane * 8;
+    if (h < H) {
+      *reinterpret_cast<float4*>(out + h) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+      *reinterpret_cast<float4*>(out + h + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+    }
+  }
+}
+template <int kC>
+__device__ __forceinline__ void store_zero_row(float* out, int H, int lane) {
+#pragma unroll
+  for (int c = 0; c < kC; ++c) {
+    const int h = c * 256 + lane * 8;
+    if (h < H) {
+      *reinterpret_cast<float4*>(out + h) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(out + h + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
+// A document is summed by the dense-regime kernel when its buckets average at least this many terms per position
+// (random-init models: ~195; trained models: ~1).  Decided per document from row_ptr[S], on the device.
+constexpr int kDenseTermsPerPosition = 8;
+
 // ---------------------------------------------------------------------------------------------
-// (2) dHidden: one warp per GROUP of kRowsPerWarp consecutive positions of one document.  row_ptr is monotone over
-//     the positions of a document, so the buckets of the group are ONE contiguous range of the sorted lists: the
-//     warp reads the group's row_ptr entries (one load), stores the EMPTY positions' zero rows at once (nearly all
-//     of them in the trained regime: the write stream does not wait for the gather chain), then reads the range
-//     (coalesced) and walks it as a segmented sum, kDepth W rows in flight.  Three dependent global latencies per
-//     GROUP instead of per position.
+// (2a) dHidden, trained (sparse) regime: one warp per GROUP of kRowsPerWarp consecutive positions of one document.
+//      row_ptr is monotone over the positions of a document, so the buckets of the group are ONE contiguous range
+//      of the sorted lists: the warp reads the group's row_ptr entries (one load), stores the EMPTY positions' zero
+//      rows at once (nearly all of them: the write stream does not wait for the gather chain), then reads the
+//      range (coalesced) and walks it as a segmented sum, kDepth W rows in flight.  Three dependent global
+//      latencies per GROUP instead of per position.
 // ---------------------------------------------------------------------------------------------
-template <int kQ, int kDepth>
+template <int kC, int kDepth>
 __global__ void __launch_bounds__(256)
-dhidden_kernel(const __grid_constant__ Segs p, const uint16_t* __restrict__ W, int H, int V) {
+dhidden_group_kernel(const __grid_constant__ Segs p, const uint16_t* __restrict__ W, int H, int V) {
   const int lane = threadIdx.x & 31;
   const long long grp = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (grp >= p.total_rows) return;
@@ -369,23 +353,25 @@ dhidden_kernel(const __grid_constant__ Segs p, const uint16_t* __restrict__ W, i
   const int b = static_cast<int>(lg / gps);
   const int s0 = static_cast<int>(lg - static_cast<long long>(b) * gps) * kRowsPerWarp;
   const int nrows = min(kRowsPerWarp, S - s0);
-  const int32_t* rp = sg.row_ptr + static_cast<size_t>(b) * (S + 1) + s0;
-  const int my_rp = lane <= nrows ? rp[lane] : 0;
+  const int32_t* rp_doc = sg.row_ptr + static_cast<size_t>(b) * (S + 1);
+  const int32_t* rp = rp_doc + s0;
+  int my_rp = lane <= nrows ? rp[lane] : 0;
+  if (lane == 31) my_rp = rp_doc[S];
+  if (__shfl_sync(0xffffffffu, my_rp, 31) >= kDenseTermsPerPosition * S) return;  // dense document: kernel (2b)
   const int beg = __shfl_sync(0xffffffffu, my_rp, 0), end = __shfl_sync(0xffffffffu, my_rp, nrows);
-  const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
   float* out = sg.dh + (static_cast<size_t>(b) * S + s0) * H;
 
   // empty positions first
   const int my_next = __shfl_down_sync(0xffffffffu, my_rp, 1);
   const uint32_t empty = __ballot_sync(0xffffffffu, lane < nrows && my_next == my_rp);
-  for (uint32_t m = empty; m; m &= m - 1) store_zero_row<kQ>(out + static_cast<size_t>(__ffs(m) - 1) * H, H, lane, stream);
+  for (uint32_t m = empty; m; m &= m - 1) store_zero_row<kC>(out + static_cast<size_t>(__ffs(m) - 1) * H, H, lane);
   if (beg == end) return;
 
   const size_t lbase = static_cast<size_t>(b) * V;
   const int32_t* __restrict__ sorted_v = sg.sorted_v;
   const float* __restrict__ sorted_c = sg.sorted_c;
-  float acc[kQ][4];
-  zero_acc<kQ>(acc);
+  float acc[kC][8];
+  zero_acc<kC>(acc);
   int row = 0;                                        // position s0 + row is being summed
   while ((empty >> row) & 1u) ++row;                  // (beg < end: some position is not empty)
   int row_end = __shfl_sync(0xffffffffu, my_rp, row + 1);
@@ -399,31 +385,83 @@ dhidden_kernel(const __grid_constant__ Segs p, const uint16_t* __restrict__ W, i
       my_c = __ldcs(sorted_c + lbase + e0 + lane);
     }
     for (int l = 0; l < n; l += kDepth) {
-      uint2 u[kDepth][kQ];
+      uint4 u[kDepth][kC];
       float c[kDepth];
 #pragma unroll
       for (int k = 0; k < kDepth; ++k) {
         const int src = min(l + k, n - 1);  // past the end: a valid row, never accumulated
         const int v = __shfl_sync(0xffffffffu, my_v, src);
         c[k] = __shfl_sync(0xffffffffu, my_c, src);
-        load_row<kQ>(u[k], W + static_cast<size_t>(v) * H, H, lane, keep);
+        load_row<kC>(u[k], W + static_cast<size_t>(v) * H, H, lane);
       }
 #pragma unroll
       for (int k = 0; k < kDepth; ++k) {
         if (l + k < n) {
           while (e0 + l + k >= row_end) {  // warp-uniform: this position's bucket is complete
-            store_row<kQ>(out + static_cast<size_t>(row) * H, acc, H, lane, stream);
-            zero_acc<kQ>(acc);
+            store_row<kC>(out + static_cast<size_t>(row) * H, acc, H, lane);
+            zero_acc<kC>(acc);
             ++row;
             while ((empty >> row) & 1u) ++row;
             row_end = __shfl_sync(0xffffffffu, my_rp, row + 1);
           }
-          fma_row<kQ>(acc, c[k], u[k], H, lane);
+          fma_row<kC>(acc, c[k], u[k], H, lane);
         }
       }
     }
   }
-  store_row<kQ>(out + static_cast<size_t>(row) * H, acc, H, lane, stream);  // the last non-empty position
+  store_row<kC>(out + static_cast<size_t>(row) * H, acc, H, lane);  // the last non-empty position
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2b) dHidden, dense regime (random init: every term of every document is active, ~V/S terms per position): one
+//      warp per (document, position) row, 64 registers so that four CTAs of 8 warps stay resident per SM - this
+//      regime is bound by the L2 -> SM gather of W rows (B*V rows of 2H bytes per head call), i.e. by how many loads
+//      are in flight per SM.
+// ---------------------------------------------------------------------------------------------
+template <int kC>
+__global__ void __launch_bounds__(256, 4)
+dhidden_row_kernel(const __grid_constant__ Segs p, const uint16_t* __restrict__ W, int H, int V) {
+  const int lane = threadIdx.x & 31;
+  const long long grp = static_cast<long long>(blockIdx.x);  // one CTA per group of 8 positions, one warp per row
+  if (grp >= p.total_rows) return;
+  int si = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxSegs; ++i)
+    if (i < p.n && grp >= p.s[i].row0) si = i;
+  const Seg& sg = p.s[si];
+  if (sg.dh == nullptr) return;
+  const int S = sg.S;
+  const int gps = (S + kRowsPerWarp - 1) / kRowsPerWarp;
+  const long long lg = grp - sg.row0;
+  const int b = static_cast<int>(lg / gps);
+  const int s = static_cast<int>(lg - static_cast<long long>(b) * gps) * kRowsPerWarp + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const int32_t* rp = sg.row_ptr + static_cast<size_t>(b) * (S + 1);
+  if (rp[S] < kDenseTermsPerPosition * S) return;  // sparse document: kernel (2a)
+  const int beg = rp[s], end = rp[s + 1];
+  const size_t lbase = static_cast<size_t>(b) * V;
+  const int32_t* __restrict__ sorted_v = sg.sorted_v;
+  const float* __restrict__ sorted_c = sg.sorted_c;
+  float acc[kC][8];
+  zero_acc<kC>(acc);
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int n = min(32, end - e0);
+    int my_v = 0;
+    float my_c = 0.f;
+    if (lane < n) {
+      my_v = __ldcs(sorted_v + lbase + e0 + lane);
+      my_c = __ldcs(sorted_c + lbase + e0 + lane);
+    }
+#pragma unroll 4
+    for (int l = 0; l < n; ++l) {
+      const int v = __shfl_sync(0xffffffffu, my_v, l);
+      const float c = __shfl_sync(0xffffffffu, my_c, l);
+      uint4 u[kC];
+      load_row<kC>(u, W + static_cast<size_t>(v) * H, H, lane);
+      fma_row<kC>(acc, c, u, H, lane);
+    }
+  }
+  store_row<kC>(sg.dh + (static_cast<size_t>(b) * S + s) * H, acc, H, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,7 +477,7 @@ dhidden_kernel(const __grid_constant__ Segs p, const uint16_t* __restrict__ W, i
 //          documents at a time) in ascending document order, kDepth hidden rows in flight.
 //     The sum order is fixed (segments in call order, documents ascending) => run-to-run bit-identical.
 // ---------------------------------------------------------------------------------------------
-template <int kQ, int kDepth>
+template <int kC, int kDepth>
 __global__ void __launch_bounds__(256)
 dw_kernel(const __grid_constant__ Segs p, int H, int V, int docs_per_pass, int stride /* odd, >= docs_per_pass */,
           float* dW, float* dbias, int accumulate) {
@@ -454,7 +492,6 @@ dw_kernel(const __grid_constant__ Segs p, int H, int V, int docs_per_pass, int s
   const int word = blockIdx.x, v0 = word * 32;
   const int words = (V + 31) >> 5;
   if (threadIdx.x < kMaxSegs) s_hid[threadIdx.x] = threadIdx.x < p.n ? p.s[threadIdx.x].hidden : nullptr;
-  const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
   const bool single_pass = p.total_docs <= docs_per_pass;
 
   for (int d0 = 0; d0 < p.total_docs; d0 += docs_per_pass) {
@@ -476,19 +513,27 @@ dw_kernel(const __grid_constant__ Segs p, int H, int V, int docs_per_pass, int s
       for (int r = 0; r < 4; ++r) {
         const int j = warp * 4 + r;
         if (v0 + j < V && !((any >> j) & 1u)) {
-          store_zero_row<kQ>(dW + static_cast<size_t>(v0 + j) * H, H, lane, stream);
+          store_zero_row<kC>(dW + static_cast<size_t>(v0 + j) * H, H, lane);
           if (lane == 0) dbias[v0 + j] = 0.f;
         }
       }
     }
-    for (int dl = warp; dl < nb; dl += 8) {  // b.
-      const uint32_t bits = s_bits[dl];
-      if (bits == 0u) continue;
-      int slot = 0;
-      if (lane == 0) slot = atomicAdd(&s_n, __popc(bits));
-      slot = __shfl_sync(0xffffffffu, slot, 0);
-      if ((bits >> lane) & 1u)
-        s_list[slot + __popc(bits & ((1u << lane) - 1u))] = static_cast<uint16_t>((dl << 5) | lane);
+    {  // b.  thread t still knows document t's word: slots by a warp scan + one shared-memory atomic per warp
+      const uint32_t bits = static_cast<int>(threadIdx.x) < nb ? s_bits[threadIdx.x] : 0u;
+      const int n = __popc(bits);
+      int incl = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      int wbase = 0;
+      const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+      if (lane == 31 && wtot) wbase = atomicAdd(&s_n, wtot);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      int slot = wbase + incl - n;
+      for (uint32_t m = bits; m; m &= m - 1)
+        s_list[slot++] = static_cast<uint16_t>((threadIdx.x << 5) | (__ffs(m) - 1));
     }
     __syncthreads();
     const int n_pairs = s_n;
@@ -507,7 +552,6 @@ dw_kernel(const __grid_constant__ Segs p, int H, int V, int docs_per_pass, int s
     __syncthreads();
 
     const bool first = (d0 == 0) && !accumulate;
-    const bool last = d0 + docs_per_pass >= p.total_docs;
     for (int r = 0; r < 4; ++r) {  // d.
       const int j = warp * 4 + r;
       const int v = v0 + j;
@@ -515,18 +559,20 @@ dw_kernel(const __grid_constant__ Segs p, int H, int V, int docs_per_pass, int s
       const bool touched = (any >> j) & 1u;
       if (!touched && (single_pass ? !accumulate : !first)) continue;  // zero row already stored / nothing to add
       float* out = dW + static_cast<size_t>(v) * H;
-      float acc[kQ][4];
+      float acc[kC][8];
       float bsum = 0.f;
       if (first) {
-        zero_acc<kQ>(acc);
+        zero_acc<kC>(acc);
       } else {  // continue this term's sum (an earlier pass of this warp, or the caller's gradient buffer)
         if (!touched) continue;
 #pragma unroll
-        for (int q = 0; q < kQ; ++q) {
-          const int h = q * 128 + lane * 4;
+        for (int c = 0; c < kC; ++c) {
+          const int h = c * 256 + lane * 8;
           if (h < H) {
             const float4 a = *reinterpret_cast<const float4*>(out + h);
-            acc[q][0] = a.x, acc[q][1] = a.y, acc[q][2] = a.z, acc[q][3] = a.w;
+            const float4 b4 = *reinterpret_cast<const float4*>(out + h + 4);
+            acc[c][0] = a.x, acc[c][1] = a.y, acc[c][2] = a.z, acc[c][3] = a.w;
+            acc[c][4] = b4.x, acc[c][5] = b4.y, acc[c][6] = b4.z, acc[c][7] = b4.w;
           }
         }
         bsum = dbias[v];
@@ -539,7 +585,7 @@ dw_kernel(const __grid_constant__ Segs p, int H, int V, int docs_per_pass, int s
         while (m) {  // up to kDepth active documents per trip: their hidden rows are independent loads
           int d[kDepth];
           float c[kDepth];
-          uint2 u[kDepth][kQ];
+          uint4 u[kDepth][kC];
 #pragma unroll
           for (int k = 0; k < kDepth; ++k) {
             d[k] = m ? (c0 + __ffs(m) - 1) : -1;
@@ -547,27 +593,19 @@ dw_kernel(const __grid_constant__ Segs p, int H, int V, int docs_per_pass, int s
             const int dk = d[k] < 0 ? d[0] : d[k];
             c[k] = cj[dk];  // broadcast reads
             const uint32_t pw = pj[dk];
-            load_row<kQ>(u[k], s_hid[pw >> 28] + static_cast<size_t>(pw & 0x0FFFFFFFu) * H, H, lane, keep);
+            load_row<kC>(u[k], s_hid[pw >> 28] + static_cast<size_t>(pw & 0x0FFFFFFFu) * H, H, lane);
           }
 #pragma unroll
           for (int k = 0; k < kDepth; ++k) {
             if (d[k] >= 0) {
               bsum += c[k];
-              fma_row<kQ>(acc, c[k], u[k], H, lane);
+              fma_row<kC>(acc, c[k], u[k], H, lane);
             }
           }
         }
       }
       if (lane == 0) dbias[v] = bsum;
-      if (last) {
-        store_row<kQ>(out, acc, H, lane, stream);
-      } else {  // read back by this very lane in the next pass
-#pragma unroll
-        for (int q = 0; q < kQ; ++q) {
-          const int h = q * 128 + lane * 4;
-          if (h < H) *reinterpret_cast<float4*>(out + h) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
-        }
-      }
+      store_row<kC>(out, acc, H, lane);  // (a later pass reads it back: same lane, same addresses)
     }
   }
 }
@@ -631,42 +669,51 @@ int launch_sort_dhidden(const Segs& p, const void* W, int H, int V, int s_max, b
   if (!any_dh) return kOk;
   const uint16_t* Wb = static_cast<const uint16_t*>(W);
   const unsigned grid_h = static_cast<unsigned>((p.total_rows + 7) / 8);  // 8 warps = 8 row groups per CTA
-  switch ((H + 127) / 128) {
-    case 1: dhidden_kernel<1, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
-    case 2: dhidden_kernel<2, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
+  // both regimes are enqueued; every warp / CTA looks at its document's row_ptr[S] and the kernel whose regime it is
+  // not exits at once (no host synchronisation, mixed batches are handled per document)
+  const unsigned grid_rows = static_cast<unsigned>(p.total_rows);
+  switch ((H + 255) / 256) {
+    case 1:
+      dhidden_group_kernel<1, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V);
+      dhidden_row_kernel<1><<<grid_rows, 256, 0, stream>>>(p, Wb, H, V);
+      break;
+    case 2:
+      dhidden_group_kernel<2, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V);
+      dhidden_row_kernel<2><<<grid_rows, 256, 0, stream>>>(p, Wb, H, V);
+      break;
     case 3:
-    case 4: dhidden_kernel<4, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
-    case 5:
-    case 6: dhidden_kernel<6, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
-    default: dhidden_kernel<8, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V); break;
+      dhidden_group_kernel<3, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V);
+      dhidden_row_kernel<3><<<grid_rows, 256, 0, stream>>>(p, Wb, H, V);
+      break;
+    default:
+      dhidden_group_kernel<4, 4><<<grid_h, 256, 0, stream>>>(p, Wb, H, V);
+      dhidden_row_kernel<4><<<grid_rows, 256, 0, stream>>>(p, Wb, H, V);
+      break;
   }
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }
 
-template <int kQ>
+template <int kC>
 int launch_dw_t(const Segs& p, int H, int V, float* dW, float* dbias, int accumulate, cudaStream_t stream) {
   const int docs = std::max(1, std::min(kDwDocs, p.total_docs));
   const int stride = docs | 1;  // odd: the transposed staging writes are bank-conflict free
   const size_t smem = static_cast<size_t>(32) * stride * 8 + static_cast<size_t>(32) * docs * sizeof(uint16_t);
   if (smem > 44 * 1024)  // (static shared memory counts against the 48 KB default too)
-    SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<kQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPLADE_CUDA_OK(cudaFuncSetAttribute(dw_kernel<kC, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-  dw_kernel<kQ, 4><<<static_cast<unsigned>((V + 31) / 32), 256, smem, stream>>>(p, H, V, docs, stride, dW, dbias,
+  dw_kernel<kC, 4><<<static_cast<unsigned>((V + 31) / 32), 256, smem, stream>>>(p, H, V, docs, stride, dW, dbias,
                                                                                 accumulate);
   SPLADE_CUDA_OK(cudaGetLastError());
   return kOk;
 }
 
 int launch_dw(const Segs& p, int H, int V, float* dW, float* dbias, int accumulate, cudaStream_t stream) {
-  switch ((H + 127) / 128) {
+  switch ((H + 255) / 256) {
     case 1: return launch_dw_t<1>(p, H, V, dW, dbias, accumulate, stream);
     case 2: return launch_dw_t<2>(p, H, V, dW, dbias, accumulate, stream);
-    case 3:
-    case 4: return launch_dw_t<4>(p, H, V, dW, dbias, accumulate, stream);
-    case 5:
-    case 6: return launch_dw_t<6>(p, H, V, dW, dbias, accumulate, stream);
-    default: return launch_dw_t<8>(p, H, V, dW, dbias, accumulate, stream);
+    case 3: return launch_dw_t<3>(p, H, V, dW, dbias, accumulate, stream);
+    default: return launch_dw_t<4>(p, H, V, dW, dbias, accumulate, stream);
   }
 }
 

@@ -113,10 +113,19 @@ int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq
                     const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
                     const float* g_loss, float* dq, float* ddocs, float* dnegs, cudaStream_t stream);
 
+// loss_bwd_tc.cu: tcgen05 backward of the score GEMM on the bf16 operands the forward packed
+size_t loss_bwd_tc_workspace_bytes(int Bq, int N);
+int loss_bwd_tc_launch(const float* q, const float* negs, const void* q16, const void* d16, int Bq, int N, int k, int V,
+                       int label_offset, const float* g_inbatch, const float* g_hard, const float* colmean_q,
+                       const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
+                       const float* g_loss, float* dq, float* ddocs, float* dnegs, void* workspace, size_t ws_bytes,
+                       cudaStream_t stream);
+
 // scores_tc.cu (tcgen05 path used when round_bf16 != 0)
 size_t scores_tc_workspace_bytes(int Bq, int N, int V);
 int scores_tc_launch(const float* q, int Bq, const float* docs, int N, int V, void* workspace, size_t ws_bytes,
-                     float** partial_out, int* ksplit_out, bool docs_prepacked, cudaStream_t stream);
+                     float** partial_out, int* ksplit_out, bool docs_prepacked, cudaStream_t stream,
+                     bool q_prepacked = false);
 void* scores_tc_docs16(void* workspace, int Bq, int N, int V, int* Vp_out);
 
 // peer.cu: cross-GPU negatives over NVLink peer memory (include/splade_b200.h, splade_peer_*)

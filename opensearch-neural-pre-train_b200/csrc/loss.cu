@@ -247,105 +247,109 @@ rowdot_kernel(const float* __restrict__ q, const float* __restrict__ docs, int k
 // Scalar stage: one warp per query row (8 rows per CTA) writes that row's loss terms and gradient rows;
 // v33_finalize_kernel then adds the rows up in index order (deterministic) and forms the total.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) v33_scalars_kernel(const splade_v33_scalar_args a) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One query row of the scalar stage, by one warp: that row's loss terms (returned on every lane) and its gradient
+// rows g_inbatch[i,:] / g_hard[i,:].
+__device__ __forceinline__ void v33_scalars_row(const splade_v33_scalar_args& a, int i, int lane, float& acc_nce,
+                                                float& acc_kd, float& acc_mm) {
   const int Bq = a.Bq, N = a.N, k = a.k;
   const float invB = 1.f / static_cast<float>(Bq);
-  float acc_nce = 0.f, acc_kd = 0.f, acc_mm = 0.f;
+  const float* rin = a.raw_inbatch + static_cast<size_t>(i) * N;
+  const float* rh = a.raw_hard + static_cast<size_t>(i) * k;
+  float* gin = a.g_inbatch + static_cast<size_t>(i) * N;
+  float* gh = a.g_hard + static_cast<size_t>(i) * k;
+  const int label = a.label_offset + i;
 
-  const int i = blockIdx.x * 8 + warp;
-  if (i < Bq) {
-    const float* rin = a.raw_inbatch + static_cast<size_t>(i) * N;
-    const float* rh = a.raw_hard + static_cast<size_t>(i) * k;
-    float* gin = a.g_inbatch + static_cast<size_t>(i) * N;
-    float* gh = a.g_hard + static_cast<size_t>(i) * k;
-    const int label = a.label_offset + i;
+  // ---- InfoNCE: CE over [in-batch | hard] scores (losses.py:155-181)
+  float m = -INFINITY;
+  for (int j = lane; j < N; j += 32) {
+    float s = rin[j];
+    s = a.round_bf16 ? bf16_round(bf16_round(s) / a.temperature) : s / a.temperature;
+    m = fmaxf(m, s);
+  }
+  for (int j = lane; j < k; j += 32) m = fmaxf(m, rh[j] / a.temperature);
+  m = warp_max(m);
+  float se = 0.f, s_lab = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    float s = rin[j];
+    s = a.round_bf16 ? bf16_round(bf16_round(s) / a.temperature) : s / a.temperature;
+    se += expf(s - m);
+    if (j == label) s_lab = s;
+  }
+  for (int j = lane; j < k; j += 32) se += expf(rh[j] / a.temperature - m);
+  se = warp_sum(se);
+  s_lab = warp_sum(s_lab);
+  const float lse = m + logf(se);
+  acc_nce += lse - s_lab;
+  const float gscale = invB / a.temperature;
+  for (int j = lane; j < N; j += 32) {
+    float s = rin[j];
+    s = a.round_bf16 ? bf16_round(bf16_round(s) / a.temperature) : s / a.temperature;
+    gin[j] = (expf(s - lse) - (j == label ? 1.f : 0.f)) * gscale;
+  }
+  for (int j = lane; j < k; j += 32) gh[j] = expf(rh[j] / a.temperature - lse) * gscale;
+  __syncwarp();
 
-    // ---- InfoNCE: CE over [in-batch | hard] scores (losses.py:155-181)
-    float m = -INFINITY;
+  // ---- optional KL-KD on the in-batch matrix (losses.py:239-253); requires N == Bq
+  if (a.has_kd) {
+    const float* tr = a.teacher_kd + static_cast<size_t>(i) * N;
+    float ms = -INFINITY, mt = -INFINITY;
     for (int j = lane; j < N; j += 32) {
       float s = rin[j];
-      s = a.round_bf16 ? bf16_round(bf16_round(s) / a.temperature) : s / a.temperature;
-      m = fmaxf(m, s);
+      s = a.round_bf16 ? bf16_round(bf16_round(s) / a.kd_temperature) : s / a.kd_temperature;
+      ms = fmaxf(ms, s);
+      mt = fmaxf(mt, tr[j] / a.kd_temperature);
     }
-    for (int j = lane; j < k; j += 32) m = fmaxf(m, rh[j] / a.temperature);
-    m = warp_max(m);
-    float se = 0.f, s_lab = 0.f;
+    ms = warp_max(ms);
+    mt = warp_max(mt);
+    float ss = 0.f, st = 0.f;
     for (int j = lane; j < N; j += 32) {
       float s = rin[j];
-      s = a.round_bf16 ? bf16_round(bf16_round(s) / a.temperature) : s / a.temperature;
-      se += expf(s - m);
-      if (j == label) s_lab = s;
+      s = a.round_bf16 ? bf16_round(bf16_round(s) / a.kd_temperature) : s / a.kd_temperature;
+      ss += expf(s - ms);
+      st += expf(tr[j] / a.kd_temperature - mt);
     }
-    for (int j = lane; j < k; j += 32) se += expf(rh[j] / a.temperature - m);
-    se = warp_sum(se);
-    s_lab = warp_sum(s_lab);
-    const float lse = m + logf(se);
-    acc_nce += lse - s_lab;
-    const float gscale = invB / a.temperature;
+    ss = warp_sum(ss);
+    st = warp_sum(st);
+    const float lss = ms + logf(ss), lst = mt + logf(st);
+    float kl = 0.f;
     for (int j = lane; j < N; j += 32) {
       float s = rin[j];
-      s = a.round_bf16 ? bf16_round(bf16_round(s) / a.temperature) : s / a.temperature;
-      gin[j] = (expf(s - lse) - (j == label ? 1.f : 0.f)) * gscale;
+      s = a.round_bf16 ? bf16_round(bf16_round(s) / a.kd_temperature) : s / a.kd_temperature;
+      const float logp = s - lss;
+      const float logt = tr[j] / a.kd_temperature - lst;
+      const float t = expf(logt);
+      if (t > 0.f) kl += t * (logt - logp);
+      gin[j] += a.lambda_kd * (expf(logp) - t) * invB / a.kd_temperature;
     }
-    for (int j = lane; j < k; j += 32) gh[j] = expf(rh[j] / a.temperature - lse) * gscale;
+    acc_kd += warp_sum(kl);
     __syncwarp();
-
-    // ---- optional KL-KD on the in-batch matrix (losses.py:239-253); requires N == Bq
-    if (a.has_kd) {
-      const float* tr = a.teacher_kd + static_cast<size_t>(i) * N;
-      float ms = -INFINITY, mt = -INFINITY;
-      for (int j = lane; j < N; j += 32) {
-        float s = rin[j];
-        s = a.round_bf16 ? bf16_round(bf16_round(s) / a.kd_temperature) : s / a.kd_temperature;
-        ms = fmaxf(ms, s);
-        mt = fmaxf(mt, tr[j] / a.kd_temperature);
-      }
-      ms = warp_max(ms);
-      mt = warp_max(mt);
-      float ss = 0.f, st = 0.f;
-      for (int j = lane; j < N; j += 32) {
-        float s = rin[j];
-        s = a.round_bf16 ? bf16_round(bf16_round(s) / a.kd_temperature) : s / a.kd_temperature;
-        ss += expf(s - ms);
-        st += expf(tr[j] / a.kd_temperature - mt);
-      }
-      ss = warp_sum(ss);
-      st = warp_sum(st);
-      const float lss = ms + logf(ss), lst = mt + logf(st);
-      float kl = 0.f;
-      for (int j = lane; j < N; j += 32) {
-        float s = rin[j];
-        s = a.round_bf16 ? bf16_round(bf16_round(s) / a.kd_temperature) : s / a.kd_temperature;
-        const float logp = s - lss;
-        const float logt = tr[j] / a.kd_temperature - lst;
-        const float t = expf(logt);
-        if (t > 0.f) kl += t * (logt - logp);
-        gin[j] += a.lambda_kd * (expf(logp) - t) * invB / a.kd_temperature;
-      }
-      acc_kd += warp_sum(kl);
-      __syncwarp();
-    }
-
-    // ---- optional MarginMSE (losses.py:92-134): raw (un-tempered) fp32 dots
-    if (a.has_mmse) {
-      const float sp = a.raw_pos[i];
-      const float tp = a.teacher_pos[i];
-      const float c = 2.f * invB / static_cast<float>(k);
-      float sq = 0.f, gpos = 0.f;
-      for (int j = lane; j < k; j += 32) {
-        const float diff = (sp - rh[j]) - (tp - a.teacher_neg[static_cast<size_t>(i) * k + j]);
-        sq += diff * diff;
-        gpos += c * diff;
-        gh[j] += a.lambda_mmse * (-c * diff);
-      }
-      acc_mm += warp_sum(sq);
-      gpos = warp_sum(gpos);
-      if (lane == 0) gin[label] += a.lambda_mmse * gpos;
-      __syncwarp();
-    }
   }
 
+  // ---- optional MarginMSE (losses.py:92-134): raw (un-tempered) fp32 dots
+  if (a.has_mmse) {
+    const float sp = a.raw_pos[i];
+    const float tp = a.teacher_pos[i];
+    const float c = 2.f * invB / static_cast<float>(k);
+    float sq = 0.f, gpos = 0.f;
+    for (int j = lane; j < k; j += 32) {
+      const float diff = (sp - rh[j]) - (tp - a.teacher_neg[static_cast<size_t>(i) * k + j]);
+      sq += diff * diff;
+      gpos += c * diff;
+      gh[j] += a.lambda_mmse * (-c * diff);
+    }
+    acc_mm += warp_sum(sq);
+    gpos = warp_sum(gpos);
+    if (lane == 0) gin[label] += a.lambda_mmse * gpos;
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) v33_scalars_kernel(const splade_v33_scalar_args a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Bq = a.Bq;
+  float acc_nce = 0.f, acc_kd = 0.f, acc_mm = 0.f;
+  const int i = blockIdx.x * 8 + warp;
+  if (i < Bq) v33_scalars_row(a, i, lane, acc_nce, acc_kd, acc_mm);
   if (i < Bq && lane == 0) {
     a.row_scratch[i] = acc_nce;
     a.row_scratch[Bq + i] = acc_kd;
@@ -353,11 +357,13 @@ __global__ void __launch_bounds__(256) v33_scalars_kernel(const splade_v33_scala
   }
 }
 
-__global__ void __launch_bounds__(256) v33_finalize_kernel(const splade_v33_scalar_args a) {
-  __shared__ float s_part[3][256];
+// Adds the per-row terms up in index order (fixed assignment + fixed tree => deterministic) and forms the total.
+// Called by the first 256 threads of a CTA; `flops` = {flops_q, nnz_q, flops_d, nnz_d, flops_neg, nnz_neg}.
+__device__ __forceinline__ void v33_finalize_block(const splade_v33_scalar_args& a, const float* flops,
+                                                   float (*s_part)[256]) {
   const int Bq = a.Bq, k = a.k;
   float nce = 0.f, kd = 0.f, mm = 0.f;
-  for (int i = threadIdx.x; i < Bq; i += 256) {  // fixed assignment + fixed tree => deterministic
+  for (int i = threadIdx.x; i < Bq; i += 256) {
     nce += a.row_scratch[i];
     kd += a.row_scratch[Bq + i];
     mm += a.row_scratch[2 * Bq + i];
@@ -365,20 +371,20 @@ __global__ void __launch_bounds__(256) v33_finalize_kernel(const splade_v33_scal
   s_part[0][threadIdx.x] = nce;
   s_part[1][threadIdx.x] = kd;
   s_part[2][threadIdx.x] = mm;
-  __syncthreads();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) s_part[c][threadIdx.x] += s_part[c][threadIdx.x + o];
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   }
   if (threadIdx.x == 0) {
     const float invB = 1.f / static_cast<float>(Bq);
     nce = s_part[0][0] * invB;
     kd = s_part[1][0] * invB;                            // kl_div(reduction="batchmean")
     mm = s_part[2][0] * invB / static_cast<float>(k);    // mse_loss mean over [Bq,k]
-    const float fq = a.flops3[0], fd = a.flops3[2], fn = a.flops3[4];
+    const float fq = flops[0], fd = flops[2], fn = flops[4];
     float loss = nce + a.lambda_q * fq + a.lambda_d * fd + a.lambda_neg * fn;
     if (a.has_kd) loss += a.lambda_kd * kd;
     if (a.has_mmse) loss += a.lambda_mmse * mm;
@@ -389,9 +395,222 @@ __global__ void __launch_bounds__(256) v33_finalize_kernel(const splade_v33_scal
     a.scalars[4] = fn;
     a.scalars[5] = a.has_kd ? kd : 0.f;
     a.scalars[6] = a.has_mmse ? mm : 0.f;
-    a.scalars[7] = a.flops3[1];
-    a.scalars[8] = a.flops3[3];
+    a.scalars[7] = flops[1];
+    a.scalars[8] = flops[3];
   }
+}
+
+__global__ void __launch_bounds__(256) v33_finalize_kernel(const splade_v33_scalar_args a) {
+  __shared__ float s_part[3][256];
+  v33_finalize_block(a, a.flops3, s_part);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused forward (splade_v33_loss_fwd): three launches + the score GEMM instead of fourteen.
+//
+// (F1) v33_prep_kernel - ONE pass over q, the local positives and the negatives, one thread per vocabulary column
+//      (coalesced across the CTA, 8 query rows = 8 (2 + k) loads in flight per thread):
+//        * FLOPS column means of the three tensors + per-CTA partials of sum mean^2 and of the >0 counts
+//          (same summation order as splade_flops_nnz => bit-identical),
+//        * the bf16 operands of the score GEMM (the cast autocast performs),
+//        * per-CTA partial dot products q_i . neg_{i,kk} and (MarginMSE) q_i . pos_i.
+// (F2) the score GEMM (tcgen05 split-K under autocast, CUDA cores in fp32 mode) -> partial tiles
+// (F3) v33_reduce2_kernel - fixed-order reductions of the split-K score tiles and of the dot-product partials
+// (F4) v33_scalars_fused_kernel - ONE CTA: a warp per query row (CE / KL-KD / MarginMSE + gradient rows), then
+//      the fixed-order totals, the FLOPS partials and the scalars in the same kernel (Bq <= 256).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPrepRows = 8;
+
+struct PrepParams {
+  const float* q;       // [Bq, V]
+  const float* docs;    // [N, V]   (local positives = rows label_offset .. label_offset + Bq)
+  const float* negs;    // [Bq * k, V]
+  int Bq, N, k, V, Vp, label_offset;
+  int pack_q, pack_docs, want_pos;
+  float* colmean;       // [3][V]
+  float2* fpart;        // [3][nblk]
+  __nv_bfloat16* q16;   // [Bq, Vp]
+  __nv_bfloat16* d16;   // [N, Vp]
+  float* rd_part;       // [nblk][Bq * (k + 1)]   (slot k of a row = q . pos)
+};
+
+template <int KMAX>  // k <= KMAX in {1, 2, 4, 8}
+__global__ void __launch_bounds__(256) v33_prep_kernel(const PrepParams p) {
+  __shared__ float s_rd[8][kPrepRows * (KMAX + 1)];  // [warp][row-in-chunk * (k+1) + kk]
+  __shared__ float s_red[3][2][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x * 256 + tid;
+  const bool live = j < p.V;
+  const int Bq = p.Bq, k = p.k, V = p.V;
+  const int kk1 = k + 1;
+  const float* qc = p.q + j;
+  const float* dc = p.docs + static_cast<size_t>(p.label_offset) * V + j;
+  const float* nc = p.negs + j;
+  float sum_q = 0.f, cnt_q = 0.f, sum_d = 0.f, cnt_d = 0.f, sum_n = 0.f, cnt_n = 0.f;
+
+  for (int i0 = 0; i0 < Bq; i0 += kPrepRows) {
+    float xq[kPrepRows], xd[kPrepRows], xn[kPrepRows][KMAX];
+#pragma unroll
+    for (int u = 0; u < kPrepRows; ++u) {  // 8 (2 + k) independent loads in flight
+      const int i = i0 + u;
+      const bool ok = live && i < Bq;
+      xq[u] = ok ? qc[static_cast<size_t>(i) * V] : 0.f;
+      xd[u] = ok ? dc[static_cast<size_t>(i) * V] : 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KMAX; ++kk)
+        xn[u][kk] = (ok && kk < k) ? nc[(static_cast<size_t>(i) * k + kk) * V] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kPrepRows; ++u) {
+      const int i = i0 + u;
+      if (i < Bq) {
+        sum_q += xq[u];
+        cnt_q += (xq[u] > 0.f);
+        sum_d += xd[u];
+        cnt_d += (xd[u] > 0.f);
+        if (j < p.Vp) {
+          if (p.pack_q) p.q16[static_cast<size_t>(i) * p.Vp + j] = __float2bfloat16_rn(xq[u]);
+          if (p.pack_docs)
+            p.d16[static_cast<size_t>(p.label_offset + i) * p.Vp + j] = __float2bfloat16_rn(xd[u]);
+        }
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk) {  // in row order: the FLOPS sums run over rows r = i*k + kk ascending
+          if (kk < k) {
+            sum_n += xn[u][kk];
+            cnt_n += (xn[u][kk] > 0.f);
+            const float dot = warp_sum(xq[u] * xn[u][kk]);
+            if (lane == 0) s_rd[warp][u * (KMAX + 1) + kk] = dot;
+          }
+        }
+        if (p.want_pos) {
+          const float dot = warp_sum(xq[u] * xd[u]);
+          if (lane == 0) s_rd[warp][u * (KMAX + 1) + KMAX] = dot;
+        }
+      }
+    }
+    __syncthreads();  // the eight warps' partials of this chunk of rows, added in warp order
+    if (tid < kPrepRows * (KMAX + 1)) {
+      const int u = tid / (KMAX + 1), kk = tid - u * (KMAX + 1);
+      const int i = i0 + u;
+      if (i < Bq && (kk < k || (kk == KMAX && p.want_pos))) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_rd[w][tid];
+        p.rd_part[static_cast<size_t>(blockIdx.x) * Bq * kk1 + static_cast<size_t>(i) * kk1 + (kk == KMAX ? k : kk)] = t;
+      }
+    }
+    __syncthreads();
+  }
+  // documents that are not this rank's positives (gathered negatives, NCCL statement): only the bf16 operand
+  if (p.pack_docs && j < p.Vp) {
+    for (int r = 0; r < p.N; ++r) {
+      if (r >= p.label_offset && r < p.label_offset + Bq) continue;
+      const float x = live ? p.docs[static_cast<size_t>(r) * V + j] : 0.f;
+      p.d16[static_cast<size_t>(r) * p.Vp + j] = __float2bfloat16_rn(x);
+    }
+  }
+  const float mq = sum_q / static_cast<float>(Bq), md = sum_d / static_cast<float>(Bq);
+  const float mn = sum_n / static_cast<float>(Bq * k);
+  if (live) {
+    p.colmean[j] = mq;
+    p.colmean[static_cast<size_t>(V) + j] = md;
+    p.colmean[2 * static_cast<size_t>(V) + j] = mn;
+  }
+  // per-CTA partials, exactly as flops_cols_kernel forms them
+  const float sq[3] = {warp_sum(mq * mq), warp_sum(md * md), warp_sum(mn * mn)};
+  const float ct[3] = {warp_sum(cnt_q), warp_sum(cnt_d), warp_sum(cnt_n)};
+  if (lane == 0) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      s_red[t][0][warp] = sq[t];
+      s_red[t][1][warp] = ct[t];
+    }
+  }
+  __syncthreads();
+  if (tid < 3) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += s_red[tid][0][w];
+      b += s_red[tid][1][w];
+    }
+    p.fpart[static_cast<size_t>(tid) * gridDim.x + blockIdx.x] = make_float2(a, b);
+  }
+}
+
+// One warp per output element: lanes stride over the partials, then a fixed-order shuffle tree (deterministic).
+// Elements [0, nA) reduce partialA (the split-K score tiles), elements [nA, nA + nB) reduce partialB (the dots).
+__global__ void __launch_bounds__(256)
+v33_reduce2_kernel(const float* __restrict__ partialA, int ksA, size_t nA, float* __restrict__ outA,
+                   const float* __restrict__ partialB, int ksB, size_t nB, float* __restrict__ outB, int k,
+                   float* __restrict__ out_pos) {
+  size_t i = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i < nA) {
+    float s = 0.f;
+    for (int t = lane; t < ksA; t += 32) s += partialA[static_cast<size_t>(t) * nA + i];
+    s = warp_sum(s);
+    if (lane == 0) outA[i] = s;
+    return;
+  }
+  i -= nA;
+  if (i >= nB) return;
+  float s = 0.f;
+  for (int t = lane; t < ksB; t += 32) s += partialB[static_cast<size_t>(t) * nB + i];
+  s = warp_sum(s);
+  if (lane == 0) {  // element i = row * (k+1) + kk; slot k is q . pos
+    const int row = static_cast<int>(i / (k + 1)), kk = static_cast<int>(i % (k + 1));
+    if (kk < k) {
+      outB[static_cast<size_t>(row) * k + kk] = s;
+    } else if (out_pos) {
+      out_pos[row] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+v33_scalars_fused_kernel(const splade_v33_scalar_args a, const float2* __restrict__ fpart, int nblk, int rows_neg) {
+  __shared__ float s_part[3][256];
+  __shared__ float s_fa[3][256], s_fb[3][256];
+  __shared__ float s_flops[6];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Bq = a.Bq;
+  for (int i = warp; i < Bq; i += 32) {
+    float acc_nce = 0.f, acc_kd = 0.f, acc_mm = 0.f;
+    v33_scalars_row(a, i, lane, acc_nce, acc_kd, acc_mm);
+    if (lane == 0) {
+      a.row_scratch[i] = acc_nce;
+      a.row_scratch[Bq + i] = acc_kd;
+      a.row_scratch[2 * Bq + i] = acc_mm;
+    }
+  }
+  // FLOPS partials of the three tensors: threads 0-255 / 256-511 / 512-767, the tree of flops_final_kernel
+  const int t3 = threadIdx.x >> 8, tl = threadIdx.x & 255;
+  if (t3 < 3) {
+    float x = 0.f, y = 0.f;
+    for (int i = tl; i < nblk; i += 256) {
+      const float2 v = fpart[static_cast<size_t>(t3) * nblk + i];
+      x += v.x;
+      y += v.y;
+    }
+    s_fa[t3][tl] = x;
+    s_fb[t3][tl] = y;
+  }
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t3 < 3 && tl < o) {
+      s_fa[t3][tl] += s_fa[t3][tl + o];
+      s_fb[t3][tl] += s_fb[t3][tl + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) {
+    const float n_rows = static_cast<float>(threadIdx.x == 2 ? rows_neg : Bq);
+    s_flops[2 * threadIdx.x] = s_fa[threadIdx.x][0];
+    s_flops[2 * threadIdx.x + 1] = s_fb[threadIdx.x][0] / n_rows;
+  }
+  __syncthreads();  // row_scratch (global, written by this CTA) and s_flops are visible to the finalising threads
+  if (threadIdx.x < 256) v33_finalize_block(a, s_flops, s_part);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -723,19 +942,24 @@ int v33_scalars_launch(const splade_v33_scalar_args* a, cudaStream_t stream) {
   return kOk;
 }
 
+// Workspace of splade_v33_loss_fwd: [FLOPS partials 3 x nblk float2 | score GEMM workspace | raw_in [Bq,N] |
+// raw_hard [Bq,k] | raw_pos [Bq] | flops3 [6] | row_scratch [3 Bq] | dot-product partials [nblk][Bq (k+1)]].
+static size_t v33_flops_area(int Bq, int k, int V) {
+  return align256(3 * std::max(flops_workspace_bytes(Bq, V), flops_workspace_bytes(Bq * k, V)));
+}
+
 size_t v33_loss_fwd_workspace_bytes(int Bq, int N, int V, int k) {
   if (Bq < 1 || N < 1 || V < 1 || k < 1) return 0;
-  const size_t flops_ws = std::max(flops_workspace_bytes(Bq, V), flops_workspace_bytes(Bq * k, V));
-  return align256(flops_ws) + align256(scores_workspace_bytes(Bq, N, V)) +
+  const size_t nblk = (static_cast<size_t>((V + 7) / 8 * 8) + 255) / 256;
+  return v33_flops_area(Bq, k, V) + align256(scores_workspace_bytes(Bq, N, V)) +
          align256(static_cast<size_t>(Bq) * N * 4) + align256(static_cast<size_t>(Bq) * k * 4) +
-         align256(static_cast<size_t>(Bq) * 4) + align256(6 * 4) + align256(static_cast<size_t>(3) * Bq * 4);
+         align256(static_cast<size_t>(Bq) * 4) + align256(6 * 4) + align256(static_cast<size_t>(3) * Bq * 4) +
+         align256(nblk * Bq * (k + 1) * 4);
 }
 
 // The scores workspace inside the forward workspace (layout of v33_loss_fwd_launch below).
 void* v33_loss_fwd_scores_ws(const splade_v33_fwd_args* a) {
-  const size_t flops_ws =
-      align256(std::max(flops_workspace_bytes(a->Bq, a->V), flops_workspace_bytes(a->Bq * a->k, a->V)));
-  return static_cast<uint8_t*>(a->workspace) + flops_ws;
+  return static_cast<uint8_t*>(a->workspace) + v33_flops_area(a->Bq, a->k, a->V);
 }
 
 int v33_loss_fwd_launch(const splade_v33_fwd_args* a, cudaStream_t stream, bool docs_prepacked) {
@@ -751,9 +975,9 @@ int v33_loss_fwd_launch(const splade_v33_fwd_args* a, cudaStream_t stream, bool 
   if (!a->workspace || a->ws_bytes < need)
     return set_error(kErrWorkspace, "splade_v33_loss_fwd: workspace too small (%zu < %zu bytes)", a->ws_bytes, need);
   uint8_t* ws = static_cast<uint8_t*>(a->workspace);
-  const size_t flops_ws = align256(std::max(flops_workspace_bytes(Bq, V), flops_workspace_bytes(Bq * k, V)));
+  const size_t flops_area = v33_flops_area(Bq, k, V);
   void* w_flops = ws;
-  ws += flops_ws;
+  ws += flops_area;
   const size_t scores_ws = align256(scores_workspace_bytes(Bq, N, V));
   void* w_scores = ws;
   ws += scores_ws;
@@ -766,24 +990,9 @@ int v33_loss_fwd_launch(const splade_v33_fwd_args* a, cudaStream_t stream, bool 
   float* flops3 = reinterpret_cast<float*>(ws);
   ws += align256(6 * 4);
   float* row_scratch = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(3) * Bq * 4);
+  float* rd_part = reinterpret_cast<float*>(ws);
 
-  const float* local_docs = a->docs + static_cast<size_t>(a->label_offset) * V;
-  int rc = flops_nnz_launch(a->q, Bq, V, a->colmean, flops3, w_flops, flops_ws, stream);
-  if (rc != kOk) return rc;
-  rc = flops_nnz_launch(local_docs, Bq, V, a->colmean + V, flops3 + 2, w_flops, flops_ws, stream);
-  if (rc != kOk) return rc;
-  rc = flops_nnz_launch(a->negs, Bq * k, V, a->colmean + 2 * static_cast<size_t>(V), flops3 + 4, w_flops, flops_ws,
-                        stream);
-  if (rc != kOk) return rc;
-  rc = scores_launch(a->q, Bq, a->docs, N, V, a->round_bf16, raw_in, w_scores, scores_ws, stream,
-                     docs_prepacked && a->round_bf16);
-  if (rc != kOk) return rc;
-  rc = rowdot_launch(a->q, a->negs, Bq, k, V, raw_hard, stream);
-  if (rc != kOk) return rc;
-  if (a->has_mmse) {
-    rc = rowdot_launch(a->q, local_docs, Bq, 1, V, raw_pos, stream);
-    if (rc != kOk) return rc;
-  }
   splade_v33_scalar_args sa{};
   sa.Bq = Bq;
   sa.N = N;
@@ -810,7 +1019,85 @@ int v33_loss_fwd_launch(const splade_v33_fwd_args* a, cudaStream_t stream, bool 
   sa.g_inbatch = a->g_inbatch;
   sa.g_hard = a->g_hard;
   sa.row_scratch = row_scratch;
-  return v33_scalars_launch(&sa, stream);
+  if (a->has_kd && (!a->teacher_kd || N != Bq))
+    return set_error(kErrInvalidArg, "splade_v33_loss_fwd: KL-KD needs teacher_scores [Bq,Bq] and N == Bq");
+  if (a->has_mmse && (!a->teacher_pos || !a->teacher_neg))
+    return set_error(kErrInvalidArg, "splade_v33_loss_fwd: MarginMSE needs teacher_pos and teacher_neg");
+  if (!(a->temperature > 0.f) || (a->has_kd && !(a->kd_temperature > 0.f)))
+    return set_error(kErrInvalidArg, "splade_v33_loss_fwd: temperatures must be positive");
+
+  const float* local_docs = a->docs + static_cast<size_t>(a->label_offset) * V;
+  if (k > 8 || Bq > 256) {
+    // ---- general shapes: one kernel per term (the launch sequence of round 1)
+    const size_t one = flops_area / 3;
+    int rc = flops_nnz_launch(a->q, Bq, V, a->colmean, flops3, w_flops, one, stream);
+    if (rc != kOk) return rc;
+    rc = flops_nnz_launch(local_docs, Bq, V, a->colmean + V, flops3 + 2, w_flops, one, stream);
+    if (rc != kOk) return rc;
+    rc = flops_nnz_launch(a->negs, Bq * k, V, a->colmean + 2 * static_cast<size_t>(V), flops3 + 4, w_flops, one, stream);
+    if (rc != kOk) return rc;
+    rc = scores_launch(a->q, Bq, a->docs, N, V, a->round_bf16, raw_in, w_scores, scores_ws, stream,
+                       docs_prepacked && a->round_bf16);
+    if (rc != kOk) return rc;
+    rc = rowdot_launch(a->q, a->negs, Bq, k, V, raw_hard, stream);
+    if (rc != kOk) return rc;
+    if (a->has_mmse) {
+      rc = rowdot_launch(a->q, local_docs, Bq, 1, V, raw_pos, stream);
+      if (rc != kOk) return rc;
+    }
+    return v33_scalars_launch(&sa, stream);
+  }
+
+  // ---- fused forward: prep -> score GEMM -> reduce2 -> scalars (one CTA)
+  const int Vp = (V + 7) / 8 * 8;
+  const int nblk = (Vp + 255) / 256;
+  PrepParams pp{};
+  pp.q = a->q, pp.docs = a->docs, pp.negs = a->negs;
+  pp.Bq = Bq, pp.N = N, pp.k = k, pp.V = V, pp.Vp = Vp, pp.label_offset = a->label_offset;
+  pp.pack_q = a->round_bf16 ? 1 : 0;
+  pp.pack_docs = (a->round_bf16 && !docs_prepacked) ? 1 : 0;
+  pp.want_pos = a->has_mmse ? 1 : 0;
+  pp.colmean = a->colmean;
+  pp.fpart = static_cast<float2*>(w_flops);
+  pp.rd_part = rd_part;
+  if (a->round_bf16) {
+    int Vp2 = 0;
+    pp.q16 = static_cast<__nv_bfloat16*>(w_scores);
+    pp.d16 = static_cast<__nv_bfloat16*>(scores_tc_docs16(w_scores, Bq, N, V, &Vp2));
+    if (Vp2 != Vp) return set_error(kErrInvalidArg, "splade_v33_loss_fwd: internal layout mismatch");
+  }
+  if (k <= 1) {
+    v33_prep_kernel<1><<<nblk, 256, 0, stream>>>(pp);
+  } else if (k <= 2) {
+    v33_prep_kernel<2><<<nblk, 256, 0, stream>>>(pp);
+  } else if (k <= 4) {
+    v33_prep_kernel<4><<<nblk, 256, 0, stream>>>(pp);
+  } else {
+    v33_prep_kernel<8><<<nblk, 256, 0, stream>>>(pp);
+  }
+  SPLADE_CUDA_OK(cudaGetLastError());
+
+  float* partial = nullptr;
+  int ksplit = 0;
+  if (a->round_bf16) {
+    const int rc = scores_tc_launch(a->q, Bq, a->docs, N, V, w_scores, scores_ws, &partial, &ksplit,
+                                    /*docs_prepacked=*/true, stream, /*q_prepacked=*/true);
+    if (rc != kOk) return rc;
+  } else {
+    int chunk;
+    scores_plan(Bq, N, V, &ksplit, &chunk);
+    partial = static_cast<float*>(w_scores);
+    dim3 grid((N + TJ - 1) / TJ, (Bq + TI - 1) / TI, ksplit);
+    scores_partial_kernel<<<grid, 256, 0, stream>>>(a->q, Bq, a->docs, N, V, 0, chunk, partial);
+    SPLADE_CUDA_OK(cudaGetLastError());
+  }
+  const size_t nA = static_cast<size_t>(Bq) * N, nB = static_cast<size_t>(Bq) * (k + 1);
+  v33_reduce2_kernel<<<static_cast<unsigned>((nA + nB + 7) / 8), 256, 0, stream>>>(
+      partial, ksplit, nA, raw_in, rd_part, nblk, nB, raw_hard, k, a->has_mmse ? raw_pos : nullptr);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  v33_scalars_fused_kernel<<<1, 1024, 0, stream>>>(sa, static_cast<const float2*>(w_flops), nblk, Bq * k);
+  SPLADE_CUDA_OK(cudaGetLastError());
+  return kOk;
 }
 
 int loss_bwd_launch(const float* q, const float* docs, const float* negs, int Bq, int N, int k, int V,

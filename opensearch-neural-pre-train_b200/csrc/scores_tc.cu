@@ -202,7 +202,8 @@ void* scores_tc_docs16(void* workspace, int Bq, int N, int V, int* Vp_out) {
 
 // Returns the number of k-splits written to `*partial_out` ([ksplit][Bq][N]); the caller reduces them.
 int scores_tc_launch(const float* q, int Bq, const float* docs, int N, int V, void* workspace, size_t ws_bytes,
-                     float** partial_out, int* ksplit_out, bool docs_prepacked, cudaStream_t stream) {
+                     float** partial_out, int* ksplit_out, bool docs_prepacked, cudaStream_t stream,
+                     bool q_prepacked) {
   int rc = require_sm100("splade_scores");
   if (rc != kOk) return rc;
   int Vp, n_tile, m_tiles, n_tiles, kb_total, kb_per_cta, ksplit;
@@ -218,7 +219,7 @@ int scores_tc_launch(const float* q, int Bq, const float* docs, int N, int V, vo
   float* partial = reinterpret_cast<float*>(ws);
 
   const unsigned chunks = static_cast<unsigned>((Vp / 8 + 255) / 256);
-  pack_bf16_kernel<<<dim3(chunks, Bq), 256, 0, stream>>>(q, V, Vp, q16);
+  if (!q_prepacked) pack_bf16_kernel<<<dim3(chunks, Bq), 256, 0, stream>>>(q, V, Vp, q16);
   if (!docs_prepacked) pack_bf16_kernel<<<dim3(chunks, N), 256, 0, stream>>>(docs, V, Vp, d16);
   SPLADE_CUDA_OK(cudaGetLastError());
 

@@ -429,18 +429,7 @@ class SpladeHeadFunction(torch.autograd.Function):
     that share the weight (``_DeferredDW``)."""
 
     @staticmethod
-    def forward(ctx, hidden, weight, bias, attention_mask, want_token_weights: bool, round_bias: bool):
-        _require_cuda(hidden, "hidden")
-        h16 = hidden.detach().to(torch.bfloat16).contiguous()
-        w16 = cached_bf16(weight)
-        if bias is None:
-            b32 = torch.zeros(weight.shape[0], dtype=torch.float32, device=hidden.device)
-        else:
-            b32 = bias.detach()
-            if round_bias:  # autocast hands F.linear a bf16 bias
-                b32 = b32.to(torch.bfloat16)
-            b32 = b32.to(torch.float32).contiguous()
-        m32 = attention_mask.detach().to(torch.int32).contiguous()
+    def forward(ctx, hidden, weight, bias, h16, w16, b32, m32, want_token_weights: bool):
         rep, argmax, tokw = head_forward(h16, w16, b32, m32, want_token_weights)
         active = rep_bitmap(rep) if any(ctx.needs_input_grad[:3]) else rep.new_empty((0,), dtype=torch.int32)
         ctx.save_for_backward(rep, argmax, h16, w16, active)
@@ -477,7 +466,7 @@ class SpladeHeadFunction(torch.autograd.Function):
                 dW, dbias = head_backward_dw(segments, H, V)
                 dW = dW.to(wd) if ctx.needs_input_grad[1] else None
                 dbias = dbias.to(bd) if (bd is not None and ctx.needs_input_grad[2]) else None
-        return (d_hidden.to(hd) if need_h else None, dW, dbias, None, None, None)
+        return (d_hidden.to(hd) if need_h else None, dW, dbias, None, None, None, None, None)
 
 
 def autocast_is_bf16() -> bool:
@@ -492,12 +481,94 @@ def autocast_is_bf16() -> bool:
     return True
 
 
+class LazyTokenWeights(torch.Tensor):
+    """``token_weights [B,S]`` that is computed only if somebody reads it.
+
+    Every caller in the reference discards the second return value of ``SPLADEModernBERT.forward``
+    (``anchor_repr, _ = model(...)``, src/train/cli/train_v33_ddp.py:339-343; ``encode`` drops it at
+    splade_modern.py:96), yet ``forward`` must return it, and the per-position reduction over the vocabulary costs
+    11 % of the fused kernel (30 % on query batches).  This wrapper tensor reports shape / dtype / device without
+    touching the GPU; the first operation on it runs the forward kernel variant that also produces token_weights
+    (bit-identical to the eager path) and every operation is then forwarded to the real tensor."""
+
+    @staticmethod
+    def __new__(cls, shape, device, thunk):
+        t = torch.Tensor._make_wrapper_subclass(cls, tuple(shape), dtype=torch.float32, device=device,
+                                                requires_grad=False)
+        t._thunk, t._value = thunk, None
+        return t
+
+    def materialize(self) -> torch.Tensor:
+        if self._value is None:
+            self._value = self._thunk()
+            self._thunk = None  # drop the references to the forward's operands
+        return self._value
+
+    @property
+    def is_materialized(self) -> bool:
+        return self._value is not None
+
+    def __repr__(self):
+        return (f"LazyTokenWeights(shape={tuple(self.shape)}, device={self.device}, "
+                f"materialized={self._value is not None})")
+
+    # accessors implemented in C against the storage (a wrapper subclass has none)
+    def numpy(self, *a, **k):
+        return self.materialize().numpy(*a, **k)
+
+    def tolist(self):
+        return self.materialize().tolist()
+
+    def item(self):
+        return self.materialize().item()
+
+    def data_ptr(self):
+        return self.materialize().data_ptr()
+
+    def __array__(self, *a, **k):
+        return self.materialize().__array__(*a, **k)
+
+    @classmethod
+    def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
+        from torch.utils._pytree import tree_map
+
+        def unwrap(x):
+            return x.materialize() if isinstance(x, LazyTokenWeights) else x
+
+        return func(*tree_map(unwrap, args), **tree_map(unwrap, kwargs or {}))
+
+
+def lazy_token_weights_enabled() -> bool:
+    return os.environ.get("SPLADE_B200_LAZY_TOKEN_WEIGHTS", "1") != "0"
+
+
 def splade_head(hidden, weight, bias, attention_mask, want_token_weights: bool = True,
-                round_bias: Optional[bool] = None):
+                round_bias: Optional[bool] = None, lazy_token_weights: Optional[bool] = None):
+    """(sparse_repr [B,V] fp32, token_weights [B,S] fp32 | None).  ``lazy_token_weights`` (default: env
+    SPLADE_B200_LAZY_TOKEN_WEIGHTS, on): token_weights is a ``LazyTokenWeights`` - computed on first use."""
+    _require_cuda(hidden, "hidden")
     if round_bias is None:
-        round_bias = autocast_is_bf16() if hidden.is_cuda else False
-    rep, tokw = SpladeHeadFunction.apply(hidden, weight, bias, attention_mask, want_token_weights, round_bias)
-    return rep, (tokw if want_token_weights else None)
+        round_bias = autocast_is_bf16()
+    if lazy_token_weights is None:
+        lazy_token_weights = lazy_token_weights_enabled()
+    h16 = hidden.detach().to(torch.bfloat16).contiguous()
+    w16 = cached_bf16(weight)
+    if bias is None:
+        b32 = torch.zeros(weight.shape[0], dtype=torch.float32, device=hidden.device)
+    else:
+        b32 = bias.detach()
+        if round_bias:  # autocast hands F.linear a bf16 bias
+            b32 = b32.to(torch.bfloat16)
+        b32 = b32.to(torch.float32).contiguous()
+    m32 = attention_mask.detach().to(torch.int32).contiguous()
+    eager = want_token_weights and not lazy_token_weights
+    rep, tokw = SpladeHeadFunction.apply(hidden, weight, bias, h16, w16, b32, m32, eager)
+    if not want_token_weights:
+        return rep, None
+    if eager:
+        return rep, tokw
+    B, S, _ = h16.shape
+    return rep, LazyTokenWeights((B, S), hidden.device, lambda: head_forward(h16, w16, b32, m32, True)[2])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -546,6 +617,14 @@ class V33LossFunction(torch.autograd.Function):
                 g_hard=g_hard.data_ptr(), workspace=ws_ptr, ws_bytes=nbytes)
             check(lib.splade_v33_loss_fwd(ctypes.byref(args), _stream(q)), "splade_v33_loss_fwd")
             cm_q, cm_d, cm_n = colmean[0], colmean[1], colmean[2]
+            # autocast mode: the forward leaves the bf16 operands of the score GEMM in its workspace; the backward's
+            # two products run on them with tcgen05 (splade_loss_bwd_tc), so the workspace stays alive until then
+            ctx.tc = None
+            if round_bf16 and V % 4 == 0 and os.environ.get("SPLADE_B200_LOSS_BWD_TC", "1") != "0":
+                q16, d16, vp = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int(0)
+                check(lib.splade_v33_loss_fwd_operands(ctypes.byref(args), ctypes.byref(q16), ctypes.byref(d16),
+                                                       ctypes.byref(vp)), "splade_v33_loss_fwd_operands")
+                ctx.tc = (ws, q16.value, d16.value)
         ctx.save_for_backward(q, d, n, g_in, g_hard, cm_q, cm_d, cm_n)
         ctx.meta = (Bq, N, k, V, off, cfg["lambda_q"], cfg["lambda_d"], cfg["lambda_neg"],
                     anchor.dtype, docs.dtype, negatives.dtype, tuple(negatives.shape))
@@ -564,11 +643,21 @@ class V33LossFunction(torch.autograd.Function):
             dq = torch.empty_like(q)
             ddocs = torch.empty_like(d)
             dnegs = torch.empty_like(n)
-            check(lib.splade_loss_bwd(q.data_ptr(), d.data_ptr(), n.data_ptr(), Bq, N, k, V, off,
-                                      g_in.data_ptr(), g_hard.data_ptr(), cm_q.data_ptr(), cm_d.data_ptr(),
-                                      cm_n.data_ptr(), 2.0 * lq / Bq, 2.0 * ld / Bq, 2.0 * ln / (Bq * k),
-                                      gl.data_ptr(), dq.data_ptr(), ddocs.data_ptr(), dnegs.data_ptr(),
-                                      _stream(q)), "splade_loss_bwd")
+            if ctx.tc is not None:
+                _keep, q16, d16 = ctx.tc
+                nbytes = lib.splade_workspace_bytes(_lib.OP_LOSS_BWD_TC, Bq, 0, 0, 0, N)
+                ws, ws_ptr = _ws(nbytes, dev)
+                check(lib.splade_loss_bwd_tc(q.data_ptr(), n.data_ptr(), q16, d16, Bq, N, k, V, off,
+                                             g_in.data_ptr(), g_hard.data_ptr(), cm_q.data_ptr(), cm_d.data_ptr(),
+                                             cm_n.data_ptr(), 2.0 * lq / Bq, 2.0 * ld / Bq, 2.0 * ln / (Bq * k),
+                                             gl.data_ptr(), dq.data_ptr(), ddocs.data_ptr(), dnegs.data_ptr(),
+                                             ws_ptr, nbytes, _stream(q)), "splade_loss_bwd_tc")
+            else:
+                check(lib.splade_loss_bwd(q.data_ptr(), d.data_ptr(), n.data_ptr(), Bq, N, k, V, off,
+                                          g_in.data_ptr(), g_hard.data_ptr(), cm_q.data_ptr(), cm_d.data_ptr(),
+                                          cm_n.data_ptr(), 2.0 * lq / Bq, 2.0 * ld / Bq, 2.0 * ln / (Bq * k),
+                                          gl.data_ptr(), dq.data_ptr(), ddocs.data_ptr(), dnegs.data_ptr(),
+                                          _stream(q)), "splade_loss_bwd")
         return dq.to(qd), ddocs.to(dd), dnegs.view(nshape).to(nd), None, None, None, None
 
 

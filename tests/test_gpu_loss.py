@@ -176,3 +176,34 @@ def test_tensor_core_scores_shapes(cuda_device, Bq, N, V):
     torch.testing.assert_close(raw.double(), want, rtol=2e-5, atol=1e-4)
     raw2 = splade_b200.scores(q, d, True)
     assert torch.equal(raw, raw2)          # fixed-order split-K reduction: run-to-run deterministic
+
+
+@pytest.mark.parametrize("Bq,N,k,off,V", [(64, 64, 1, 0, 50000), (64, 512, 1, 128, 50000), (16, 16, 7, 0, 50000),
+                                          (24, 200, 3, 40, 4100), (5, 9, 2, 3, 260)])
+def test_tensor_core_backward_matches_the_fp32_backward(cuda_device, monkeypatch, Bq, N, k, off, V):
+    """Autocast mode: dq / ddocs / dnegs from splade_loss_bwd_tc (tcgen05 on the bf16 operands the forward packed,
+    G rounded to bf16 - what the reference's autocast backward of torch.mm computes, minus its bf16 output rounding)
+    against splade_loss_bwd (fp32 CUDA cores) on the same forward.  Stated tolerance: 1e-2 of the gradient scale
+    (north_star); measured ~2e-3.  Covers gathered documents (N > Bq, label offset), N and Bq that are not multiples
+    of 64 / 128, several hard negatives, a vocabulary tail."""
+    from splade_b200.ops import V33LossFunction
+    q = _reps(Bq, V, 21, 0.05, cuda_device)
+    docs = _reps(N, V, 22, 0.08, cuda_device)
+    negs = _reps(Bq * k, V, 23, 0.08, cuda_device).view(Bq, k, V)
+    cfg = dict(round_bf16=True, temperature=1.0, kd_temperature=1.0, lambda_q=1e-2, lambda_d=3e-3, lambda_neg=3e-3,
+               lambda_kd=0.0, lambda_mmse=0.0, label_offset=off)
+    outs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("SPLADE_B200_LOSS_BWD_TC", tc)
+        a, b, c = (t.clone().requires_grad_(True) for t in (q, docs, negs))
+        loss, _ = V33LossFunction.apply(a, b, c, None, None, None, cfg)
+        (loss * 1.7).backward()
+        outs[tc] = (float(loss), a.grad, b.grad, c.grad)
+    assert outs["1"][0] == outs["0"][0]                       # same forward
+    for got, ref, name in zip(outs["1"][1:], outs["0"][1:], ("dq", "ddocs", "dnegs")):
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max())
+        assert err <= 1e-2 * scale + 1e-9, (name, err, scale)
+        rel = float((got - ref).norm() / ref.norm().clamp_min(1e-20))
+        assert rel <= 5e-3, (name, rel)
+    torch.testing.assert_close(outs["1"][3], outs["0"][3], rtol=1e-6, atol=1e-12)   # dnegs has no GEMM term

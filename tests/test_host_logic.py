@@ -372,3 +372,32 @@ def test_one_backward_one_dw_sweep_host_logic(monkeypatch):
     sum((ops.splade_head(h, W, bias, m, round_bias=False)[0] ** 2).sum() for h, m in zip(hs, ms)).backward()
     assert [c for c in calls if c != "dhidden"] == [("dw", 1)] * 3
     torch.testing.assert_close(W.grad, got[0], rtol=1e-5, atol=1e-6)
+
+
+def test_token_weights_are_computed_only_when_read(monkeypatch):
+    """forward() must return token_weights, but every reference caller discards it (train_v33_ddp.py:339-343): the
+    returned LazyTokenWeights runs the token_weights variant of the kernel on first use only, reports shape / dtype /
+    device without touching the device, and then behaves like the eager tensor."""
+    from splade_b200 import ops
+    calls = []
+    _fake_head_kernels(monkeypatch, calls)
+    real_fwd = ops.head_forward
+    fwd_calls = []
+    monkeypatch.setattr(ops, "head_forward", lambda *a, **k: (fwd_calls.append(bool(a[4])), real_fwd(*a, **k))[1])
+    g = torch.Generator().manual_seed(1)
+    W = torch.randn(30, 16, generator=g) * 0.3
+    h = torch.randn(2, 5, 16, generator=g)
+    m = torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1]])
+    rep, tokw = ops.splade_head(h, W, None, m, round_bias=False)
+    assert isinstance(tokw, ops.LazyTokenWeights) and not tokw.is_materialized and fwd_calls == [False]
+    assert tuple(tokw.shape) == (2, 5) and tokw.dtype == torch.float32 and tokw.device == h.device
+    assert fwd_calls == [False]                       # metadata is free
+    s = tokw.sum()                                    # first real use
+    assert tokw.is_materialized and fwd_calls == [False, True]
+    _, eager = ops.splade_head(h, W, None, m, round_bias=False, lazy_token_weights=False)
+    assert type(eager) is torch.Tensor and torch.equal(tokw + 0, eager) and float(s) == float(eager.sum())
+    assert torch.equal(tokw[:, 3:], eager[:, 3:]) and float(tokw[0, 3]) == 0.0
+    n = len(fwd_calls)
+    _ = tokw.max(), tokw.cpu().numpy()
+    assert len(fwd_calls) == n                        # materialised once
+    assert ops.splade_head(h, W, None, m, want_token_weights=False, round_bias=False)[1] is None

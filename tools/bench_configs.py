@@ -161,7 +161,52 @@ def main():
     torch.cuda.synchronize()
     dt = max_ranks(time.perf_counter() - t0)
     nnz = float(torch.cat(out_counts).float().mean())
+    # ---- the emit leg behind it (benchmark/indexer.py:112-138 / scripts/neural_sparse_search_aws.py:980-1036): the
+    #      compact top-k buffers of this rank's shard -> the OpenSearch _bulk request body (splade_emit_bulk, host C),
+    #      (a) alone on one host thread, (b) on a side thread WHILE the GPU encodes the shard again (ctypes releases
+    #      the GIL), i.e. what a pipelined indexer pays in wall time.
+    import threading
+    shard = (torch.cat(out_ids), torch.cat(out_vals), torch.cat(out_counts))
+    doc_ids = [f"d{rank}_{i}" for i in range(n_local)]
+    chunk = 8192
+
+    def emit_all():
+        total = 0
+        for c0 in range(0, n_local, chunk):
+            body = emitter.to_bulk(shard[0][c0:c0 + chunk], shard[1][c0:c0 + chunk], shard[2][c0:c0 + chunk],
+                                   "bench", doc_ids[c0:c0 + chunk], round_decimals=4)
+            total += len(body)
+        return total
+
+    emit_all()  # warm-up (token table, allocator)
+    t0 = time.perf_counter()
+    body_bytes = emit_all()
+    dt_emit = time.perf_counter() - t0
+    box = {}
+    th = threading.Thread(target=lambda: box.setdefault("bytes", emit_all()))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    th.start()
+    with torch.no_grad():
+        for b0 in range(lo, hi, 64):
+            ib = ids_all[b0:b0 + 64].to(dev, non_blocking=True)
+            mb = mask_all[b0:b0 + 64].to(dev, non_blocking=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                rep = model.encode(ib, mb)
+            emitter.select(rep, 64)
+    torch.cuda.synchronize()
+    dt_enc_overlapped = time.perf_counter() - t0
+    th.join()
+    dt_both = max_ranks(time.perf_counter() - t0)
+    emit = {"what": "SparseEmitter.to_bulk (splade_emit_bulk): _bulk action + source lines, sparse_vector format, "
+                    "4-decimal weights, for this rank's shard; one host thread",
+            "docs": n_local, "body_bytes": body_bytes, "bytes_per_doc": body_bytes / max(1, n_local),
+            "seconds_alone": dt_emit, "docs_per_s_alone": n_local / dt_emit, "MB_per_s_alone": body_bytes / dt_emit / 1e6,
+            "seconds_encode_plus_emit_overlapped": dt_both, "encode_seconds_while_emitting": dt_enc_overlapped,
+            "docs_per_s_overlapped_whole_job": n_total / dt_both,
+            "projected_seconds_for_1M_docs_with_bulk_bodies": 1e6 / (n_total / dt_both)}
     out["config5_bulk_encode"] = {"docs_total": n_total, "docs_per_gpu": n_local, "seq_len": 256, "top_k": 64,
+                                  "emit": emit,
                                   "seconds": dt, "docs_per_s": n_total / dt, "mean_terms_emitted": nnz,
                                   "projected_seconds_for_1M_docs": 1e6 / (n_total / dt),
                                   "d2h_bytes_per_doc": 64 * 8 + 4,

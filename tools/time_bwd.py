@@ -18,13 +18,17 @@ H, V = 768, 50000
 K_NEG = int(os.environ.get("K_NEG", "1"))
 
 
+COLD = os.environ.get("COLD", "1") == "1"   # flush L2 before every timed call (the default) or leave it warm
+
+
 def timeit(fn, n=10):
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
     tot = 0.0
     for _ in range(n):
-        flush.zero_()
+        if COLD:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
@@ -68,7 +72,7 @@ for off, tag in ((0.0, "dense"), (-2.0, "sparse")):
     def bitmaps_only():   # paid in the forward (rep is L2-hot there; here it is cold: an upper bound)
         return [splade_b200.rep_bitmap(s[1]) for s in segs]
 
-    row = {"nnz_per_doc": nnz, "k_neg": K_NEG}
+    row = {"nnz_per_doc": nnz, "k_neg": K_NEG, "l2": "flushed before every call" if COLD else "warm"}
     for name, fn in (("three_single_calls_plus_autograd_adds_ms", three_singles), ("multi_ms", multi),
                      ("two_phase_ms", two_phase), ("phase1_bucket_dhidden_ms", phase1_only), ("dw_sweep_ms", dw_only),
                      ("rep_bitmaps_cold_ms", bitmaps_only)):

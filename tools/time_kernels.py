@@ -92,6 +92,30 @@ for k in (1, 7):
     report(f"SPLADELossV33 forward k={k} (incl. the one D2H sync)", ms, (2 + k) * 64 * V * 4 * 2)
     ms2 = timeit(fwdbwd)
     report(f"SPLADELossV33 forward+backward k={k}", ms2, (2 + k) * 64 * V * 4 * 4)
+    os.environ["SPLADE_B200_LOSS_BWD_TC"] = "0"
+    ms3 = timeit(fwdbwd)
+    os.environ["SPLADE_B200_LOSS_BWD_TC"] = "1"
+    report(f"   ... with the fp32 CUDA-core backward (round 1)", ms3, (2 + k) * 64 * V * 4 * 4)
+
+# gathered negatives as at 8 GPUs (N = 512 in-batch documents), one rank's view, virtual (no exchange)
+from splade_b200.ops import V33LossFunction  # noqa: E402
+for N in (64, 512):
+    qq = q.clone().requires_grad_(True)
+    dd = (torch.rand(N, V, device=dev) * (torch.rand(N, V, device=dev) < 0.1)).requires_grad_(True)
+    nn_ = (torch.rand(64, 1, V, device=dev) * (torch.rand(64, 1, V, device=dev) < 0.1)).requires_grad_(True)
+    cfg = dict(round_bf16=True, temperature=1.0, kd_temperature=1.0, lambda_q=1e-2, lambda_d=3e-3, lambda_neg=3e-3,
+               lambda_kd=0.0, lambda_mmse=0.0, label_offset=0)
+    for tc in ("1", "0"):
+        os.environ["SPLADE_B200_LOSS_BWD_TC"] = tc
+        loss, _ = V33LossFunction.apply(qq, dd, nn_, None, None, None, cfg)
+
+        def bwd():
+            torch.autograd.grad(loss, [qq, dd, nn_], retain_graph=True)
+
+        ms = timeit(bwd)
+        report(f"loss backward only, N={N} docs, {'tcgen05' if tc == '1' else 'fp32 CUDA cores'}", ms,
+               (64 * 3 + N * 2) * V * 4)
+    os.environ["SPLADE_B200_LOSS_BWD_TC"] = "1"
 
 for (Bt, k) in ((64, 64), (512, 64), (512, 100)):
     x = torch.log1p(torch.relu(torch.randn(Bt, V, device=dev).to(torch.bfloat16).float()))
