@@ -285,10 +285,16 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    import gc
+    gc.collect()
+    gc.disable()   # no collector pause inside the timed region (a step is ~3 ms)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(steps):
-        d = step(i)
+    try:
+        for i in range(steps):
+            d = step(i)
+    finally:
+        gc.enable()
     e1.record()
     if world > 1:
         dist.barrier()
@@ -504,7 +510,7 @@ def run_peer_parity(dev, world, rank, exchange="peer"):
     return res
 
 
-def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=1, exchange="peer"):
+def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, exchange="peer"):
     """The FULL training step of the reference (src/train/cli/train_v33_ddp.py:337-374) on the A.X-Encoder-base
     shape, BASELINE config 4: per GPU 64 queries x 64 + 64 positives x 256 + 64 negatives x 256 tokens through the
     22-layer transformers trunk WITH autograd, three head calls, SPLADELossV33, (loss / accum).backward() under
@@ -516,6 +522,8 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=1, excha
       peer_negatives       + cross-GPU in-batch negatives through the NVLink peer exchange (N > 1)
       reference_statement  the reference's own head/loss statement (oracle/torch_reference.py) on the same trunk
     tokens/s = whole job (all ranks, real padded tokens of the collator shape) / max-over-ranks CUDA-event time."""
+    import gc
+
     import torch
     import torch.distributed as dist
 
@@ -557,22 +565,34 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=1, excha
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        # the eager 22-layer trunk is host-launch-bound: a generation-2 garbage collection in the middle of a
+        # micro-step shows up as a 50-90 ms hiccup (seen at N = 2) - collect now, keep the collector off while timing
+        gc.collect()
+        gc.disable()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_micro - accum + 1)]
         e0.record()
-        for i in range(accum, n_micro):
-            loss, d, gs = train_micro_step(model, loss_fn, opt, None, batches[i], i, gs, scfg, dev)
+        marks[0].record()
+        try:
+            for i in range(accum, n_micro):
+                loss, d, gs = train_micro_step(model, loss_fn, opt, None, batches[i], i, gs, scfg, dev)
+                marks[i - accum + 1].record()
+        finally:
+            gc.enable()
         e1.record()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / (n_micro - accum)
+        per_step = [round(marks[j].elapsed_time(marks[j + 1]), 2) for j in range(n_micro - accum)]
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         res = {"ms_per_micro_step": ms, "tokens_per_s": tokens_per_micro / ms * 1e3,
-               "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30, "last_loss": float(loss),
-               "nonzero_d": d.get("nonzero_d")}
+               "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30, "last_loss": float(loss.detach()),
+               "nonzero_d": d.get("nonzero_d"), "ms_each_micro_step_rank0": per_step,
+               "median_ms_rank0": sorted(per_step)[len(per_step) // 2]}
         del opt, model
         module.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()
@@ -636,8 +656,11 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=1, excha
             out["limiting_collective"] = (
                 f"DDP bucketed all-reduce of all gradients ({nbytes / 1e6:.0f} MB fp32 per micro-step, NCCL over "
                 f"NVLink): {coll['all_gradients_fp32']['ms']:.2f} ms alone; exposed per micro-step = "
-                f"{a['ms_per_micro_step'] - b['ms_per_micro_step'] * accum / (accum - 1 + 1):.2f} ms "
-                f"(reference_semantics - no_sync, the latter still pays it on 1 of {accum} micro-steps)")
+                f"{(a['ms_per_micro_step'] - b['ms_per_micro_step']) * accum / (accum - 1):.2f} ms "
+                f"((reference_semantics - no_sync) x {accum}/{accum - 1}: no_sync still pays it on 1 of {accum} "
+                f"micro-steps); the tied decoder matrix is the LAST gradient of a backward pass (its last producer is "
+                f"the embedding lookup), so its bucket's all-reduce "
+                f"({coll['tied_decoder_matrix_fp32']['ms']:.2f} ms alone) is never overlapped")
     a, r = out.get("reference_semantics", {}), out.get("reference_statement", {})
     if "ms_per_micro_step" in a and "ms_per_micro_step" in r:
         out["speedup_vs_reference_statement"] = r["ms_per_micro_step"] / a["ms_per_micro_step"]

@@ -372,12 +372,14 @@ int splade_peer_v33_loss_fwd(const splade_v33_fwd_args* args, const splade_peer_
 /*
  * Backward of the same (formulas of splade_loss_bwd); ddocs_local [Bq,V] is the gradient of the LOCAL positives
  * summed over every rank's queries.  workspace: splade_workspace_bytes(SPLADE_OP_PEER_LOSS_BWD, Bq,0,0,0, world).
+ * q16 / d16_all: the bf16 operands the forward left in its workspace (splade_v33_loss_fwd_operands on the forward's
+ * args; autocast mode) - dq then runs on the tensor cores (splade_loss_bwd_tc); both NULL = fp32 CUDA-core dq.
  */
 int splade_peer_loss_bwd(const splade_peer_group* group, uint32_t epoch, const float* q, const float* docs_all,
                          const float* negs, int Bq, int k, int V, const float* g_hard, const float* colmean_q,
                          const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
-                         const float* g_loss, float* dq, float* ddocs_local, float* dnegs, void* workspace,
-                         size_t ws_bytes, void* stream);
+                         const float* g_loss, float* dq, float* ddocs_local, float* dnegs, const void* q16,
+                         const void* d16_all, void* workspace, size_t ws_bytes, void* stream);
 
 /*
  * ---------------------------------------------------------------------------------------------------------------

@@ -166,7 +166,7 @@ EXPORTS = {
     "splade_peer_v33_loss_fwd": (c_int, [POINTER(V33FwdArgs), POINTER(PeerGroup), c_uint32, c_void_p, c_void_p]),
     "splade_peer_loss_bwd": (c_int, [POINTER(PeerGroup), c_uint32, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

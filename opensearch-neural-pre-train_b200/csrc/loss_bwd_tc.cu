@@ -13,11 +13,13 @@
 // Both products are C[m, v] = sum_k A[m,k] * X[k,v] with X = a [K, Vp] bf16 matrix whose ROWS are the contraction
 // index (D: rows = documents, Q: rows = queries):
 //   A  K-major  [rows, Kp] bf16   dq: G16 [Bq, N]      ddocs: G16^T [N, Bq]      TMA box (64 k, 128 rows), SW128
-//   B  MN-major                   the TMA-loaded [64 k rows][64 v] tile as it lies in X (128 B swizzle rows): four
-//                                 64-column atoms per CTA = 256 vocabulary columns, four 128x64 TMEM accumulators
+//   B  MN-major                   the TMA-loaded [64 k rows][64 v] tile as it lies in X (128 B swizzle rows): two
+//                                 64-column atoms per CTA = 128 vocabulary columns, two 128x64 TMEM accumulators
 //   tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 64, K = 16 per instruction; 4-stage TMA ring over K blocks of 64.
-// Grid = (ceil(V / 256), ceil(rows / 128)).  Epilogue: a thread = one output row (TMEM lane), 32 consecutive columns
-// per tcgen05.ld, the element-wise terms added in registers, 128-byte row segments stored with float4.
+// Grid = (ceil(V / 128), ceil(rows / 128)), ~68 KB of shared memory => three CTAs per SM, one wave at V = 50 000.
+// Epilogue: the accumulator tile goes TMEM -> shared memory, then all threads walk (row, 4 columns) items so that every
+// warp instruction touches 512 contiguous bytes of one fp32 row (the first version kept a thread = one row: half-used
+// sectors and a serial chain of dependent loads per thread, 101 us at N = 64 against 61 us for the CUDA-core kernels).
 // Memory-bound by construction: X is read once per row tile (51 MB at N = 512), the outputs written once.
 #include "common.cuh"
 #include "kernels.h"
@@ -30,14 +32,17 @@ namespace {
 constexpr int TM = 128;
 constexpr int BK = 64;
 constexpr int UK = 16;
-constexpr int NATOM = 4;                   // 64-column atoms per CTA
+constexpr int NATOM = 2;                   // 64-column atoms per CTA
 constexpr int TV = 64 * NATOM;             // vocabulary columns per CTA
-constexpr int STAGES = 4;
+constexpr int STAGES = 2;                  // the contraction is at most 8 blocks long
 constexpr int A_BYTES = TM * BK * 2;       // 16 KB
 constexpr int B_ATOM_BYTES = BK * 64 * 2;  // 8 KB
 constexpr int STAGE_BYTES = A_BYTES + NATOM * B_ATOM_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
-constexpr int TMEM_COLS = 256;
+constexpr int TILE_LD = TV + 4;            // padded row of the staged fp32 accumulator tile (conflict-free float4)
+constexpr int TILE_BYTES = TM * TILE_LD * 4;
+constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+constexpr int SMEM_BYTES = (PIPE_BYTES > TILE_BYTES ? PIPE_BYTES : TILE_BYTES) + 256 + 1024;  // ~68 KB: 3 CTAs/SM
+constexpr int TMEM_COLS = 128;
 
 // MN-major operand tile with 128-byte swizzle: 64 contiguous MN elements (128 B) per K row, 8-row groups 1024 B apart
 // (the layout the attention kernel of trunk.cu uses for V).
@@ -49,16 +54,6 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
-}
-
-__device__ __forceinline__ void ld8(float (&x)[8], const float* ptr, bool two) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(ptr));
-  const float4 b = two ? __ldg(reinterpret_cast<const float4*>(ptr) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-  x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
-}
-__device__ __forceinline__ void st8(float* ptr, const float (&x)[8], bool two) {
-  *reinterpret_cast<float4*>(ptr) = make_float4(x[0], x[1], x[2], x[3]);
-  if (two) *(reinterpret_cast<float4*>(ptr) + 1) = make_float4(x[4], x[5], x[6], x[7]);
 }
 
 struct BwdTcParams {
@@ -83,13 +78,13 @@ struct BwdTcParams {
   float* ddocs;
 };
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 3)
 loss_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_x,
                    const BwdTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (PIPE_BYTES > TILE_BYTES ? PIPE_BYTES : TILE_BYTES));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* done_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done_bar + 1);
@@ -156,60 +151,96 @@ loss_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
   __syncwarp();
 
-  // ---- epilogue: a thread = one output row; 8 chunks of 32 columns
+  // ---- epilogue.  Phase 1: TMEM -> shared memory (the pipeline stages are free: every MMA has completed), a thread
+  //      = one accumulator row.  Phase 2: all 128 threads walk (row, 4 columns) items so that a warp touches 512
+  //      contiguous bytes of ONE row of q / negs / dq / dnegs / ddocs per instruction, four items in flight.
   mbar_wait(done_bar, 0);
   tcgen05_fence_after();
   __syncwarp();
-  const int row = m0 + static_cast<int>(warp * 32u + lane);
-  const bool row_ok = row < p.rows;
+  float* tile = reinterpret_cast<float*>(smem);
+  {
+    const uint32_t my_row = warp * 32u + lane;
+    for (int c0 = 0; c0 < TV; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((warp * 32u) << 16) + static_cast<uint32_t>(c0), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(tile + my_row * TILE_LD + c0 + j) =
+            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                        __uint_as_float(r[j + 3]));
+    }
+  }
+  __syncthreads();
+  const int rows_valid = min(TM, p.rows - m0);
   const float gl = __ldg(p.g_loss);
   const int V = p.V;
-  float f_local = 0.f;
-  if (p.mode == 1 && row_ok && row >= p.label_offset && row < p.label_offset + p.Bq) f_local = p.cd;
-
-  for (int c0 = 0; c0 < TV; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(tmem_base + ((warp * 32u) << 16) + static_cast<uint32_t>(c0), r);  // warp-collective
-    tmem_ld_wait();
-    const int vc = v0 + c0;
-    if (!row_ok || vc >= V) continue;
-    const size_t orow = static_cast<size_t>(row) * V;
-    // 8 columns (one 32-byte sector of every fp32 row touched) per step; V % 4 == 0, so a step is 1 or 2 float4 groups
+  constexpr int C4 = TV / 4;
+  const int n_items = rows_valid * C4;
+  for (int it0 = static_cast<int>(threadIdx.x); it0 < n_items; it0 += 128 * 4) {
+    if (p.mode == 0) {
+      float4 acc[4], qv[4], mq[4], mn[4];
+      int rr[4], vv[4];
+      bool ok[4];
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      const int v = vc + j;
-      if (v >= V) break;
-      const bool two = v + 4 < V;
-      float a[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] = __uint_as_float(r[j + e]);
-      if (p.mode == 0) {
-        float mq[8], mn[8], qv[8];
-        ld8(mq, p.cm_q + v, two);
-        ld8(mn, p.cm_n + v, two);
-        ld8(qv, p.q + orow + v, two);
-        for (int kk = 0; kk < p.k; ++kk) {
-          const float gh = __ldg(&p.g_hard[static_cast<size_t>(row) * p.k + kk]);
-          const size_t on = (static_cast<size_t>(row) * p.k + kk) * V + v;
-          float nv[8], o[8];
-          ld8(nv, p.negs + on, two);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            a[e] = fmaf(gh, nv[e], a[e]);
-            o[e] = gl * (gh * qv[e] + p.cn * mn[e]);
-          }
-          st8(p.dnegs + on, o, two);
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * 128;
+        rr[u] = it / C4;
+        vv[u] = v0 + (it - rr[u] * C4) * 4;
+        ok[u] = it < n_items && vv[u] < V;
+        if (ok[u]) {
+          acc[u] = *reinterpret_cast<const float4*>(tile + rr[u] * TILE_LD + (vv[u] - v0));
+          qv[u] = __ldg(reinterpret_cast<const float4*>(p.q + static_cast<size_t>(m0 + rr[u]) * V + vv[u]));
+          mq[u] = __ldg(reinterpret_cast<const float4*>(p.cm_q + vv[u]));
+          mn[u] = __ldg(reinterpret_cast<const float4*>(p.cm_n + vv[u]));
         }
-        float o[8];
+      }
+      for (int kk = 0; kk < p.k; ++kk) {
+        float4 nv[4];
+        float gh[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = gl * (a[e] + p.cq * mq[e]);
-        st8(p.dq + orow + v, o, two);
-      } else {
-        float md[8], o[8];
-        ld8(md, p.cm_d + v, two);
+        for (int u = 0; u < 4; ++u) {
+          if (ok[u]) {
+            const size_t rk = static_cast<size_t>(m0 + rr[u]) * p.k + kk;
+            gh[u] = __ldg(&p.g_hard[rk]);
+            nv[u] = __ldg(reinterpret_cast<const float4*>(p.negs + rk * V + vv[u]));
+          }
+        }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = gl * (a[e] + f_local * md[e]);
-        st8(p.ddocs + orow + v, o, two);
+        for (int u = 0; u < 4; ++u) {
+          if (ok[u]) {
+            const size_t rk = static_cast<size_t>(m0 + rr[u]) * p.k + kk;
+            acc[u].x = fmaf(gh[u], nv[u].x, acc[u].x);
+            acc[u].y = fmaf(gh[u], nv[u].y, acc[u].y);
+            acc[u].z = fmaf(gh[u], nv[u].z, acc[u].z);
+            acc[u].w = fmaf(gh[u], nv[u].w, acc[u].w);
+            *reinterpret_cast<float4*>(p.dnegs + rk * V + vv[u]) =
+                make_float4(gl * (gh[u] * qv[u].x + p.cn * mn[u].x), gl * (gh[u] * qv[u].y + p.cn * mn[u].y),
+                            gl * (gh[u] * qv[u].z + p.cn * mn[u].z), gl * (gh[u] * qv[u].w + p.cn * mn[u].w));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ok[u])
+          *reinterpret_cast<float4*>(p.dq + static_cast<size_t>(m0 + rr[u]) * V + vv[u]) =
+              make_float4(gl * (acc[u].x + p.cq * mq[u].x), gl * (acc[u].y + p.cq * mq[u].y),
+                          gl * (acc[u].z + p.cq * mq[u].z), gl * (acc[u].w + p.cq * mq[u].w));
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u * 128;
+        const int r_ = it / C4;
+        const int v = v0 + (it - r_ * C4) * 4;
+        if (it < n_items && v < V) {
+          const int row = m0 + r_;
+          const float f = (row >= p.label_offset && row < p.label_offset + p.Bq) ? p.cd : 0.f;
+          const float4 a = *reinterpret_cast<const float4*>(tile + r_ * TILE_LD + (v - v0));
+          const float4 md = __ldg(reinterpret_cast<const float4*>(p.cm_d + v));
+          *reinterpret_cast<float4*>(p.ddocs + static_cast<size_t>(row) * V + v) =
+              make_float4(gl * (a.x + f * md.x), gl * (a.y + f * md.y), gl * (a.z + f * md.z), gl * (a.w + f * md.w));
+        }
       }
     }
   }

@@ -185,7 +185,10 @@ struct BwdParams {
   const float* cm_d;      // [V]
   float cd;
   float* ddocs;           // [Bq,V]
+  int round_bf16;         // autocast mode: G and q enter the product rounded to bf16 (what splade_loss_bwd_tc multiplies)
 };
+
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 __global__ void __launch_bounds__(256) peer_bwd_sync_kernel(const BwdParams p) {
   const int s = blockIdx.x;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(256) peer_bwd_sync_kernel(const BwdParams p) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int e = base + u * 256 + static_cast<int>(threadIdx.x);
-      if (e < Bq * Bq) out[e] = gls * v[u];
+      if (e < Bq * Bq) out[e] = gls * (p.round_bf16 ? bf16r(v[u]) : v[u]);
     }
   }
 }
@@ -315,6 +318,10 @@ __global__ void __launch_bounds__(128) peer_ddocs_kernel(const BwdParams p) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)  // rows past the batch were not loaded: never touch their (stale) bytes
         x[u] = (live && i0 + h + u < Bq) ? *reinterpret_cast<const float2*>(xs + (h + u) * PCOLS) : make_float2(0.f, 0.f);
+      if (p.round_bf16) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = make_float2(bf16r(x[u].x), bf16r(x[u].y));
+      }
 #pragma unroll
       for (int jj = 0; jj < PD; ++jj) {
         const float4 g = *reinterpret_cast<const float4*>(&Gt[jj][h]);
@@ -380,7 +387,8 @@ size_t peer_window_bytes(int Bq, int V, int world) {
 
 size_t peer_loss_bwd_workspace_bytes(int Bq, int world) {
   if (Bq < 1 || world < 1) return 0;
-  return al256(static_cast<size_t>(world) * Bq * Bq * sizeof(float));
+  // [gloc: world * Bq * Bq fp32 | scratch of the tensor-core dq (bf16 G)]
+  return al256(static_cast<size_t>(world) * Bq * Bq * sizeof(float)) + loss_bwd_tc_workspace_bytes(Bq, world * Bq);
 }
 
 }  // namespace splade
@@ -525,8 +533,8 @@ int splade_peer_v33_loss_fwd(const splade_v33_fwd_args* args, const splade_peer_
 int splade_peer_loss_bwd(const splade_peer_group* group, uint32_t epoch, const float* q, const float* docs_all,
                          const float* negs, int Bq, int k, int V, const float* g_hard, const float* colmean_q,
                          const float* colmean_d, const float* colmean_n, float cq, float cd, float cn,
-                         const float* g_loss, float* dq, float* ddocs_local, float* dnegs, void* workspace,
-                         size_t ws_bytes, void* stream_) {
+                         const float* g_loss, float* dq, float* ddocs_local, float* dnegs, const void* q16,
+                         const void* d16_all, void* workspace, size_t ws_bytes, void* stream_) {
   const char* who = "splade_peer_loss_bwd";
   int rc = check_group(group, who);
   if (rc != kOk) return rc;
@@ -547,7 +555,8 @@ int splade_peer_loss_bwd(const splade_peer_group* group, uint32_t epoch, const f
   {
     auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
     if (!aligned16(q) || !aligned16(docs_all) || !aligned16(negs) || !aligned16(dq) || !aligned16(dnegs) ||
-        !aligned16(colmean_q) || !aligned16(colmean_n) || !aligned16(colmean_d) || !aligned16(ddocs_local))
+        !aligned16(colmean_q) || !aligned16(colmean_n) || !aligned16(colmean_d) || !aligned16(ddocs_local) ||
+        !aligned16(q16) || !aligned16(d16_all))
       return set_error(kErrUnsupportedShape, "%s: 16-byte aligned rows are required", who);
   }
   rc = require_sm100(who);
@@ -558,8 +567,16 @@ int splade_peer_loss_bwd(const splade_peer_group* group, uint32_t epoch, const f
   uint8_t* mine = static_cast<uint8_t*>(group->window[group->rank]);
 
   SPLADE_CUDA_OK(cudaMemcpyAsync(mine + L.gl[b], g_loss, sizeof(float), cudaMemcpyDeviceToDevice, stream));
-  rc = loss_bwd_dq_launch(q, docs_all, negs, Bq, W * Bq, k, V, reinterpret_cast<const float*>(mine + L.g[b]), g_hard,
-                          colmean_q, colmean_n, cq, cn, g_loss, dq, dnegs, stream);
+  const float* g_win = reinterpret_cast<const float*>(mine + L.g[b]);
+  if (q16 && d16_all) {  // autocast mode: dq = G D on tcgen05, on the bf16 operands the forward packed
+    uint8_t* tc_ws = static_cast<uint8_t*>(workspace) + al256(static_cast<size_t>(W) * Bq * Bq * sizeof(float));
+    rc = loss_bwd_tc_launch(q, negs, q16, d16_all, Bq, W * Bq, k, V, group->rank * Bq, g_win, g_hard, colmean_q,
+                            nullptr, colmean_n, cq, 0.f, cn, g_loss, dq, /*ddocs=*/nullptr, dnegs, tc_ws,
+                            loss_bwd_tc_workspace_bytes(Bq, W * Bq), stream);
+  } else {
+    rc = loss_bwd_dq_launch(q, docs_all, negs, Bq, W * Bq, k, V, g_win, g_hard, colmean_q, colmean_n, cq, cn, g_loss,
+                            dq, dnegs, stream);
+  }
   if (rc != kOk) return rc;
 
   BwdParams p{};
@@ -575,6 +592,7 @@ int splade_peer_loss_bwd(const splade_peer_group* group, uint32_t epoch, const f
   p.cm_d = colmean_d;
   p.cd = cd;
   p.ddocs = ddocs_local;
+  p.round_bf16 = (q16 && d16_all) ? 1 : 0;
   peer_bwd_sync_kernel<<<W, 256, 0, stream>>>(p);
   // (the kernel's dynamic shared memory limit is raised once per device in splade_peer_alloc)
   const unsigned cx = static_cast<unsigned>((V + PCOLS - 1) / PCOLS);

@@ -574,6 +574,13 @@ def splade_head(hidden, weight, bias, attention_mask, want_token_weights: bool =
 # ------------------------------------------------------------------------------------------------
 # autograd: SPLADELossV33 on the pooled vectors
 # ------------------------------------------------------------------------------------------------
+def _loss_bwd_tc_wanted(n_docs: int) -> bool:
+    """Autocast mode: run the backward's two products on tcgen05 (splade_loss_bwd_tc)?  On by default
+    (profiles/r02_time_loss.log: 43 vs 59 us at N = 64 in-batch documents, 82 vs 236 us at N = 512);
+    SPLADE_B200_LOSS_BWD_TC=0 keeps the fp32 CUDA-core kernels."""
+    return os.environ.get("SPLADE_B200_LOSS_BWD_TC", "1") != "0"
+
+
 class V33LossFunction(torch.autograd.Function):
     """total loss + packed scalars from (anchor [Bq,V], docs [N,V], negatives [Bq,k,V]).
 
@@ -620,7 +627,7 @@ class V33LossFunction(torch.autograd.Function):
             # autocast mode: the forward leaves the bf16 operands of the score GEMM in its workspace; the backward's
             # two products run on them with tcgen05 (splade_loss_bwd_tc), so the workspace stays alive until then
             ctx.tc = None
-            if round_bf16 and V % 4 == 0 and os.environ.get("SPLADE_B200_LOSS_BWD_TC", "1") != "0":
+            if round_bf16 and V % 4 == 0 and _loss_bwd_tc_wanted(N):
                 q16, d16, vp = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int(0)
                 check(lib.splade_v33_loss_fwd_operands(ctypes.byref(args), ctypes.byref(q16), ctypes.byref(d16),
                                                        ctypes.byref(vp)), "splade_v33_loss_fwd_operands")
@@ -705,6 +712,12 @@ class V33PeerLossFunction(torch.autograd.Function):
                 g_hard=g_hard.data_ptr(), workspace=ws_ptr, ws_bytes=nbytes)
             check(lib.splade_peer_v33_loss_fwd(ctypes.byref(args), ctypes.byref(exchange.group_struct), epoch,
                                                docs_all.data_ptr(), _stream(q)), "splade_peer_v33_loss_fwd")
+            ctx.tc = None
+            if round_bf16 and _loss_bwd_tc_wanted(W * Bq):
+                q16, d16, vp = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int(0)
+                check(lib.splade_v33_loss_fwd_operands(ctypes.byref(args), ctypes.byref(q16), ctypes.byref(d16),
+                                                       ctypes.byref(vp)), "splade_v33_loss_fwd_operands")
+                ctx.tc = (ws, q16.value, d16.value)  # the forward workspace (bf16 operands) lives until the backward
         ctx.save_for_backward(q, docs_all, n, g_hard, colmean)
         ctx.exchange, ctx.epoch = exchange, epoch
         ctx.meta = (Bq, k, V, cfg["lambda_q"], cfg["lambda_d"], cfg["lambda_neg"],
@@ -731,6 +744,8 @@ class V33PeerLossFunction(torch.autograd.Function):
                                            docs_all.data_ptr(), n.data_ptr(), Bq, k, V, g_hard.data_ptr(),
                                            colmean[0].data_ptr(), colmean[1].data_ptr(), colmean[2].data_ptr(),
                                            2.0 * lq / Bq, 2.0 * ld / Bq, 2.0 * ln / (Bq * k), gl.data_ptr(),
-                                           dq.data_ptr(), ddocs.data_ptr(), dnegs.data_ptr(), ws_ptr, nbytes,
+                                           dq.data_ptr(), ddocs.data_ptr(), dnegs.data_ptr(),
+                                           None if ctx.tc is None else ctx.tc[1],
+                                           None if ctx.tc is None else ctx.tc[2], ws_ptr, nbytes,
                                            _stream(q)), "splade_peer_loss_bwd")
         return dq.to(qd), ddocs.to(dd), dnegs.view(nshape).to(nd), None, None, None, None

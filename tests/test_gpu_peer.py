@@ -98,7 +98,9 @@ def test_peer_exchange_matches_concatenation(cuda_device, W, Bq, V, k, autocast)
                 q, p, n = leaves[r]
                 torch.testing.assert_close(q.grad, dq[r], rtol=1e-5, atol=1e-8)
                 torch.testing.assert_close(n.grad, dn[r], rtol=1e-5, atol=1e-8)
-                torch.testing.assert_close(p.grad, dp_sum[sl], rtol=2e-5, atol=1e-7)
+                # autocast: both statements multiply the SAME bf16-rounded G and q (tcgen05 in the concatenation
+                # path, fp32 FMAs on rounded operands in the pull-GEMM) - they differ by fp32 summation order only
+                torch.testing.assert_close(p.grad, dp_sum[sl], rtol=1e-4 if autocast else 2e-5, atol=1e-7)
     finally:
         for x in xs:
             x.close()
