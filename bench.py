@@ -116,10 +116,11 @@ class ClockSampler:
         if self.thread is not None:
             self.thread.join(timeout=2)
 
-    def summary(self, t0: float, t1: float):
+    def summary(self, windows):
+        """`windows` = [(t0, t1), ...] of time.perf_counter() stamps: the timed regions."""
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
-        win = [s for s in self.samples if t0 <= s[0] <= t1]
+        win = [s for s in self.samples if any(t0 <= s[0] <= t1 for t0, t1 in windows)]
         note = "sampled inside the timed regions"
         if len(win) < 3:
             win = self.samples
@@ -289,10 +290,13 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
     gc.collect()
     gc.disable()   # no collector pause inside the timed region (a step is ~3 ms)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     e0.record()
+    marks[0].record()
     try:
         for i in range(steps):
             d = step(i)
+            marks[i + 1].record()
     finally:
         gc.enable()
     e1.record()
@@ -310,9 +314,11 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
         ms = float(t.item())
     if exchange_failed:
         raise RuntimeError("a peer-exchange barrier timed out inside the timed region; the training leg is invalid")
+    per_step = sorted(round(marks[j].elapsed_time(marks[j + 1]), 3) for j in range(steps))
     tokens = world * Bq * (64 + SEQ + SEQ * k_neg) * steps
     head_flop = 2.0 * HIDDEN * VOCAB * Bq * (64 + SEQ + SEQ * k_neg)
     return {"tokens_per_s": tokens / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
+            "ms_step_rank0_min_median_max": [per_step[0], per_step[len(per_step) // 2], per_step[-1]],
             "workload": f"C4 hot path per GPU: head fwd+bwd for q 64x64 / pos 64x256 / neg {64 * k_neg}x256 + "
                         f"SPLADELossV33 fwd+bwd (k={k_neg}, gather_negatives={gather}) + all-reduce of the tied "
                         f"decoder matrix ({'bf16-compressed' if grad_bf16 else 'fp32'}) and bias grads; trunk excluded",
@@ -532,14 +538,15 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
     from splade_b200.training import (StepConfig, enable_bf16_gradient_compression, synthetic_triplet_batch,
                                       train_micro_step)
     B = B_DOCS
-    n_micro = accum * (1 + opt_steps)
+    warm = 2 * accum          # two optimizer steps of warm-up: DDP rebuilds its buckets after the first synchronised backward
+    n_micro = warm + accum * opt_steps
     batches = [synthetic_triplet_batch(B, 64, SEQ, 1, VOCAB, VOCAB - 1, seed=1000 * (42 + rank) + i, ragged=False)
                for i in range(n_micro)]
     tokens_per_micro = world * B * (64 + SEQ + SEQ)
     out = {"workload": "C4 full training step per GPU: q 64x64 / pos 64x256 / neg 64x256 tokens, A.X-Encoder-base "
                        "shape (22L, 149 M params, transformers trunk with autograd) + 3 head calls + SPLADELossV33 + "
                        f"clip + AdamW, gradient accumulation {accum}, autocast(bf16), DDP when n_gpus > 1",
-           "n_gpus": world, "accum": accum, "micro_steps_timed": accum * opt_steps,
+           "n_gpus": world, "accum": accum, "micro_steps_timed": accum * opt_steps, "micro_steps_warmup": 2 * accum,
            "tokens_per_micro_step": tokens_per_micro, "scaling": "weak"}
     base = build_axbase_model(bias_offset=-2.0)
     sched = splade_b200.SPLADELossV33()
@@ -560,7 +567,7 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
         scfg = StepConfig(gradient_accumulation_steps=accum, skip_allreduce_on_accumulation=no_sync)
         gs, d = 20000, {}
         torch.cuda.reset_peak_memory_stats(dev)
-        for i in range(accum):  # one full optimizer step of warm-up
+        for i in range(warm):
             loss, d, gs = train_micro_step(model, loss_fn, opt, None, batches[i], i, gs, scfg, dev)
         if world > 1:
             dist.barrier()
@@ -570,21 +577,21 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
         gc.collect()
         gc.disable()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_micro - accum + 1)]
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_micro - warm + 1)]
         e0.record()
         marks[0].record()
         try:
-            for i in range(accum, n_micro):
+            for i in range(warm, n_micro):
                 loss, d, gs = train_micro_step(model, loss_fn, opt, None, batches[i], i, gs, scfg, dev)
-                marks[i - accum + 1].record()
+                marks[i - warm + 1].record()
         finally:
             gc.enable()
         e1.record()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / (n_micro - accum)
-        per_step = [round(marks[j].elapsed_time(marks[j + 1]), 2) for j in range(n_micro - accum)]
+        ms = e0.elapsed_time(e1) / (n_micro - warm)
+        per_step = [round(marks[j].elapsed_time(marks[j + 1]), 2) for j in range(n_micro - warm)]
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -652,15 +659,21 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
             coll[label] = {"bytes": sz, "ms": ms, "busbw_GBps": sz * 2 * (world - 1) / world / ms / 1e6}
         out["collectives_timed_alone"] = coll
         a, b = out.get("reference_semantics", {}), out.get("no_sync", {})
-        if "ms_per_micro_step" in a and "ms_per_micro_step" in b:
-            out["limiting_collective"] = (
-                f"DDP bucketed all-reduce of all gradients ({nbytes / 1e6:.0f} MB fp32 per micro-step, NCCL over "
-                f"NVLink): {coll['all_gradients_fp32']['ms']:.2f} ms alone; exposed per micro-step = "
-                f"{(a['ms_per_micro_step'] - b['ms_per_micro_step']) * accum / (accum - 1):.2f} ms "
-                f"((reference_semantics - no_sync) x {accum}/{accum - 1}: no_sync still pays it on 1 of {accum} "
-                f"micro-steps); the tied decoder matrix is the LAST gradient of a backward pass (its last producer is "
-                f"the embedding lookup), so its bucket's all-reduce "
-                f"({coll['tied_decoder_matrix_fp32']['ms']:.2f} ms alone) is never overlapped")
+        if "ms_each_micro_step_rank0" in a and "ms_each_micro_step_rank0" in b:
+            # micro-steps that do not end an accumulation window: with no_sync they issue no collective at all
+            inner = [j for j in range(accum * opt_steps) if (j + 1) % accum != 0]
+            mean = lambda xs, idx: sum(xs[j] for j in idx) / len(idx)  # noqa: E731
+            exposed = mean(a["ms_each_micro_step_rank0"], inner) - mean(b["ms_each_micro_step_rank0"], inner)
+            out["limiting_collective"] = {
+                "name": f"DDP's bucketed all-reduce of every gradient: {nbytes / 1e6:.0f} MB fp32 per micro-step, NCCL "
+                        f"ring/NVLS over NVLink, {world} ranks",
+                "ms_timed_alone": coll["all_gradients_fp32"]["ms"],
+                "exposed_ms_per_micro_step": exposed,
+                "how": "mean over the micro-steps that do not end an accumulation window of (reference_semantics - "
+                       "no_sync), rank 0 CUDA events: with no_sync those micro-steps issue no collective",
+                "note": "the tied decoder / embedding matrix is the LAST gradient of a backward pass (its last producer "
+                        f"is the embedding lookup), so its bucket's all-reduce ({coll['tied_decoder_matrix_fp32']['ms']:.2f} "
+                        "ms alone) can never overlap the backward; everything before it overlaps the 22-layer trunk"}
     a, r = out.get("reference_semantics", {}), out.get("reference_statement", {})
     if "ms_per_micro_step" in a and "ms_per_micro_step" in r:
         out["speedup_vs_reference_statement"] = r["ms_per_micro_step"] / a["ms_per_micro_step"]
@@ -807,7 +820,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    t_load3 = time.perf_counter()
+    clock_windows = [(t_load0, t_load1), (t_load2, time.perf_counter())]
     e2e_value = world * B_DOCS * n_e2e / e2e_s
     h2d_bytes = host_in[0].numel() * 2 + host_mask.numel() * 4
     d2h_bytes = host_out[0].numel() * 4
@@ -827,12 +840,16 @@ def run_ours(args):
     if not args.no_full_model:
         try:
             model = build_axbase_model().to(dev).eval()
+            t_a = time.perf_counter()
             e2e = run_e2e_encode_leg(dev, model, K, Wm, world, barrier, max_over_ranks, native_trunk=True)
             e2e_hf = run_e2e_encode_leg(dev, model, max(3, min(K, 20)), 2, world, barrier, max_over_ranks,
                                         native_trunk=False)
+            clock_windows.append((t_a, time.perf_counter()))
         except Exception as e:  # noqa: BLE001 - never lose the headline line; every rank fails alike (same code)
             e2e_err = f"{type(e).__name__}: {e}"[:300]
-    t_load3 = time.perf_counter()
+    # the clock / throttle samples cover the headline and the e2e regions (clock_windows); the NVML polling thread
+    # (one per rank, every 10 ms) stops here so that it cannot perturb the host-bound training legs below
+    sampler.stop()
 
     train = None
     if not args.no_train:
@@ -912,8 +929,7 @@ def run_ours(args):
         except Exception as e:  # context only: never fail the bench line over it
             full = {"error": repr(e)[:200]}
 
-    sampler.stop()
-    clocks = sampler.summary(t_load0, t_load3)
+    clocks = sampler.summary(clock_windows)
 
     if rank != 0:
         if world > 1:

@@ -435,9 +435,9 @@ dhidden_row_kernel(const __grid_constant__ Segs p, const uint16_t* __restrict__ 
   const long long lg = grp - sg.row0;
   const int b = static_cast<int>(lg / gps);
   const int s = static_cast<int>(lg - static_cast<long long>(b) * gps) * kRowsPerWarp + (threadIdx.x >> 5);
-  if (s >= S) return;
   const int32_t* rp = sg.row_ptr + static_cast<size_t>(b) * (S + 1);
   if (rp[S] < kDenseTermsPerPosition * S) return;  // sparse document: kernel (2a)
+  if (s >= S) return;
   const int beg = rp[s], end = rp[s + 1];
   const size_t lbase = static_cast<size_t>(b) * V;
   const int32_t* __restrict__ sorted_v = sg.sorted_v;

@@ -503,10 +503,20 @@ __global__ void __launch_bounds__(256) v33_prep_kernel(const PrepParams p) {
   }
   // documents that are not this rank's positives (gathered negatives, NCCL statement): only the bf16 operand
   if (p.pack_docs && j < p.Vp) {
-    for (int r = 0; r < p.N; ++r) {
-      if (r >= p.label_offset && r < p.label_offset + Bq) continue;
-      const float x = live ? p.docs[static_cast<size_t>(r) * V + j] : 0.f;
-      p.d16[static_cast<size_t>(r) * p.Vp + j] = __float2bfloat16_rn(x);
+    for (int r0 = 0; r0 < p.N; r0 += 8) {  // eight independent loads in flight
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u;
+        const bool other = r < p.N && !(r >= p.label_offset && r < p.label_offset + Bq);
+        x[u] = (other && live) ? p.docs[static_cast<size_t>(r) * V + j] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u;
+        if (r < p.N && !(r >= p.label_offset && r < p.label_offset + Bq))
+          p.d16[static_cast<size_t>(r) * p.Vp + j] = __float2bfloat16_rn(x[u]);
+      }
     }
   }
   const float mq = sum_q / static_cast<float>(Bq), md = sum_d / static_cast<float>(Bq);

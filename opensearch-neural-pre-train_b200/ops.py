@@ -538,6 +538,22 @@ class LazyTokenWeights(torch.Tensor):
         return func(*tree_map(unwrap, args), **tree_map(unwrap, kwargs or {}))
 
 
+_WARNED_FP32 = False
+
+
+def _warn_fp32_once() -> None:
+    """Outside autocast the reference's decoder Linear runs in fp32 (benchmark/encoders.py:309-318); the fused head
+    always multiplies bf16 operands (fp32 accumulate, logits rounded once to bf16).  Say so once."""
+    global _WARNED_FP32
+    if not _WARNED_FP32:
+        _WARNED_FP32 = True
+        import warnings
+        warnings.warn("splade_b200: the fused SPLADE head computes with bf16 operands also outside torch.autocast "
+                      "(the reference is fp32 there): weights agree within atol 1e-2 + rtol 1e-2, top-64 term sets "
+                      "overlap >= 95 %; wrap the call in torch.autocast('cuda', dtype=torch.bfloat16) to mirror the "
+                      "reference's own bf16 recipe bit for bit.", stacklevel=3)
+
+
 def lazy_token_weights_enabled() -> bool:
     return os.environ.get("SPLADE_B200_LAZY_TOKEN_WEIGHTS", "1") != "0"
 
@@ -549,6 +565,8 @@ def splade_head(hidden, weight, bias, attention_mask, want_token_weights: bool =
     _require_cuda(hidden, "hidden")
     if round_bias is None:
         round_bias = autocast_is_bf16()
+        if not round_bias and hidden.dtype == torch.float32:
+            _warn_fp32_once()
     if lazy_token_weights is None:
         lazy_token_weights = lazy_token_weights_enabled()
     h16 = hidden.detach().to(torch.bfloat16).contiguous()

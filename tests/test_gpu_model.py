@@ -46,6 +46,14 @@ def test_config1_forward_autocast_and_fp32(models, cuda_device):
         torch.testing.assert_close(rep32, r32, rtol=1e-2, atol=1e-2)
         torch.testing.assert_close(tokw32, rt32, rtol=1e-2, atol=1e-2)
         assert torch.equal(ours.encode(ids, mask), rep32)
+        # ... and what production emits from it (benchmark/encoders.py:320-343): the top-64 term sets may differ only
+        # where bf16 operand rounding reorders near-equal weights - stated threshold: mean overlap >= 0.95, and every
+        # term the fused path ranks in its top 64 is inside the reference's top 96
+        t_ours, t_ref = rep32.topk(64, dim=1).indices.tolist(), r32.topk(64, dim=1).indices.tolist()
+        t_ref96 = r32.topk(96, dim=1).indices.tolist()
+        overlap = [len(set(a) & set(b)) / 64 for a, b in zip(t_ours, t_ref)]
+        assert sum(overlap) / len(overlap) >= 0.95, overlap
+        assert all(set(a) <= set(b) for a, b in zip(t_ours, t_ref96))
 
 
 def test_gradients_reach_every_parameter_and_match(models, cuda_device):
