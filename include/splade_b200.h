@@ -152,6 +152,13 @@ int splade_head_bwd_dhidden(const splade_head_bwd_segment* seg, const void* W, i
                             void* workspace, size_t ws_bytes, void* stream);
 int splade_head_bwd_dw(const splade_head_bwd_segment* segs, const uint32_t* const* bitmaps, int n_segs, int H, int V,
                        float* dW, float* dbias, int accumulate, void* stream);
+/* The last head node of a backward pass: splade_head_bwd_dhidden for `last` and splade_head_bwd_dw over all `segs`
+ * (which include `last`) in one call; the sweep runs CONCURRENTLY with the bucket sort / dHidden kernels on a side
+ * stream forked from and joined back into `stream` (as splade_head_bwd_multi does; SPLADE_B200_BWD_CONCURRENT=0
+ * serialises them). */
+int splade_head_bwd_last(const splade_head_bwd_segment* last, const splade_head_bwd_segment* segs,
+                         const uint32_t* const* bitmaps, int n_segs, const void* W, int H, int V, uint32_t* bitmap,
+                         float* dW, float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream);
 
 /*
  * FLOPS regulariser (src/model/losses.py:57-73) and nonzero monitoring (losses.py:272-273) in one pass.

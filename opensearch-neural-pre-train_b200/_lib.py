@@ -126,6 +126,9 @@ EXPORTS = {
                                       c_int, c_void_p, c_size_t, c_void_p]),
     "splade_head_bwd_dhidden": (c_int, [POINTER(HeadBwdSegment), c_void_p, c_int, c_int, c_void_p, c_void_p,
                                         c_size_t, c_void_p]),
+    "splade_head_bwd_last": (c_int, [POINTER(HeadBwdSegment), POINTER(HeadBwdSegment), POINTER(c_void_p), c_int,
+                                     c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                     c_void_p]),
     "splade_head_bwd_dw": (c_int, [POINTER(HeadBwdSegment), POINTER(c_void_p), c_int, c_int, c_int, c_void_p,
                                    c_void_p, c_int, c_void_p]),
     "splade_flops_nnz": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -231,6 +231,13 @@ int splade_head_bwd_dhidden(const splade_head_bwd_segment* seg, const void* W, i
   return head_bwd_dhidden_launch(seg, W, H, V, bitmap, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int splade_head_bwd_last(const splade_head_bwd_segment* last, const splade_head_bwd_segment* segs,
+                         const uint32_t* const* bitmaps, int n_segs, const void* W, int H, int V, uint32_t* bitmap,
+                         float* dW, float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream) {
+  return head_bwd_last_launch(last, segs, bitmaps, n_segs, W, H, V, bitmap, dW, dbias, accumulate, workspace, ws_bytes,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int splade_head_bwd_dw(const splade_head_bwd_segment* segs, const uint32_t* const* bitmaps, int n_segs, int H, int V,
                        float* dW, float* dbias, int accumulate, void* stream) {
   return head_bwd_dw_launch(segs, bitmaps, n_segs, H, V, dW, dbias, accumulate, static_cast<cudaStream_t>(stream));

@@ -30,6 +30,8 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
 
 namespace splade {
 namespace {
@@ -618,6 +620,70 @@ size_t seg_sort_bytes(int B, int S, int V) {
          2 * align256(static_cast<size_t>(B) * V * sizeof(int32_t));
 }
 
+// The dW sweep does not depend on the bucket sort / dHidden kernels (it needs the bitmaps, g / rep / argmax and the
+// hidden rows only) and all three are chains of dependent latencies that leave most issue slots idle: they run
+// CONCURRENTLY, the sweep on a side stream forked from and joined back into the caller's stream with events.  One
+// non-blocking side stream + two events per device, created on first use (the only device-side state of the library).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  std::mutex enqueue;  // one fork / launch / join sequence at a time per device (the two events are shared)
+};
+
+int side_stream(SideStream** out) {
+  static SideStream table[64];
+  static std::mutex mu;
+  int dev = 0;
+  SPLADE_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return set_error(kErrInvalidArg, "splade_head_bwd: device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& s = table[dev];
+  if (!s.stream) {
+    SPLADE_CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    SPLADE_CUDA_OK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    SPLADE_CUDA_OK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return kOk;
+}
+
+bool concurrent_sweep_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = std::getenv("SPLADE_B200_BWD_CONCURRENT");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// dW sweep over `p_dw` on the side stream while `p_sort` is bucketed / dHidden-summed on the caller's stream.
+int launch_sort_dhidden(const Segs& p, const void* W, int H, int V, int s_max, bool any_dh, cudaStream_t stream);
+int launch_dw(const Segs& p, int H, int V, float* dW, float* dbias, int accumulate, cudaStream_t stream);
+
+int launch_concurrent(const Segs& p_sort, int s_max, bool any_dh, const Segs& p_dw, const void* W, int H, int V,
+                      float* dW, float* dbias, int accumulate, cudaStream_t stream) {
+  if (!concurrent_sweep_enabled()) {
+    int rc = launch_sort_dhidden(p_sort, W, H, V, s_max, any_dh, stream);
+    if (rc != kOk) return rc;
+    return launch_dw(p_dw, H, V, dW, dbias, accumulate, stream);
+  }
+  SideStream* side = nullptr;
+  int rc = side_stream(&side);
+  if (rc != kOk) return rc;
+  std::lock_guard<std::mutex> lock(side->enqueue);
+  SPLADE_CUDA_OK(cudaEventRecord(side->fork, stream));
+  SPLADE_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  rc = launch_dw(p_dw, H, V, dW, dbias, accumulate, side->stream);
+  if (rc == kOk) rc = launch_sort_dhidden(p_sort, W, H, V, s_max, any_dh, stream);
+  // always join: the caller's stream must not run ahead of work already forked
+  const cudaError_t e1 = cudaEventRecord(side->join, side->stream);
+  const cudaError_t e2 = cudaStreamWaitEvent(stream, side->join, 0);
+  if (rc != kOk) return rc;
+  SPLADE_CUDA_OK(e1);
+  SPLADE_CUDA_OK(e2);
+  return kOk;
+}
+
 int validate_common(const char* who, int H, int V) {
   if (V < 1 || H < 1) return set_error(kErrInvalidArg, "%s: bad sizes H=%d V=%d", who, H, V);
   if (H % 8 != 0 || H > 1024)
@@ -878,9 +944,71 @@ int head_bwd_multi_launch(const splade_head_bwd_segment* segs, int n_segs, const
     }
     return kOk;
   }
-  rc = launch_sort_dhidden(p, W, H, V, s_max, any_dh, stream);
+  return launch_concurrent(p, s_max, any_dh, p, W, H, V, dW, dbias, accumulate, stream);
+}
+
+// Autograd's last head node of a backward pass: bucket + dHidden of ITS segment (workspace / bitmap as for
+// splade_head_bwd_dhidden) concurrently with the dW sweep over ALL segments of the pass.
+int head_bwd_last_launch(const splade_head_bwd_segment* last, const splade_head_bwd_segment* segs,
+                         const uint32_t* const* bitmaps, int n_segs, const void* W, int H, int V, uint32_t* bitmap,
+                         float* dW, float* dbias, int accumulate, void* workspace, size_t ws_bytes,
+                         cudaStream_t stream) {
+  const char* who = "splade_head_bwd_last";
+  if (!last || !W || (!bitmap && !last->active) || !dW || !dbias || n_segs < 1 || n_segs > kMaxSegs || !segs ||
+      !bitmaps)
+    return set_error(kErrInvalidArg, "%s: bad argument", who);
+  int rc = validate_common(who, H, V);
   if (rc != kOk) return rc;
-  return launch_dw(p, H, V, dW, dbias, accumulate, stream);
+  rc = validate_seg(who, *last, 0, /*need_dh=*/false);
+  if (rc != kOk) return rc;
+  rc = require_sm100(who);
+  if (rc != kOk) return rc;
+  const size_t need = seg_sort_bytes(last->B, last->S, V);
+  if (!workspace || ws_bytes < need)
+    return set_error(kErrWorkspace, "%s: workspace too small (%zu < %zu bytes)", who, ws_bytes, need);
+  Segs pd{};
+  for (int i = 0; i < n_segs; ++i) {
+    rc = validate_seg(who, segs[i], i, /*need_dh=*/false);
+    if (rc != kOk) return rc;
+    if (segs[i].B > 0 && !bitmaps[i]) return set_error(kErrInvalidArg, "%s: segment %d has no bitmap", who, i);
+    Seg& s = pd.s[i];
+    s.g = segs[i].g_rep, s.rep = segs[i].rep, s.arg = segs[i].argmax;
+    s.hidden = static_cast<const uint16_t*>(segs[i].hidden);
+    s.B = segs[i].B, s.S = segs[i].S, s.bitmap = const_cast<uint32_t*>(bitmaps[i]);
+    s.doc0 = pd.total_docs, s.row0 = pd.total_rows;
+    pd.total_docs += s.B;
+    pd.total_rows += static_cast<long long>(s.B) * ((s.S + kRowsPerWarp - 1) / kRowsPerWarp);
+  }
+  pd.n = n_segs;
+  Segs ps{};
+  {
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    Seg& s = ps.s[0];
+    s.g = last->g_rep, s.rep = last->rep, s.arg = last->argmax, s.hidden = static_cast<const uint16_t*>(last->hidden);
+    s.dh = last->d_hidden, s.B = last->B, s.S = last->S, s.doc0 = 0, s.row0 = 0;
+    if (last->active) {
+      s.bitmap = const_cast<uint32_t*>(last->active);
+    } else {
+      rc = launch_rep_bitmap(last->rep, last->B, V, bitmap, stream);
+      if (rc != kOk) return rc;
+      s.bitmap = bitmap;
+    }
+    s.row_ptr = reinterpret_cast<int32_t*>(ws);
+    ws += align256(static_cast<size_t>(s.B) * (s.S + 1) * sizeof(int32_t));
+    s.sorted_v = reinterpret_cast<int32_t*>(ws);
+    ws += align256(static_cast<size_t>(s.B) * V * sizeof(int32_t));
+    s.sorted_c = reinterpret_cast<float*>(ws);
+    ps.n = 1, ps.total_docs = s.B;
+    ps.total_rows = static_cast<long long>(s.B) * ((s.S + kRowsPerWarp - 1) / kRowsPerWarp);
+  }
+  if (pd.total_docs == 0) {
+    if (!accumulate) {
+      SPLADE_CUDA_OK(cudaMemsetAsync(dW, 0, static_cast<size_t>(V) * H * sizeof(float), stream));
+      SPLADE_CUDA_OK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * sizeof(float), stream));
+    }
+    return launch_sort_dhidden(ps, W, H, V, last->S, last->d_hidden != nullptr, stream);
+  }
+  return launch_concurrent(ps, last->S, last->d_hidden != nullptr, pd, W, H, V, dW, dbias, accumulate, stream);
 }
 
 int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden,

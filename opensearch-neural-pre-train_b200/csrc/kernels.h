@@ -87,6 +87,10 @@ int head_bwd_multi_launch(const struct splade_head_bwd_segment* segs, int n_segs
                           cudaStream_t stream);
 int head_bwd_dhidden_launch(const struct splade_head_bwd_segment* seg, const void* W, int H, int V, uint32_t* bitmap,
                             void* workspace, size_t ws_bytes, cudaStream_t stream);
+int head_bwd_last_launch(const struct splade_head_bwd_segment* last, const struct splade_head_bwd_segment* segs,
+                         const uint32_t* const* bitmaps, int n_segs, const void* W, int H, int V, uint32_t* bitmap,
+                         float* dW, float* dbias, int accumulate, void* workspace, size_t ws_bytes,
+                         cudaStream_t stream);
 int head_bwd_dw_launch(const struct splade_head_bwd_segment* segs, const uint32_t* const* bitmaps, int n_segs, int H,
                        int V, float* dW, float* dbias, int accumulate, cudaStream_t stream);
 int head_bwd_launch(const float* g_rep, const float* rep, const int32_t* argmax, const void* hidden,

@@ -209,6 +209,34 @@ def head_backward_dw(segments, H: int, V: int, accumulate_into=None):
     return dW, dbias
 
 
+def head_backward_last(last, segments, weight: torch.Tensor, want_d_hidden: bool = True, accumulate_into=None):
+    """What autograd's last head node of a backward pass runs (``splade_head_bwd_last``): dHidden of ``last`` =
+    (g_rep, rep, argmax, hidden, bitmap) and the dW / dbias sweep over ``segments`` (same 5-tuples, ``last`` among
+    them), the sweep concurrently on a side stream.  -> (d_hidden | None, dW, dbias)."""
+    lib = load_library()
+    n = len(segments)
+    assert 1 <= n <= _lib.HEAD_BWD_MAX_SEGMENTS
+    g_rep, rep, argmax, hidden, bitmap = last
+    B, S, H = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    with torch.cuda.device(dev):
+        d_hidden = torch.empty((B, S, H), dtype=torch.float32, device=dev) if want_d_hidden else None
+        dW, dbias = _grad_buffers(accumulate_into, V, H, dev)
+        segs = (_lib.HeadBwdSegment * n)()
+        maps = (ctypes.c_void_p * n)()
+        for i, (g_i, rep_i, arg_i, hid_i, bm_i) in enumerate(segments):
+            segs[i] = _segment_struct(g_i, rep_i, arg_i, hid_i, None)
+            maps[i] = bm_i.data_ptr()
+        seg_last = _segment_struct(g_rep, rep, argmax, hidden, d_hidden, bitmap)
+        nbytes = lib.splade_workspace_bytes(_lib.OP_HEAD_BWD_DHIDDEN, B, S, H, V, 0)
+        ws, ws_ptr = _ws(nbytes, dev)
+        check(lib.splade_head_bwd_last(ctypes.byref(seg_last), segs, maps, n, weight.data_ptr(), H, V, None,
+                                       dW.data_ptr(), dbias.data_ptr(), int(accumulate_into is not None), ws_ptr,
+                                       nbytes, _stream(hidden)), "splade_head_bwd_last")
+    return d_hidden, dW, dbias
+
+
 def head_backward_multi(segments, weight: torch.Tensor, accumulate_into=None):
     """All phases for several head calls in three launches (``splade_head_bwd_multi``).
     ``segments`` = [(g_rep, rep, argmax, hidden[, active bitmap]), ...] -> ([d_hidden_i], dW, dbias)."""
@@ -452,20 +480,25 @@ class SpladeHeadFunction(torch.autograd.Function):
         need_h = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or (bd is not None and ctx.needs_input_grad[2])
         g32 = _f32c(g_rep)
-        d_hidden, bitmap = head_backward_dhidden(g32, rep, argmax, h16, w16, want_d_hidden=need_h,
-                                                 active=active if active.numel() else None)
-        dW = dbias = None
+        act = active if active.numel() else rep_bitmap(rep)
+        dW = dbias = d_hidden = None
+        segments = None
         if need_w:
-            segment = (g32, rep, argmax, h16, bitmap)
+            segment = (g32, rep, argmax, h16, act)
             weight = ctx.weight_ref() if ctx.weight_ref is not None else None
             segments = [segment]
             if ctx.ticket is not None and weight is not None:
                 segments = _DEFERRED_DW.arrive(weight, ctx.ticket, segment)
-            if segments is not None:
-                V, H = w16.shape
-                dW, dbias = head_backward_dw(segments, H, V)
-                dW = dW.to(wd) if ctx.needs_input_grad[1] else None
-                dbias = dbias.to(bd) if (bd is not None and ctx.needs_input_grad[2]) else None
+        if segments is None:
+            # not the last head node of this pass: its dHidden now, its share of dW with the others later
+            d_hidden, _ = head_backward_dhidden(g32, rep, argmax, h16, w16, want_d_hidden=need_h, active=act)
+        else:
+            # the last head node (or the only one): bucket + dHidden of this segment and, concurrently on a side
+            # stream, the ONE dW / dbias sweep over every segment of the pass
+            V, H = w16.shape
+            d_hidden, dW, dbias = head_backward_last((g32, rep, argmax, h16, act), segments, w16, want_d_hidden=need_h)
+            dW = dW.to(wd) if ctx.needs_input_grad[1] else None
+            dbias = dbias.to(bd) if (bd is not None and ctx.needs_input_grad[2]) else None
         return (d_hidden.to(hd) if need_h else None, dW, dbias, None, None, None, None, None)
 
 

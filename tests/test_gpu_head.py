@@ -226,6 +226,12 @@ def test_multi_segment_backward_equals_the_sum_of_single_calls(cuda_device, shap
     dh5, bm5 = splade_b200.head_backward_dhidden(g0, rep0, arg0, h0, w16, active=act0)
     assert bm5 is act0 and torch.equal(bm5, phase[-1][1]) and torch.equal(dh5, [d for d, s in zip(dhs, segs) if s[3].shape[0] > 0][-1])
 
+    # the combined entry autograd's last node uses (its dHidden + the sweep over all segments, concurrently)
+    last5 = (g0, rep0, arg0, h0, act0)
+    all5 = [(*s_, a) for s_, a in zip(live, [splade_b200.rep_bitmap(s_[1]) for s_ in live])]
+    dh6, dW6, db6 = splade_b200.ops.head_backward_last(last5, all5, w16)
+    assert torch.equal(dh6, dh5) and torch.equal(dW6, dW) and torch.equal(db6, dbias)
+
     # accumulate: adds into the caller's gradient buffers (same sweep, starting from their contents)
     base_W = torch.randn(V, H, generator=torch.Generator().manual_seed(5)).to(cuda_device)
     base_b = torch.randn(V, generator=torch.Generator().manual_seed(6)).to(cuda_device)
@@ -251,8 +257,9 @@ def test_three_head_calls_one_backward_one_dw_sweep(cuda_device, monkeypatch):
     ins = [make_head_inputs(B, S, H, V, seed=22 + i, device=cuda_device)[::3] for i, (B, S) in
            enumerate(((4, 16), (4, 48), (8, 48)))]
     sweeps = []
-    real_dw = ops.head_backward_dw
-    monkeypatch.setattr(ops, "head_backward_dw", lambda segs, *a, **k: (sweeps.append(len(segs)), real_dw(segs, *a, **k))[1])
+    real_last = ops.head_backward_last
+    monkeypatch.setattr(ops, "head_backward_last",
+                        lambda last, segs, *a, **k: (sweeps.append(len(segs)), real_last(last, segs, *a, **k))[1])
     grads = {}
     for defer in ("1", "0"):
         monkeypatch.setenv("SPLADE_B200_DEFER_DW", defer)

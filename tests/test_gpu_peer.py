@@ -27,7 +27,7 @@ def _reps(n, v, seed, density, dev):
     return x.to(dev)
 
 
-def _expected(q_all, p_all, n_all, W, Bq, k, cfg, scale):
+def _expected(q_all, p_all, n_all, W, Bq, k, cfg, scale, t_pos=None, t_neg=None):
     """Per-rank losses / scalars / dq / dnegs and the summed positive gradients from the concatenation path."""
     from splade_b200.ops import V33LossFunction
     losses, scal, dq, dn = [], [], [], []
@@ -37,7 +37,8 @@ def _expected(q_all, p_all, n_all, W, Bq, k, cfg, scale):
         q = q_all[sl].clone().requires_grad_(True)
         docs = p_all.clone().requires_grad_(True)
         n = n_all[sl].clone().requires_grad_(True)
-        loss, s = V33LossFunction.apply(q, docs, n, None, None, None, dict(cfg, label_offset=r * Bq))
+        loss, s = V33LossFunction.apply(q, docs, n, None, None if t_pos is None else t_pos[sl],
+                                        None if t_neg is None else t_neg[sl], dict(cfg, label_offset=r * Bq))
         (loss * scale[r]).backward()
         losses.append(float(loss.detach()))
         scal.append(s[:9].cpu().numpy())
@@ -47,7 +48,7 @@ def _expected(q_all, p_all, n_all, W, Bq, k, cfg, scale):
     return losses, scal, dq, dn, dp_sum
 
 
-def _run_virtual(xs, q_all, p_all, n_all, W, Bq, cfg, scale, backward=True):
+def _run_virtual(xs, q_all, p_all, n_all, W, Bq, cfg, scale, backward=True, t_pos=None, t_neg=None):
     from splade_b200.ops import V33PeerLossFunction
     cur = torch.cuda.current_stream()
     streams = [torch.cuda.Stream() for _ in range(W)]
@@ -59,7 +60,8 @@ def _run_virtual(xs, q_all, p_all, n_all, W, Bq, cfg, scale, backward=True):
             q = q_all[sl].clone().requires_grad_(True)
             p = p_all[sl].clone().requires_grad_(True)
             n = n_all[sl].clone().requires_grad_(True)
-            loss, s = V33PeerLossFunction.apply(q, p, n, None, None, cfg, xs[r])
+            loss, s = V33PeerLossFunction.apply(q, p, n, None if t_pos is None else t_pos[sl],
+                                                None if t_neg is None else t_neg[sl], cfg, xs[r])
             leaves.append((q, p, n))
             outs.append((loss, s))
     if backward:
@@ -100,6 +102,41 @@ def test_peer_exchange_matches_concatenation(cuda_device, W, Bq, V, k, autocast)
                 torch.testing.assert_close(n.grad, dn[r], rtol=1e-5, atol=1e-8)
                 # autocast: both statements multiply the SAME bf16-rounded G and q (tcgen05 in the concatenation
                 # path, fp32 FMAs on rounded operands in the pull-GEMM) - they differ by fp32 summation order only
+                torch.testing.assert_close(p.grad, dp_sum[sl], rtol=1e-4 if autocast else 2e-5, atol=1e-7)
+    finally:
+        for x in xs:
+            x.close()
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_peer_exchange_with_margin_mse_teachers(cuda_device, autocast):
+    """MarginMSE through the gathered path: the teacher term adds to gin[label] inside the exchange
+    window G, i.e. to a column the peers read - loss, loss_dict and all three gradients must equal the
+    concatenation statement."""
+    import splade_b200
+    W, Bq, V, k = 3, 8, 2048, 2
+    q_all = _reps(W * Bq, V, 41, 0.1, cuda_device)
+    p_all = _reps(W * Bq, V, 42, 0.1, cuda_device)
+    n_all = _reps(W * Bq * k, V, 43, 0.1, cuda_device).view(W * Bq, k, V)
+    g = torch.Generator().manual_seed(44)
+    t_pos = (torch.randn(W * Bq, generator=g) * 3 + 5).to(cuda_device)
+    t_neg = (torch.randn(W * Bq, k, generator=g) * 3).to(cuda_device)
+    cfg = dict(round_bf16=autocast, temperature=1.0, kd_temperature=1.0, lambda_q=1e-2, lambda_d=3e-3,
+               lambda_neg=2e-3, lambda_kd=0.0, lambda_mmse=0.7)
+    scale = [1.0 / (1 + r) for r in range(W)]
+    losses, scal, dq, dn, dp_sum = _expected(q_all, p_all, n_all, W, Bq, k, cfg, scale, t_pos, t_neg)
+    assert all(s_[6] > 0 for s_ in scal)          # the MarginMSE term is really there
+    xs = splade_b200.PeerExchange.virtual_world(Bq, V, W, cuda_device)
+    try:
+        for epoch in range(2):
+            leaves, outs = _run_virtual(xs, q_all, p_all, n_all, W, Bq, cfg, scale, t_pos=t_pos, t_neg=t_neg)
+            for r in range(W):
+                sl = slice(r * Bq, (r + 1) * Bq)
+                assert float(outs[r][0]) == pytest.approx(losses[r], rel=1e-6), (epoch, r)
+                np.testing.assert_allclose(outs[r][1][:9].cpu().numpy(), scal[r], rtol=1e-6, atol=1e-7)
+                q, p, n = leaves[r]
+                torch.testing.assert_close(q.grad, dq[r], rtol=1e-5, atol=1e-8)
+                torch.testing.assert_close(n.grad, dn[r], rtol=1e-5, atol=1e-8)
                 torch.testing.assert_close(p.grad, dp_sum[sl], rtol=1e-4 if autocast else 2e-5, atol=1e-7)
     finally:
         for x in xs:
