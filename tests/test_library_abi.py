@@ -61,7 +61,9 @@ def test_peer_exchange_sizing_and_struct():
     # header + 2 parities x (Q, P, G, gl), every region 256-byte aligned
     assert lib.splade_peer_window_bytes(B, V, W) == 512 + 2 * (2 * rep + g + 256)
     assert lib.splade_peer_window_bytes(B, V, _lib.MAX_PEERS + 1) == 0
-    assert lib.splade_workspace_bytes(_lib.OP_PEER_LOSS_BWD, B, 0, 0, 0, W) == W * B * B * 4
+    # gloc [W,B,B] fp32 + the bf16 copies of G [B, W*B] and G^T [W*B, B] the tensor-core dq works on
+    assert lib.splade_workspace_bytes(_lib.OP_PEER_LOSS_BWD, B, 0, 0, 0, W) == W * B * B * 4 + 2 * (B * W * B * 2)
+    assert lib.splade_workspace_bytes(_lib.OP_LOSS_BWD_TC, B, 0, 0, 0, W * B) == 2 * (B * W * B * 2)
     with pytest.raises(RuntimeError, match="process group"):
         splade_b200.PeerExchange(B, V)
 
