@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPLADE_B200_ABI_VERSION 4
+#define SPLADE_B200_ABI_VERSION 5
 
 /* error codes */
 #define SPLADE_OK 0
@@ -50,6 +50,7 @@ extern "C" {
 #define SPLADE_OP_HEAD_BWD_DHIDDEN 10 /* (B,S,-,V)            splade_head_bwd_dhidden scratch (one segment)   */
 #define SPLADE_OP_HEAD_BWD_BITMAP 11  /* (B,-,-,V)            bytes of one segment's activity bitmap          */
 #define SPLADE_OP_LOSS_BWD_TC 12      /* (B=Bq, k=N docs)     splade_loss_bwd_tc scratch                      */
+#define SPLADE_OP_HEAD_PROLOGUE 13    /* (B=T rows, H)        splade_head_prologue_fwd / _bwd scratch         */
 
 int splade_abi_version(void);
 const char* splade_last_error(void);
@@ -451,6 +452,32 @@ int splade_trunk_gemm(int epi, const void* A, int rows, const void* W, int N, in
 int splade_trunk_attn(void* qkv_packed, const int32_t* mask, int B, int S, int H, int n_heads, int window,
                       float rope_theta, void* out_packed, uint32_t* meta_out, void* workspace, size_t ws_bytes,
                       void* stream);
+
+/*
+ * Head prologue on the training / default path: transformers' ModernBertPredictionHead
+ * `norm(act(dense(x)))` (modeling_modernbert.py:493-502), which the reference runs between the trunk and the decoder
+ * (src/model/splade_modern.py:69-73), as the reference computes it under torch.autocast(bf16):
+ *   y = bf16(x @ dense_w^T)   g = bf16(gelu_erf(y))   hidden = bf16(LayerNorm_fp32(g) * norm_w)
+ * classifier_bias = norm_bias = false (the ModernBERT / A.X-Encoder configuration); H in {256, 512, 768, 1024}.
+ *
+ *   x       [rows_cap,H] bf16  trunk output cast to bf16 (what autocast hands F.linear); T valid rows
+ *   dense_w [H,H] bf16         head.dense.weight;   dense_w_t = its transpose (row i = input feature i)
+ *   norm_w  [H] fp32           head.norm.weight
+ *   y       [rows_cap,H] bf16  out, kept for the backward (the dense output autograd would keep)
+ *   hidden  [rows_cap,H] bf16  out, the input of splade_head_fwd
+ *   stats   [T,2] fp32         out, per-row (mean, rstd) of the LayerNorm
+ * rows_cap = rows allocated in every [rows_cap,H] buffer, >= max(T, 128) (the GEMM tiles 128 rows; rows >= T are
+ * scratch).  Backward: d_hidden [T,H] fp32 (splade_head_bwd's output) -> dy [rows_cap,H] bf16 (gradient of y),
+ * dx [rows_cap,H] bf16 (gradient of x; NULL to skip), d_norm_w [H] fp32 (deterministic two-stage sum).  The dense
+ * weight gradient dy^T x is a plain GEMM left to the caller's BLAS.
+ * Workspace: SPLADE_OP_HEAD_PROLOGUE.
+ */
+int splade_head_prologue_fwd(const void* x, const void* dense_w, const float* norm_w, float eps, int T, int rows_cap,
+                             int H, void* y, void* hidden, float* stats, void* workspace, size_t ws_bytes,
+                             void* stream);
+int splade_head_prologue_bwd(const float* d_hidden, const void* y, const float* stats, const float* norm_w,
+                             const void* dense_w_t, int T, int rows_cap, int H, void* dy, void* dx, float* d_norm_w,
+                             void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

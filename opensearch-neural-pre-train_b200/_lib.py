@@ -12,7 +12,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_siz
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libsplade_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # op ids for splade_workspace_bytes (include/splade_b200.h)
 OP_HEAD_FWD = 0
@@ -28,6 +28,7 @@ OP_PEER_LOSS_BWD = 9
 OP_HEAD_BWD_DHIDDEN = 10
 OP_HEAD_BWD_BITMAP = 11
 OP_LOSS_BWD_TC = 12
+OP_HEAD_PROLOGUE = 13
 HEAD_BWD_MAX_SEGMENTS = 8
 MAX_PEERS = 16
 
@@ -156,6 +157,10 @@ EXPORTS = {
     "splade_packed_rows": (c_size_t, [c_int, c_int]),
     "splade_trunk_gemm": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                   c_size_t, c_void_p]),
+    "splade_head_prologue_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "splade_head_prologue_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "splade_trunk_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "splade_topk": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -164,6 +164,8 @@ size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k) {
       return head_bwd_bitmap_bytes(B, V);
     case SPLADE_OP_LOSS_BWD_TC:
       return loss_bwd_tc_workspace_bytes(B, k);
+    case SPLADE_OP_HEAD_PROLOGUE:
+      return head_prologue_workspace_bytes(B, H);
     default:
       return 0;
   }
@@ -312,6 +314,24 @@ int splade_trunk_gemm(int epi, const void* A, int rows, const void* W, int N, in
   SPLADE_CUDA_OK(cudaMemcpyAsync(t_rows, &rows, sizeof(int32_t), cudaMemcpyHostToDevice, st));
   if (epi == EPI_QKV_ROPE) return set_error(kErrInvalidArg, "splade_trunk_gemm: epilogue 4 (RoPE) is internal to splade_trunk_encode");
   return trunk_gemm_launch(epi, A, rows, W, N, K, t_rows, out, ldo, nullptr, 0.f, 0, st);
+}
+
+int splade_head_prologue_fwd(const void* x, const void* dense_w, const float* norm_w, float eps, int T, int rows_cap,
+                             int H, void* y, void* hidden, float* stats, void* workspace, size_t ws_bytes,
+                             void* stream) {
+  int rc = require_sm100("splade_head_prologue_fwd");
+  if (rc != kOk) return rc;
+  return head_prologue_fwd_launch(x, rows_cap, dense_w, norm_w, eps, T, H, y, hidden, stats, workspace, ws_bytes,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int splade_head_prologue_bwd(const float* d_hidden, const void* y, const float* stats, const float* norm_w,
+                             const void* dense_w_t, int T, int rows_cap, int H, void* dy, void* dx, float* d_norm_w,
+                             void* workspace, size_t ws_bytes, void* stream) {
+  int rc = require_sm100("splade_head_prologue_bwd");
+  if (rc != kOk) return rc;
+  return head_prologue_bwd_launch(d_hidden, y, stats, norm_w, dense_w_t, rows_cap, T, H, dy, dx, d_norm_w, workspace,
+                                  ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int splade_trunk_attn(void* qkv_packed, const int32_t* mask, int B, int S, int H, int n_heads, int window,

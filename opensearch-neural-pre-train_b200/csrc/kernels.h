@@ -76,6 +76,15 @@ size_t trunk_workspace_bytes(int B, int S, int H, int I, int V);
 int trunk_encode_launch(const struct splade_trunk_args* a, cudaStream_t stream);
 size_t varlen_rows_public(int B, int S);
 
+// head_prologue.cu: ModernBertPredictionHead (dense -> GELU -> LayerNorm) forward / backward on the training path
+size_t head_prologue_workspace_bytes(int T, int H);
+int head_prologue_fwd_launch(const void* x, int rows_cap, const void* dense_w, const float* norm_w, float eps, int T,
+                             int H, void* y, void* hidden, float* stats, void* workspace, size_t ws_bytes,
+                             cudaStream_t stream);
+int head_prologue_bwd_launch(const float* d_hidden, const void* y, const float* stats, const float* norm_w,
+                             const void* dense_w_t, int rows_cap, int T, int H, void* dy, void* dx, float* d_norm_w,
+                             void* workspace, size_t ws_bytes, cudaStream_t stream);
+
 // head_bwd.cu
 size_t head_bwd_workspace_bytes(int B, int S, int V);
 size_t head_bwd_bitmap_bytes(int B, int V);

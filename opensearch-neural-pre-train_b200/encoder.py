@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 from transformers import AutoModelForMaskedLM
 
-from .ops import splade_head
+from .ops import autocast_is_bf16, head_prologue_enabled, prologue_of, splade_head
 
 
 class SPLADEModernBERT(nn.Module):
@@ -69,8 +69,17 @@ class SPLADEModernBERT(nn.Module):
         return mlm.head(outputs[0])
 
     def _forward_impl(self, input_ids, attention_mask, want_token_weights: bool):
+        mlm = self.model
+        decoder = mlm.decoder
+        # N1: under autocast(bf16) the prediction head (dense -> GELU -> LayerNorm) runs fused in front of the SPLADE
+        # head (tcgen05 GEMM + one GELU/LayerNorm pass emitting bf16; fused backward); otherwise - fp32 evaluation, a
+        # head with biases, another activation - the transformers module runs as in the reference
+        prologue = prologue_of(mlm.head) if head_prologue_enabled() and input_ids.is_cuda else None
+        if prologue is not None and autocast_is_bf16():
+            trunk_out = mlm.model(input_ids=input_ids, attention_mask=attention_mask)[0]
+            return splade_head(trunk_out, decoder.weight, decoder.bias, attention_mask,
+                               want_token_weights=want_token_weights, prologue=prologue)
         hidden = self._head_hidden(input_ids, attention_mask)
-        decoder = self.model.decoder
         return splade_head(hidden, decoder.weight, decoder.bias, attention_mask,
                            want_token_weights=want_token_weights)
 

@@ -333,6 +333,48 @@ def topk(rep: torch.Tensor, k: int, blocklist: Optional[torch.Tensor] = None):
     return ids, vals, counts
 
 
+def head_prologue_forward(x16: torch.Tensor, dense_w16: torch.Tensor, norm_w: torch.Tensor, eps: float, T: int):
+    """ModernBertPredictionHead under autocast(bf16) (``splade_head_prologue_fwd``):
+    x16 [rows_cap,H] bf16 (T valid rows, rows_cap >= max(T,128)) -> (y, hidden) bf16 [rows_cap,H], stats [T,2] fp32."""
+    lib = load_library()
+    _require_cuda(x16, "x")
+    rows_cap, H = x16.shape
+    assert x16.dtype == torch.bfloat16 and x16.is_contiguous() and rows_cap >= max(T, 128)
+    assert dense_w16.dtype == torch.bfloat16 and dense_w16.is_contiguous() and tuple(dense_w16.shape) == (H, H)
+    assert norm_w.dtype == torch.float32 and norm_w.is_contiguous() and norm_w.numel() == H
+    dev = x16.device
+    with torch.cuda.device(dev):
+        y = torch.empty((rows_cap, H), dtype=torch.bfloat16, device=dev)
+        hidden = torch.empty((rows_cap, H), dtype=torch.bfloat16, device=dev)
+        stats = torch.empty((T, 2), dtype=torch.float32, device=dev)
+        nbytes = lib.splade_workspace_bytes(_lib.OP_HEAD_PROLOGUE, T, 0, H, 0, 0)
+        ws, ws_ptr = _ws(nbytes, dev)
+        check(lib.splade_head_prologue_fwd(x16.data_ptr(), dense_w16.data_ptr(), norm_w.data_ptr(), float(eps), T,
+                                           rows_cap, H, y.data_ptr(), hidden.data_ptr(), stats.data_ptr(), ws_ptr,
+                                           nbytes, _stream(x16)), "splade_head_prologue_fwd")
+    return y, hidden, stats
+
+
+def head_prologue_backward(d_hidden: torch.Tensor, y: torch.Tensor, stats: torch.Tensor, norm_w: torch.Tensor,
+                           dense_w16_t: Optional[torch.Tensor], T: int):
+    """``splade_head_prologue_bwd``: d_hidden [T,H] fp32 -> (dy bf16 [rows_cap,H], dx bf16 [rows_cap,H] | None
+    (when ``dense_w16_t`` is None), d_norm_w [H] fp32)."""
+    lib = load_library()
+    rows_cap, H = y.shape
+    dev = y.device
+    assert d_hidden.dtype == torch.float32 and d_hidden.is_contiguous() and d_hidden.numel() == T * H
+    with torch.cuda.device(dev):
+        dy = torch.empty((rows_cap, H), dtype=torch.bfloat16, device=dev)
+        dx = torch.empty((rows_cap, H), dtype=torch.bfloat16, device=dev) if dense_w16_t is not None else None
+        d_norm_w = torch.empty((H,), dtype=torch.float32, device=dev)
+        nbytes = lib.splade_workspace_bytes(_lib.OP_HEAD_PROLOGUE, T, 0, H, 0, 0)
+        ws, ws_ptr = _ws(nbytes, dev)
+        check(lib.splade_head_prologue_bwd(d_hidden.data_ptr(), y.data_ptr(), stats.data_ptr(), norm_w.data_ptr(),
+                                           _ptr(dense_w16_t), T, rows_cap, H, dy.data_ptr(), _ptr(dx),
+                                           d_norm_w.data_ptr(), ws_ptr, nbytes, _stream(y)), "splade_head_prologue_bwd")
+    return dy, dx, d_norm_w
+
+
 # ------------------------------------------------------------------------------------------------
 # autograd: fused head
 # ------------------------------------------------------------------------------------------------
@@ -342,6 +384,7 @@ _WEIGHT_CACHE = []  # at most one entry: (weakref to the parameter, _version, da
 def clear_weight_cache() -> None:
     """Drop the cached bf16 copy (call after mutating a weight through ``.data``, which bumps no version)."""
     _WEIGHT_CACHE.clear()
+    _DENSE_CACHE.clear()
 
 
 def cached_bf16(weight: torch.Tensor) -> torch.Tensor:
@@ -365,6 +408,28 @@ def cached_bf16(weight: torch.Tensor) -> torch.Tensor:
     except TypeError:  # not weak-referenceable: do not cache
         pass
     return w
+
+
+_DENSE_CACHE = {}  # id(parameter) -> (weakref, _version, data_ptr, bf16 copy, bf16 transposed copy)
+
+
+def cached_dense_bf16(weight: torch.Tensor):
+    """(bf16 copy, bf16 transposed copy) of ``head.dense.weight`` [H,H], reused until the parameter changes; tied to
+    the parameter object like ``cached_bf16``.  The transposed copy is the K-major operand of the backward's dgrad."""
+    key = id(weight)
+    hit = _DENSE_CACHE.get(key)
+    if hit is not None:
+        ref, version, ptr, w16, w16_t = hit
+        if ref() is weight and version == weight._version and ptr == weight.data_ptr():
+            return w16, w16_t
+    w16 = weight.detach().to(torch.bfloat16).contiguous()
+    w16_t = w16.t().contiguous()
+    try:
+        _DENSE_CACHE[key] = (weakref.ref(weight, lambda _r, k=key: _DENSE_CACHE.pop(k, None)), weight._version,
+                             weight.data_ptr(), w16, w16_t)
+    except TypeError:
+        pass
+    return w16, w16_t
 
 
 class _HeadTicket:
@@ -477,29 +542,106 @@ class SpladeHeadFunction(torch.autograd.Function):
     def backward(ctx, g_rep, _g_tokw):
         rep, argmax, h16, w16, active = ctx.saved_tensors
         hd, wd, bd = ctx.in_dtypes
-        need_h = ctx.needs_input_grad[0]
-        need_w = ctx.needs_input_grad[1] or (bd is not None and ctx.needs_input_grad[2])
-        g32 = _f32c(g_rep)
-        act = active if active.numel() else rep_bitmap(rep)
-        dW = dbias = d_hidden = None
-        segments = None
-        if need_w:
-            segment = (g32, rep, argmax, h16, act)
-            weight = ctx.weight_ref() if ctx.weight_ref is not None else None
-            segments = [segment]
-            if ctx.ticket is not None and weight is not None:
-                segments = _DEFERRED_DW.arrive(weight, ctx.ticket, segment)
-        if segments is None:
-            # not the last head node of this pass: its dHidden now, its share of dW with the others later
-            d_hidden, _ = head_backward_dhidden(g32, rep, argmax, h16, w16, want_d_hidden=need_h, active=act)
-        else:
-            # the last head node (or the only one): bucket + dHidden of this segment and, concurrently on a side
-            # stream, the ONE dW / dbias sweep over every segment of the pass
-            V, H = w16.shape
-            d_hidden, dW, dbias = head_backward_last((g32, rep, argmax, h16, act), segments, w16, want_d_hidden=need_h)
-            dW = dW.to(wd) if ctx.needs_input_grad[1] else None
-            dbias = dbias.to(bd) if (bd is not None and ctx.needs_input_grad[2]) else None
-        return (d_hidden.to(hd) if need_h else None, dW, dbias, None, None, None, None, None)
+        d_hidden, dW, dbias = _head_backward_core(ctx, g_rep, rep, argmax, h16, w16, active, ctx.needs_input_grad[0],
+                                                  ctx.needs_input_grad[1], bd is not None and ctx.needs_input_grad[2])
+        return (d_hidden.to(hd) if d_hidden is not None else None, None if dW is None else dW.to(wd),
+                None if dbias is None else dbias.to(bd), None, None, None, None, None)
+
+
+def _head_backward_core(ctx, g_rep, rep, argmax, h16, w16, active, need_h: bool, need_dw: bool, need_db: bool):
+    """Shared by the head Functions: -> (d_hidden fp32 | None, dW fp32 | None, dbias fp32 | None).  dHidden of this
+    call at once; dW / dbias ONCE per backward pass, by the last head node of the pass (``_DeferredDW``)."""
+    need_w = need_dw or need_db
+    g32 = _f32c(g_rep)
+    act = active if active.numel() else rep_bitmap(rep)
+    dW = dbias = d_hidden = None
+    segments = None
+    if need_w:
+        segment = (g32, rep, argmax, h16, act)
+        weight = ctx.weight_ref() if ctx.weight_ref is not None else None
+        segments = [segment]
+        if ctx.ticket is not None and weight is not None:
+            segments = _DEFERRED_DW.arrive(weight, ctx.ticket, segment)
+    if segments is None:
+        # not the last head node of this pass: its dHidden now, its share of dW with the others later
+        d_hidden, _ = head_backward_dhidden(g32, rep, argmax, h16, w16, want_d_hidden=need_h, active=act)
+    else:
+        # the last head node (or the only one): bucket + dHidden of this segment and, concurrently on a side
+        # stream, the ONE dW / dbias sweep over every segment of the pass
+        d_hidden, dW, dbias = head_backward_last((g32, rep, argmax, h16, act), segments, w16, want_d_hidden=need_h)
+        dW = dW if need_dw else None
+        dbias = dbias if need_db else None
+    return d_hidden, dW, dbias
+
+
+def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 x bf16 library GEMM with an fp32 result (cuBLAS accumulates in fp32 either way)."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return torch.mm(a, b).to(torch.float32)
+
+
+class SpladeHeadWithPrologueFunction(torch.autograd.Function):
+    """``SpladeHeadFunction`` preceded by the trunk's prediction head, ``hidden = LayerNorm(GELU(dense(x)))``
+    (transformers modeling_modernbert.py:493-502, called at src/model/splade_modern.py:69-73), as autocast(bf16)
+    computes it: one tcgen05 GEMM + one fused GELU/LayerNorm pass emitting the bf16 head input directly (no
+    separate cast), and a fused LayerNorm/GELU backward + tcgen05 dgrad.  dHidden stays fp32 between the two
+    backward stages (the reference rounds it to bf16 there).  The dense weight gradient is one library GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, dense_w, norm_w, weight, bias, w16, b32, m32, eps: float, want_token_weights: bool):
+        B, S, H = x.shape
+        T = B * S
+        rows_cap = max(T, 128)
+        x16 = x.detach().reshape(T, H).to(torch.bfloat16)
+        if rows_cap != T:
+            pad = torch.zeros((rows_cap, H), dtype=torch.bfloat16, device=x.device)
+            pad[:T] = x16
+            x16 = pad
+        x16 = x16.contiguous()
+        dw16, dw16_t = cached_dense_bf16(dense_w)
+        gamma = _f32c(norm_w)
+        y, hidden, stats = head_prologue_forward(x16, dw16, gamma, eps, T)
+        h16 = hidden[:T].view(B, S, H)
+        rep, argmax, tokw = head_forward(h16, w16, b32, m32, want_token_weights)
+        any_grad = any(ctx.needs_input_grad[:5])
+        active = rep_bitmap(rep) if any_grad else rep.new_empty((0,), dtype=torch.int32)
+        ctx.save_for_backward(rep, argmax, h16, w16, active, x16, y, stats, gamma, dw16_t)
+        ctx.in_dtypes = (x.dtype, dense_w.dtype, norm_w.dtype, weight.dtype, None if bias is None else bias.dtype)
+        ctx.shape = (B, S, H, T)
+        ctx.weight_ref = None
+        ctx.ticket = None
+        needs_w = ctx.needs_input_grad[3] or (bias is not None and ctx.needs_input_grad[4])
+        if needs_w and _defer_dw_enabled():
+            ctx.weight_ref = weakref.ref(weight)
+            ctx.ticket = _DEFERRED_DW.open(weight, ctx)
+        if tokw is None:
+            tokw = torch.zeros((0,), dtype=torch.float32, device=x.device)
+        ctx.mark_non_differentiable(tokw, h16)
+        return rep, tokw, h16
+
+    @staticmethod
+    def backward(ctx, g_rep, _g_tokw, _g_h16):
+        rep, argmax, h16, w16, active, x16, y, stats, gamma, dw16_t = ctx.saved_tensors
+        xd, dd, nd, wd, bd = ctx.in_dtypes
+        B, S, H, T = ctx.shape
+        need_x, need_dense, need_norm = ctx.needs_input_grad[:3]
+        need_pro = need_x or need_dense or need_norm
+        d_hidden, dW, dbias = _head_backward_core(ctx, g_rep, rep, argmax, h16, w16, active, need_pro,
+                                                  ctx.needs_input_grad[3],
+                                                  bd is not None and ctx.needs_input_grad[4])
+        dx = d_dense = d_norm = None
+        if need_pro:
+            dy, dx16, d_norm = head_prologue_backward(d_hidden.view(T, H), y, stats, gamma,
+                                                      dw16_t if need_x else None, T)
+            if need_x:
+                dx = dx16[:T].view(B, S, H).to(xd)
+            if need_dense:  # dWd[o,i] = sum_t dy[t,o] x[t,i]: a plain [H,T]x[T,H] library GEMM, fp32 out
+                d_dense = _mm_f32(dy[:T].t(), x16[:T]).to(dd)
+            d_norm = d_norm.to(nd) if need_norm else None
+        return (dx, d_dense, d_norm, None if dW is None else dW.to(wd), None if dbias is None else dbias.to(bd),
+                None, None, None, None, None)
 
 
 def autocast_is_bf16() -> bool:
@@ -591,10 +733,37 @@ def lazy_token_weights_enabled() -> bool:
     return os.environ.get("SPLADE_B200_LAZY_TOKEN_WEIGHTS", "1") != "0"
 
 
+def head_prologue_enabled() -> bool:
+    return os.environ.get("SPLADE_B200_HEAD_PROLOGUE", "1") != "0"
+
+
+def prologue_of(head_module) -> Optional[tuple]:
+    """(dense.weight, norm.weight, eps) of a transformers ``ModernBertPredictionHead`` when the fused prologue can
+    stand in for it - no biases (classifier_bias = norm_bias = false), exact-erf GELU, hidden size 256..1024 in
+    steps of 256 - else None (the module itself runs, as before)."""
+    dense, norm, act = getattr(head_module, "dense", None), getattr(head_module, "norm", None), \
+        getattr(head_module, "act", None)
+    if not isinstance(dense, torch.nn.Linear) or not isinstance(norm, torch.nn.LayerNorm):
+        return None
+    if dense.bias is not None or norm.bias is not None or norm.weight is None:
+        return None
+    H = dense.in_features
+    if dense.out_features != H or H % 256 != 0 or not 256 <= H <= 1024 or tuple(norm.normalized_shape) != (H,):
+        return None
+    cfg_act = getattr(getattr(head_module, "config", None), "classifier_activation", None)
+    exact_gelu = cfg_act == "gelu" or (isinstance(act, torch.nn.GELU) and act.approximate == "none")
+    if not exact_gelu:
+        return None
+    return dense.weight, norm.weight, float(norm.eps)
+
+
 def splade_head(hidden, weight, bias, attention_mask, want_token_weights: bool = True,
-                round_bias: Optional[bool] = None, lazy_token_weights: Optional[bool] = None):
+                round_bias: Optional[bool] = None, lazy_token_weights: Optional[bool] = None,
+                prologue: Optional[tuple] = None):
     """(sparse_repr [B,V] fp32, token_weights [B,S] fp32 | None).  ``lazy_token_weights`` (default: env
-    SPLADE_B200_LAZY_TOKEN_WEIGHTS, on): token_weights is a ``LazyTokenWeights`` - computed on first use."""
+    SPLADE_B200_LAZY_TOKEN_WEIGHTS, on): token_weights is a ``LazyTokenWeights`` - computed on first use.
+    ``prologue`` = ``prologue_of(model.head)``: ``hidden`` is then the TRUNK output and the prediction head
+    (dense -> GELU -> LayerNorm) runs inside this call (bf16 autocast arithmetic; ``SpladeHeadWithPrologueFunction``)."""
     _require_cuda(hidden, "hidden")
     if round_bias is None:
         round_bias = autocast_is_bf16()
@@ -602,7 +771,6 @@ def splade_head(hidden, weight, bias, attention_mask, want_token_weights: bool =
             _warn_fp32_once()
     if lazy_token_weights is None:
         lazy_token_weights = lazy_token_weights_enabled()
-    h16 = hidden.detach().to(torch.bfloat16).contiguous()
     w16 = cached_bf16(weight)
     if bias is None:
         b32 = torch.zeros(weight.shape[0], dtype=torch.float32, device=hidden.device)
@@ -613,7 +781,13 @@ def splade_head(hidden, weight, bias, attention_mask, want_token_weights: bool =
         b32 = b32.to(torch.float32).contiguous()
     m32 = attention_mask.detach().to(torch.int32).contiguous()
     eager = want_token_weights and not lazy_token_weights
-    rep, tokw = SpladeHeadFunction.apply(hidden, weight, bias, h16, w16, b32, m32, eager)
+    if prologue is not None:
+        dense_w, norm_w, eps = prologue
+        rep, tokw, h16 = SpladeHeadWithPrologueFunction.apply(hidden, dense_w, norm_w, weight, bias, w16, b32, m32,
+                                                              eps, eager)
+    else:
+        h16 = hidden.detach().to(torch.bfloat16).contiguous()
+        rep, tokw = SpladeHeadFunction.apply(hidden, weight, bias, h16, w16, b32, m32, eager)
     if not want_token_weights:
         return rep, None
     if eager:

@@ -62,7 +62,7 @@ def test_header_is_c99_and_library_is_callable_from_c(tmp_path):
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, run.stdout + run.stderr
     lines = run.stdout.splitlines()
-    assert lines[0] == "abi=4"
+    assert lines[0] == "abi=5"
     assert int(lines[1].split("=")[1]) >= 2 * 64 * 50000 * 4
     assert int(lines[2].split("=")[1]) == 512 + 2 * (2 * 64 * 50000 * 4 + 64 * 8 * 64 * 4 + 256)
     assert lines[3] == '{"index":{"_index":"idx","_id":"d0"}}'
