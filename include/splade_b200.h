@@ -294,6 +294,13 @@ int splade_emit_json(const int32_t* ids_host, const float* vals_host, const int3
                      char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed);
 
 /*
+ * The emitters split large batches (>= 1024 documents, output buffer given) into contiguous document ranges
+ * formatted on worker threads and concatenated in order - byte-identical to one thread.  n > 0 fixes the thread
+ * count, 0 = automatic (env SPLADE_B200_EMIT_THREADS, else the host's cores, at most 16).  Returns the old value.
+ */
+int splade_emit_set_threads(int n);
+
+/*
  * HOST-side: the body of an OpenSearch `_bulk` request for B documents - per document the action line and the
  * source line that opensearch-py's helpers.bulk serialises from the reference's actions
  *   benchmark/indexer.py:112-138            {"_index", "_id", "_source": {"doc_id", "content", "sparse_embedding"}}

@@ -146,6 +146,7 @@ EXPORTS = {
     "splade_loss_bwd_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "splade_emit_set_threads": (c_int, [c_int]),
     "splade_emit_json": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                  c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
     "splade_emit_bulk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,

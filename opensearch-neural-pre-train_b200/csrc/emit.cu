@@ -9,21 +9,170 @@
 #include "../../include/splade_b200.h"
 #include "common.cuh"
 
+#include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 using namespace splade;
 
 namespace {
 
-// Bounded byte sink that keeps counting after it is full, so one pass yields either the output or its size.
+// ------------------------------------------------------------------------------------------------ numbers
+// The emitters print fp32 weights either with a fixed number of decimals (printf "%.{d}f": the AWS script's
+// round(w, 4)) or as "%.9g" (round-trips every fp32).  snprintf + strtod per term was 90 % of the emit time
+// (30 MB/s on one thread), so both formats are produced with exact integer arithmetic instead:
+//   v = m * 2^e (m < 2^24)  =>  v * 10^P = m * 5^P * 2^(e+P),   m * 5^P < 2^24 * 5^12 < 2^52   for P <= 12
+// and one right shift with round-half-even on the exact remainder gives the correctly rounded decimal digits -
+// what glibc's printf computes.  Anything outside the fast range (non-finite, negative, huge, exponent notation)
+// goes through snprintf, so the output bytes are identical to the printf formats in every case.
+const uint64_t kPow10[13] = {1ull,          10ull,          100ull,          1000ull,         10000ull,
+                             100000ull,     1000000ull,     10000000ull,     100000000ull,    1000000000ull,
+                             10000000000ull, 100000000000ull, 1000000000000ull};
+const uint64_t kPow5[13] = {1ull,      5ull,      25ull,      125ull,      625ull,       3125ull,     15625ull,
+                            78125ull,  390625ull, 1953125ull, 9765625ull,  48828125ull,  244140625ull};
+
+bool force_printf() {
+  static const bool f = [] {
+    const char* e = std::getenv("SPLADE_B200_EMIT_PRINTF");
+    return e && e[0] == '1';
+  }();
+  return f;
+}
+
+// round_half_even(v * 10^P) for a positive finite fp32 v and 0 <= P <= 12; false when it does not fit 63 bits
+inline bool scaled_round(float v, int P, uint64_t* q_out) {
+  uint32_t bits;
+  memcpy(&bits, &v, 4);
+  const uint32_t ex = (bits >> 23) & 0xFFu;
+  uint64_t m = bits & 0x7FFFFFu;
+  int e;
+  if (ex == 0) {
+    e = -149;  // subnormal
+  } else {
+    m |= 0x800000u;
+    e = static_cast<int>(ex) - 150;
+  }
+  const uint64_t N = m * kPow5[P];  // < 2^52
+  const int sh = -(e + P);          // v * 10^P = N / 2^sh
+  if (sh <= 0) {
+    if (-sh > 11) return false;     // N << (-sh) must stay below 2^63
+    *q_out = N << (-sh);
+    return true;
+  }
+  if (sh >= 64) {
+    *q_out = 0;
+    return true;
+  }
+  uint64_t q = N >> sh;
+  const uint64_t rem = N & ((1ull << sh) - 1), half = 1ull << (sh - 1);
+  if (rem > half || (rem == half && (q & 1ull))) ++q;
+  *q_out = q;
+  return true;
+}
+
+inline int put_uint(char* dst, uint64_t x) {  // decimal digits of x, returns their count
+  char tmp[24];
+  int n = 0;
+  do {
+    tmp[n++] = static_cast<char>('0' + x % 10);
+    x /= 10;
+  } while (x);
+  for (int i = 0; i < n; ++i) dst[i] = tmp[n - 1 - i];
+  return n;
+}
+
+// q with `decimals` fractional digits: "<int>.<frac zero-padded>"; strip = drop trailing zeros (and a bare '.')
+inline int put_fixed(char* dst, uint64_t q, int decimals, bool strip) {
+  const uint64_t ip = q / kPow10[decimals];
+  uint64_t fp = q % kPow10[decimals];
+  int n = put_uint(dst, ip);
+  if (decimals == 0) return n;
+  int nd = decimals;
+  if (strip) {
+    while (nd > 0 && fp % 10 == 0) {
+      fp /= 10;
+      --nd;
+    }
+    if (nd == 0) return n;
+  }
+  dst[n++] = '.';
+  for (int i = nd - 1; i >= 0; --i) {
+    dst[n + i] = static_cast<char>('0' + fp % 10);
+    fp /= 10;
+  }
+  return n + nd;
+}
+
+// printf("%.{decimals}f", v); *is_zero = the printed value is 0 (the rounded format drops such terms)
+inline int format_fixed(char* dst, size_t cap, float v, int decimals, bool* is_zero) {
+  uint64_t q;
+  if (!force_printf() && v > 0.f && v < 3.0e38f && decimals <= 9 && scaled_round(v, decimals, &q)) {
+    *is_zero = q == 0;
+    return put_fixed(dst, q, decimals, false);
+  }
+  const int m = snprintf(dst, cap, "%.*f", decimals, static_cast<double>(v));
+  *is_zero = !(strtod(dst, nullptr) > 0.0) && !(strtod(dst, nullptr) < 0.0);
+  return m;
+}
+
+// printf("%.9g", v)
+inline int format_g9(char* dst, size_t cap, float v) {
+  if (!force_printf() && v >= 1.0e-4f && v < 1.0e9f) {
+    // decimal exponent E with 10^E <= v < 10^(E+1), then 9 significant digits = round(v * 10^(8-E))
+    int E = static_cast<int>(floorf(log10f(v)));
+    if (E < -4) E = -4;
+    if (E > 8) E = 8;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      uint64_t q;
+      const int P = 8 - E;
+      if (P < 0 || P > 12 || !scaled_round(v, P, &q)) break;
+      if (q >= kPow10[9]) {  // 10^(E+1) <= v (or the rounding carried): one digit more in front
+        ++E;
+        continue;
+      }
+      if (q < kPow10[8]) {
+        --E;
+        continue;
+      }
+      if (E < -4 || E > 8) break;  // printf switches to exponent notation
+      return put_fixed(dst, q, P, true);
+    }
+  }
+  return snprintf(dst, cap, "%.9g", static_cast<double>(v));
+}
+
+// ------------------------------------------------------------------------------------------------ byte sink
+// Either a bounded caller buffer that keeps counting after it is full (one pass yields the output or its size),
+// or a growing private buffer (the worker threads of the parallel emitters).
 struct Sink {
-  char* out;
-  size_t cap;
+  char* out = nullptr;
+  size_t cap = 0;
   size_t o = 0;
   bool overflow = false;
+  bool grow = false;
+  Sink(char* out_, size_t cap_) : out(out_), cap(cap_) {}
+  explicit Sink(size_t reserve) : grow(true) {
+    cap = reserve < 4096 ? 4096 : reserve;
+    out = static_cast<char*>(malloc(cap));
+    if (!out) cap = 0, overflow = true;
+  }
+  Sink(const Sink&) = delete;
+  Sink& operator=(const Sink&) = delete;
+  ~Sink() {
+    if (grow) free(out);
+  }
   void raw(const char* s, size_t n) {
+    if (o + n > cap && grow && !overflow) {
+      size_t want = cap * 2;
+      while (want < o + n) want *= 2;
+      char* p = static_cast<char*>(realloc(out, want));
+      if (p) out = p, cap = want;
+      else overflow = true;
+    }
     if (o + n <= cap) memcpy(out + o, s, n);
     else overflow = true;
     o += n;
@@ -80,12 +229,13 @@ int emit_object(Sink& w, const int32_t* ids, const float* vals, int n, const cha
     const int32_t id = ids[j];
     int m;
     if (round_decimals >= 0) {
-      m = snprintf(num, sizeof(num), "%.*f", round_decimals, static_cast<double>(vals[j]));
       // the rounded format drops what rounds to zero: `weight = round(w, 4); if weight <= 0.0: continue`
       // (scripts/neural_sparse_search_aws.py:753-755)
-      if (strtod(num, nullptr) <= 0.0) continue;
+      bool zero;
+      m = format_fixed(num, sizeof(num), vals[j], round_decimals, &zero);
+      if (zero || vals[j] < 0.f) continue;
     } else {
-      m = snprintf(num, sizeof(num), "%.9g", static_cast<double>(vals[j]));  // round-trips every fp32
+      m = format_g9(num, sizeof(num), vals[j]);  // round-trips every fp32
     }
     if (!first) w.raw(", ", compact ? 1 : 2);
     first = false;
@@ -96,7 +246,15 @@ int emit_object(Sink& w, const int32_t* ids, const float* vals, int n, const cha
       w.json_string(token_bytes + token_offsets[id], static_cast<size_t>(token_offsets[id + 1] - token_offsets[id]));
     } else {
       char key[32];
-      const int mk = snprintf(key, sizeof(key), "\"%d\"", id);
+      int mk = 0;
+      key[mk++] = '"';
+      if (id < 0) {
+        key[mk++] = '-';
+        mk += put_uint(key + mk, static_cast<uint64_t>(-static_cast<int64_t>(id)));
+      } else {
+        mk += put_uint(key + mk, static_cast<uint64_t>(id));
+      }
+      key[mk++] = '"';
       w.raw(key, static_cast<size_t>(mk));
     }
     w.raw(": ", compact ? 1 : 2);
@@ -106,7 +264,106 @@ int emit_object(Sink& w, const int32_t* ids, const float* vals, int n, const cha
   return splade::kOk;
 }
 
+// ------------------------------------------------------------------------------------------------ threads
+std::atomic<int> g_emit_threads{0};  // 0 = automatic
+
+int emit_threads_for(int B) {
+  int t = g_emit_threads.load();
+  if (t <= 0) {
+    const char* e = std::getenv("SPLADE_B200_EMIT_THREADS");
+    t = e ? std::atoi(e) : 0;
+  }
+  if (t <= 0) {
+    t = static_cast<int>(std::thread::hardware_concurrency());
+    if (t > 16) t = 16;
+  }
+  const int by_work = B / 512;  // a thread is worth starting for a few hundred documents
+  if (t > by_work) t = by_work;
+  return t < 1 ? 1 : t;
+}
+
+// Runs doc(w, b) for b in [0,B): in the caller's sink directly, or - when the output buffer is known to be writable
+// (cap > 0) and the batch is large - over contiguous document ranges on worker threads, each into a private growing
+// buffer, concatenated in range order afterwards (byte-identical to the serial pass).
+template <typename DocFn>
+int run_documents(Sink& w, int B, int64_t* out_offsets, const DocFn& doc) {
+  const int T = (w.cap > 0) ? emit_threads_for(B) : 1;
+  if (T <= 1) {
+    for (int b = 0; b < B; ++b) {
+      out_offsets[b] = static_cast<int64_t>(w.o);
+      const int rc = doc(w, b);
+      if (rc != kOk) return rc;
+    }
+    out_offsets[B] = static_cast<int64_t>(w.o);
+    return kOk;
+  }
+  struct Part {
+    Sink* sink = nullptr;
+    int rc = kOk;
+    int b0 = 0, b1 = 0;
+  };
+  std::vector<Part> parts(static_cast<size_t>(T));
+  std::vector<std::thread> pool;
+  const size_t guess = w.cap / static_cast<size_t>(T) + 4096;
+  for (int t = 0; t < T; ++t) {
+    Part& p = parts[static_cast<size_t>(t)];
+    p.b0 = static_cast<int>(static_cast<int64_t>(B) * t / T);
+    p.b1 = static_cast<int>(static_cast<int64_t>(B) * (t + 1) / T);
+    p.sink = new Sink(guess);
+    pool.emplace_back([&p, &doc, out_offsets] {
+      for (int b = p.b0; b < p.b1; ++b) {
+        out_offsets[b] = static_cast<int64_t>(p.sink->o);  // relative to the part; rebased below
+        p.rc = doc(*p.sink, b);
+        if (p.rc != kOk) return;
+      }
+    });
+  }
+  for (auto& th : pool) th.join();
+  int rc = kOk;
+  for (int t = 0; t < T && rc == kOk; ++t) {
+    Part& p = parts[static_cast<size_t>(t)];
+    if (p.rc != kOk) rc = p.rc;  // (its message sits in the worker's thread-local slot: repeated below)
+    else if (p.sink->overflow) rc = -1;  // a private buffer could not grow
+  }
+  if (rc == kOk) {
+    // rebase the per-document offsets and copy the parts into place (in parallel: the copy is bandwidth-bound)
+    std::vector<size_t> base(static_cast<size_t>(T) + 1, w.o);
+    for (int t = 0; t < T; ++t) base[static_cast<size_t>(t) + 1] = base[static_cast<size_t>(t)] + parts[static_cast<size_t>(t)].sink->o;
+    const size_t total = base[static_cast<size_t>(T)];
+    const bool fits = total <= w.cap;
+    std::vector<std::thread> copiers;
+    for (int t = 0; t < T; ++t) {
+      Part& p = parts[static_cast<size_t>(t)];
+      const size_t off = base[static_cast<size_t>(t)];
+      copiers.emplace_back([&p, off, fits, &w, out_offsets] {
+        for (int b = p.b0; b < p.b1; ++b) out_offsets[b] += static_cast<int64_t>(off);
+        if (fits && p.sink->o) memcpy(w.out + off, p.sink->out, p.sink->o);
+      });
+    }
+    for (auto& th : copiers) th.join();
+    if (!fits) w.overflow = true;
+    w.o = total;
+    out_offsets[B] = static_cast<int64_t>(w.o);
+  }
+  for (auto& p : parts) delete p.sink;
+  if (rc == -1) return set_error(kErrWorkspace, "emit: out of host memory for the worker buffers");
+  if (rc != kOk) {
+    // a worker's set_error went to its own thread-local slot: rerun serially so the caller's thread holds the message
+    Sink probe(nullptr, 0);
+    for (int b = 0; b < B; ++b) {
+      const int r = doc(probe, b);
+      if (r != kOk) return r;
+    }
+  }
+  return rc;
+}
+
 }  // namespace
+
+extern "C" int splade_emit_set_threads(int n) {
+  const int prev = g_emit_threads.exchange(n < 0 ? 0 : n);
+  return prev;
+}
 
 extern "C" int splade_emit_json(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
                                 int k, const char* token_bytes, const int64_t* token_offsets, int n_tokens,
@@ -117,15 +374,12 @@ extern "C" int splade_emit_json(const int32_t* ids_host, const float* vals_host,
   if (B < 0 || k < 1 || round_decimals > 9)
     return set_error(kErrInvalidArg, "splade_emit_json: bad arguments B=%d k=%d decimals=%d", B, k, round_decimals);
   Sink w{out, out_cap};
-  for (int b = 0; b < B; ++b) {
-    out_offsets[b] = static_cast<int64_t>(w.o);
+  const int rc_all = run_documents(w, B, out_offsets, [&](Sink& sk, int b) {
     const int n = counts_host[b] < k ? (counts_host[b] > 0 ? counts_host[b] : 0) : k;
-    const int rc = emit_object(w, ids_host + static_cast<size_t>(b) * k, vals_host + static_cast<size_t>(b) * k, n,
-                               token_bytes, token_offsets, n_tokens, round_decimals, /*compact=*/false,
-                               "splade_emit_json");
-    if (rc != kOk) return rc;
-  }
-  out_offsets[B] = static_cast<int64_t>(w.o);
+    return emit_object(sk, ids_host + static_cast<size_t>(b) * k, vals_host + static_cast<size_t>(b) * k, n,
+                       token_bytes, token_offsets, n_tokens, round_decimals, /*compact=*/false, "splade_emit_json");
+  });
+  if (rc_all != kOk) return rc_all;
   *bytes_needed = w.o;
   if (w.overflow)
     return set_error(kErrWorkspace, "splade_emit_json: output buffer too small (%zu < %zu bytes)", out_cap, w.o);
@@ -147,42 +401,44 @@ extern "C" int splade_emit_bulk(const int32_t* ids_host, const float* vals_host,
     return set_error(kErrInvalidArg, "splade_emit_bulk: head_bytes and head_offsets go together");
   Sink w{out, out_cap};
   const size_t index_len = strlen(index_name), field_len = strlen(field_name);
-  for (int b = 0; b < B; ++b) {
-    out_offsets[b] = static_cast<int64_t>(w.o);
+  const int rc_all = run_documents(w, B, out_offsets, [&](Sink& sk, int b) -> int {
     const int n = counts_host[b] < k ? (counts_host[b] > 0 ? counts_host[b] : 0) : k;
     if (skip_empty) {  // `if not clean_vec: continue` (scripts/neural_sparse_search_aws.py:997-1001), after rounding
-      int alive = 0;
+      bool alive = false;
       char num[64];
       for (int j = 0; j < n && !alive; ++j) {
+        const float v = vals_host[static_cast<size_t>(b) * k + j];
         if (round_decimals < 0) {
-          alive = 1;
+          alive = true;
         } else {
-          snprintf(num, sizeof(num), "%.*f", round_decimals, static_cast<double>(vals_host[static_cast<size_t>(b) * k + j]));
-          alive = strtod(num, nullptr) > 0.0;
+          bool zero;
+          format_fixed(num, sizeof(num), v, round_decimals, &zero);
+          alive = !zero && v > 0.f;
         }
       }
-      if (!alive) continue;
+      if (!alive) return kOk;
     }
     // action line: what opensearch-py's helpers.bulk expands {"_index", "_id", "_source"} into
-    w.lit("{\"index\":{\"_index\":");
-    w.json_string(index_name, index_len);
-    w.lit(",\"_id\":");
-    w.json_string(id_bytes + id_offsets[b], static_cast<size_t>(id_offsets[b + 1] - id_offsets[b]));
-    w.lit("}}\n{");
+    sk.lit("{\"index\":{\"_index\":");
+    sk.json_string(index_name, index_len);
+    sk.lit(",\"_id\":");
+    sk.json_string(id_bytes + id_offsets[b], static_cast<size_t>(id_offsets[b + 1] - id_offsets[b]));
+    sk.lit("}}\n{");
     // source line: caller-serialised leading members, then the sparse field
     if (head_bytes && head_offsets[b + 1] > head_offsets[b]) {
-      w.raw(head_bytes + head_offsets[b], static_cast<size_t>(head_offsets[b + 1] - head_offsets[b]));
-      w.raw(",", 1);
+      sk.raw(head_bytes + head_offsets[b], static_cast<size_t>(head_offsets[b + 1] - head_offsets[b]));
+      sk.raw(",", 1);
     }
-    w.json_string(field_name, field_len);
-    w.raw(":", 1);
-    const int rc = emit_object(w, ids_host + static_cast<size_t>(b) * k, vals_host + static_cast<size_t>(b) * k, n,
+    sk.json_string(field_name, field_len);
+    sk.raw(":", 1);
+    const int rc = emit_object(sk, ids_host + static_cast<size_t>(b) * k, vals_host + static_cast<size_t>(b) * k, n,
                                token_bytes, token_offsets, n_tokens, round_decimals, /*compact=*/true,
                                "splade_emit_bulk");
     if (rc != kOk) return rc;
-    w.lit("}\n");
-  }
-  out_offsets[B] = static_cast<int64_t>(w.o);
+    sk.lit("}\n");
+    return kOk;
+  });
+  if (rc_all != kOk) return rc_all;
   *bytes_needed = w.o;
   if (w.overflow)
     return set_error(kErrWorkspace, "splade_emit_bulk: output buffer too small (%zu < %zu bytes)", out_cap, w.o);
@@ -224,7 +480,7 @@ extern "C" int splade_emit_search(const int32_t* ids_host, const float* vals_hos
       w.json_field_path(field_name, field_len, token_bytes + token_offsets[id],
                         static_cast<size_t>(token_offsets[id + 1] - token_offsets[id]));
       w.lit(",\"boost\":");
-      m = snprintf(num, sizeof(num), "%.9g", static_cast<double>(vals_host[static_cast<size_t>(b) * k + j]));
+      m = format_g9(num, sizeof(num), vals_host[static_cast<size_t>(b) * k + j]);
       w.raw(num, static_cast<size_t>(m));
       w.lit("}}");
     }

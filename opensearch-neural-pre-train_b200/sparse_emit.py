@@ -179,15 +179,27 @@ class SparseEmitter:
         offsets = np.zeros(B + 1, dtype=np.int64)
         need = ctypes.c_size_t(0)
         dec = -1 if round_decimals is None else int(round_decimals)
-        cap = 0  # first call sizes the buffer, second fills it
+        # capacity estimate (so the FIRST call already writes - and may use the emitter's worker threads): exact for
+        # the per-document strings, average-based for the terms; an underestimate costs one retry at the exact size
+        n_terms = np.minimum(np.maximum(counts_h, 0), k)
+        valid = np.arange(k)[None, :] < n_terms[:, None]
+        if table is not None:
+            tok_len = np.diff(table[1])
+            safe = np.clip(ids_h, 0, len(tok_len) - 1)
+            key_bytes = int(tok_len[safe][valid].sum())
+        else:
+            key_bytes = 11 * int(valid.sum())
+        per_term = 5 + (dec + 6 if dec >= 0 else 13)
+        cap = int(1.05 * (B * (40 + 2 * len(index_name.encode("utf-8")) + len(field.encode("utf-8")))
+                          + int(id_off[-1]) + (int(head_off[-1]) + B if sources is not None else 0)
+                          + key_bytes + per_term * int(valid.sum()))) + 4096
         rc = 0
         for _ in range(2):
-            out = ctypes.create_string_buffer(max(cap, 1))
+            out = np.empty(max(cap, 1), dtype=np.uint8)
             rc = lib.splade_emit_bulk(ids_h.ctypes.data, vals_h.ctypes.data, counts_h.ctypes.data, B, k, tok_ptr,
                                       off_ptr, n_tok, dec, index_name.encode("utf-8"), field.encode("utf-8"),
                                       ctypes.addressof(id_buf), id_off.ctypes.data, head_ptr, head_off_ptr,
-                                      int(skip_empty), ctypes.addressof(out) if cap else None, cap,
-                                      offsets.ctypes.data, ctypes.byref(need))
+                                      int(skip_empty), out.ctypes.data, cap, offsets.ctypes.data, ctypes.byref(need))
             if rc == 0:
                 break
             if need.value > cap:
@@ -195,7 +207,7 @@ class SparseEmitter:
                 continue
             break
         check(rc, "splade_emit_bulk")
-        return out.raw[: need.value]
+        return out[: need.value].tobytes()
 
     def to_search_bodies(self, ids: torch.Tensor, vals: torch.Tensor, counts: torch.Tensor, size: int = 10,
                          field: str = "sparse_embedding", max_clauses: int = 64,
