@@ -124,6 +124,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Non-blocking phase test (try_wait may suspend the thread for a hardware time slice; test_wait never does): for a
+// thread that polls several barriers and acts on whichever completes first.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 #ifndef SPLADE_MBAR_TIMEOUT_CYCLES
 #define SPLADE_MBAR_TIMEOUT_CYCLES 4000000000ll
@@ -139,6 +155,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
              blockIdx.x, threadIdx.x, addr, parity);
       __trap();
     }
+  }
+}
+
+// The same bounded wait without the printf (no stack frame, fewer live registers): for kernels whose register budget
+// is tight; a timeout still traps.
+__device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(addr, parity)) {
+    if (clock64() - t0 > SPLADE_MBAR_TIMEOUT_CYCLES) __trap();
   }
 }
 

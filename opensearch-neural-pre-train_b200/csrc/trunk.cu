@@ -222,6 +222,7 @@ struct AttnParams {
   int window;  // < 0: global attention; otherwise |pos_q - pos_k| <= window
   float scale;
   int skip_tc_tiles;  // mma.sync kernel: 1 = tiles the tcgen05 kernel handles are skipped
+  int debug;          // timing ablations of the pipelined tcgen05 kernel (SPLADE_B200_ATTN_DEBUG; results are WRONG)
 };
 
 // 2^x on the SFU in one instruction (fast_exp2() adds a denormal-range fix-up around it that softmax does not need)
@@ -719,6 +720,471 @@ trunk_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ attention, tcgen05,
+// persistent and software-pipelined (the default).  Same tiles and arithmetic as trunk_attn_tc_kernel above, but
+//   * ONE CTA per SM loops over its tiles: barriers, the TMEM allocation (all 512 columns) and the tensor maps are set
+//     up once; a producer warp TMA-loads the Q / K / V tiles of tile n+1 (and n+2) into a two-stage ring while tile n
+//     is in its softmax, and an MMA warp issues S(n+1) = Q K^T into the other half of TMEM as soon as they land:
+//     loads, both MMAs and the per-tile metadata reads are off the softmax warps' critical path;
+//   * two softmax groups of 256 threads (two threads per query row) alternate tiles, each with its own S buffer
+//     (256 TMEM columns), so one group's TMEM-load / barrier latencies are filled by the other's arithmetic;
+//   * P never touches shared memory: each thread packs its 32 probabilities of a chunk to bf16 pairs and stores
+//     them with tcgen05.st over S columns it has ALREADY consumed; O = P V runs as tcgen05.mma with the A operand
+//     in tensor memory (lane = query row, column j = keys 2j, 2j+1 - checked by tools/probes/tmem_a_operand.cu)
+//     and V as the MN-major B operand.  This is what frees the 64 KB of P staging for the second Q/K/V stage.
+// TMEM map of a slot (256 columns): S chunk c (32 keys) at [32c, 32c+32); the bf16 P of chunk c (16 columns) at 32c
+// for c < 6, chunk 6 at 16, chunk 7 at 48 (the consumed upper halves of chunks 0 and 1 - same thread: a thread owns
+// the even or the odd chunks of its row); O (64 columns) at 192, over chunks 6 / 7 once every thread is through.
+constexpr int TP_STAGE_BYTES = 16384 + 32768 + 32768;  // Q | K | V
+constexpr int TP_Q_OFF = 0;
+constexpr int TP_K_OFF = 16384;
+constexpr int TP_V_OFF = 49152;
+constexpr int TP_QK_BYTES = 16384 + 32768;
+constexpr int TP_V_BYTES = 32768;
+constexpr int TP_BAR_OFF = 2 * TP_STAGE_BYTES;
+constexpr int TP_KPOS_OFF = TP_BAR_OFF + 128;               // [4 sets][256] key positions
+constexpr int TP_XCHG_OFF = TP_KPOS_OFF + 4 * TA_BKV * 4;    // [2 groups][max | sum][2 halves][128]
+constexpr int TP_TILES_OFF = TP_XCHG_OFF + 2 * 2 * 2 * 128 * 4;
+constexpr int TP_MAX_TILES = 256;                            // tiles per CTA the table holds
+constexpr int TP_OST_OFF = TP_TILES_OFF + TP_MAX_TILES * 16 + 16;   // [4 sets][32 rows][128 B] output staging
+constexpr int TP_SMEM_BYTES = TP_OST_OFF + 4 * 4096 + 1024;
+constexpr int TP_THREADS = 512 + 64;
+
+// One (128 queries, head, document) tile of this CTA's list, decoded once at kernel start
+struct __align__(16) AttnTile {
+  int32_t q_row;     // first packed row of the query tile (base + q0)
+  int32_t k_row;     // first packed row of the visible keys (base + kstart)
+  int32_t rows_h;    // (valid query rows in the tile << 8) | head
+  int32_t nkeys;     // visible keys, 1..256
+};
+
+__device__ __forceinline__ uint32_t attn_p_col(int chunk) {
+  return chunk < 6 ? 32u * static_cast<uint32_t>(chunk) : (chunk == 6 ? 16u : 48u);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TP_THREADS, 1)
+trunk_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                      const AttnParams p, int n_tiles, int nqt, int n_heads) {
+  extern __shared__ uint8_t attn_tp_smem[];
+  const uint32_t raw_addr = smem_u32(attn_tp_smem);
+  uint8_t* smem = attn_tp_smem + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TP_BAR_OFF);
+  uint64_t* bar_full_qk = bars;      // [2] Q and K of the stage have landed                   (producer -> MMA)
+  uint64_t* bar_full_v = bars + 2;   // [2] V of the stage has landed                          (producer -> MMA, group)
+  uint64_t* bar_s_ready = bars + 4;  // [2] S = Q K^T is in the slot's TMEM; Q / K are dead    (MMA -> group, producer)
+  uint64_t* bar_p_ready = bars + 6;  // [2] P is in TMEM, the V tail rows are cleared          (256 threads -> MMA)
+  uint64_t* bar_o_ready = bars + 8;  // [2] O = P V done: O readable, V dead                   (MMA -> group, producer)
+  uint64_t* bar_s_free = bars + 10;  // [2] the group has read O: the slot's TMEM is reusable  (256 threads -> MMA)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  AttnTile* tiles = reinterpret_cast<AttnTile*>(smem + TP_TILES_OFF);
+  int* n_valid_smem = reinterpret_cast<int*>(smem + TP_TILES_OFF + TP_MAX_TILES * 16);
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t warp = tid >> 5;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_full_qk[s], 1);
+      mbar_init(&bar_full_v[s], 1);
+      mbar_init(&bar_s_ready[s], 1);
+      mbar_init(&bar_p_ready[s], 16);   // one arrival per softmax warp
+      mbar_init(&bar_o_ready[s], 1);
+      mbar_init(&bar_s_free[s], 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 17) tmem_alloc(tmem_ptr_smem, 512);
+  if (warp == 16) {
+    // this CTA's tile list (t = blockIdx.x, + gridDim.x, ...), invalid tiles (past a document's end, documents the
+    // mma.sync kernel handles) dropped: one warp, 32 candidates per round, order preserved
+    const uint32_t lane = tid & 31u;
+    int count = 0;
+    for (int k0 = 0; k0 < TP_MAX_TILES; k0 += 32) {
+      const int t = static_cast<int>(blockIdx.x) + (k0 + static_cast<int>(lane)) * static_cast<int>(gridDim.x);
+      bool valid = false;
+      AttnTile ti{};
+      if (t < n_tiles) {
+        const int qt = t % nqt, bh = t / nqt;
+        const int b = bh / n_heads, h = bh - b * n_heads;
+        const int q0 = qt * TA_BQ;
+        const int L = __ldg(&p.len[b]);
+        const int L8 = (L + 7) & ~7;
+        valid = L > 0 && q0 < L8 && attn_tc_eligible(L, p.window);
+        if (valid) {
+          const int base = __ldg(&p.off[b]);
+          const int kstart = p.window < 0 ? 0 : max(0, q0 - p.window);
+          const int kend = p.window < 0 ? L : min(L, q0 + TA_BQ + p.window);
+          ti.q_row = base + q0;
+          ti.k_row = base + kstart;
+          ti.rows_h = (min(TA_BQ, L8 - q0) << 8) | h;
+          ti.nkeys = kend - kstart;
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, valid);
+      if (valid) tiles[count + __popc(m & ((1u << lane) - 1u))] = ti;
+      count += __popc(m);
+      if (__all_sync(0xffffffffu, t >= n_tiles)) break;
+    }
+    if (lane == 0) *n_valid_smem = count;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  const int n_valid = *n_valid_smem;
+
+  // 18 warps: 0..15 softmax (a thread keeps its 64 scores in registers: 112 registers per thread at 576 threads),
+  // 16 producer, 17 MMA issuer
+  if (warp == 16) {
+    // ---------------------------------------------------------------- producer: Q/K two tiles ahead, V one behind them
+    if ((tid & 31u) == 0) {
+      auto load_v = [&](int m) {
+        const int s = m & 1;
+        if (m >= 2) mbar_wait_quiet(&bar_o_ready[s], static_cast<uint32_t>(((m >> 1) - 1) & 1));  // P V of tile m-2 done
+        const AttnTile ti = tiles[m];
+        if (p.debug & 16) {
+          mbar_arrive(&bar_full_v[s]);
+          return;
+        }
+        mbar_arrive_expect_tx(&bar_full_v[s], TP_V_BYTES);
+        tma_load_2d(smem + s * TP_STAGE_BYTES + TP_V_OFF, &tmap_kv, &bar_full_v[s], 2 * p.H + (ti.rows_h & 0xFF) * AT_D,
+                    ti.k_row);
+      };
+      for (int n = 0; n < n_valid; ++n) {
+        const int s = n & 1;
+        if (n >= 2) mbar_wait_quiet(&bar_s_ready[s], static_cast<uint32_t>(((n >> 1) - 1) & 1));  // Q K^T of tile n-2 done
+        const AttnTile ti = tiles[n];
+        const int hcol = (ti.rows_h & 0xFF) * AT_D;
+        uint8_t* st = smem + s * TP_STAGE_BYTES;
+        if (p.debug & 32) {
+          mbar_arrive(&bar_full_qk[s]);
+        } else {
+          mbar_arrive_expect_tx(&bar_full_qk[s], TP_QK_BYTES);
+          tma_load_2d(st + TP_Q_OFF, &tmap_q, &bar_full_qk[s], hcol, ti.q_row);
+          tma_load_2d(st + TP_K_OFF, &tmap_kv, &bar_full_qk[s], p.H + hcol, ti.k_row);
+        }
+        if (n >= 1) load_v(n - 1);
+      }
+      if (n_valid >= 1) load_v(n_valid - 1);
+    }
+  } else if (warp == 17) {
+    // ---------------------------------------------------------------- MMA issuer: whichever of S(n1) = Q K^T and
+    // O(n2) = P V (n2 < n1) has its inputs first
+    if ((tid & 31u) == 0) {
+      const uint32_t idesc_pv = make_idesc_bf16_f32(TA_BQ, AT_D) | (1u << 16);  // B (= V) is MN-major
+      int n1 = 0, n2 = 0;
+      long long t0 = clock64();
+      while (n2 < n_valid) {
+        bool progress = false;
+        if (n2 < n1) {
+          const int s = n2 & 1;
+          const uint32_t ph = static_cast<uint32_t>((n2 >> 1) & 1);
+          if (mbar_test_wait(smem_u32(&bar_p_ready[s]), ph) && mbar_test_wait(smem_u32(&bar_full_v[s]), ph)) {
+            tcgen05_fence_after();
+            const uint32_t slot = tmem + 256u * static_cast<uint32_t>(s);
+            const uint32_t v_addr = smem_u32(smem + s * TP_STAGE_BYTES + TP_V_OFF);
+            const int ksteps = (p.debug & 4) ? 1 : (tiles[n2].nkeys + 15) >> 4;
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_bf16_ts(slot + 192u, slot + 8u * static_cast<uint32_t>(ks),
+                           make_smem_desc_sw128_mn(v_addr + ks * 2048), idesc_pv, ks != 0 ? 1u : 0u);
+            umma_commit(&bar_o_ready[s]);
+            ++n2;
+            progress = true;
+          }
+        }
+        if (n1 < n_valid && n1 - n2 < 2) {
+          const int s = n1 & 1;
+          const uint32_t ph = static_cast<uint32_t>((n1 >> 1) & 1);
+          if (mbar_test_wait(smem_u32(&bar_full_qk[s]), ph) &&
+              (n1 < 2 || mbar_test_wait(smem_u32(&bar_s_free[s]), ph ^ 1u))) {
+            tcgen05_fence_after();
+            const uint32_t n16 = static_cast<uint32_t>(max(16, (tiles[n1].nkeys + 15) & ~15));
+            const uint32_t idesc = make_idesc_bf16_f32(TA_BQ, n16);
+            const uint32_t q_addr = smem_u32(smem + s * TP_STAGE_BYTES + TP_Q_OFF);
+            const uint32_t k_addr = smem_u32(smem + s * TP_STAGE_BYTES + TP_K_OFF);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem + 256u * static_cast<uint32_t>(s), make_smem_desc_sw128(q_addr + k * 32),
+                        make_smem_desc_sw128(k_addr + k * 32), idesc, k != 0 ? 1u : 0u);
+            umma_commit(&bar_s_ready[s]);
+            ++n1;
+            progress = true;
+          }
+        }
+        if (progress) t0 = clock64();
+        else if (clock64() - t0 > SPLADE_MBAR_TIMEOUT_CYCLES) __trap();
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax: 512 threads, FOUR per query row
+    // (TMEM lane = row; warp wg reads lane quarter wg & 3 and owns the 32-key chunks cq = wg >> 2 and cq + 4 of its
+    // rows).  A thread's 64 scores stay in registers from the TMEM load to the bf16 P store: S is read ONCE (TMEM
+    // reads, 64 B/clk/SM, were the floor of the two-pass version).
+    const uint32_t wg = warp;
+    const uint32_t gt = tid;
+    const uint32_t row_t = (wg & 3u) * 32u + (tid & 31u);
+    const int cq = static_cast<int>(wg >> 2);
+    // The four warps that share a lane quarter (32 query rows) form a SET: everything they exchange (row maxima and
+    // sums, the staged key positions) is per set, with a 128-thread named barrier - so the four sets drift apart and
+    // one set's TMEM loads overlap another's exponentials instead of all sixteen warps moving in lock step
+    const uint32_t set = wg & 3u;
+    const uint32_t st_t = (wg >> 2) * 32u + (tid & 31u);  // 0..127 inside the set
+    const uint32_t set_bar = 1u + set;
+    int* kpos = reinterpret_cast<int*>(smem + TP_KPOS_OFF) + set * TA_BKV;
+    uint8_t* ostage = smem + TP_OST_OFF + set * 4096u;  // the set's 32 output rows x 128 B
+    float* xmax = reinterpret_cast<float*>(smem + TP_XCHG_OFF);  // [4][128]
+    float* xsum = xmax + 512;                                    // [4][128]
+    const uint32_t lane_off = ((wg & 3u) * 32u) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    // positions of this thread's query row and of "its" key (thread gt < 256 stages key gt), fetched one tile ahead
+    uint32_t qmeta = 0, kmeta0 = 0, kmeta1 = 0;
+    auto fetch_meta = [&](int n) {
+      if (n < n_valid) {
+        const AttnTile ti = tiles[n];
+        qmeta = __ldg(&p.meta[ti.q_row + min(static_cast<int>(row_t), (ti.rows_h >> 8) - 1)]);
+        if (p.window >= 0) {  // thread st_t of the set stages keys st_t and st_t + 128
+          if (static_cast<int>(st_t) < ti.nkeys) kmeta0 = __ldg(&p.meta[ti.k_row + static_cast<int>(st_t)]);
+          if (static_cast<int>(st_t) + 128 < ti.nkeys) kmeta1 = __ldg(&p.meta[ti.k_row + static_cast<int>(st_t) + 128]);
+        }
+      }
+    };
+    // epilogue of tile m (its O is in TMEM once the P V MMAs have completed): 16 of the 64 output dims per thread
+    auto epilogue = [&](int m, float inv) {
+      const int s = m & 1;
+      mbar_wait_quiet(&bar_o_ready[s], static_cast<uint32_t>((m >> 1) & 1));
+      tcgen05_fence_after();
+      uint32_t o[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]),
+            "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
+          : "r"(tmem + 256u * static_cast<uint32_t>(s) + lane_off + 192u + 16u * static_cast<uint32_t>(cq))
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;"
+                   : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]),
+                     "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(o[12]), "+r"(o[13]), "+r"(o[14]), "+r"(o[15])
+                   :
+                   : "memory");
+      tcgen05_fence_before();
+      __syncwarp();
+      if ((tid & 31u) == 0) mbar_arrive(&bar_s_free[s]);  // O is in registers: the slot may take the next S
+      // through shared memory so that a warp's store instruction covers four whole 128-byte lines (a thread's own 32
+      // bytes of a row would make it 32 different lines: the output stores were 10 us of the 48 us kernel)
+      const uint32_t lane = tid & 31u;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        uint4 v;
+        v.x = cvt_bf16x2(__uint_as_float(o[8 * i + 1]) * inv, __uint_as_float(o[8 * i + 0]) * inv);
+        v.y = cvt_bf16x2(__uint_as_float(o[8 * i + 3]) * inv, __uint_as_float(o[8 * i + 2]) * inv);
+        v.z = cvt_bf16x2(__uint_as_float(o[8 * i + 5]) * inv, __uint_as_float(o[8 * i + 4]) * inv);
+        v.w = cvt_bf16x2(__uint_as_float(o[8 * i + 7]) * inv, __uint_as_float(o[8 * i + 6]) * inv);
+        const uint32_t chunk = static_cast<uint32_t>(2 * cq + i);
+        *reinterpret_cast<uint4*>(ostage + lane * 128u + ((chunk ^ (lane & 7u)) << 4)) = v;
+      }
+      named_bar_sync(set_bar, 128);
+      const AttnTile ti = tiles[m];
+      const int rows = ti.rows_h >> 8;
+      if (!(p.debug & 64)) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t q = st_t + 128u * static_cast<uint32_t>(i);
+          const uint32_t r = q >> 3, chunk = q & 7u;
+          const int row = static_cast<int>(set * 32u + r);
+          if (row < rows) {
+            const uint4 v = *reinterpret_cast<const uint4*>(ostage + r * 128u + ((chunk ^ (r & 7u)) << 4));
+            *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(ti.q_row + row) * p.H + (ti.rows_h & 0xFF) * AT_D +
+                                      chunk * 8u) = v;
+          }
+        }
+      }
+    };
+    fetch_meta(0);
+    float inv_prev = 0.f;
+    for (int n = 0; n < n_valid; ++n) {
+      const int s = n & 1;
+      const uint32_t ph = static_cast<uint32_t>((n >> 1) & 1);
+      const int nkeys = tiles[n].nkeys;
+      const uint32_t t_lane = tmem + 256u * static_cast<uint32_t>(s) + lane_off;
+      const int qpos = static_cast<int>(qmeta & 0xFFFFu);
+      int lo = 0, hi = nkeys;
+      if (p.window >= 0) {
+        kpos[st_t] = static_cast<int>(st_t) < nkeys ? static_cast<int>(kmeta0 & 0xFFFFu) : 0x3FFFFFFF;
+        kpos[st_t + 128u] = static_cast<int>(st_t) + 128 < nkeys ? static_cast<int>(kmeta1 & 0xFFFFu) : 0x3FFFFFFF;
+        named_bar_sync(set_bar, 128);
+        int l = 0, r = nkeys;  // first key with pos >= qpos - window
+        while (l < r) {
+          const int m = (l + r) >> 1;
+          if (kpos[m] < qpos - p.window) l = m + 1; else r = m;
+        }
+        lo = l;
+        r = nkeys;             // first key with pos > qpos + window
+        while (l < r) {
+          const int m = (l + r) >> 1;
+          if (kpos[m] <= qpos + p.window) l = m + 1; else r = m;
+        }
+        hi = l;
+      }
+      fetch_meta(n + 1);  // in flight during this tile's softmax
+      const int nchunks = (nkeys + 31) >> 5;
+      const int ca = cq, cb = cq + 4;
+      const bool va = ca < nchunks && !__all_sync(0xffffffffu, hi <= 32 * ca || lo >= 32 * ca + 32);
+      const bool vb = cb < nchunks && !__all_sync(0xffffffffu, hi <= 32 * cb || lo >= 32 * cb + 32);
+      const bool fa = __all_sync(0xffffffffu, lo <= 32 * ca && hi >= 32 * ca + 32);
+      const bool fb = __all_sync(0xffffffffu, lo <= 32 * cb && hi >= 32 * cb + 32);
+      mbar_wait_quiet(&bar_s_ready[s], ph);
+      tcgen05_fence_after();
+
+      // ---- the thread's scores: two 32-key chunks, both loads in flight; masked entries become -inf
+      uint32_t ra[32], rb[32];
+      if (p.debug & 8) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ra[j] = rb[j] = __float_as_uint(static_cast<float>(j + n));
+      }
+      if (va && !(p.debug & 8)) tmem_ld_32x32b_x32(t_lane + 32u * static_cast<uint32_t>(ca), ra);
+      if (vb && !(p.debug & 8)) tmem_ld_32x32b_x32(t_lane + 32u * static_cast<uint32_t>(cb), rb);
+      float mx = -INFINITY;
+      if (va) {
+        tmem_ld_wait_for(ra);
+        if (!fa) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (!(32 * ca + j >= lo && 32 * ca + j < hi)) ra[j] = 0xFF800000u;
+        }
+        float m0 = __uint_as_float(ra[0]), m1 = __uint_as_float(ra[1]), m2 = __uint_as_float(ra[2]),
+              m3 = __uint_as_float(ra[3]);
+#pragma unroll
+        for (int j = 4; j < 32; j += 4) {
+          m0 = fmaxf(m0, __uint_as_float(ra[j]));
+          m1 = fmaxf(m1, __uint_as_float(ra[j + 1]));
+          m2 = fmaxf(m2, __uint_as_float(ra[j + 2]));
+          m3 = fmaxf(m3, __uint_as_float(ra[j + 3]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      if (vb) {
+        tmem_ld_wait_for(rb);
+        if (!fb) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (!(32 * cb + j >= lo && 32 * cb + j < hi)) rb[j] = 0xFF800000u;
+        }
+        float m0 = __uint_as_float(rb[0]), m1 = __uint_as_float(rb[1]), m2 = __uint_as_float(rb[2]),
+              m3 = __uint_as_float(rb[3]);
+#pragma unroll
+        for (int j = 4; j < 32; j += 4) {
+          m0 = fmaxf(m0, __uint_as_float(rb[j]));
+          m1 = fmaxf(m1, __uint_as_float(rb[j + 1]));
+          m2 = fmaxf(m2, __uint_as_float(rb[j + 2]));
+          m3 = fmaxf(m3, __uint_as_float(rb[j + 3]));
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+      }
+      xmax[cq * 128 + static_cast<int>(row_t)] = mx;
+      named_bar_sync(set_bar, 128);  // the set's threads hold their scores in registers: P may overwrite their S lanes
+
+      // ---- the previous tile's output, while this tile's P V inputs are still being produced
+      if (n >= 1) epilogue(n - 1, inv_prev);
+
+      mx = fmaxf(fmaxf(xmax[row_t], xmax[128 + row_t]), fmaxf(xmax[256 + row_t], xmax[384 + row_t]));
+      if (mx == -INFINITY) mx = 0.f;  // rows past the document (never stored)
+      const float moff = mx * sl2;
+
+      // ---- p = 2^(s * scale * log2 e - max) (2^-inf = 0 for masked keys), row sum, bf16 P into TMEM columns
+      // [16 c, 16 c + 16) of the slot
+      float sum0 = 0.f, sum1 = 0.f;
+      {
+        uint32_t pk[16];
+        if (va) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float p0 = fmaf(__uint_as_float(ra[2 * j]), sl2, -moff);
+            float p1 = fmaf(__uint_as_float(ra[2 * j + 1]), sl2, -moff);
+            if (!(p.debug & 1)) p0 = fast_exp2(p0), p1 = fast_exp2(p1);
+            sum0 += p0;
+            sum1 += p1;
+            pk[j] = (p.debug & 2) ? ((__float_as_uint(p0) >> 16) | (__float_as_uint(p1) & 0xFFFF0000u)) : cvt_bf16x2(p1, p0);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        }
+        if (ca < nchunks) tmem_st_32x32b_x16(t_lane + 16u * static_cast<uint32_t>(ca), pk);
+        if (vb) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float p0 = fmaf(__uint_as_float(rb[2 * j]), sl2, -moff);
+            float p1 = fmaf(__uint_as_float(rb[2 * j + 1]), sl2, -moff);
+            if (!(p.debug & 1)) p0 = fast_exp2(p0), p1 = fast_exp2(p1);
+            sum0 += p0;
+            sum1 += p1;
+            pk[j] = (p.debug & 2) ? ((__float_as_uint(p0) >> 16) | (__float_as_uint(p1) & 0xFFFF0000u)) : cvt_bf16x2(p1, p0);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        }
+        if (cb < nchunks) tmem_st_32x32b_x16(t_lane + 16u * static_cast<uint32_t>(cb), pk);
+      }
+      // The second MMA reads ceil(nkeys / 16) 16-key steps.  The V rows behind the last key belong to other
+      // documents or to never-written workspace: 0 * NaN would poison O, so they are cleared (generic-proxy
+      // stores into the TMA-written stage - after V has landed - made visible to the tensor core by the proxy fence).
+      // Only the writing warps fence, and only when there is a tail (nkeys % 16 != 0): the proxy fence is a full
+      // memory barrier for the thread - it would wait for the previous tile's output stores and the next tile's
+      // metadata loads on every tile.
+      if ((nkeys & 15) != 0 && gt < 128u) {
+        const int vrow = nkeys + static_cast<int>(gt >> 3);
+        if (vrow < ((nkeys + 15) & ~15)) {
+          mbar_wait_quiet(&bar_full_v[s], ph);
+          *reinterpret_cast<uint4*>(smem + s * TP_STAGE_BYTES + TP_V_OFF + vrow * 128 + (gt & 7u) * 16) =
+              make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if ((tid & 31u) == 0) mbar_arrive(&bar_p_ready[s]);  // (512 arrivals on one mbarrier word serialise)
+      xsum[cq * 128 + static_cast<int>(row_t)] = sum0 + sum1;
+      named_bar_sync(set_bar, 128);
+      const float sum = (xsum[row_t] + xsum[128 + row_t]) + (xsum[256 + row_t] + xsum[384 + row_t]);
+      inv_prev = sum > 0.f ? 1.0f / sum : 0.f;
+    }
+    if (n_valid >= 1) epilogue(n_valid - 1, inv_prev);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace
 
 int trunk_rope_table_launch(float2* table, int max_pos, float theta, cudaStream_t stream) {
@@ -771,6 +1237,15 @@ int trunk_ln_launch(const void* in, int in_is_bf16, const float* gamma, float ep
   return ln_launch_typed(static_cast<const float*>(in), gamma, eps, t_rows, H, out, stream);
 }
 
+// SPLADE_B200_ATTN_TC_V1=1 pins the one-tile-per-CTA tcgen05 kernel (A/B timing)
+static bool attn_tc_pipelined() {
+  static const bool on = [] {
+    const char* e = std::getenv("SPLADE_B200_ATTN_TC_V1");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return on;
+}
+
 int trunk_rope_launch(void* qkv, const float2* rope, const VarlenLayout& lay, int H, cudaStream_t stream) {
   trunk_rope_kernel<<<8 * sm_count(), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(qkv), rope, lay.meta,
                                                         &lay.plan->T, H);
@@ -799,6 +1274,10 @@ int trunk_attn_launch(const void* qkv, void* out, const VarlenLayout& lay, int B
   p.H = H;
   p.window = window;
   p.scale = 0.125f;  // head_dim ** -0.5
+  {
+    const char* e = std::getenv("SPLADE_B200_ATTN_DEBUG");
+    p.debug = e ? std::atoi(e) : 0;
+  }
   const int s8 = (S + 7) & ~7;
   // tcgen05 kernel: every tile whose visible keys fit 256 (decided per document on the device)
   // (query-length batches, S <= 64, stay on the 64-row mma.sync kernel: a 128-row tcgen05 tile per 10-token query
@@ -815,9 +1294,21 @@ int trunk_attn_launch(const void* qkv, void* out, const VarlenLayout& lay, int B
     if (rc != kOk) return rc;
     rc = encode_tmap_bf16(&tmap_kv, qkv, 2, dims, strides, box_kv);
     if (rc != kOk) return rc;
-    SPLADE_CUDA_OK(cudaFuncSetAttribute(trunk_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        TA_SMEM_BYTES));
-    trunk_attn_tc_kernel<<<dim3((s8 + TA_BQ - 1) / TA_BQ, n_heads, B), 256, TA_SMEM_BYTES, stream>>>(tmap_q, tmap_kv, p);
+    const long long tiles_all = static_cast<long long>((s8 + TA_BQ - 1) / TA_BQ) * n_heads * B;
+    if (attn_tc_pipelined() && tiles_all <= static_cast<long long>(TP_MAX_TILES) * sm_count()) {
+      // persistent, software-pipelined kernel: one CTA per SM over the (q tile, head, document) list
+      const int nqt = (s8 + TA_BQ - 1) / TA_BQ;
+      const int n_tiles = nqt * n_heads * B;
+      SPLADE_CUDA_OK(cudaFuncSetAttribute(trunk_attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          TP_SMEM_BYTES));
+      const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+      trunk_attn_tc2_kernel<<<grid, TP_THREADS, TP_SMEM_BYTES, stream>>>(tmap_q, tmap_kv, p, n_tiles, nqt, n_heads);
+    } else {
+      SPLADE_CUDA_OK(cudaFuncSetAttribute(trunk_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          TA_SMEM_BYTES));
+      trunk_attn_tc_kernel<<<dim3((s8 + TA_BQ - 1) / TA_BQ, n_heads, B), 256, TA_SMEM_BYTES, stream>>>(tmap_q, tmap_kv,
+                                                                                                     p);
+    }
     SPLADE_CUDA_OK(cudaGetLastError());
   }
   if (!tc_covers_all) {

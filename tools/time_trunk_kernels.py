@@ -32,11 +32,13 @@ cases = {
     "wo2  resid [T,1152]x[768,1152]": (lambda: splade_b200.trunk_gemm(L.EPI_RESID, A1152, Wo2, out=x), 2 * T * I * H),
     "head gelu  [T,768]x[768,768]": (lambda: splade_b200.trunk_gemm(L.EPI_GELU, A768, Wo, out=o_h), 2 * T * H * H),
 }
+if os.environ.get("ONLY_ATTN") == "1":
+    cases = {}
 for name, (fn, flop) in cases.items():
     us = timed(fn)
     print(json.dumps({"kernel": name, "us": round(us, 1), "tflops": round(flop / us / 1e6, 1)}), flush=True)
 # the same GEMMs through cuBLAS (torch.matmul, bf16) for reference
-for name, a, w in (("cublas qkv", A768, Wqkv), ("cublas wo", A768, Wo), ("cublas wi", A768, Wi), ("cublas wo2", A1152, Wo2)):
+for name, a, w in () if os.environ.get("ONLY_ATTN") == "1" else (("cublas qkv", A768, Wqkv), ("cublas wo", A768, Wo), ("cublas wi", A768, Wi), ("cublas wo2", A1152, Wo2)):
     us = timed(lambda: torch.matmul(a, w.t()))
     print(json.dumps({"kernel": name, "us": round(us, 1), "tflops": round(2 * a.shape[0] * a.shape[1] * w.shape[0] / us / 1e6, 1)}), flush=True)
 # attention: 64 documents x 256 tokens, 12 heads
