@@ -205,7 +205,7 @@ def run_reference(args):
 # secondary metric: training-step tokens/s of the hot path (BASELINE config 4)
 # ------------------------------------------------------------------------------------------------------
 def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_offset=-1.0, exchange="peer",
-                  grad_bf16=False):
+                  grad_bf16=False, accum=1):
     """One C4 micro-step of the HOT PATH per rank: fused head forward for query (64x64), positive (64x256)
     and k negatives (64k x 256) hidden states, SPLADELossV33 (InfoNCE + FLOPS, optional cross-GPU negatives),
     backward through the loss and the sparse head backward, then the gradient all-reduce DDP would do for the
@@ -251,7 +251,8 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
 
     def step(i):
         loss_fn = loss_box[0]
-        for t in (hq, hp, hn, W, bias):
+        last = (i + 1) % accum == 0
+        for t in (hq, hp, hn) + ((W, bias) if i % accum == 0 else ()):
             t.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             a, _ = splade_b200.splade_head(hq, W, bias, mq)
@@ -260,7 +261,9 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
             if k_neg > 1:
                 n = n.view(Bq, k_neg, -1)
             loss, d = loss_fn(a, p, n, global_step=1000 + i)
-        loss.backward()
+        (loss / accum if accum > 1 else loss).backward()
+        if not last:
+            return d
         if world > 1:
             if grad_bf16:  # N3: the tied matrix's gradient travels as bf16 (what DDP's bf16_compress_hook does)
                 g16 = W.grad.to(torch.bfloat16)
@@ -273,6 +276,8 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
             W.add_(W.grad, alpha=-1e-6)
         return d
 
+    warmup = -(-warmup // accum) * accum  # whole accumulation windows
+    steps = -(-steps // accum) * accum
     for i in range(warmup):
         d = step(i)
     if exchange_obj is not None and not exchange_ok():
@@ -283,14 +288,16 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
         loss_box[0] = splade_b200.SPLADELossV33(gather_negatives=gather)
         for i in range(warmup):
             d = step(i)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     import gc
     gc.collect()
     gc.disable()   # no collector pause inside the timed region (a step is ~3 ms)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    # barrier + synchronize LAST: the collection above takes a different time on every rank, and a rank that enters
+    # the timed region early spends the difference (measured: ~5 ms at N = 2) waiting in its first collective
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     e0.record()
     marks[0].record()
     try:
@@ -315,13 +322,26 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
     if exchange_failed:
         raise RuntimeError("a peer-exchange barrier timed out inside the timed region; the training leg is invalid")
     per_step = sorted(round(marks[j].elapsed_time(marks[j + 1]), 3) for j in range(steps))
+    # robust companion of the mean: per accumulation window (so the all-reduce micro-step is included), the median
+    # window of every rank, max over ranks
+    windows = sorted(marks[j].elapsed_time(marks[j + accum]) / accum for j in range(0, steps, accum))
+    med = windows[len(windows) // 2]
+    if world > 1:
+        t = torch.tensor([med], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        med = float(t.item())
     tokens = world * Bq * (64 + SEQ + SEQ * k_neg) * steps
     head_flop = 2.0 * HIDDEN * VOCAB * Bq * (64 + SEQ + SEQ * k_neg)
     return {"tokens_per_s": tokens / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
             "ms_step_rank0_min_median_max": [per_step[0], per_step[len(per_step) // 2], per_step[-1]],
+            "ms_per_step_median_window_max_over_ranks": med,
+            "tokens_per_s_median_window": world * Bq * (64 + SEQ + SEQ * k_neg) / (med * 1e-3),
             "workload": f"C4 hot path per GPU: head fwd+bwd for q 64x64 / pos 64x256 / neg {64 * k_neg}x256 + "
                         f"SPLADELossV33 fwd+bwd (k={k_neg}, gather_negatives={gather}) + all-reduce of the tied "
-                        f"decoder matrix ({'bf16-compressed' if grad_bf16 else 'fp32'}) and bias grads; trunk excluded",
+                        f"decoder matrix ({'bf16-compressed' if grad_bf16 else 'fp32'}) and bias grads"
+                        + (f" once per {accum} micro-steps (gradient accumulation, no_sync on the others)" if accum > 1
+                           else "") + "; trunk excluded",
+            "accum": accum,
             "head_fwd_tflop_per_step_per_gpu": head_flop / 1e12, "nonzero_d": d["nonzero_d"],
             "regime": f"decoder.bias offset {bias_offset}: {d['nonzero_d']:.0f} active terms per document",
             "negatives_exchange": exchange_used, "scaling": "weak"}
@@ -569,15 +589,15 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
         torch.cuda.reset_peak_memory_stats(dev)
         for i in range(warm):
             loss, d, gs = train_micro_step(model, loss_fn, opt, None, batches[i], i, gs, scfg, dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
         # the eager 22-layer trunk is host-launch-bound: a generation-2 garbage collection in the middle of a
         # micro-step shows up as a 50-90 ms hiccup (seen at N = 2) - collect now, keep the collector off while timing
         gc.collect()
         gc.disable()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_micro - warm + 1)]
+        if world > 1:  # after the collection, whose duration differs between ranks
+            dist.barrier()
+        torch.cuda.synchronize()
         e0.record()
         marks[0].record()
         try:
@@ -862,6 +882,10 @@ def run_ours(args):
             # the same step in the trained-like sparse regime (bias offset sweeps the density)
             train["sparse_regime"] = run_train_leg(dev, world, rank, steps=n_train, warmup=3, k_neg=1, gather=gather,
                                                    bias_offset=-2.0, exchange=args.exchange)
+            # N3 variant: gradient accumulation over 4 micro-steps with the all-reduce on the last one only
+            train["sparse_regime_accum4_no_sync"] = run_train_leg(
+                dev, world, rank, steps=n_train, warmup=4, k_neg=1, gather=gather, bias_offset=-2.0,
+                exchange=args.exchange, accum=4)
             if world > 1:  # N3 variant: the same sparse-regime step with the gradient all-reduce in bf16
                 train["sparse_regime_bf16_allreduce"] = run_train_leg(
                     dev, world, rank, steps=n_train, warmup=3, k_neg=1, gather=gather, bias_offset=-2.0,
