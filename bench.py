@@ -175,6 +175,34 @@ def time_cpu_reference(docs_per_step: int, steps: int, warmup: int):
     return docs_per_step * steps / dt, dt / steps, cores
 
 
+def time_cpu_full_encode(docs: int = 8, passes: int = 2):
+    """the reference's WHOLE encode (22-layer A.X-Encoder-base-shaped trunk + head chain, fp32,
+    no autocast - benchmark/encoders.py:309-318) on the host cores, on a bounded sample; the CPU counterpart of our
+    arm's `e2e` (which also runs the whole model).  -> dict, or {"error": ...}."""
+    try:
+        import torch
+
+        from oracle import torch_reference as TR
+        cores = host_cores()
+        torch.set_num_threads(cores)
+        model = build_axbase_model()          # stays on the CPU; the drop-in class only wraps the HF model here
+        ref = TR.ReferenceSpladeModule(model.model).eval()
+        g = torch.Generator().manual_seed(1)
+        ids = torch.randint(6, VOCAB - 1, (docs, SEQ), generator=g)
+        mask = torch.ones(docs, SEQ, dtype=torch.int64)
+        with torch.no_grad():
+            ref(ids, mask)
+            t0 = time.perf_counter()
+            for _ in range(passes):
+                ref(ids, mask)
+            dt = (time.perf_counter() - t0) / passes
+        return {"value": docs / dt, "unit": "docs/s", "cores": cores, "seconds_per_pass": dt,
+                "sample": f"{docs} docs x L={SEQ} per pass, {passes} timed passes after 1 warm-up, fp32 torch CPU, the "
+                          f"reference module chain (trunk + decoder + log1p/relu/mask/max)"}
+    except Exception as e:  # noqa: BLE001 - context only
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args):
     """`--impl reference`: rank 0 times the reference's own CPU implementation of the path."""
     rank = int(os.environ.get("RANK", "0"))
@@ -193,7 +221,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(int(os.environ.get("WORLD_SIZE", "1"))),
-        "cpu_baseline": {"value": value, "unit": "docs/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "docs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "full_encode": None if args.no_full_model else time_cpu_full_encode()},
         "e2e": {"value": value, "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -984,7 +1013,9 @@ def run_ours(args):
             v, t_step, cores = time_cpu_reference(docs, steps=3, warmup=1)
         cpu = {"value": v, "unit": "docs/s", "cores": cores, "kind": "port",
                "sample": f"{docs} docs x L={SEQ} per pass, 3 timed passes after 1 warm-up, fp32 torch CPU head chain "
-                         f"(oracle/torch_reference.py)"}
+                         f"(oracle/torch_reference.py)",
+               # the CPU counterpart of `e2e` (whole 22-layer model, not only the head)
+               "full_encode": None if args.no_full_model else time_cpu_full_encode()}
 
     line = {
         "metric": "splade_head_encode_docs_per_sec", "value": value, "unit": "docs/s", "n_gpus": world,
