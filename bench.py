@@ -576,6 +576,8 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
       bf16_grad_hook       + bf16 gradient compression of the all-reduce (N3)
       peer_negatives       + cross-GPU in-batch negatives through the NVLink peer exchange (N > 1)
       reference_statement  the reference's own head/loss statement (oracle/torch_reference.py) on the same trunk
+      native_trunk         opt-in: the trunk too runs natively (NativeTrunkTrain: tcgen05 forward kernels, hand-driven
+                           backward - DESIGN 3.9); same drop-in classes, same DDP semantics as reference_semantics
     tokens/s = whole job (all ranks, real padded tokens of the collator shape) / max-over-ranks CUDA-event time."""
     import gc
 
@@ -658,12 +660,16 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
     if world > 1:
         variants += [("no_sync", "ours", True, False, "local"), ("bf16_grad_hook", "ours", True, True, "local"),
                      ("peer_negatives", "ours", True, False, exchange)]
+    variants.insert(1, ("native_trunk", "ours_native", False, False, "local"))
+    if world > 1:
+        variants.insert(2, ("native_trunk_no_sync", "ours_native", True, False, "local"))
     variants.append(("reference_statement", "ref", False, False, "local"))
     ref_module = None
     for name, side, no_sync, hook, negs in variants:
         x = None
         try:
-            if side == "ours":
+            if side in ("ours", "ours_native"):
+                base.use_native_trunk(False, train=(side == "ours_native"))
                 module = base
                 loss_fn = splade_b200.SPLADELossV33()
                 if negs == "peer":
@@ -726,6 +732,10 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
     a, r = out.get("reference_semantics", {}), out.get("reference_statement", {})
     if "ms_per_micro_step" in a and "ms_per_micro_step" in r:
         out["speedup_vs_reference_statement"] = r["ms_per_micro_step"] / a["ms_per_micro_step"]
+    nt = out.get("native_trunk", {})
+    if "ms_per_micro_step" in nt and "ms_per_micro_step" in r:
+        out["speedup_native_trunk_vs_reference_statement"] = r["ms_per_micro_step"] / nt["ms_per_micro_step"]
+    base.use_native_trunk(False, train=False)
     del base, ref_module
     torch.cuda.empty_cache()
     return out

@@ -51,6 +51,8 @@ extern "C" {
 #define SPLADE_OP_HEAD_BWD_BITMAP 11  /* (B,-,-,V)            bytes of one segment's activity bitmap          */
 #define SPLADE_OP_LOSS_BWD_TC 12      /* (B=Bq, k=N docs)     splade_loss_bwd_tc scratch                      */
 #define SPLADE_OP_HEAD_PROLOGUE 13    /* (B=T rows, H)        splade_head_prologue_fwd / _bwd scratch         */
+#define SPLADE_OP_TRUNK_TRAIN_FWD 14  /* (B,S,H)              splade_trunk_train_fwd scratch                  */
+#define SPLADE_OP_TRUNK_LN_BWD 15     /* (-,-,H)              splade_trunk_ln_bwd scratch                     */
 
 int splade_abi_version(void);
 const char* splade_last_error(void);
@@ -459,6 +461,43 @@ int splade_trunk_gemm(int epi, const void* A, int rows, const void* W, int N, in
 int splade_trunk_attn(void* qkv_packed, const int32_t* mask, int B, int S, int H, int n_heads, int window,
                       float rope_theta, void* out_packed, uint32_t* meta_out, void* workspace, size_t ws_bytes,
                       void* stream);
+
+/*
+ * Native trunk, TRAINING side (opt-in, NativeTrunkTrain in trunk_train.py).  splade_trunk_train_fwd runs
+ * the layer loop of splade_trunk_encode up to final_norm (same kernels, same autocast arithmetic as transformers'
+ * ModernBertModel.forward, modeling_modernbert.py:424-490) and writes everything the backward needs into the caller's
+ * save buffers, which must arrive ZERO-FILLED (rows behind the last token then stay zero in every buffer, so the
+ * backward can run over whole buffers).  rows = splade_packed_rows(B, S); the head fields of `args` are ignored.
+ * The backward is orchestrated by the caller: dgrad GEMMs = splade_trunk_gemm on the transposed weights, wgrad GEMMs =
+ * the caller's BLAS, attention backward = the caller's (library) attention on the saved q/k/v, and the two row-wise
+ * kernels below:
+ *   splade_trunk_ln_bwd    dx (+)= LayerNorm_backward(dy bf16 or fp32; x fp32, gamma) in fp32, dgamma [H] (deterministic)
+ *   splade_trunk_geglu_bwd h = [a | g] [rows,2I] bf16 (Wi output), dgg [rows,I] bf16 -> dh = [da | dg] [rows,2I] bf16
+ *   splade_trunk_dqkv_pack the attention backward's (dq, dk, dv) -> the gradient rows of the Wqkv output (RoPE transposed)
+ */
+typedef struct splade_trunk_train_saves {
+  float* x_attn_in; /* [n_layers][rows][H] fp32  residual stream entering each layer                      */
+  float* x_mlp_in;  /* [n_layers][rows][H] fp32  residual stream after the attention block                */
+  void* xb;         /* [n_layers][rows][H] bf16  attention-norm output (layer 0: bf16 embedding LayerNorm) */
+  void* qkv;        /* [n_layers][rows][3H] bf16 Wqkv output with RoPE applied to q and k                 */
+  void* ab;         /* [n_layers][rows][H] bf16  attention output                                         */
+  void* xb2;        /* [n_layers][rows][H] bf16  mlp-norm output                                          */
+  void* gg;         /* [n_layers][rows][I] bf16  GeGLU output                                             */
+  float* x_final;   /* [rows][H] fp32            residual stream entering final_norm                      */
+  void* out;        /* [rows][H] bf16            final_norm output: the trunk's output, packed            */
+  uint32_t* meta;   /* [rows]                    (doc << 16 | position) of every packed row               */
+  int32_t* plan;    /* int32[5]                  {1, packed rows T, tiles, last-tile N, real tokens}      */
+} splade_trunk_train_saves;
+int splade_trunk_train_fwd(const splade_trunk_args* args, const splade_trunk_train_saves* saves, void* stream);
+int splade_trunk_ln_bwd(const void* dy, int dy_is_f32, const float* x, const float* gamma, float eps, int rows, int H,
+                        float* dx, int accumulate, float* dgamma, void* workspace, size_t ws_bytes, void* stream);
+int splade_trunk_geglu_bwd(const void* h, const void* dgg, int rows, int I, void* dh, void* stream);
+/* gradients of the rotated q / k and of v ([B,heads,S,64] bf16, element strides given) -> dqkv [rows,3H] bf16: transpose of
+ * the RoPE rotation (cos / sin [S,32] fp32) + interleave; row_of [B,S] int64 = packed row of a token (>= rows: padding),
+ * NULL = row b*S+s */
+int splade_trunk_dqkv_pack(const void* dq, const void* dk, const void* dv, int64_t stride_b, int64_t stride_h,
+                           int64_t stride_s, const int64_t* row_of, const float* cos_t, const float* sin_t, int B, int S,
+                           int n_heads, int64_t rows, void* dqkv, void* stream);
 
 /*
  * Head prologue on the training / default path: transformers' ModernBertPredictionHead

@@ -14,11 +14,12 @@ from .ops import (HostEncodeSlot, clear_weight_cache, flops_nnz, head_backward, 
 from .peer_exchange import PeerExchange  # noqa: F401
 from .sparse_emit import SparseEmitter, build_blocklist, bulk_encode  # noqa: F401
 from .trunk import NativeTrunk, trunk_attention, trunk_gemm  # noqa: F401
+from .trunk_train import NativeTrunkTrain  # noqa: F401
 from .v33_loss import SPLADELossV33  # noqa: F401
 
 __all__ = [
     "SPLADEModernBERT", "SPLADELossV33", "PeerExchange", "SparseEmitter", "build_blocklist", "bulk_encode",
     "splade_head", "head_forward", "head_forward_host", "HostEncodeSlot", "head_backward", "head_backward_multi",
     "head_backward_dhidden", "head_backward_dw", "rep_bitmap", "clear_weight_cache", "flops_nnz", "scores", "rowdot", "topk",
-    "NativeTrunk", "trunk_gemm", "trunk_attention", "all_gather_documents", "shard_range", "load_library", "LIB_PATH", "ABI_VERSION",
+    "NativeTrunk", "NativeTrunkTrain", "trunk_gemm", "trunk_attention", "all_gather_documents", "shard_range", "load_library", "LIB_PATH", "ABI_VERSION",
 ]

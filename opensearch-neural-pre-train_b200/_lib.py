@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_uint32, c_void_p)
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p)
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libsplade_b200.so")
@@ -29,6 +29,8 @@ OP_HEAD_BWD_DHIDDEN = 10
 OP_HEAD_BWD_BITMAP = 11
 OP_LOSS_BWD_TC = 12
 OP_HEAD_PROLOGUE = 13
+OP_TRUNK_TRAIN_FWD = 14
+OP_TRUNK_LN_BWD = 15
 HEAD_BWD_MAX_SEGMENTS = 8
 MAX_PEERS = 16
 
@@ -100,6 +102,14 @@ class TrunkArgs(Structure):
     ]
 
 
+class TrunkTrainSaves(Structure):
+    """Mirror of ``splade_trunk_train_saves`` (include/splade_b200.h)."""
+
+    _fields_ = [("x_attn_in", c_void_p), ("x_mlp_in", c_void_p), ("xb", c_void_p), ("qkv", c_void_p),
+                ("ab", c_void_p), ("xb2", c_void_p), ("gg", c_void_p), ("x_final", c_void_p), ("out", c_void_p),
+                ("meta", c_void_p), ("plan", c_void_p)]
+
+
 class PeerGroup(Structure):
     """Mirror of ``splade_peer_group`` (include/splade_b200.h)."""
 
@@ -156,6 +166,12 @@ EXPORTS = {
                                    c_int, c_char_p, c_char_p, c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
     "splade_trunk_encode": (c_int, [POINTER(TrunkArgs), c_void_p]),
     "splade_packed_rows": (c_size_t, [c_int, c_int]),
+    "splade_trunk_train_fwd": (c_int, [POINTER(TrunkArgs), POINTER(TrunkTrainSaves), c_void_p]),
+    "splade_trunk_ln_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
+    "splade_trunk_geglu_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "splade_trunk_dqkv_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p]),
     "splade_trunk_gemm": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                   c_size_t, c_void_p]),
     "splade_head_prologue_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p,

@@ -166,6 +166,10 @@ size_t splade_workspace_bytes(int op, int B, int S, int H, int V, int k) {
       return loss_bwd_tc_workspace_bytes(B, k);
     case SPLADE_OP_HEAD_PROLOGUE:
       return head_prologue_workspace_bytes(B, H);
+    case SPLADE_OP_TRUNK_TRAIN_FWD:
+      return trunk_train_workspace_bytes(B, S, H, 1);
+    case SPLADE_OP_TRUNK_LN_BWD:
+      return trunk_ln_bwd_workspace_bytes(H);
     default:
       return 0;
   }
@@ -302,6 +306,31 @@ int splade_trunk_encode(const splade_trunk_args* args, void* stream) {
 }
 
 size_t splade_packed_rows(int B, int S) { return varlen_rows_public(B, S); }
+
+int splade_trunk_train_fwd(const splade_trunk_args* args, const splade_trunk_train_saves* saves, void* stream) {
+  return trunk_train_fwd_launch(args, saves, static_cast<cudaStream_t>(stream));
+}
+
+int splade_trunk_ln_bwd(const void* dy, int dy_is_f32, const float* x, const float* gamma, float eps, int rows, int H,
+                        float* dx, int accumulate, float* dgamma, void* workspace, size_t ws_bytes, void* stream) {
+  int rc = require_sm100("splade_trunk_ln_bwd");
+  if (rc != kOk) return rc;
+  return trunk_ln_bwd_launch(dy, dy_is_f32, x, gamma, eps, rows, H, dx, accumulate, dgamma, workspace, ws_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int splade_trunk_dqkv_pack(const void* dq, const void* dk, const void* dv, int64_t stride_b, int64_t stride_h,
+                           int64_t stride_s, const int64_t* row_of, const float* cos_t, const float* sin_t, int B, int S,
+                           int n_heads, int64_t rows, void* dqkv, void* stream) {
+  return trunk_dqkv_pack_launch(dq, dk, dv, stride_b, stride_h, stride_s, reinterpret_cast<const long long*>(row_of),
+                                cos_t, sin_t, B, S, n_heads, rows, dqkv, static_cast<cudaStream_t>(stream));
+}
+
+int splade_trunk_geglu_bwd(const void* h, const void* dgg, int rows, int I, void* dh, void* stream) {
+  int rc = require_sm100("splade_trunk_geglu_bwd");
+  if (rc != kOk) return rc;
+  return trunk_geglu_bwd_launch(h, dgg, rows, I, dh, static_cast<cudaStream_t>(stream));
+}
 
 int splade_trunk_gemm(int epi, const void* A, int rows, const void* W, int N, int K, void* out, int ldo,
                       void* workspace, size_t ws_bytes, void* stream) {

@@ -19,6 +19,7 @@
 #include "../../include/splade_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "rowwise.cuh"
 
 #include <math.h>
 
@@ -27,45 +28,7 @@ namespace {
 
 constexpr int PRO_THREADS = 256;  // 8 warps, one row per warp at a time
 
-// Exact-erf GELU and its derivative with ONE exponential: Abramowitz-Stegun 7.1.26 for erfc(|x|) = poly(t) e^{-x^2},
-// t = 1 / (1 + p |x|) (absolute error <= 1.5e-7 - five decimal orders below the bf16 rounding that follows; erff()
-// made these HBM-bound kernels ALU-bound: 25.6 us for the forward pass over 16 384 rows), and e^{-x^2} with x = y/sqrt 2
-// IS the Gaussian the derivative needs: Phi'(y) = e^{-y^2/2} / sqrt(2 pi).
-__device__ __forceinline__ void gelu_parts(float y, float* cdf, float* pdf) {
-  const float ax = fabsf(y) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float e = __expf(-ax * ax);
-  const float half_erfc = 0.5f * t * poly * e;  // 0.5 erfc(|x|)
-  *cdf = y >= 0.f ? 1.0f - half_erfc : half_erfc;
-  *pdf = 0.39894228040143267794f * e;
-}
-__device__ __forceinline__ float gelu_erf(float y) {
-  float cdf, pdf;
-  gelu_parts(y, &cdf, &pdf);
-  return y * cdf;
-}
-__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  return make_uint4(cvt_bf16x2(f[1], f[0]), cvt_bf16x2(f[3], f[2]), cvt_bf16x2(f[5], f[4]), cvt_bf16x2(f[7], f[6]));
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  return v;
-}
+using namespace rowwise;
 
 // H = 256 * NCH; lane l owns columns [256 c + 8 l, 256 c + 8 l + 8) of every chunk c: every warp access is a
 // contiguous 512 B (bf16) or 1 KB (fp32).

@@ -10,6 +10,7 @@ struct splade_v33_scalar_args;
 struct splade_v33_fwd_args;
 struct splade_trunk_args;
 struct splade_head_bwd_segment;
+struct splade_trunk_train_saves;
 
 namespace splade {
 
@@ -75,6 +76,19 @@ int trunk_attn_launch(const void* qkv, void* out, const VarlenLayout& lay, int B
 size_t trunk_workspace_bytes(int B, int S, int H, int I, int V);
 int trunk_encode_launch(const struct splade_trunk_args* a, cudaStream_t stream);
 size_t varlen_rows_public(int B, int S);
+size_t trunk_train_workspace_bytes(int B, int S, int H, int V);
+int trunk_train_fwd_launch(const struct splade_trunk_args* a, const struct splade_trunk_train_saves* saves,
+                           cudaStream_t stream);
+
+// trunk_bwd.cu: row-wise backward kernels of the trunk's training path
+size_t trunk_ln_bwd_workspace_bytes(int H);
+int trunk_ln_bwd_launch(const void* dy, int dy_is_f32, const float* x, const float* gamma, float eps, int rows, int H,
+                        float* dx, int accumulate, float* dgamma, void* workspace, size_t ws_bytes,
+                        cudaStream_t stream);
+int trunk_geglu_bwd_launch(const void* h, const void* dgg, int rows, int I, void* dh, cudaStream_t stream);
+int trunk_dqkv_pack_launch(const void* dq, const void* dk, const void* dv, long long sb, long long sh, long long ss,
+                           const long long* row_of, const float* cos_t, const float* sin_t, int B, int S, int nh,
+                           long long rows, void* dqkv, cudaStream_t stream);
 
 // head_prologue.cu: ModernBertPredictionHead (dense -> GELU -> LayerNorm) forward / backward on the training path
 size_t head_prologue_workspace_bytes(int T, int H);

@@ -1418,4 +1418,82 @@ int trunk_encode_launch(const splade_trunk_args* a, cudaStream_t stream) {
   return head_fwd_packed_launch(xb, lay, a->dec_w, a->dec_bias, B, S, H, V, a->rep, a->argmax, stream);
 }
 
+// ------------------------------------------------------------------------------------------------ training forward
+// The same layer loop as trunk_encode_launch with every tensor the backward needs written straight into the caller's
+// save buffers instead of scratch (the residual stream is copied at the two points a LayerNorm reads it), stopping at
+// final_norm: the prediction head and the SPLADE head run as autograd nodes of their own (ops.py).  The save buffers
+// must arrive zero-filled: rows behind the last token then stay zero everywhere (the kernels write real rows, or
+// products of zero rows), which is what lets the backward run over whole buffers without knowing the row count.
+size_t trunk_train_workspace_bytes(int B, int S, int H, int V) {
+  const size_t rows = (static_cast<size_t>(B) * ((static_cast<size_t>(S) + 7) / 8 * 8) + 255) / 256 * 256;
+  return al256(varlen_layout_bytes(B, S, V)) + al256(rows * H * 4) + 256;
+}
+
+int trunk_train_fwd_launch(const splade_trunk_args* a, const splade_trunk_train_saves* sv, cudaStream_t stream) {
+  if (!a || !sv || !a->input_ids || !a->mask || !a->tok_emb || !a->layers || !a->emb_norm || !a->final_norm)
+    return set_error(kErrInvalidArg, "splade_trunk_train_fwd: null pointer argument");
+  if (!sv->x_attn_in || !sv->x_mlp_in || !sv->xb || !sv->qkv || !sv->ab || !sv->xb2 || !sv->gg || !sv->x_final ||
+      !sv->out || !sv->meta || !sv->plan)
+    return set_error(kErrInvalidArg, "splade_trunk_train_fwd: null save buffer");
+  const int B = a->B, S = a->S, H = a->H, I = a->I;
+  if (B < 1 || S < 1 || H % 64 != 0 || H < 256 || I % 128 != 0 || a->n_heads * 64 != H || a->n_layers < 1)
+    return set_error(kErrUnsupportedShape,
+                     "splade_trunk_train_fwd: needs hidden %% 64 == 0 and >= 256, 64-wide heads, intermediate %% 128 == 0 "
+                     "(B=%d S=%d H=%d I=%d heads=%d)", B, S, H, I, a->n_heads);
+  int rc = require_sm100("splade_trunk_train_fwd");
+  if (rc != kOk) return rc;
+  const size_t need = trunk_train_workspace_bytes(B, S, H, 1);
+  if (!a->workspace || a->ws_bytes < need)
+    return set_error(kErrWorkspace, "splade_trunk_train_fwd: workspace too small (%zu < %zu bytes)", a->ws_bytes, need);
+
+  uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+  VarlenLayout lay{};
+  rc = varlen_layout_build(a->mask, B, S, 1, ws, varlen_layout_bytes(B, S, 1), &lay, stream);
+  if (rc != kOk) return rc;
+  ws += al256(varlen_layout_bytes(B, S, 1));
+  const size_t rows = lay.rows;
+  float* x = reinterpret_cast<float*>(ws);
+  const int32_t* t_rows = &lay.plan->T;
+  const int rows_i = static_cast<int>(rows);
+  const size_t rh = rows * static_cast<size_t>(H);
+  SPLADE_CUDA_OK(cudaMemsetAsync(x, 0, rh * sizeof(float), stream));
+
+  auto bf = [](void* base, size_t elems) { return static_cast<void*>(static_cast<__nv_bfloat16*>(base) + elems); };
+  // embeddings -> x (fp32) and, for layer 0 whose attn_norm is Identity, its bf16 copy
+  if ((rc = trunk_embed_ln_launch(a->input_ids, a->tok_emb, a->emb_norm, a->norm_eps, lay, S, H, x, sv->xb, stream)) != kOk)
+    return rc;
+  for (int l = 0; l < a->n_layers; ++l) {
+    const splade_trunk_layer& ly = a->layers[l];
+    void* xb = bf(sv->xb, l * rh);
+    void* qkv = bf(sv->qkv, l * rh * 3);
+    void* ab = bf(sv->ab, l * rh);
+    void* xb2 = bf(sv->xb2, l * rh);
+    void* gg = bf(sv->gg, l * rows * static_cast<size_t>(I));
+    SPLADE_CUDA_OK(cudaMemcpyAsync(sv->x_attn_in + l * rh, x, rh * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    if (ly.attn_norm != nullptr) {
+      if ((rc = trunk_ln_launch(x, 0, ly.attn_norm, a->norm_eps, t_rows, rows_i, H, xb, stream)) != kOk) return rc;
+    } else if (l != 0) {
+      return set_error(kErrUnsupportedShape, "splade_trunk_train_fwd: only layer 0 may lack attn_norm");
+    }
+    if ((rc = trunk_gemm_launch(EPI_QKV_ROPE, xb, rows_i, ly.wqkv, 3 * H, H, t_rows, qkv, 3 * H, lay.meta,
+                                ly.is_global ? a->global_theta : a->local_theta, 2 * H, stream)) != kOk)
+      return rc;
+    if ((rc = trunk_attn_launch(qkv, ab, lay, B, S, H, a->n_heads, ly.is_global ? -1 : a->local_window, stream)) != kOk)
+      return rc;
+    if ((rc = trunk_gemm_launch(EPI_RESID, ab, rows_i, ly.wo, H, H, t_rows, x, H, nullptr, 0.f, 0, stream)) != kOk)
+      return rc;
+    SPLADE_CUDA_OK(cudaMemcpyAsync(sv->x_mlp_in + l * rh, x, rh * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    if ((rc = trunk_ln_launch(x, 0, ly.mlp_norm, a->norm_eps, t_rows, rows_i, H, xb2, stream)) != kOk) return rc;
+    if ((rc = trunk_gemm_launch(EPI_GEGLU, xb2, rows_i, ly.wi, I, H, t_rows, gg, I, nullptr, 0.f, 0, stream)) != kOk)
+      return rc;
+    if ((rc = trunk_gemm_launch(EPI_RESID, gg, rows_i, ly.wo2, H, I, t_rows, x, H, nullptr, 0.f, 0, stream)) != kOk)
+      return rc;
+  }
+  SPLADE_CUDA_OK(cudaMemcpyAsync(sv->x_final, x, rh * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  if ((rc = trunk_ln_launch(x, 0, a->final_norm, a->norm_eps, t_rows, rows_i, H, sv->out, stream)) != kOk) return rc;
+  SPLADE_CUDA_OK(cudaMemcpyAsync(sv->meta, lay.meta, rows * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+  SPLADE_CUDA_OK(cudaMemcpyAsync(sv->plan, lay.plan, 5 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  return kOk;
+}
+
 }  // namespace splade

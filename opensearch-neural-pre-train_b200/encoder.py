@@ -41,11 +41,23 @@ class SPLADEModernBERT(nn.Module):
         # plain Python state (not parameters / buffers: state_dict keys must not change)
         self._native_trunk = None
         self._native_trunk_enabled = os.environ.get("SPLADE_B200_NATIVE_TRUNK", "0") == "1"
+        self._native_train = None
+        self._native_train_enabled = os.environ.get("SPLADE_B200_NATIVE_TRUNK_TRAIN", "0") == "1"
 
-    def use_native_trunk(self, enabled: bool = True) -> "SPLADEModernBERT":
-        """Route ``encode`` (inference, no autograd) through the native packed-token trunk."""
+    def use_native_trunk(self, enabled: bool = True, train: Optional[bool] = None) -> "SPLADEModernBERT":
+        """Route ``encode`` (inference, no autograd) through the native packed-token trunk.  ``train=True``
+        additionally routes ``forward`` under autocast(bf16) with autograd through ``NativeTrunkTrain`` (native
+        forward, hand-driven backward; opt-in: the reference trunk is the default for training)."""
         self._native_trunk_enabled = bool(enabled)
+        if train is not None:
+            self._native_train_enabled = bool(train)
         return self
+
+    def _native_trainer(self):
+        if getattr(self, "_native_train", None) is None:
+            from .trunk_train import NativeTrunkTrain
+            self._native_train = NativeTrunkTrain(self.model)
+        return self._native_train
 
     def _native(self):
         if getattr(self, "_native_trunk", None) is None:
@@ -76,6 +88,12 @@ class SPLADEModernBERT(nn.Module):
         # head with biases, another activation - the transformers module runs as in the reference
         prologue = prologue_of(mlm.head) if head_prologue_enabled() and input_ids.is_cuda else None
         if prologue is not None and autocast_is_bf16():
+            if getattr(self, "_native_train_enabled", False) and torch.is_grad_enabled():
+                from .trunk_train import suffix_mask
+                if suffix_mask(attention_mask):
+                    trunk_out = self._native_trainer()(input_ids, attention_mask)
+                    return splade_head(trunk_out, decoder.weight, decoder.bias, attention_mask,
+                                       want_token_weights=want_token_weights, prologue=prologue)
             trunk_out = mlm.model(input_ids=input_ids, attention_mask=attention_mask)[0]
             return splade_head(trunk_out, decoder.weight, decoder.bias, attention_mask,
                                want_token_weights=want_token_weights, prologue=prologue)
