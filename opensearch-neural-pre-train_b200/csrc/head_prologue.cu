@@ -155,13 +155,25 @@ prologue_bwd_kernel(const float* __restrict__ d_hidden, const __nv_bfloat16* __r
   }
 }
 
+// dgamma[col] = sum over the per-CTA partials in a FIXED order: a block owns 32 columns, its eight warps each sum
+// every eighth partial (coalesced 128-byte rows), then the eight slice sums are added in slice order.  (One thread
+// per column walking all ~600 partials was a 24 us chain of dependent loads for 2 KB of output.)
 __global__ void __launch_bounds__(256)
 prologue_dgamma_reduce_kernel(const float* __restrict__ partial, int n_part, int H, float* __restrict__ dgamma) {
-  const int col = blockIdx.x * blockDim.x + static_cast<int>(threadIdx.x);
-  if (col >= H) return;
+  __shared__ float s_sum[8][32];
+  const int lane = static_cast<int>(threadIdx.x & 31u), slice = static_cast<int>(threadIdx.x >> 5);
+  const int col = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int p = 0; p < n_part; ++p) s += partial[static_cast<size_t>(p) * H + col];
-  dgamma[col] = s;
+  if (col < H)
+    for (int p = slice; p < n_part; p += 8) s += partial[static_cast<size_t>(p) * H + col];
+  s_sum[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && col < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_sum[w][lane];
+    dgamma[col] = t;
+  }
 }
 
 int prologue_grid(int T) {
@@ -240,7 +252,7 @@ int head_prologue_bwd_launch(const float* d_hidden, const void* y, const float* 
     default: prologue_bwd_kernel<4><<<grid, PRO_THREADS, 0, stream>>>(d_hidden, yb, st, norm_w, T, dyb, partial); break;
   }
   SPLADE_CUDA_OK(cudaGetLastError());
-  prologue_dgamma_reduce_kernel<<<(H + 255) / 256, 256, 0, stream>>>(partial, grid, H, d_norm_w);
+  prologue_dgamma_reduce_kernel<<<(H + 31) / 32, 256, 0, stream>>>(partial, grid, H, d_norm_w);
   SPLADE_CUDA_OK(cudaGetLastError());
   if (dx == nullptr) return kOk;
   SPLADE_CUDA_OK(cudaMemcpyAsync(t_rows, &T, sizeof(int32_t), cudaMemcpyHostToDevice, stream));
