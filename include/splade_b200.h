@@ -471,7 +471,8 @@ int splade_trunk_attn(void* qkv_packed, const int32_t* mask, int B, int S, int H
  * The backward is orchestrated by the caller: dgrad GEMMs = splade_trunk_gemm on the transposed weights, wgrad GEMMs =
  * the caller's BLAS, attention backward = the caller's (library) attention on the saved q/k/v, and the two row-wise
  * kernels below:
- *   splade_trunk_ln_bwd    dx (+)= LayerNorm_backward(dy bf16 or fp32; x fp32, gamma) in fp32, dgamma [H] (deterministic)
+ *   splade_trunk_ln_bwd    dx (+)= LayerNorm_backward(dy bf16 or fp32; x fp32, gamma) in fp32, dgamma [H] (deterministic);
+ *                          dx_bf16 (optional) also receives the updated dx rounded to bf16 (the next dgrad's operand)
  *   splade_trunk_geglu_bwd h = [a | g] [rows,2I] bf16 (Wi output), dgg [rows,I] bf16 -> dh = [da | dg] [rows,2I] bf16
  *   splade_trunk_dqkv_pack the attention backward's (dq, dk, dv) -> the gradient rows of the Wqkv output (RoPE transposed)
  */
@@ -490,7 +491,8 @@ typedef struct splade_trunk_train_saves {
 } splade_trunk_train_saves;
 int splade_trunk_train_fwd(const splade_trunk_args* args, const splade_trunk_train_saves* saves, void* stream);
 int splade_trunk_ln_bwd(const void* dy, int dy_is_f32, const float* x, const float* gamma, float eps, int rows, int H,
-                        float* dx, int accumulate, float* dgamma, void* workspace, size_t ws_bytes, void* stream);
+                        float* dx, int accumulate, void* dx_bf16, float* dgamma, void* workspace, size_t ws_bytes,
+                        void* stream);
 int splade_trunk_geglu_bwd(const void* h, const void* dgg, int rows, int I, void* dh, void* stream);
 /* gradients of the rotated q / k and of v ([B,heads,S,64] bf16, element strides given) -> dqkv [rows,3H] bf16: transpose of
  * the RoPE rotation (cos / sin [S,32] fp32) + interleave; row_of [B,S] int64 = packed row of a token (>= rows: padding),

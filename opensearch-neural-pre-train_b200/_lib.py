@@ -167,7 +167,7 @@ EXPORTS = {
     "splade_trunk_encode": (c_int, [POINTER(TrunkArgs), c_void_p]),
     "splade_packed_rows": (c_size_t, [c_int, c_int]),
     "splade_trunk_train_fwd": (c_int, [POINTER(TrunkArgs), POINTER(TrunkTrainSaves), c_void_p]),
-    "splade_trunk_ln_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int, c_void_p,
+    "splade_trunk_ln_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
     "splade_trunk_geglu_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "splade_trunk_dqkv_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,

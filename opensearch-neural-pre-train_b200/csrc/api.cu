@@ -312,10 +312,11 @@ int splade_trunk_train_fwd(const splade_trunk_args* args, const splade_trunk_tra
 }
 
 int splade_trunk_ln_bwd(const void* dy, int dy_is_f32, const float* x, const float* gamma, float eps, int rows, int H,
-                        float* dx, int accumulate, float* dgamma, void* workspace, size_t ws_bytes, void* stream) {
+                        float* dx, int accumulate, void* dx_bf16, float* dgamma, void* workspace, size_t ws_bytes,
+                        void* stream) {
   int rc = require_sm100("splade_trunk_ln_bwd");
   if (rc != kOk) return rc;
-  return trunk_ln_bwd_launch(dy, dy_is_f32, x, gamma, eps, rows, H, dx, accumulate, dgamma, workspace, ws_bytes,
+  return trunk_ln_bwd_launch(dy, dy_is_f32, x, gamma, eps, rows, H, dx, accumulate, dx_bf16, dgamma, workspace, ws_bytes,
                              static_cast<cudaStream_t>(stream));
 }
 

@@ -83,7 +83,7 @@ int trunk_train_fwd_launch(const struct splade_trunk_args* a, const struct splad
 // trunk_bwd.cu: row-wise backward kernels of the trunk's training path
 size_t trunk_ln_bwd_workspace_bytes(int H);
 int trunk_ln_bwd_launch(const void* dy, int dy_is_f32, const float* x, const float* gamma, float eps, int rows, int H,
-                        float* dx, int accumulate, float* dgamma, void* workspace, size_t ws_bytes,
+                        float* dx, int accumulate, void* dx_bf16, float* dgamma, void* workspace, size_t ws_bytes,
                         cudaStream_t stream);
 int trunk_geglu_bwd_launch(const void* h, const void* dgg, int rows, int I, void* dh, cudaStream_t stream);
 int trunk_dqkv_pack_launch(const void* dq, const void* dk, const void* dv, long long sb, long long sh, long long ss,

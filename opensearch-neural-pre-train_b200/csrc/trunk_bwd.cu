@@ -25,7 +25,8 @@ constexpr int TB_THREADS = 256;
 template <int NCH, bool kDyF32>
 __global__ void __launch_bounds__(TB_THREADS)
 trunk_ln_bwd_kernel(const void* __restrict__ dy_raw, const float* __restrict__ x, const float* __restrict__ gamma,
-                    float eps, int rows, float* __restrict__ dx, int accumulate, float* __restrict__ dgamma_partial) {
+                    float eps, int rows, float* __restrict__ dx, int accumulate, __nv_bfloat16* __restrict__ dx16,
+                    float* __restrict__ dgamma_partial) {
   constexpr int H = 256 * NCH;
   __shared__ float s_part[TB_THREADS / 32][H];
   const int lane = static_cast<int>(threadIdx.x & 31u), warp = static_cast<int>(threadIdx.x >> 5);
@@ -103,6 +104,10 @@ trunk_ln_bwd_kernel(const void* __restrict__ dy_raw, const float* __restrict__ x
       }
       p0[0] = o0;
       p0[1] = o1;
+      if (dx16 != nullptr) {  // the bf16 copy the next dgrad GEMM reads (saves a separate cast pass over dx)
+        const float ob[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        *reinterpret_cast<uint4*>(dx16 + static_cast<size_t>(row) * H + 256 * c + 8 * lane) = pack8(ob);
+      }
     }
   }
 #pragma unroll
@@ -227,7 +232,7 @@ int ln_grid(int rows) {
 size_t trunk_ln_bwd_workspace_bytes(int H) { return static_cast<size_t>(4 * sm_count()) * H * sizeof(float); }
 
 int trunk_ln_bwd_launch(const void* dy, int dy_is_f32, const float* x, const float* gamma, float eps, int rows, int H,
-                        float* dx, int accumulate, float* dgamma, void* workspace, size_t ws_bytes,
+                        float* dx, int accumulate, void* dx_bf16, float* dgamma, void* workspace, size_t ws_bytes,
                         cudaStream_t stream) {
   if (!dy || !x || !gamma || !dx || !dgamma || rows < 1)
     return set_error(kErrInvalidArg, "splade_trunk_ln_bwd: bad argument");
@@ -237,12 +242,13 @@ int trunk_ln_bwd_launch(const void* dy, int dy_is_f32, const float* x, const flo
   if (!workspace || ws_bytes < static_cast<size_t>(grid) * H * sizeof(float))
     return set_error(kErrWorkspace, "splade_trunk_ln_bwd: workspace too small");
   float* partial = static_cast<float*>(workspace);
+  __nv_bfloat16* d16 = static_cast<__nv_bfloat16*>(dx_bf16);
 #define SPLADE_LN_BWD(NCH)                                                                                          \
   do {                                                                                                              \
     if (dy_is_f32)                                                                                                  \
-      trunk_ln_bwd_kernel<NCH, true><<<grid, TB_THREADS, 0, stream>>>(dy, x, gamma, eps, rows, dx, accumulate, partial);  \
+      trunk_ln_bwd_kernel<NCH, true><<<grid, TB_THREADS, 0, stream>>>(dy, x, gamma, eps, rows, dx, accumulate, d16, partial);  \
     else                                                                                                            \
-      trunk_ln_bwd_kernel<NCH, false><<<grid, TB_THREADS, 0, stream>>>(dy, x, gamma, eps, rows, dx, accumulate, partial); \
+      trunk_ln_bwd_kernel<NCH, false><<<grid, TB_THREADS, 0, stream>>>(dy, x, gamma, eps, rows, dx, accumulate, d16, partial); \
   } while (0)
   switch (H / 256) {
     case 1: SPLADE_LN_BWD(1); break;

@@ -46,7 +46,7 @@ def _ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float, 
     nbytes = lib.splade_workspace_bytes(_lib.OP_TRUNK_LN_BWD, 0, 0, H, 0, 0)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     check(lib.splade_trunk_ln_bwd(dy.data_ptr(), int(dy.dtype == torch.float32), x.data_ptr(), gamma.data_ptr(),
-                                  float(eps), rows, H, dx.data_ptr(), int(accumulate), dgamma.data_ptr(),
+                                  float(eps), rows, H, dx.data_ptr(), int(accumulate), None, dgamma.data_ptr(),
                                   ws.data_ptr(), nbytes, torch.cuda.current_stream(dev).cuda_stream),
           "splade_trunk_ln_bwd")
     return dgamma
@@ -119,14 +119,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 meta_out=None, plan_out=None, workspace=ws.data_ptr(), ws_bytes=nbytes)
             check(lib.splade_trunk_train_fwd(ctypes.byref(args), ctypes.byref(saves),
                                              torch.cuda.current_stream(dev).cuda_stream), "splade_trunk_train_fwd")
-            # packed row of token (b, s): documents back to back, each starting at a multiple of 8 rows;
-            # padding positions point at row `rows` (a zero row / a scratch row)
-            lens = m32.sum(dim=1, dtype=torch.int64)
-            l8 = (lens + 7) // 8 * 8
-            off = torch.cumsum(l8, 0) - l8
-            pos = torch.arange(S, device=dev)
-            valid = pos[None, :] < lens[:, None]
-            row_of = torch.where(valid, off[:, None] + pos[None, :], torch.full_like(off[:, None], rows))
+            row_of, valid = packed_row_index(m32, rows)
             if dense:
                 hidden = sv["out"][:rows].view(B, S, H).clone()
             else:
@@ -185,10 +178,11 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 check(lib.splade_trunk_gemm(_lib.EPI_BF16, A.data_ptr(), rows, W.data_ptr(), N, K, out.data_ptr(), N,
                                             gemm_ws.data_ptr(), 256, stream), "splade_trunk_gemm")
 
-            def ln_bwd(dy, x, gamma, slot, dx_out, accumulate):
+            def ln_bwd(dy, x, gamma, slot, dx_out, accumulate, dx16_out=None):
                 dgam = dgammas[slot]
                 check(lib.splade_trunk_ln_bwd(dy.data_ptr(), int(dy.dtype == torch.float32), x.data_ptr(),
                                               gamma.data_ptr(), eps, rows, H, dx_out.data_ptr(), int(accumulate),
+                                              None if dx16_out is None else dx16_out.data_ptr(),
                                               dgam.data_ptr(), ln_ws.data_ptr(), ln_bytes, stream),
                       "splade_trunk_ln_bwd")
                 return dgam
@@ -196,7 +190,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
             # ---- final_norm
             dy = pack(d_hidden.to(torch.bfloat16)).contiguous()
             dx = torch.empty((rows, H), dtype=torch.float32, device=dev)
-            g_final = ln_bwd(dy, sv["x_final"], c["final_norm"], 2 * L, dx, False)
+            g_final = ln_bwd(dy, sv["x_final"], c["final_norm"], 2 * L, dx, False, dx16)
             # visibility of keys for the attention backward (padded layout); padding QUERY rows see everything, so
             # that their softmax stays finite (their output gradient is zero: they contribute nothing)
             all_valid = dense or bool(valid.all())
@@ -215,7 +209,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 g = {}
                 xb2_l, gg_l, ab_l, xb_l = sv["xb2"][l], sv["gg"][l], sv["ab"][l], sv["xb"][l]
                 # ---- MLP block: x_out = x_mid + Wo2(gelu(a) * g), [a | g] = Wi(mlp_norm(x_mid))
-                dx16.copy_(dx)
+                # (dx16 = bf16(dx) comes out of the LayerNorm backward that produced dx)
                 gemm(dx16, t["wo2_t"], dgg)                                           # [rows,I]
                 g["wo2"] = _mm_f32(dx16.t(), gg_l)                                    # [H,I]
                 gemm(xb2_l, w["wi"], h)                                               # [rows,2I] recomputed
@@ -223,9 +217,8 @@ class _TrunkTrainFunction(torch.autograd.Function):
                       "splade_trunk_geglu_bwd")
                 gemm(dh, t["wi_t"], dxb2)                                             # [rows,H]
                 g["wi"] = _mm_f32(dh.t(), xb2_l)                                      # [2I,H]
-                g["mlp_norm"] = ln_bwd(dxb2, sv["x_mlp_in"][l], w["mlp_norm"], 2 * l + 1, dx, True)
+                g["mlp_norm"] = ln_bwd(dxb2, sv["x_mlp_in"][l], w["mlp_norm"], 2 * l + 1, dx, True, dx16)
                 # ---- attention block: x_mid = x_in + Wo(attention(rope(Wqkv(attn_norm(x_in)))))
-                dx16.copy_(dx)
                 gemm(dx16, t["wo_t"], dab)                                            # [rows,H]
                 g["wo"] = _mm_f32(dx16.t(), ab_l)
                 is_global = bool(c["layer_array"][l].is_global)
@@ -244,7 +237,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 gemm(dqkv, t["wqkv_t"], dxb)                                          # [rows,H]
                 g["wqkv"] = _mm_f32(dqkv.t(), xb_l)                                   # [3H,H]
                 if w["attn_norm"] is not None:
-                    g["attn_norm"] = ln_bwd(dxb, sv["x_attn_in"][l], w["attn_norm"], 2 * l, dx, True)
+                    g["attn_norm"] = ln_bwd(dxb, sv["x_attn_in"][l], w["attn_norm"], 2 * l, dx, True, dx16)
                 else:  # layer 0: attn_norm is Identity
                     dx += dxb
                 layer_grads[l] = g
@@ -332,11 +325,25 @@ class NativeTrunkTrain:
         return _TrunkTrainFunction.apply(self, input_ids, attention_mask, *self.parameters_in_order())
 
 
+def packed_row_index(mask: torch.Tensor, rows: int):
+    """Packed row of every token of a right-padded batch: documents lie back to back, each starting at a multiple of 8
+    rows (empty documents take none); padding positions point at row ``rows`` (a zero / scratch row).
+    mask [B,S] -> (row_of [B,S] int64, valid [B,S] bool); no device synchronisation."""
+    B, S = mask.shape
+    lens = (mask != 0).sum(dim=1, dtype=torch.int64)
+    l8 = (lens + 7) // 8 * 8
+    off = torch.cumsum(l8, 0) - l8
+    pos = torch.arange(S, device=mask.device)
+    valid = pos[None, :] < lens[:, None]
+    row_of = torch.where(valid, off[:, None] + pos[None, :], torch.full_like(off[:, None], rows))
+    return row_of, valid
+
+
 def suffix_mask(attention_mask: torch.Tensor) -> bool:
     """True when every row of the mask is ones followed by zeros (right padding) - one device sync."""
     m = attention_mask != 0
     return bool((m[:, 1:] <= m[:, :-1]).all())
 
 
-__all__ = ["NativeTrunkTrain", "suffix_mask"]
+__all__ = ["NativeTrunkTrain", "packed_row_index", "suffix_mask"]
 _ = math  # (kept for callers that monkeypatch tables in tests)

@@ -412,3 +412,27 @@ def test_token_weights_are_computed_only_when_read(monkeypatch):
     _ = tokw.max(), tokw.cpu().numpy()
     assert len(fwd_calls) == n                        # materialised once
     assert ops.splade_head(h, W, None, m, want_token_weights=False, round_bias=False)[1] is None
+
+
+def test_packed_row_index_and_suffix_mask():
+    """Host logic of the native training trunk: packed row of every token (documents back to back, 8-row aligned,
+    empty documents take no rows) and the right-padding check."""
+    import torch
+
+    from splade_b200.trunk_train import packed_row_index, suffix_mask
+    lens = [5, 0, 8, 13, 1]
+    S = 16
+    mask = torch.tensor([[1] * n + [0] * (S - n) for n in lens])
+    rows = 256
+    row_of, valid = packed_row_index(mask, rows)
+    expect, off = [], 0
+    for n in lens:
+        expect.append([off + s if s < n else rows for s in range(S)])
+        off += (n + 7) // 8 * 8
+    assert row_of.tolist() == expect
+    assert valid.tolist() == [[s < n for s in range(S)] for n in lens]
+    assert suffix_mask(mask)
+    holes = mask.clone()
+    holes[0, 2] = 0
+    assert not suffix_mask(holes)
+    assert suffix_mask(torch.ones(3, 7, dtype=torch.int64))
