@@ -23,7 +23,7 @@ constexpr int TB_THREADS = 256;
 // transformers modeling_modernbert.py: attn_norm / mlp_norm / final_norm / embeddings.norm are nn.LayerNorm without
 // bias; under autocast they run in fp32 on the fp32 residual stream.
 template <int NCH, bool kDyF32>
-__global__ void __launch_bounds__(TB_THREADS)
+__global__ void __launch_bounds__(TB_THREADS, 2)  // two CTAs per SM also at H = 768 (128 registers): twice the loads in flight
 trunk_ln_bwd_kernel(const void* __restrict__ dy_raw, const float* __restrict__ x, const float* __restrict__ gamma,
                     float eps, int rows, float* __restrict__ dx, int accumulate, __nv_bfloat16* __restrict__ dx16,
                     float* __restrict__ dgamma_partial) {

@@ -99,7 +99,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
         # ever left unwritten, so nothing has to be zero-filled and the backward needs no gathers (one sync to know)
         dense = rows == B * S and bool((m32 != 0).all())
         with torch.cuda.device(dev):
-            z = lambda *shape, dtype: (torch.empty if dense else torch.zeros)(shape, dtype=dtype, device=dev)  # noqa: E731
+            z = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=dev)  # noqa: E731
             sv = {"x_attn_in": z(L, rows, H, dtype=torch.float32), "x_mlp_in": z(L, rows, H, dtype=torch.float32),
                   "xb": z(L, rows, H, dtype=torch.bfloat16), "qkv": z(L, rows, 3 * H, dtype=torch.bfloat16),
                   "ab": z(L, rows, H, dtype=torch.bfloat16), "xb2": z(L, rows, H, dtype=torch.bfloat16),
@@ -121,11 +121,20 @@ class _TrunkTrainFunction(torch.autograd.Function):
                                              torch.cuda.current_stream(dev).cuda_stream), "splade_trunk_train_fwd")
             row_of, valid = packed_row_index(m32, rows)
             if dense:
+                re = rows
                 hidden = sv["out"][:rows].view(B, S, H).clone()
             else:
-                sv["out"][rows:].zero_()
+                # ragged batch: the backward works on the first `re` rows only (real tokens rounded up to a GEMM tile);
+                # rows [T, re) must be zero in every buffer it reads (the forward left them unwritten or computed them
+                # from unwritten rows) - one read-back of the row count instead of zero-filling 6 GB up front
+                T = int(sv["plan"][1])
+                re = min(rows, max(128, (T + 127) // 128 * 128))
+                for k in ("x_attn_in", "x_mlp_in", "xb", "qkv", "ab", "xb2", "gg"):
+                    sv[k][:, T:re].zero_()
+                sv["x_final"][T:re].zero_()
+                sv["out"][T:].zero_()
                 hidden = sv["out"][row_of]                  # [B,S,H] bf16, zeros at padding
-        ctx.owner, ctx.sv, ctx.dims, ctx.dense = owner, sv, (B, S, H, I, nh, L, rows), dense
+        ctx.owner, ctx.sv, ctx.dims, ctx.dense, ctx.re = owner, sv, (B, S, H, I, nh, L, rows), dense, re
         ctx.ids, ctx.row_of, ctx.valid = ids, row_of, valid
         ctx.n_params = len(params)
         return hidden
@@ -133,7 +142,8 @@ class _TrunkTrainFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_hidden):
         owner, sv = ctx.owner, ctx.sv
-        B, S, H, I, nh, L, rows = ctx.dims
+        B, S, H, I, nh, L, rows_cap = ctx.dims
+        rows = ctx.re            # rows the backward touches (all of them for a dense batch)
         cfg = owner.cfg
         dev = d_hidden.device
         c = owner.weights(dev)
@@ -141,6 +151,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
         row_of, valid = ctx.row_of, ctx.valid
         flat_rows = row_of.reshape(-1)
         row_clamped = row_of.clamp(max=rows - 1)
+        scratch = rows_cap       # packed_row_index sends padding positions to row `rows_cap`
         window = int(cfg.local_attention) // 2
 
         dense = ctx.dense
@@ -149,7 +160,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
             """[B,S,C] -> [rows,C]: padding positions land on a scratch row that is cut off."""
             if dense:
                 return padded.reshape(rows, -1)
-            out = torch.zeros((rows + 1, padded.shape[-1]), dtype=padded.dtype, device=dev)
+            out = torch.zeros((scratch + 1, padded.shape[-1]), dtype=padded.dtype, device=dev)
             out.index_copy_(0, flat_rows, padded.reshape(B * S, -1))
             return out[:rows]
 
@@ -190,7 +201,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
             # ---- final_norm
             dy = pack(d_hidden.to(torch.bfloat16)).contiguous()
             dx = torch.empty((rows, H), dtype=torch.float32, device=dev)
-            g_final = ln_bwd(dy, sv["x_final"], c["final_norm"], 2 * L, dx, False, dx16)
+            g_final = ln_bwd(dy, sv["x_final"][:rows], c["final_norm"], 2 * L, dx, False, dx16)
             # visibility of keys for the attention backward (padded layout); padding QUERY rows see everything, so
             # that their softmax stays finite (their output gradient is zero: they contribute nothing)
             all_valid = dense or bool(valid.all())
@@ -207,7 +218,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 w = c["layers"][l]
                 t = owner.transposed(dev, l)
                 g = {}
-                xb2_l, gg_l, ab_l, xb_l = sv["xb2"][l], sv["gg"][l], sv["ab"][l], sv["xb"][l]
+                xb2_l, gg_l, ab_l, xb_l = sv["xb2"][l][:rows], sv["gg"][l][:rows], sv["ab"][l][:rows], sv["xb"][l][:rows]
                 # ---- MLP block: x_out = x_mid + Wo2(gelu(a) * g), [a | g] = Wi(mlp_norm(x_mid))
                 # (dx16 = bf16(dx) comes out of the LayerNorm backward that produced dx)
                 gemm(dx16, t["wo2_t"], dgg)                                           # [rows,I]
@@ -217,12 +228,12 @@ class _TrunkTrainFunction(torch.autograd.Function):
                       "splade_trunk_geglu_bwd")
                 gemm(dh, t["wi_t"], dxb2)                                             # [rows,H]
                 g["wi"] = _mm_f32(dh.t(), xb2_l)                                      # [2I,H]
-                g["mlp_norm"] = ln_bwd(dxb2, sv["x_mlp_in"][l], w["mlp_norm"], 2 * l + 1, dx, True, dx16)
+                g["mlp_norm"] = ln_bwd(dxb2, sv["x_mlp_in"][l][:rows], w["mlp_norm"], 2 * l + 1, dx, True, dx16)
                 # ---- attention block: x_mid = x_in + Wo(attention(rope(Wqkv(attn_norm(x_in)))))
                 gemm(dx16, t["wo_t"], dab)                                            # [rows,H]
                 g["wo"] = _mm_f32(dx16.t(), ab_l)
                 is_global = bool(c["layer_array"][l].is_global)
-                qkv = unpack(sv["qkv"][l]).view(B, S, 3, nh, 64)
+                qkv = unpack(sv["qkv"][l][:rows]).view(B, S, 3, nh, 64)
                 q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))            # [B,nh,S,64]
                 d_o = unpack(dab).view(B, S, nh, 64).transpose(1, 2)
                 with torch.enable_grad():
@@ -237,12 +248,12 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 gemm(dqkv, t["wqkv_t"], dxb)                                          # [rows,H]
                 g["wqkv"] = _mm_f32(dqkv.t(), xb_l)                                   # [3H,H]
                 if w["attn_norm"] is not None:
-                    g["attn_norm"] = ln_bwd(dxb, sv["x_attn_in"][l], w["attn_norm"], 2 * l, dx, True, dx16)
+                    g["attn_norm"] = ln_bwd(dxb, sv["x_attn_in"][l][:rows], w["attn_norm"], 2 * l, dx, True, dx16)
                 else:  # layer 0: attn_norm is Identity
                     dx += dxb
                 layer_grads[l] = g
             # ---- embeddings: x0 = LayerNorm(tok_embeddings[input_ids]); the tied matrix gets a scatter-add
-            tok_of_row = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
+            tok_of_row = torch.zeros(scratch + 1, dtype=torch.int64, device=dev)
             tok_of_row.index_copy_(0, flat_rows, torch.arange(B * S, device=dev))
             ids_packed = ctx.ids.reshape(-1)[tok_of_row[:rows]]
             e = c["tok_emb"][ids_packed]                                              # [rows,H] fp32

@@ -143,3 +143,60 @@ def test_model_trains_through_the_native_trunk(cuda_device):
         g, rg = grads[name].grad, rp.grad
         assert g is not None, name
         assert _rel(g, rg) <= 5e-2, (name, _rel(g, rg))
+
+
+def test_native_trunk_training_steps_through_ddp_and_accumulation(cuda_device):
+    """The reference's call pattern (3 encoder calls + loss, (loss / accum).backward(), clip, AdamW) through
+    DistributedDataParallel (world size 1, NCCL) with gradient accumulation 2: the native training trunk against the
+    reference module, same init - loss trajectory and the parameters after two optimizer steps."""
+    import os
+
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    import splade_b200
+    from splade_b200.training import StepConfig, synthetic_triplet_batch, train_micro_step
+    from tests.model_util import tiny_modernbert_dir
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=cuda_device)
+    try:
+        d = tiny_modernbert_dir(vocab_size=5000, hidden=256, heads=4, layers=3, bias_offset=-0.6)
+        ours = splade_b200.SPLADEModernBERT(model_name=d).to(cuda_device)
+        ours.use_native_trunk(False, train=True)
+        ref = TR.ReferenceSpladeModule(copy.deepcopy(ours.model)).to(cuda_device)
+        init = {n: p.detach().clone() for n, p in ours.named_parameters()}
+        traj = {}
+        for tag, model in (("ours", ours), ("ref", ref)):
+            ddp = DDP(model, device_ids=[0], broadcast_buffers=False, find_unused_parameters=False)
+            opt = torch.optim.AdamW(ddp.parameters(), lr=5e-5, weight_decay=0.01)
+            if tag == "ours":
+                loss_fn = splade_b200.SPLADELossV33()
+            else:
+                sched = splade_b200.SPLADELossV33()
+
+                def loss_fn(anchor_repr, positive_repr, negative_repr, global_step, **kw):
+                    lam = [sched._lambda_schedule(global_step, x)
+                           for x in (sched.lambda_q, sched.lambda_d, sched.lambda_neg)]
+                    return TR.v33_loss(anchor_repr, positive_repr, negative_repr, *lam), {}
+            gs, losses = 0, []
+            cfg = StepConfig(gradient_accumulation_steps=2)
+            for i in range(4):
+                batch = synthetic_triplet_batch(4, 16, 48, 1, 5000, 4999, seed=100 + i)
+                loss, _, gs = train_micro_step(ddp, loss_fn, opt, None, batch, i, gs, cfg, cuda_device)
+                losses.append(float(loss))
+            traj[tag] = losses
+            del ddp, opt
+        assert traj["ours"] == pytest.approx(traj["ref"], rel=2e-2), traj
+        # AdamW's first steps move every element by ~lr in the direction of its gradient's sign: the two runs' UPDATES
+        # must point the same way (cosine 1 - 2 x the fraction of sign flips; flips only where the gradient is
+        # smaller than the reference's own bf16 noise)
+        for (name, p), (_, rp) in zip(ours.named_parameters(), ref.named_parameters()):
+            du, dr = (p.detach() - init[name]).flatten().float(), (rp.detach() - init[name]).flatten().float()
+            if float(dr.norm()) == 0.0:
+                assert float(du.norm()) == 0.0, name
+                continue
+            cos = float(torch.dot(du, dr) / (du.norm() * dr.norm()).clamp_min(1e-30))
+            assert cos >= 0.7, (name, cos)
+    finally:
+        dist.destroy_process_group()

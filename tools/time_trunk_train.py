@@ -30,9 +30,12 @@ def timed(fn, n=5, warm=2):
 
 
 NCU = os.environ.get("NCU") == "1"   # under ncu: one shape, one warm-up, one measured pass
-for B, S in (((64, 256),) if NCU else ((64, 256), (64, 64))):
+for B, S, lo in (((64, 256, 256),) if NCU else ((64, 256, 256), (64, 64, 64), (64, 256, 32), (64, 64, 4))):
+    # lo < S: right-padded batch with U[lo, S] real tokens per document (what the reference's collator produces)
+    lens = torch.randint(lo, S + 1, (B,), generator=g)
+    lens[0] = S
+    mask = (torch.arange(S)[None, :] < lens[:, None]).to(torch.int64).to(dev)
     ids = torch.randint(6, 49999, (B, S), generator=g).to(dev)
-    mask = torch.ones(B, S, dtype=torch.int64, device=dev)
 
     def run_native(backward=True):
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -51,7 +54,7 @@ for B, S in (((64, 256),) if NCU else ((64, 256), (64, 64))):
         run_native()
         torch.cuda.synchronize()
         continue
-    row = {"shape": f"{B}x{S}", "native_fwd_ms": timed(lambda: run_native(False)), "native_fwd_bwd_ms": timed(run_native),
+    row = {"shape": f"{B}x{S}", "real_tokens": int(lens.sum()), "native_fwd_ms": timed(lambda: run_native(False)), "native_fwd_bwd_ms": timed(run_native),
            "transformers_fwd_bwd_ms": timed(run_hf)}
     print(json.dumps(row), flush=True)
     if os.environ.get("PROFILE") == "1" and S == 256:
