@@ -7,10 +7,12 @@
 namespace splade {
 namespace rowwise {
 
-// Exact-erf GELU and its derivative with ONE exponential: Abramowitz-Stegun 7.1.26 for erfc(|x|) = poly(t) e^{-x^2},
-// t = 1 / (1 + p |x|) (absolute error <= 1.5e-7 - five decimal orders below the bf16 rounding that follows; erff()
-// made these HBM-bound kernels ALU-bound: 25.6 us for the forward pass over 16 384 rows), and e^{-x^2} with x = y/sqrt 2
-// IS the Gaussian the derivative needs: Phi'(y) = e^{-y^2/2} / sqrt(2 pi).
+// Exact-erf GELU and its derivative from ONE exponential: Abramowitz-Stegun 7.1.26, erfc(|x|) = poly(t) e^{-x^2} with
+// t = 1 / (1 + p |x|) (absolute error <= 3e-7 in fp32 - four decimal orders below the bf16 rounding that follows), and
+// e^{-x^2} with x = y / sqrt 2 IS the Gaussian the derivative needs: Phi'(y) = e^{-y^2/2} / sqrt(2 pi).  It costs two
+// MUFU operations per element (rcp, ex2): right for these memory-bound row-wise kernels, where the backward wants cdf
+// and pdf together; inside the GEMM epilogues (MUFU-starved, trunk_gemm.cu) erff's pure FMA polynomial is faster
+// (measured: GeGLU GEMM 51.8 -> 65.7 us with this form), so they keep erff.
 __device__ __forceinline__ void gelu_parts(float y, float* cdf, float* pdf) {
   const float ax = fabsf(y) * 0.70710678118654752440f;
   const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
