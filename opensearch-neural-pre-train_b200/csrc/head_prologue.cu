@@ -84,7 +84,7 @@ prologue_act_ln_kernel(const __nv_bfloat16* __restrict__ y, const float* __restr
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(PRO_THREADS)
+__global__ void __launch_bounds__(PRO_THREADS, 2)  // two CTAs per SM also at H = 768 (128 registers)
 prologue_bwd_kernel(const float* __restrict__ d_hidden, const __nv_bfloat16* __restrict__ y,
                     const float2* __restrict__ stats, const float* __restrict__ gamma, int T,
                     __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma_partial) {
@@ -176,9 +176,9 @@ prologue_dgamma_reduce_kernel(const float* __restrict__ partial, int n_part, int
   }
 }
 
-int prologue_grid(int T) {
+int prologue_grid(int T, int ctas_per_sm = 4) {
   const int want = (T + PRO_THREADS / 32 - 1) / (PRO_THREADS / 32);
-  const int cap = 4 * sm_count();
+  const int cap = ctas_per_sm * sm_count();  // one wave
   return want < cap ? (want < 1 ? 1 : want) : cap;
 }
 
@@ -236,7 +236,7 @@ int head_prologue_bwd_launch(const float* d_hidden, const void* y, const float* 
   if (rows_cap < T || rows_cap < 128)
     return set_error(kErrInvalidArg, "splade_head_prologue_bwd: buffers must hold max(T, 128) = %d rows, got %d",
                      T < 128 ? 128 : T, rows_cap);
-  const int grid = prologue_grid(T);
+  const int grid = prologue_grid(T, 2);  // the backward kernel holds two CTAs per SM
   const size_t need = 256 + static_cast<size_t>(grid) * H * sizeof(float);
   if (!workspace || ws_bytes < need)
     return set_error(kErrWorkspace, "splade_head_prologue_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, need);

@@ -15,7 +15,7 @@ namespace rowwise {
 // (measured: GeGLU GEMM 51.8 -> 65.7 us with this form), so they keep erff.
 __device__ __forceinline__ void gelu_parts(float y, float* cdf, float* pdf) {
   const float ax = fabsf(y) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));  // rcp.approx (1 ulp): the IEEE reciprocal is 8 instructions
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);

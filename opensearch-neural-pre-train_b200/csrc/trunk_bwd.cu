@@ -223,7 +223,7 @@ trunk_dqkv_pack_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bfloat16
 
 int ln_grid(int rows) {
   const int want = (rows + TB_THREADS / 32 - 1) / (TB_THREADS / 32);
-  const int cap = 4 * sm_count();
+  const int cap = 2 * sm_count();  // one wave of the two CTAs an SM holds
   return want < cap ? (want < 1 ? 1 : want) : cap;
 }
 
