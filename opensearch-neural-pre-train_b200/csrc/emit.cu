@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -310,13 +311,18 @@ int run_documents(Sink& w, int B, int64_t* out_offsets, const DocFn& doc) {
     p.b0 = static_cast<int>(static_cast<int64_t>(B) * t / T);
     p.b1 = static_cast<int>(static_cast<int64_t>(B) * (t + 1) / T);
     p.sink = new Sink(guess);
-    pool.emplace_back([&p, &doc, out_offsets] {
+    auto work = [&p, &doc, out_offsets] {
       for (int b = p.b0; b < p.b1; ++b) {
         out_offsets[b] = static_cast<int64_t>(p.sink->o);  // relative to the part; rebased below
         p.rc = doc(*p.sink, b);
         if (p.rc != kOk) return;
       }
-    });
+    };
+    try {
+      pool.emplace_back(work);
+    } catch (...) {  // no thread to be had (std::system_error must not cross the C boundary): this range runs here
+      work();
+    }
   }
   for (auto& th : pool) th.join();
   int rc = kOk;
@@ -335,10 +341,15 @@ int run_documents(Sink& w, int B, int64_t* out_offsets, const DocFn& doc) {
     for (int t = 0; t < T; ++t) {
       Part& p = parts[static_cast<size_t>(t)];
       const size_t off = base[static_cast<size_t>(t)];
-      copiers.emplace_back([&p, off, fits, &w, out_offsets] {
+      auto copy = [&p, off, fits, &w, out_offsets] {
         for (int b = p.b0; b < p.b1; ++b) out_offsets[b] += static_cast<int64_t>(off);
         if (fits && p.sink->o) memcpy(w.out + off, p.sink->out, p.sink->o);
-      });
+      };
+      try {
+        copiers.emplace_back(copy);
+      } catch (...) {
+        copy();
+      }
     }
     for (auto& th : copiers) th.join();
     if (!fits) w.overflow = true;
@@ -365,7 +376,7 @@ extern "C" int splade_emit_set_threads(int n) {
   return prev;
 }
 
-extern "C" int splade_emit_json(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
+static int splade_emit_json_impl(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
                                 int k, const char* token_bytes, const int64_t* token_offsets, int n_tokens,
                                 int round_decimals, char* out, size_t out_cap, int64_t* out_offsets,
                                 size_t* bytes_needed) {
@@ -386,7 +397,21 @@ extern "C" int splade_emit_json(const int32_t* ids_host, const float* vals_host,
   return kOk;
 }
 
-extern "C" int splade_emit_bulk(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
+extern "C" int splade_emit_json(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
+                                int k, const char* token_bytes, const int64_t* token_offsets, int n_tokens,
+                                int round_decimals, char* out, size_t out_cap, int64_t* out_offsets,
+                                size_t* bytes_needed) {
+  try {
+    return splade_emit_json_impl(ids_host, vals_host, counts_host, B, k, token_bytes, token_offsets, n_tokens, round_decimals, out, out_cap, out_offsets, bytes_needed);
+  } catch (const std::bad_alloc&) {
+    return set_error(kErrWorkspace, "splade_emit_json: out of host memory");
+  } catch (...) {
+    return set_error(kErrInvalidArg, "splade_emit_json: unexpected C++ exception");
+  }
+}
+
+
+static int splade_emit_bulk_impl(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
                                 int k, const char* token_bytes, const int64_t* token_offsets, int n_tokens,
                                 int round_decimals, const char* index_name, const char* field_name,
                                 const char* id_bytes, const int64_t* id_offsets, const char* head_bytes,
@@ -445,7 +470,23 @@ extern "C" int splade_emit_bulk(const int32_t* ids_host, const float* vals_host,
   return kOk;
 }
 
-extern "C" int splade_emit_search(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
+extern "C" int splade_emit_bulk(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
+                                int k, const char* token_bytes, const int64_t* token_offsets, int n_tokens,
+                                int round_decimals, const char* index_name, const char* field_name,
+                                const char* id_bytes, const int64_t* id_offsets, const char* head_bytes,
+                                const int64_t* head_offsets, int skip_empty, char* out, size_t out_cap,
+                                int64_t* out_offsets, size_t* bytes_needed) {
+  try {
+    return splade_emit_bulk_impl(ids_host, vals_host, counts_host, B, k, token_bytes, token_offsets, n_tokens, round_decimals, index_name, field_name, id_bytes, id_offsets, head_bytes, head_offsets, skip_empty, out, out_cap, out_offsets, bytes_needed);
+  } catch (const std::bad_alloc&) {
+    return set_error(kErrWorkspace, "splade_emit_bulk: out of host memory");
+  } catch (...) {
+    return set_error(kErrInvalidArg, "splade_emit_bulk: unexpected C++ exception");
+  }
+}
+
+
+static int splade_emit_search_impl(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
                                   int k, const char* token_bytes, const int64_t* token_offsets, int n_tokens,
                                   int max_clauses, int size, const char* field_name, const char* msearch_index,
                                   char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed) {
@@ -493,3 +534,17 @@ extern "C" int splade_emit_search(const int32_t* ids_host, const float* vals_hos
     return set_error(kErrWorkspace, "splade_emit_search: output buffer too small (%zu < %zu bytes)", out_cap, w.o);
   return kOk;
 }
+
+extern "C" int splade_emit_search(const int32_t* ids_host, const float* vals_host, const int32_t* counts_host, int B,
+                                  int k, const char* token_bytes, const int64_t* token_offsets, int n_tokens,
+                                  int max_clauses, int size, const char* field_name, const char* msearch_index,
+                                  char* out, size_t out_cap, int64_t* out_offsets, size_t* bytes_needed) {
+  try {
+    return splade_emit_search_impl(ids_host, vals_host, counts_host, B, k, token_bytes, token_offsets, n_tokens, max_clauses, size, field_name, msearch_index, out, out_cap, out_offsets, bytes_needed);
+  } catch (const std::bad_alloc&) {
+    return set_error(kErrWorkspace, "splade_emit_search: out of host memory");
+  } catch (...) {
+    return set_error(kErrInvalidArg, "splade_emit_search: unexpected C++ exception");
+  }
+}
+
