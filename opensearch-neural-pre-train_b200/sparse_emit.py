@@ -233,15 +233,21 @@ class SparseEmitter:
         tok_buf = ctypes.create_string_buffer(table[0], len(table[0]) + 1)
         offsets = np.zeros(B + 1, dtype=np.int64)
         need = ctypes.c_size_t(0)
-        cap, rc = 0, 0
         idx = None if msearch_index is None else msearch_index.encode("utf-8")
+        # capacity estimate so that the first call already writes (an underestimate costs one retry at the exact size)
+        n_terms = np.minimum(np.minimum(np.maximum(counts_h, 0), k), int(max_clauses))
+        valid = np.arange(k)[None, :] < n_terms[:, None]
+        tok_len = np.diff(table[1])
+        key_bytes = int(tok_len[np.clip(ids_h, 0, len(tok_len) - 1)][valid].sum())
+        per_clause = 48 + len(field.encode("utf-8")) + 14
+        cap = int(1.1 * (B * (64 + (len(idx) if idx else 0)) + key_bytes + per_clause * int(valid.sum()))) + 4096
+        rc = 0
         for _ in range(2):
-            out = ctypes.create_string_buffer(max(cap, 1))
+            out = np.empty(max(cap, 1), dtype=np.uint8)
             rc = lib.splade_emit_search(ids_h.ctypes.data, vals_h.ctypes.data, counts_h.ctypes.data, B, k,
                                         ctypes.addressof(tok_buf), table[1].ctypes.data, len(table[1]) - 1,
                                         int(max_clauses), int(size), field.encode("utf-8"), idx,
-                                        ctypes.addressof(out) if cap else None, cap, offsets.ctypes.data,
-                                        ctypes.byref(need))
+                                        out.ctypes.data, cap, offsets.ctypes.data, ctypes.byref(need))
             if rc == 0:
                 break
             if need.value > cap:
@@ -249,7 +255,7 @@ class SparseEmitter:
                 continue
             break
         check(rc, "splade_emit_search")
-        raw = out.raw
+        raw = out[: need.value].tobytes()
         return [raw[offsets[b]:offsets[b + 1]] for b in range(B)]
 
 
