@@ -494,6 +494,10 @@ int splade_trunk_ln_bwd(const void* dy, int dy_is_f32, const float* x, const flo
                         float* dx, int accumulate, void* dx_bf16, float* dgamma, void* workspace, size_t ws_bytes,
                         void* stream);
 int splade_trunk_geglu_bwd(const void* h, const void* dgg, int rows, int I, void* dh, void* stream);
+/* padded[t,:] = row_of[t] < rows ? packed[row_of[t],:] : 0 for n_tokens = B*S positions (rows of row_bytes, a multiple of 16):
+ * the packed -> padded gather in front of the library attention backward (ragged batches) */
+int splade_trunk_gather_rows(const void* packed, const int64_t* row_of, int64_t n_tokens, int row_bytes, int64_t rows,
+                             void* padded, void* stream);
 /* gradients of the rotated q / k and of v ([B,heads,S,64] bf16, element strides given) -> dqkv [rows,3H] bf16: transpose of
  * the RoPE rotation (cos / sin [S,32] fp32) + interleave; row_of [B,S] int64 = packed row of a token (>= rows: padding),
  * NULL = row b*S+s */

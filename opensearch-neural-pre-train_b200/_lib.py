@@ -170,6 +170,7 @@ EXPORTS = {
     "splade_trunk_ln_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
     "splade_trunk_geglu_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "splade_trunk_gather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "splade_trunk_dqkv_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p]),
     "splade_trunk_gemm": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,

@@ -327,6 +327,12 @@ int splade_trunk_dqkv_pack(const void* dq, const void* dk, const void* dv, int64
                                 cos_t, sin_t, B, S, n_heads, rows, dqkv, static_cast<cudaStream_t>(stream));
 }
 
+int splade_trunk_gather_rows(const void* packed, const int64_t* row_of, int64_t n_tokens, int row_bytes, int64_t rows,
+                             void* padded, void* stream) {
+  return trunk_gather_rows_launch(packed, reinterpret_cast<const long long*>(row_of), n_tokens, row_bytes, rows, padded,
+                                  static_cast<cudaStream_t>(stream));
+}
+
 int splade_trunk_geglu_bwd(const void* h, const void* dgg, int rows, int I, void* dh, void* stream) {
   int rc = require_sm100("splade_trunk_geglu_bwd");
   if (rc != kOk) return rc;

@@ -86,6 +86,8 @@ int trunk_ln_bwd_launch(const void* dy, int dy_is_f32, const float* x, const flo
                         float* dx, int accumulate, void* dx_bf16, float* dgamma, void* workspace, size_t ws_bytes,
                         cudaStream_t stream);
 int trunk_geglu_bwd_launch(const void* h, const void* dgg, int rows, int I, void* dh, cudaStream_t stream);
+int trunk_gather_rows_launch(const void* packed, const long long* row_of, long long n_tok, int row_bytes, long long rows,
+                             void* padded, cudaStream_t stream);
 int trunk_dqkv_pack_launch(const void* dq, const void* dk, const void* dv, long long sb, long long sh, long long ss,
                            const long long* row_of, const float* cos_t, const float* sin_t, int B, int S, int nh,
                            long long rows, void* dqkv, cudaStream_t stream);

@@ -221,6 +221,21 @@ trunk_dqkv_pack_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bfloat16
   }
 }
 
+// padded[t, :] = row_of[t] < rows ? packed[row_of[t], :] : 0   (16-byte vectors; the packed -> [B,S] gather of q / k / v
+// and of the attention output gradient in front of the library attention backward, ragged batches only)
+__global__ void __launch_bounds__(256)
+trunk_gather_rows_kernel(const uint4* __restrict__ packed, const long long* __restrict__ row_of, long long n_tok,
+                         int vec_per_row, long long rows, uint4* __restrict__ padded) {
+  const long long total = n_tok * vec_per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long t = i / vec_per_row;
+    const int v = static_cast<int>(i - t * vec_per_row);
+    const long long r = row_of[t];
+    padded[i] = r < rows ? packed[r * vec_per_row + v] : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 int ln_grid(int rows) {
   const int want = (rows + TB_THREADS / 32 - 1) / (TB_THREADS / 32);
   const int cap = 2 * sm_count();  // one wave of the two CTAs an SM holds
@@ -277,6 +292,18 @@ int trunk_dqkv_pack_launch(const void* dq, const void* dk, const void* dv, long 
       static_cast<const __nv_bfloat16*>(dv), sb, sh, ss, row_of, cos_t, sin_t, B, S, nh, rows,
       static_cast<__nv_bfloat16*>(dqkv));
   return check_cuda(cudaGetLastError(), "trunk_dqkv_pack_kernel");
+}
+
+int trunk_gather_rows_launch(const void* packed, const long long* row_of, long long n_tok, int row_bytes, long long rows,
+                             void* padded, cudaStream_t stream) {
+  if (!packed || !row_of || !padded || n_tok < 1 || row_bytes < 16 || row_bytes % 16 != 0)
+    return set_error(kErrInvalidArg, "splade_trunk_gather_rows: bad argument (rows of a multiple of 16 bytes)");
+  const int vec = row_bytes / 16;
+  const long long want = (n_tok * vec + 255) / 256;
+  const int grid = static_cast<int>(want < 16LL * sm_count() ? want : 16LL * sm_count());
+  trunk_gather_rows_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(packed), row_of, n_tok, vec, rows,
+                                                     static_cast<uint4*>(padded));
+  return check_cuda(cudaGetLastError(), "trunk_gather_rows_kernel");
 }
 
 int trunk_geglu_bwd_launch(const void* h, const void* dgg, int rows, int I, void* dh, cudaStream_t stream) {

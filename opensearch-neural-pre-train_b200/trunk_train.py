@@ -150,7 +150,6 @@ class _TrunkTrainFunction(torch.autograd.Function):
         eps = float(cfg.norm_eps)
         row_of, valid = ctx.row_of, ctx.valid
         flat_rows = row_of.reshape(-1)
-        row_clamped = row_of.clamp(max=rows - 1)
         scratch = rows_cap       # packed_row_index sends padding positions to row `rows_cap`
         window = int(cfg.local_attention) // 2
 
@@ -164,11 +163,18 @@ class _TrunkTrainFunction(torch.autograd.Function):
             out.index_copy_(0, flat_rows, padded.reshape(B * S, -1))
             return out[:rows]
 
-        def unpack(packed: torch.Tensor) -> torch.Tensor:
-            """[rows,C] -> [B,S,C] with zeros at padding positions."""
+        def unpack(packed: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+            """[rows,C] -> [B,S,C] with zeros at padding positions (``splade_trunk_gather_rows``; a view when dense)."""
             if dense:
                 return packed.view(B, S, -1)
-            return packed[row_clamped] * valid[..., None].to(packed.dtype)
+            C = packed.shape[1]
+            if out is None:
+                out = torch.empty((B, S, C), dtype=packed.dtype, device=dev)
+            check(load_library().splade_trunk_gather_rows(packed.data_ptr(), flat_rows.data_ptr(), B * S,
+                                                          C * packed.element_size(), rows, out.data_ptr(),
+                                                          torch.cuda.current_stream(dev).cuda_stream),
+                  "splade_trunk_gather_rows")
+            return out
 
         with torch.cuda.device(dev), torch.no_grad():
             # The loop below is host-bound (22 layers x ~25 launches): outputs are allocated once and reused, and the
@@ -179,6 +185,10 @@ class _TrunkTrainFunction(torch.autograd.Function):
             dx16, dgg, h, dh = bf(rows, H), bf(rows, I), bf(rows, 2 * I), bf(rows, 2 * I)
             dxb2, dab, dxb = bf(rows, H), bf(rows, H), bf(rows, H)
             dqkv = (torch.empty if dense else torch.zeros)((rows, 3 * H), dtype=torch.bfloat16, device=dev)
+            qkv_pad = dab_pad = None
+            if not dense:  # padded staging of q / k / v and dO for the attention backward, reused by every layer
+                qkv_pad = torch.empty((B, S, 3 * H), dtype=torch.bfloat16, device=dev)
+                dab_pad = torch.empty((B, S, H), dtype=torch.bfloat16, device=dev)
             gemm_ws = torch.empty(256, dtype=torch.uint8, device=dev)
             ln_bytes = lib.splade_workspace_bytes(_lib.OP_TRUNK_LN_BWD, 0, 0, H, 0, 0)
             ln_ws = torch.empty(ln_bytes, dtype=torch.uint8, device=dev)
@@ -233,9 +243,9 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 gemm(dx16, t["wo_t"], dab)                                            # [rows,H]
                 g["wo"] = _mm_f32(dx16.t(), ab_l)
                 is_global = bool(c["layer_array"][l].is_global)
-                qkv = unpack(sv["qkv"][l][:rows]).view(B, S, 3, nh, 64)
+                qkv = unpack(sv["qkv"][l][:rows], qkv_pad).view(B, S, 3, nh, 64)
                 q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))            # [B,nh,S,64]
-                d_o = unpack(dab).view(B, S, nh, 64).transpose(1, 2)
+                d_o = unpack(dab, dab_pad).view(B, S, nh, 64).transpose(1, 2)
                 with torch.enable_grad():
                     q_, k_, v_ = (x.detach().requires_grad_(True) for x in (q, k, v))
                     o = F.scaled_dot_product_attention(q_, k_, v_, attn_mask=mask_global if is_global else mask_local,
