@@ -748,7 +748,8 @@ constexpr int TP_XCHG_OFF = TP_KPOS_OFF + 4 * TA_BKV * 4;    // [2 groups][max |
 constexpr int TP_TILES_OFF = TP_XCHG_OFF + 2 * 2 * 2 * 128 * 4;
 constexpr int TP_MAX_TILES = 256;                            // tiles per CTA the table holds
 constexpr int TP_OST_OFF = TP_TILES_OFF + TP_MAX_TILES * 16 + 16;   // [4 sets][32 rows][128 B] output staging
-constexpr int TP_SMEM_BYTES = TP_OST_OFF + 4 * 4096 + 1024;
+constexpr int TP_META_OFF = TP_OST_OFF + 4 * 4096;                  // [512 threads][4] prefetched token descriptors
+constexpr int TP_SMEM_BYTES = TP_META_OFF + 512 * 16 + 1024;
 constexpr int TP_THREADS = 512 + 64;
 
 // One (128 queries, head, document) tile of this CTA's list, decoded once at kernel start
@@ -962,16 +963,24 @@ trunk_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const uint32_t lane_off = ((wg & 3u) * 32u) << 16;
     const float sl2 = p.scale * 1.4426950408889634f;
     // positions of this thread's query row and of "its" key (thread gt < 256 stages key gt), fetched one tile ahead
-    uint32_t qmeta = 0, kmeta0 = 0, kmeta1 = 0;
+    // They are fetched one tile ahead with cp.async straight into a per-thread shared-memory slot: a prefetch into
+    // REGISTERS was spilled by the compiler at once, and the spill store waited for the global load (10 % of all
+    // stall samples, at the start of every tile).
+    uint32_t* meta_slot = reinterpret_cast<uint32_t*>(smem + TP_META_OFF) + tid * 4u;
+    auto cp_async4 = [](uint32_t* dst, const uint32_t* src) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    };
     auto fetch_meta = [&](int n) {
       if (n < n_valid) {
         const AttnTile ti = tiles[n];
-        qmeta = __ldg(&p.meta[ti.q_row + min(static_cast<int>(row_t), (ti.rows_h >> 8) - 1)]);
+        cp_async4(meta_slot, &p.meta[ti.q_row + min(static_cast<int>(row_t), (ti.rows_h >> 8) - 1)]);
         if (p.window >= 0) {  // thread st_t of the set stages keys st_t and st_t + 128
-          if (static_cast<int>(st_t) < ti.nkeys) kmeta0 = __ldg(&p.meta[ti.k_row + static_cast<int>(st_t)]);
-          if (static_cast<int>(st_t) + 128 < ti.nkeys) kmeta1 = __ldg(&p.meta[ti.k_row + static_cast<int>(st_t) + 128]);
+          if (static_cast<int>(st_t) < ti.nkeys) cp_async4(meta_slot + 1, &p.meta[ti.k_row + static_cast<int>(st_t)]);
+          if (static_cast<int>(st_t) + 128 < ti.nkeys)
+            cp_async4(meta_slot + 2, &p.meta[ti.k_row + static_cast<int>(st_t) + 128]);
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // epilogue of tile m (its O is in TMEM once the P V MMAs have completed): 16 of the 64 output dims per thread
     auto epilogue = [&](int m, float inv) {
@@ -1031,6 +1040,8 @@ trunk_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       const uint32_t ph = static_cast<uint32_t>((n >> 1) & 1);
       const int nkeys = tiles[n].nkeys;
       const uint32_t t_lane = tmem + 256u * static_cast<uint32_t>(s) + lane_off;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const uint32_t qmeta = meta_slot[0], kmeta0 = meta_slot[1], kmeta1 = meta_slot[2];
       const int qpos = static_cast<int>(qmeta & 0xFFFFu);
       int lo = 0, hi = nkeys;
       if (p.window >= 0) {
