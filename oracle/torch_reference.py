@@ -32,6 +32,22 @@ def head_chain_autocast(hidden, weight, bias, attention_mask):
         return head_chain(hidden, weight, bias, attention_mask)
 
 
+def head_prologue_chain(x: torch.Tensor, dense_weight: torch.Tensor, norm_weight: torch.Tensor, eps: float,
+                        autocast: bool = True):
+    """transformers' ModernBertPredictionHead, ``norm(act(dense(x)))`` (modeling_modernbert.py:493-502; no biases,
+    exact GELU), which the reference runs between trunk and decoder (src/model/splade_modern.py:69-73), with stock
+    torch ops -> (dense output, GELU output, LayerNorm output).  Under autocast: bf16 Linear, bf16 GELU, fp32 LayerNorm."""
+    if autocast:
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+            y = F.linear(x, dense_weight)
+            g = F.gelu(y)
+            h = F.layer_norm(g, (x.shape[-1],), norm_weight, None, eps)
+        return y, g, h
+    y = F.linear(x, dense_weight)
+    g = F.gelu(y)
+    return y, g, F.layer_norm(g, (x.shape[-1],), norm_weight, None, eps)
+
+
 def flops_reg(rep: torch.Tensor) -> torch.Tensor:
     return (rep.mean(dim=0) ** 2).sum()
 

@@ -6,7 +6,6 @@ import copy
 
 import pytest
 import torch
-import torch.nn.functional as F
 
 from oracle import torch_reference as TR
 from tests.gpu_util import assert_weights_parity
@@ -16,12 +15,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _torch_chain(x, dense_w, norm_w, eps):
-    """The reference chain under autocast(bf16): bf16 Linear, bf16 GELU, fp32 LayerNorm, bf16 decoder input."""
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        y = F.linear(x, dense_w)
-        g = F.gelu(y)
-        h = F.layer_norm(g, (x.shape[-1],), norm_w, None, eps)
-    return y, g, h
+    """The reference chain under autocast(bf16): bf16 Linear, bf16 GELU, fp32 LayerNorm (oracle/torch_reference.py)."""
+    return TR.head_prologue_chain(x, dense_w, norm_w, eps, autocast=True)
 
 
 @pytest.mark.parametrize("T,H", [(1000, 768), (64, 256), (16384, 768), (129, 1024)])
@@ -62,7 +57,7 @@ def test_prologue_backward_matches_autocast_autograd(cuda_device, T, H):
     d_hidden = torch.randn(T, H, generator=g).to(cuda_device)
     eps = 1e-5
     # exact (fp32 arithmetic) gradients and the reference's own autocast gradients
-    h32 = F.layer_norm(F.gelu(F.linear(x, dense_w)), (H,), norm_w, None, eps)
+    h32 = TR.head_prologue_chain(x, dense_w, norm_w, eps, autocast=False)[2]
     ex = torch.autograd.grad(h32, (x, dense_w, norm_w), d_hidden)
     _, _, rh = _torch_chain(x, dense_w, norm_w, eps)
     ac = torch.autograd.grad(rh, (x, dense_w, norm_w), d_hidden)
