@@ -15,7 +15,8 @@ Inference can additionally run the NATIVE trunk (``tr
 encoder on packed real tokens in one C-ABI call, 3-12x faster than the transformers trunk on this GPU.  It is
 opt-in for ``encode`` (``model.use_native_trunk(True)`` or ``SPLADE_B200_NATIVE_TRUNK=1``) because its bf16
 arithmetic differs from the transformers trunk by rounding noise (cosine > 0.99999, top-64 overlap ~99.4 %);
-``forward`` (the training path, which needs autograd through the trunk) always uses the reference trunk.
+``forward`` (the training path, which needs autograd through the trunk) uses the reference trunk unless
+``use_native_trunk(train=True)`` selects ``trunk_train.NativeTrunkTrain`` (native forward, hand-driven backward).
 """
 from __future__ import annotations
 

@@ -5,7 +5,7 @@
 layer, final norm, MLM head prologue and the fused SPLADE head, on the real tokens only, in ONE C-ABI call.  The
 module's parameters stay the single source of truth: bf16 copies of the Linear weights are cached here (plain
 Python state, not buffers: ``state_dict`` keys do not change) and refreshed when a parameter's version changes.
-Inference only (no autograd); training keeps the reference trunk.
+This class is inference only (no autograd); the training side is ``trunk_train.NativeTrunkTrain``.
 """
 from __future__ import annotations
 
