@@ -578,6 +578,7 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
       reference_statement  the reference's own head/loss statement (oracle/torch_reference.py) on the same trunk
       native_trunk         opt-in: the trunk too runs natively (NativeTrunkTrain: tcgen05 forward kernels, hand-driven
                            backward - DESIGN 3.9); same drop-in classes, same DDP semantics as reference_semantics
+      native_trunk_fused_calls  + one encoder call per micro-step for queries, positives and negatives (N3)
     tokens/s = whole job (all ranks, real padded tokens of the collator shape) / max-over-ranks CUDA-event time."""
     import gc
 
@@ -607,7 +608,7 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
         loss = TR.v33_loss(anchor_repr, positive_repr, negative_repr, *lam)
         return loss, {"nonzero_d": float((positive_repr > 0).sum(1).float().mean())}
 
-    def time_variant(module, loss_fn, no_sync, bf16_hook):
+    def time_variant(module, loss_fn, no_sync, bf16_hook, fuse_calls=False):
         model = module.to(dev).train()
         if world > 1:
             from torch.nn.parallel import DistributedDataParallel as DDP
@@ -615,7 +616,8 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
             if bf16_hook:
                 enable_bf16_gradient_compression(model)
         opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.01)
-        scfg = StepConfig(gradient_accumulation_steps=accum, skip_allreduce_on_accumulation=no_sync)
+        scfg = StepConfig(gradient_accumulation_steps=accum, skip_allreduce_on_accumulation=no_sync,
+                          fuse_encoder_calls=fuse_calls)
         gs, d = 20000, {}
         torch.cuda.reset_peak_memory_stats(dev)
         for i in range(warm):
@@ -661,8 +663,10 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
         variants += [("no_sync", "ours", True, False, "local"), ("bf16_grad_hook", "ours", True, True, "local"),
                      ("peer_negatives", "ours", True, False, exchange)]
     variants.insert(1, ("native_trunk", "ours_native", False, False, "local"))
+    # + ONE encoder call per micro-step for queries, positives and negatives (StepConfig.fuse_encoder_calls, N3)
+    variants.insert(2, ("native_trunk_fused_calls", "ours_native", False, False, "local"))
     if world > 1:
-        variants.insert(2, ("native_trunk_no_sync", "ours_native", True, False, "local"))
+        variants.insert(3, ("native_trunk_no_sync", "ours_native", True, False, "local"))
     variants.append(("reference_statement", "ref", False, False, "local"))
     ref_module = None
     for name, side, no_sync, hook, negs in variants:
@@ -683,7 +687,7 @@ def run_train_full_leg(dev, world, rank, local_rank, accum=4, opt_steps=2, excha
                     torch.cuda.empty_cache()
                     ref_module = TR.ReferenceSpladeModule(base.model)
                 module, loss_fn = ref_module, ref_loss
-            out[name] = time_variant(module, loss_fn, no_sync, hook)
+            out[name] = time_variant(module, loss_fn, no_sync, hook, fuse_calls=name.endswith("fused_calls"))
         except Exception as e:  # noqa: BLE001 - keep the other variants
             out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if x is not None:

@@ -27,6 +27,12 @@ class StepConfig:
     gradient_clip: float = 1.0
     skip_allreduce_on_accumulation: bool = False  # N3: DDP.no_sync() on non-final micro-steps
     autocast_dtype: torch.dtype = torch.bfloat16
+    # N3, opt-in: ONE encoder call for queries, positives and negatives (right-padded to the longest of the three and
+    # concatenated along the batch) instead of three.  Documents are independent in the encoder, so the sparse vectors
+    # are the same; what changes is the cost: with the packed native trunks only real tokens are processed, so the
+    # padding added here is free, while the GEMMs see one large batch and the host drives one layer loop instead of
+    # three.  (Pointless with the transformers trunk, which computes the padding.)
+    fuse_encoder_calls: bool = False
 
 
 def enable_bf16_gradient_compression(ddp_model) -> None:
@@ -60,9 +66,15 @@ def train_micro_step(model, loss_fn, optimizer, scheduler, batch: Dict[str, torc
 
     with sync_ctx:
         with torch.autocast(device_type="cuda", dtype=cfg.autocast_dtype):
-            anchor_repr, _ = model(q_ids, q_mask)
-            positive_repr, _ = model(p_ids, p_mask)
-            negative_repr, _ = model(n_ids, n_mask)
+            if cfg.fuse_encoder_calls:
+                ids, mask = concat_padded((q_ids, p_ids, n_ids), (q_mask, p_mask, n_mask))
+                rep, _ = model(ids, mask)
+                anchor_repr, positive_repr, negative_repr = rep.split(
+                    [q_ids.shape[0], p_ids.shape[0], n_ids.shape[0]], dim=0)
+            else:
+                anchor_repr, _ = model(q_ids, q_mask)
+                positive_repr, _ = model(p_ids, p_mask)
+                negative_repr, _ = model(n_ids, n_mask)
             if num_negatives > 1:
                 negative_repr = negative_repr.view(anchor_repr.shape[0], num_negatives, -1)
             loss, loss_dict = loss_fn(anchor_repr=anchor_repr, positive_repr=positive_repr,
@@ -81,6 +93,14 @@ def train_micro_step(model, loss_fn, optimizer, scheduler, batch: Dict[str, torc
         optimizer.zero_grad()
         global_step += 1
     return loss, loss_dict, global_step
+
+
+def concat_padded(ids_list, mask_list, pad_id: int = 0):
+    """Right-pads every (ids, mask) pair to the longest sequence length among them and concatenates along the batch."""
+    S = max(t.shape[1] for t in ids_list)
+    ids = [torch.nn.functional.pad(t, (0, S - t.shape[1]), value=pad_id) for t in ids_list]
+    mask = [torch.nn.functional.pad(t, (0, S - t.shape[1]), value=0) for t in mask_list]
+    return torch.cat(ids, dim=0), torch.cat(mask, dim=0)
 
 
 def synthetic_triplet_batch(batch_size: int, q_len: int, d_len: int, num_negatives: int, vocab_size: int,

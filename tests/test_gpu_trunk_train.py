@@ -200,3 +200,35 @@ def test_native_trunk_training_steps_through_ddp_and_accumulation(cuda_device):
             assert cos >= 0.7, (name, cos)
     finally:
         dist.destroy_process_group()
+
+
+def test_fused_encoder_calls_give_the_same_vectors_and_gradients(cuda_device):
+    """StepConfig.fuse_encoder_calls: one encoder call for queries + positives + negatives (padded to a common
+    length) against three calls - same sparse vectors (bit for bit through the packed native trunk: a token's row
+    does not depend on its neighbours) and the same parameter gradients up to summation order."""
+    import splade_b200
+    from splade_b200.training import concat_padded
+    from tests.model_util import tiny_modernbert_dir
+    d = tiny_modernbert_dir(vocab_size=5000, hidden=256, heads=4, layers=3, bias_offset=-0.3)
+    model = splade_b200.SPLADEModernBERT(model_name=d).to(cuda_device).train()
+    model.use_native_trunk(False, train=True)
+    q, p = _batch(8, 16, 5000, cuda_device, 17), _batch(8, 64, 5000, cuda_device, 18)
+    loss_fn = splade_b200.SPLADELossV33()
+
+    def run(fused):
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if fused:
+                ids, mask = concat_padded((q[0], p[0]), (q[1], p[1]))
+                a, pp = model(ids, mask)[0].split([8, 8])
+            else:
+                a, pp = model(*q)[0], model(*p)[0]
+            loss, _ = loss_fn(a, pp, pp.flip(0), global_step=100)
+        loss.backward()
+        return a.detach(), pp.detach(), {n: t.grad.clone() for n, t in model.named_parameters() if t.grad is not None}
+
+    a1, p1, g1 = run(False)
+    a2, p2, g2 = run(True)
+    assert torch.equal(a1, a2) and torch.equal(p1, p2)
+    for n in g1:
+        assert _rel(g2[n], g1[n]) <= 1e-3, (n, _rel(g2[n], g1[n]))

@@ -436,3 +436,13 @@ def test_packed_row_index_and_suffix_mask():
     holes[0, 2] = 0
     assert not suffix_mask(holes)
     assert suffix_mask(torch.ones(3, 7, dtype=torch.int64))
+
+
+def test_concat_padded():
+    import torch
+
+    from splade_b200.training import concat_padded
+    a, am = torch.tensor([[5, 6]]), torch.tensor([[1, 1]])
+    b, bm = torch.tensor([[7, 8, 9, 0]]), torch.tensor([[1, 1, 1, 0]])
+    ids, mask = concat_padded((a, b), (am, bm), pad_id=3)
+    assert ids.tolist() == [[5, 6, 3, 3], [7, 8, 9, 0]] and mask.tolist() == [[1, 1, 0, 0], [1, 1, 1, 0]]
