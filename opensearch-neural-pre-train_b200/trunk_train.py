@@ -23,7 +23,6 @@ right-padded (suffix) attention masks.
 from __future__ import annotations
 
 import ctypes
-import math
 from typing import List
 
 import torch
@@ -32,7 +31,7 @@ import torch.nn.functional as F
 from . import _lib
 from ._lib import check, load_library
 from .ops import _mm_f32
-from .trunk import NativeTrunk, trunk_gemm
+from .trunk import NativeTrunk
 
 
 def _ln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float, dx: torch.Tensor, accumulate: bool):
@@ -367,4 +366,3 @@ def suffix_mask(attention_mask: torch.Tensor) -> bool:
 
 
 __all__ = ["NativeTrunkTrain", "packed_row_index", "suffix_mask"]
-_ = math  # (kept for callers that monkeypatch tables in tests)
