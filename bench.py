@@ -372,6 +372,10 @@ def run_train_leg(dev, world, rank, steps, warmup, k_neg=1, gather=False, bias_o
                            else "") + "; trunk excluded",
             "accum": accum,
             "head_fwd_tflop_per_step_per_gpu": head_flop / 1e12, "nonzero_d": d["nonzero_d"],
+            # north-star figure: the WHOLE hot-path step (3 head forwards + sparse backward + loss forward / backward +
+            # the gradient exchange) counted with the forward's algorithmic flop only, against the measured bf16 peak
+            "head_fwd_tflops_over_whole_step": head_flop / 1e12 / (ms / steps * 1e-3),
+            "fraction_of_bf16_peak_whole_step": head_flop / 1e12 / (ms / steps * 1e-3) / load_peaks()["burst"],
             "regime": f"decoder.bias offset {bias_offset}: {d['nonzero_d']:.0f} active terms per document",
             "negatives_exchange": exchange_used, "scaling": "weak"}
 
