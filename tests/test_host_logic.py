@@ -446,3 +446,30 @@ def test_concat_padded():
     b, bm = torch.tensor([[7, 8, 9, 0]]), torch.tensor([[1, 1, 1, 0]])
     ids, mask = concat_padded((a, b), (am, bm), pad_id=3)
     assert ids.tolist() == [[5, 6, 3, 3], [7, 8, 9, 0]] and mask.tolist() == [[1, 1, 0, 0], [1, 1, 1, 0]]
+
+
+def test_prologue_of_eligibility():
+    """Which prediction heads the fused prologue may stand in for (no biases, exact GELU, hidden 256..1024 in steps
+    of 256); anything else keeps the transformers module."""
+    import torch
+    from transformers import ModernBertConfig
+    from transformers.models.modernbert.modeling_modernbert import ModernBertPredictionHead
+
+    from splade_b200.ops import prologue_of
+
+    def head(**kw):
+        hidden = kw.pop("hidden", 256)
+        cfg = ModernBertConfig(vocab_size=100, hidden_size=hidden, intermediate_size=hidden * 3 // 2,
+                               num_hidden_layers=2, num_attention_heads=hidden // 64, pad_token_id=99, bos_token_id=0,
+                               eos_token_id=1, cls_token_id=0, sep_token_id=1, max_position_embeddings=512,
+                               global_attn_every_n_layers=2, local_attention=128, **kw)
+        return ModernBertPredictionHead(cfg)
+
+    ok = prologue_of(head())
+    assert ok is not None and ok[0].shape == (256, 256) and ok[1].shape == (256,) and ok[2] > 0
+    assert prologue_of(head(hidden=768)) is not None
+    assert prologue_of(head(hidden=128)) is None                      # not a multiple of 256
+    assert prologue_of(head(classifier_bias=True)) is None
+    assert prologue_of(head(norm_bias=True)) is None
+    assert prologue_of(head(classifier_activation="relu")) is None
+    assert prologue_of(torch.nn.Linear(4, 4)) is None
