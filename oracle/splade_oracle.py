@@ -18,12 +18,41 @@ Reference lines restated:
   InfoNCE             src/model/losses.py:136-181
   total / KD / dict   src/model/losses.py:183-297
   top-k emit          benchmark/encoders.py:320-343 ; src/model/splade_modern.py:99-114
+  head prologue       transformers modeling_modernbert.py:493-502 (ModernBertPredictionHead), called from
+                      src/model/splade_modern.py:69-73 through self.model(...)  [SURVEY 8(f) N1]
 """
 from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# head prologue (SURVEY 8(f) N1): hidden = LayerNorm(GELU(dense(x))), no biases, exact-erf GELU
+# ------------------------------------------------------------------------------------------------
+def head_prologue(x: np.ndarray, dense_w: np.ndarray, norm_w: np.ndarray, eps: float, mode: str = "bf16"):
+    """x [T,H], dense_w [H,H], norm_w [H] -> (y, g, hidden).  mode "fp32": the module as written (float64 arithmetic);
+    mode "bf16": what torch.autocast(bf16) computes - operands rounded to bf16, the Linear output rounded to bf16, GELU
+    evaluated in fp32 and rounded to bf16, LayerNorm in fp32 on those values (its fp32 result is what the decoder's
+    own bf16 cast then rounds)."""
+    from math import erf, sqrt
+    verf = np.vectorize(erf, otypes=[np.float64])
+    x64 = np.asarray(x, dtype=np.float64)
+    w64 = np.asarray(dense_w, dtype=np.float64)
+    if mode == "bf16":
+        x64 = bf16_round(x64.astype(np.float32)).astype(np.float64)
+        w64 = bf16_round(w64.astype(np.float32)).astype(np.float64)
+    y = x64 @ w64.T
+    if mode == "bf16":
+        y = bf16_round(y.astype(np.float32)).astype(np.float64)
+    g = 0.5 * y * (1.0 + verf(y / sqrt(2.0)))
+    if mode == "bf16":
+        g = bf16_round(g.astype(np.float32)).astype(np.float64)
+    mean = g.mean(axis=-1, keepdims=True)
+    var = ((g - mean) ** 2).mean(axis=-1, keepdims=True)
+    hidden = (g - mean) / np.sqrt(var + eps) * np.asarray(norm_w, dtype=np.float64)
+    return y.astype(np.float32), g.astype(np.float32), hidden.astype(np.float32)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -177,3 +177,31 @@ def test_model_gradients_through_the_fused_prologue(models256, cuda_device):
         assert rel <= 2e-2, (name, rel)
     for name in ("model.head.dense.weight", "model.head.norm.weight"):
         assert float(grads[name].grad.abs().max()) > 0
+
+
+def test_prologue_forward_against_the_numpy_oracle(cuda_device):
+    """The CUDA prologue against oracle/splade_oracle.py::head_prologue (autocast form), itself pinned to the
+    transformers module in the CPU suite."""
+    import numpy as np
+
+    from oracle import splade_oracle as O
+    from splade_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    T, H = 200, 256
+    x = torch.randn(T, H, generator=g)
+    dense_w = torch.randn(H, H, generator=g) * H ** -0.5
+    norm_w = 1.0 + 0.1 * torch.randn(H, generator=g)
+    ry, rg, rh = O.head_prologue(x.numpy(), dense_w.numpy(), norm_w.numpy(), 1e-5, mode="bf16")
+    x16 = x.to(torch.bfloat16).to(cuda_device).contiguous()
+    y, hidden, stats = ops.head_prologue_forward(x16, dense_w.to(torch.bfloat16).to(cuda_device).contiguous(),
+                                                 norm_w.to(cuda_device), 1e-5, T)
+    y = y[:T].float().cpu().numpy()
+    assert float(np.mean(y != ry)) <= 2e-2                                   # accumulation order at rounding boundaries
+    assert float(np.max(np.abs(y - ry) - 2.0 ** -7 * np.abs(ry))) <= 1e-6    # never more than one bf16 ulp
+    rows_same = (y == ry).all(axis=1)
+    assert rows_same.sum() >= 1
+    want = O.bf16_round(rh)[rows_same]
+    got = hidden[:T].float().cpu().numpy()[rows_same]
+    bad = np.abs(got - want) > 2.0 ** -7 * np.abs(want) + 1e-3              # one bf16 ulp
+    assert float(bad.mean()) <= 1e-3
+    np.testing.assert_allclose(stats[:, 0].cpu().numpy()[rows_same], rg[rows_same].mean(axis=1), rtol=1e-3, atol=1e-4)
