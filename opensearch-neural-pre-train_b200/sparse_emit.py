@@ -117,9 +117,9 @@ class SparseEmitter:
         dec = -1 if round_decimals is None else int(round_decimals)
         cap = B * (2 + k * 40)  # first guess; grown once if tokens are long
         for _ in range(2):
-            out = ctypes.create_string_buffer(max(cap, 1))
+            out = np.empty(max(cap, 1), dtype=np.uint8)   # (no zero-fill: the emitter writes every byte it reports)
             rc = lib.splade_emit_json(ids_h.ctypes.data, vals_h.ctypes.data, counts_h.ctypes.data, B, k, tok_ptr,
-                                      off_ptr, n_tok, dec, ctypes.addressof(out), cap, offsets.ctypes.data,
+                                      off_ptr, n_tok, dec, out.ctypes.data, cap, offsets.ctypes.data,
                                       ctypes.byref(need))
             if rc == 0:
                 break
@@ -129,7 +129,7 @@ class SparseEmitter:
             check(rc, "splade_emit_json")
         else:
             check(rc, "splade_emit_json")
-        raw = out.raw
+        raw = out[: need.value].tobytes()
         return [raw[offsets[b]:offsets[b + 1]] for b in range(B)]
 
     def to_bulk(self, ids: torch.Tensor, vals: torch.Tensor, counts: torch.Tensor, index_name: str,
